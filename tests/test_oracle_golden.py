@@ -1,0 +1,183 @@
+"""Pin the oracle: (1) against golden outputs of the unmodified reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py), (2) port vs closed forms,
+(3) the invariants the reference's own docstring demos show.
+CPU only."""
+import numpy as np
+import pytest
+import scipy.fft
+import scipy.sparse
+
+import oracle
+
+TOL = 1e-11  # float64 vs float64 of the same operation sequence
+
+
+def close(a, b, tol=TOL):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return
+    scale = max(1.0, float(np.max(np.abs(b))))
+    assert float(np.max(np.abs(a - b))) <= tol * scale
+
+
+# ------------------------------------------------------------------ golden: stft / istft
+def test_stft_istft_match_reference(golden):
+    g = golden("stft")
+    for case in g.cases():
+        w = g.get(case, "w")
+        hop = int(g.get(case, "hop"))
+        if g.has(case, "x"):
+            x = g.get(case, "x")
+            close(oracle.stft(x, w, hop), g.get(case, "stft"))
+            spec = g.get(case, "stft")
+        else:
+            spec = g.get(case, "spec")
+        close(oracle.istft(spec, w, hop), g.get(case, "istft"))
+
+
+def test_geometry_matches_reference(golden):
+    g = golden("geometry")
+    for ns, n, hop, nt, ilen in g.raw("stft_rows"):
+        pad, nt_o, tail = oracle.stft_geometry(int(ns), int(n), int(hop))
+        assert nt_o == nt
+        assert pad == n // 2 and tail >= 0
+        assert oracle.istft_length(int(n), int(nt), int(hop))[2] == ilen
+    for ns, n, nt, ilen in g.raw("mdct_rows"):
+        half, nt_o, front, tail = oracle.mdct_geometry(int(ns), int(n))
+        assert (half, nt_o, front) == (n // 2, nt, n // 2) and tail >= 0
+        assert oracle.imdct_length(int(half), int(nt))[1] == ilen
+
+
+# ------------------------------------------------------------------ golden: mel / mfcc
+def test_melfilterbank_matches_reference(golden):
+    g = golden("mel")
+    close(oracle.melfilterbank(16000, 1024, 128), g.raw("fb_16k_1024_128"), 0)
+    close(oracle.melfilterbank(44100, 2048, 128), g.raw("fb_44k_2048_128"), 0)
+    close(oracle.melfilterbank(8000, 256, 20), g.raw("fb_8k_256_20"), 0)
+
+
+def test_mel_mfcc_match_reference(golden):
+    g = golden("mel")
+    for case in g.cases():
+        x, w, hop = g.get(case, "x"), g.get(case, "w"), int(g.get(case, "hop"))
+        fb = oracle.melfilterbank(int(g.get(case, "fs")), len(w), int(g.get(case, "nmel")))
+        close(oracle.melspectrogram(x, w, hop, fb), g.get(case, "mel"))
+        close(oracle.mfcc(x, w, hop, fb, int(g.get(case, "ncoef"))), g.get(case, "mfcc"), 1e-9)
+    assert np.max(np.abs(g.get("silent", "mfcc"))) < 1e-12
+
+
+def test_mfcc_dct_is_the_closed_form_matrix():
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal((128, 5))
+    close(oracle.dct2_ortho_matrix(128) @ v, scipy.fft.dct(v, axis=0, norm="ortho"))
+
+
+# ------------------------------------------------------------------ golden: CQT
+def _kernel(g, tag):
+    shape = tuple(int(s) for s in g.get(tag, "kernel_shape"))
+    return scipy.sparse.csr_matrix(
+        (g.get(tag, "kernel_data"), g.get(tag, "kernel_indices"), g.get(tag, "kernel_indptr")), shape=shape)
+
+
+def test_cqt_matches_reference(golden):
+    g = golden("cqt")
+    for tag in g.cases():
+        fs, res, fmin, fmax = g.get(tag, "params")
+        k_ref = _kernel(g, tag)
+        k = oracle.cqtkernel(int(fs), int(res), fmin, fmax)
+        close(k, k_ref.toarray(), 1e-15)
+        x = g.get(tag, "x")
+        tr = int(g.get(tag, "time_resolution"))
+        close(oracle.cqtspectrogram(x, int(fs), tr, k_ref), g.get(tag, "spec"))
+        close(oracle.cqtspectrogram(x, int(fs), tr, k), g.get(tag, "spec"))
+        close(oracle.cqtchromagram(x, int(fs), tr, int(res), k_ref), g.get(tag, "chroma"))
+
+
+def test_cqt_kernel_structure(golden):
+    """Facts the packed GPU format relies on: every row is one
+    contiguous band and the kernel is real to rounding."""
+    g = golden("cqt")
+    for tag in g.cases():
+        k = _kernel(g, tag)
+        assert np.max(np.abs(k.data.imag)) <= 1e-12 * np.max(np.abs(k.data.real))
+        for r in range(k.shape[0]):
+            cols = k.indices[k.indptr[r]:k.indptr[r + 1]]
+            assert len(cols) > 0 and np.all(np.diff(cols) == 1)
+
+
+# ------------------------------------------------------------------ golden: dct / dst
+def test_dct_dst_match_reference_and_scipy(golden):
+    g = golden("dctdst")
+    for case in g.cases():
+        x = g.get(case, "x")
+        for t in (1, 2, 3, 4):
+            close(oracle.dct(x, t), g.get(case, f"dct{t}"))
+            close(oracle.dst(x, t), g.get(case, f"dst{t}"))
+            close(oracle.dct_direct(x, t), g.get(case, f"dct{t}"))
+            close(oracle.dst_direct(x, t), g.get(case, f"dst{t}"))
+            # the reference's own demo (zaf.py:734-753): equals SciPy's orthonormal transforms
+            close(scipy.fft.dct(x, type=t, norm="ortho"), g.get(case, f"dct{t}"))
+            close(scipy.fft.dst(x, type=t, norm="ortho"), g.get(case, f"dst{t}"))
+    assert oracle.dct(np.ones(8), 5) is None and oracle.dst(np.ones(8), 0) is None
+
+
+def test_dst_inverse_pairs():
+    """zaf.py:872-895: DST-I and DST-IV are involutions, DST-III inverts DST-II."""
+    x = np.random.default_rng(2).standard_normal(256)
+    close(oracle.dst(oracle.dst(x, 1), 1), x)
+    close(oracle.dst(oracle.dst(x, 2), 3), x)
+    close(oracle.dst(oracle.dst(x, 4), 4), x)
+    close(oracle.dct(oracle.dct(x, 2), 3), x)
+
+
+# ------------------------------------------------------------------ golden: mdct / imdct
+def test_mdct_imdct_match_reference(golden):
+    g = golden("mdct")
+    for case in g.cases():
+        x, w = g.get(case, "x"), g.get(case, "w")
+        close(oracle.mdct(x, w), g.get(case, "mdct"))
+        close(oracle.imdct(g.get(case, "mdct"), w), g.get(case, "imdct"))
+        if len(w) <= 256:
+            close(oracle.mdct_direct(x, w), g.get(case, "mdct"), 1e-10)
+            close(oracle.imdct_direct(g.get(case, "mdct"), w), g.get(case, "imdct"), 1e-10)
+
+
+def test_mdct_tdac_round_trip():
+    """zaf.py:1098-1109: perfect reconstruction with a Princen-Bradley window."""
+    x = np.random.default_rng(3).uniform(-1, 1, 5000)
+    for w in (oracle.sine_window(512), oracle.kbd_window(512)):
+        y = oracle.imdct(oracle.mdct(x, w), w)
+        close(y[:len(x)], x, 1e-10)
+    with pytest.raises(ValueError):
+        oracle.mdct(x, np.ones(255))
+
+
+# ------------------------------------------------------------------ port vs closed forms
+def test_stft_port_vs_direct():
+    rng = np.random.default_rng(4)
+    for ns, n, hop in ((500, 64, 16), (333, 128, 50), (10, 32, 8), (0, 16, 4), (200, 63, 10)):
+        x = rng.uniform(-1, 1, ns)
+        w = oracle.hamming_periodic(n)
+        spec = oracle.stft(x, w, hop)
+        close(oracle.stft_direct(x, w, hop), spec, 1e-10)
+        close(oracle.istft_direct(spec, w, hop), oracle.istft(spec, w, hop), 1e-10)
+
+
+def test_stft_istft_round_trip_and_shift_quirk():
+    """hop=N/2 is the identity; hop=N/4 returns x advanced by N/4."""
+    x = np.random.default_rng(5).uniform(-1, 1, 4000)
+    n = 256
+    w = oracle.hamming_periodic(n)
+    y = oracle.istft(oracle.stft(x, w, n // 2), w, n // 2)
+    close(y[:len(x)], x, 1e-12)
+    y = oracle.istft(oracle.stft(x, w, n // 4), w, n // 4)
+    shift = (n - n // 4) - n // 2
+    m = min(len(y), len(x) - shift)
+    close(y[:m], x[shift:shift + m], 1e-12)
+
+
+def test_stft_rejects_2d():
+    with pytest.raises(ValueError):
+        oracle.stft(np.zeros((4, 100)), np.ones(16), 4)
