@@ -1,0 +1,176 @@
+/*
+ * zafb200.h -- C ABI of libzafb200.so: the B200 (sm_100a) implementation of the
+ * data-parallel transform hot path of zafarrafii/Zaf-Python (zaf.py).
+ *
+ * The reference has no FFI of its own: its boundary is the module-level Python
+ * signatures.  Each compute entry point below names the
+ * reference function (file:line in /root/reference) whose body it replaces; the
+ * ctypes binding that calls it lives in zaf-python_b200/_lib.py and the drop-in
+ * functions with the reference's signatures in zaf-python_b200/__init__.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions cross the boundary.
+ *   - every function returns 0 (ZAFB_OK) or a negative ZAFB_E_* code;
+ *     zafb_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns every data buffer; the library owns only opaque plans
+ *     (immutable after creation: window / twiddle / filterbank tables in HBM).
+ *   - "_f32" entry points take DEVICE pointers and a CUDA stream (cudaStream_t
+ *     passed as void*; NULL = default stream) and never synchronise.
+ *   - "_host_f32" entry points take HOST pointers, do H2D -> kernels -> D2H in
+ *     pipelined chunks on the library's own streams and return when the output
+ *     is complete.
+ *   - complex data is interleaved (re, im) float32.
+ *   - arithmetic type: fp32 (tables are generated in float64 and rounded once).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails
+ *     with ZAFB_E_CUDA.
+ */
+#ifndef ZAFB200_H
+#define ZAFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZAFB_OK 0
+#define ZAFB_E_BADARG (-1)      /* -> ValueError            */
+#define ZAFB_E_UNSUPPORTED (-2) /* -> NotImplementedError   */
+#define ZAFB_E_CUDA (-3)        /* -> RuntimeError          */
+#define ZAFB_E_NOMEM (-4)       /* -> MemoryError           */
+#define ZAFB_E_NCCL (-5)        /* -> RuntimeError          */
+
+/* Output layouts of the (frequency, time) matrices.
+ *   ZAFB_LAYOUT_FRAME_MAJOR: memory is [clip][frame][bin]   (bin contiguous; the Python
+ *                            wrapper exposes it as a transposed view of shape (bins, frames))
+ *   ZAFB_LAYOUT_BIN_MAJOR  : memory is [clip][bin][frame]   (frame contiguous; the reference's
+ *                            C-order (window_length, number_times) array, zaf.py:128) */
+#define ZAFB_LAYOUT_FRAME_MAJOR 0
+#define ZAFB_LAYOUT_BIN_MAJOR 1
+
+/* ---------------------------------------------------------------- runtime */
+const char* zafb_last_error(void);
+const char* zafb_version(void);
+int zafb_device_count(int* count);
+int zafb_init(int device);              /* cudaSetDevice + context warm-up            */
+int zafb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
+                     size_t* total_mem, char* name, size_t name_len);
+
+int zafb_malloc(void** dev_ptr, size_t bytes);
+int zafb_free(void* dev_ptr);
+int zafb_host_alloc(void** host_ptr, size_t bytes);   /* pinned */
+int zafb_host_free(void* host_ptr);
+int zafb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int zafb_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int zafb_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+int zafb_memset(void* dev_ptr, int value, size_t bytes, void* stream);
+
+int zafb_stream_create(void** stream);
+int zafb_stream_destroy(void* stream);
+int zafb_stream_sync(void* stream);
+int zafb_device_sync(void);
+int zafb_event_create(void** event);
+int zafb_event_destroy(void* event);
+int zafb_event_record(void* event, void* stream);
+int zafb_event_sync(void* event);
+int zafb_event_elapsed_ms(void* start, void* stop, float* ms);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t zafb_launch_count(void);
+
+/* ------------------------------------------------------- integer bookkeeping
+ * Bit-exact restatements of the reference's frame arithmetic (no device needed). */
+/* zaf.py:99-121   pad = floor(N/2); nt = ceil((ns+2*pad-N)/hop)+1; tail pad          */
+int zafb_stft_geometry(int64_t number_samples, int64_t window_length, int64_t step_length,
+                       int64_t* pad, int64_t* number_times, int64_t* tail);
+/* zaf.py:217,236-238  OLA length nt*hop+(N-hop); output = ola[N-hop : ola-(N-hop)] with Python
+ * slice semantics; `trim` receives the slice start (N-hop whenever hop <= N)            */
+int zafb_istft_geometry(int64_t window_length, int64_t number_times, int64_t step_length,
+                        int64_t* ola_length, int64_t* trim, int64_t* number_samples);
+/* zaf.py:1029-1041 */
+int zafb_mdct_geometry(int64_t number_samples, int64_t window_length, int64_t* half,
+                       int64_t* number_times, int64_t* tail);
+/* zaf.py:1132,1182   OLA length M*(nt+1); output = [M : -M-1]                        */
+int zafb_imdct_geometry(int64_t number_frequencies, int64_t number_times, int64_t* ola_length,
+                        int64_t* number_samples);
+/* zaf.py:603-620; `step` is computed by the caller (Python round-half-even of a float) */
+int zafb_cqt_geometry(int64_t number_samples, int64_t step_length, int64_t fft_length,
+                      int64_t* number_times, int64_t* front_pad, int64_t* back_pad);
+
+/* ------------------------------------------------------------- STFT / ISTFT
+ * Plan: window (float64 on host, rounded once to fp32), twiddle tables. */
+typedef struct zafb_stft_plan zafb_stft_plan;
+int zafb_stft_plan_create(zafb_stft_plan** plan, const double* window, int64_t window_length,
+                          int64_t step_length);
+int zafb_stft_plan_destroy(zafb_stft_plan* plan);
+
+/* Replaces the body of zaf.stft (zaf.py:95-141) for a batch of n_clips signals of ns samples
+ * (clip c starts at x + c*clip_stride).  out: n_clips * window_length * number_times complex64
+ * in `layout`; the full two-sided spectrum, like the reference. */
+int zafb_stft_f32(const zafb_stft_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                  int64_t clip_stride, float* out, int layout, void* stream);
+/* Replaces zaf.istft (zaf.py:214-243).  spec: n_clips * window_length * nt complex64 in `layout`;
+ * y: n_clips rows of nt*hop-(N-hop) samples, row c at y + c*y_stride. */
+int zafb_istft_f32(const zafb_stft_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
+                   int layout, float* y, int64_t y_stride, void* stream);
+/* Host-buffer versions (pinned or pageable host memory; chunked and pipelined). */
+int zafb_stft_host_f32(const zafb_stft_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
+                       int64_t clip_stride, float* out_host, int layout);
+int zafb_istft_host_f32(const zafb_stft_plan* plan, const float* spec_host, int64_t n_clips,
+                        int64_t nt, int layout, float* y_host, int64_t y_stride);
+
+/* ------------------------------------------------------------- MDCT / IMDCT */
+typedef struct zafb_mdct_plan zafb_mdct_plan;
+int zafb_mdct_plan_create(zafb_mdct_plan** plan, const double* window, int64_t window_length);
+int zafb_mdct_plan_destroy(zafb_mdct_plan* plan);
+/* zaf.mdct (zaf.py:1025-1075): out is n_clips * (N/2) * nt float32 in `layout`. */
+int zafb_mdct_f32(const zafb_mdct_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                  int64_t clip_stride, float* out, int layout, void* stream);
+/* zaf.imdct (zaf.py:1125-1184): y rows of M*(nt-1)-1 samples. */
+int zafb_imdct_f32(const zafb_mdct_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
+                   int layout, float* y, int64_t y_stride, void* stream);
+
+/* ---------------------------------------------------------------- DCT / DST
+ * zaf.dct (zaf.py:759-839) / zaf.dst (zaf.py:901-981): orthonormal types 1..4 of `batch`
+ * vectors of length n (vector b at x + b*stride).  kind: 0 = DCT, 1 = DST. */
+typedef struct zafb_dct_plan zafb_dct_plan;
+int zafb_dct_plan_create(zafb_dct_plan** plan, int kind, int type, int64_t n);
+int zafb_dct_plan_destroy(zafb_dct_plan* plan);
+int zafb_dct_f32(const zafb_dct_plan* plan, const float* x, int64_t batch, int64_t stride,
+                 float* out, int64_t out_stride, void* stream);
+
+/* ----------------------------------------------------- mel spectrogram / MFCC
+ * The filterbank is passed dense row-major (n_mels x N/2, float64) -- the wrapper calls
+ * .toarray() exactly like zaf.py:373 -- and packed into per-row bands at plan creation.
+ * n_coef = 0 builds a melspectrogram-only plan. */
+typedef struct zafb_mel_plan zafb_mel_plan;
+int zafb_mel_plan_create(zafb_mel_plan** plan, const double* window, int64_t window_length,
+                         int64_t step_length, const double* filterbank, int64_t n_mels,
+                         int64_t n_coef);
+int zafb_mel_plan_destroy(zafb_mel_plan* plan);
+/* zaf.melspectrogram (zaf.py:369-375): out n_clips * n_mels * nt float32 in `layout`. */
+int zafb_melspectrogram_f32(const zafb_mel_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                            int64_t clip_stride, float* out, int layout, void* stream);
+/* zaf.mfcc (zaf.py:436-454): out n_clips * n_coef * nt float32 in `layout`. */
+int zafb_mfcc_f32(const zafb_mel_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                  int64_t clip_stride, float* out, int layout, void* stream);
+
+/* ------------------------------------------------------- CQT spectrogram/chroma
+ * The kernel is passed as CSR (complex128 data as interleaved doubles), i.e. the
+ * scipy.sparse.csr_matrix zaf.cqtkernel returns (zaf.py:554-557). */
+typedef struct zafb_cqt_plan zafb_cqt_plan;
+int zafb_cqt_plan_create(zafb_cqt_plan** plan, int64_t n_freqs, int64_t fft_length,
+                         const int32_t* indptr, const int32_t* indices, const double* data_ri,
+                         int64_t step_length);
+int zafb_cqt_plan_destroy(zafb_cqt_plan* plan);
+/* zaf.cqtspectrogram (zaf.py:603-635): out n_clips * n_freqs * nt float32 in `layout`.
+ * octave_resolution > 0 additionally folds rows i::octave_resolution (zaf.cqtchromagram,
+ * zaf.py:682-700) and the output has octave_resolution rows instead. */
+int zafb_cqt_f32(const zafb_cqt_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                 int64_t clip_stride, int64_t octave_resolution, float* out, int layout,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZAFB200_H */

@@ -60,7 +60,7 @@ def istft_length(window_length: int, number_times: int, step_length: int):
     """(overlap-add length, trim at each end, output length) -- zaf.py:217, 236-238."""
     total = number_times * step_length + (window_length - step_length)         # :217
     trim = window_length - step_length                                         # :236-238
-    return total, trim, max(total - 2 * trim, 0)
+    return total, trim, len(range(total)[trim:total - trim])                   # Python slice semantics
 
 
 def mdct_geometry(number_samples: int, window_length: int):

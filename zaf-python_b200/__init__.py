@@ -1,0 +1,451 @@
+"""zaf-python_b200: B200 (sm_100a) drop-in for the transform hot path of zaf.py.
+
+    import zaf_python_b200 as zaf          # repo-root shim for the hyphenated directory name
+    X = zaf.stft(x, w, hop)                # same signatures as the reference module
+
+Every function keeps the positional signature of its reference counterpart (zaf.py line cited in
+each docstring) and returns arrays of the same *shape*; values are computed in fp32 on the GPU
+(complex64 / float32 results) by the hand-written CUDA kernels in ``csrc/`` through the C ABI in
+``include/zafb200.h``.  Extensions, all keyword-only or by type:
+
+* a leading batch axis: ``(B, number_samples)`` in -> ``(B, ...)`` out (the reference rejects 2-D);
+* ``DeviceArray`` in -> ``DeviceArray`` out (device-resident pipelines, no host round trip);
+* ``layout="frame_major"`` (default: memory is ``[frame][bin]`` and the result is the transposed
+  view, i.e. the reference's shape with Fortran-like strides) or ``layout="bin_major"`` (the
+  reference's C-order memory).
+
+There is no CPU fallback and no dependency on PyTorch/CuPy/cuFFT: without the shared library or a
+CUDA device the functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from ._device import (DeviceArray, Event, PinnedArray, Stream, device_count, empty, ensure_init, init,  # noqa: F401
+                      launch_count, synchronize, to_device)
+from ._lib import LAYOUT_BIN_MAJOR, LAYOUT_FRAME_MAJOR, ZafbError  # noqa: F401
+from ._operators import cqtkernel, melfilterbank  # noqa: F401
+
+__all__ = [
+    "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
+    "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
+    "to_device", "empty", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count",
+    "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry",
+]
+
+_LAYOUTS = {"frame_major": LAYOUT_FRAME_MAJOR, "bin_major": LAYOUT_BIN_MAJOR}
+
+
+# ------------------------------------------------------------------ integer bookkeeping
+def _geom(fn, n_out, *args):
+    outs = [C.c_int64(0) for _ in range(n_out)]
+    _lib.check(getattr(_lib.lib(), fn)(*[int(a) for a in args], *[C.byref(o) for o in outs]))
+    return tuple(o.value for o in outs)
+
+
+def stft_geometry(number_samples, window_length, step_length):
+    """(front pad, number_times, tail pad) -- zaf.py:99-121, bit-exact."""
+    return _geom("zafb_stft_geometry", 3, number_samples, window_length, step_length)
+
+
+def istft_geometry(window_length, number_times, step_length):
+    """(overlap-add length, slice start, number_samples) -- zaf.py:217, 236-238."""
+    return _geom("zafb_istft_geometry", 3, window_length, number_times, step_length)
+
+
+def mdct_geometry(number_samples, window_length):
+    """(M, number_times, tail pad) -- zaf.py:1029-1041."""
+    return _geom("zafb_mdct_geometry", 3, number_samples, window_length)
+
+
+def imdct_geometry(number_frequencies, number_times):
+    """(overlap-add length, number_samples) -- zaf.py:1132, 1182."""
+    return _geom("zafb_imdct_geometry", 2, number_frequencies, number_times)
+
+
+def cqt_geometry(number_samples, sampling_frequency, time_resolution, fft_length):
+    """(step, number_times, front pad, back pad) -- zaf.py:603-620.  ``round`` is Python's
+    round-half-to-even on the float quotient, as in the reference."""
+    step = round(sampling_frequency / time_resolution)
+    return (step,) + _geom("zafb_cqt_geometry", 3, number_samples, step, fft_length)
+
+
+# ------------------------------------------------------------------ plan caches
+class _PlanCache:
+    def __init__(self, create, destroy, capacity=16):
+        self._create, self._destroy, self._cap = create, destroy, capacity
+        self._d = OrderedDict()
+
+    def get(self, key, *args):
+        p = self._d.get(key)
+        if p is not None:
+            self._d.move_to_end(key)
+            return p
+        ensure_init()
+        handle = C.c_void_p()
+        _lib.check(getattr(_lib.lib(), self._create)(C.byref(handle), *args))
+        self._d[key] = handle
+        while len(self._d) > self._cap:
+            _, old = self._d.popitem(last=False)
+            getattr(_lib.lib(), self._destroy)(old)
+        return handle
+
+
+_stft_plans = _PlanCache("zafb_stft_plan_create", "zafb_stft_plan_destroy")
+_mdct_plans = _PlanCache("zafb_mdct_plan_create", "zafb_mdct_plan_destroy")
+_dct_plans = _PlanCache("zafb_dct_plan_create", "zafb_dct_plan_destroy", capacity=64)
+_mel_plans = _PlanCache("zafb_mel_plan_create", "zafb_mel_plan_destroy", capacity=8)
+_cqt_plans = _PlanCache("zafb_cqt_plan_create", "zafb_cqt_plan_destroy", capacity=4)
+
+
+def _window64(window_function):
+    w = np.ascontiguousarray(window_function, dtype=np.float64)
+    if w.ndim != 1:
+        raise ValueError("window_function must be 1-D")
+    return w
+
+
+def _stft_plan(window_function, step_length):
+    w = _window64(window_function)
+    hop = int(step_length)
+    return _stft_plans.get(("stft", len(w), hop, w.tobytes()), w.ctypes.data, len(w), hop), w
+
+
+def _layout_id(layout):
+    try:
+        return _LAYOUTS[layout]
+    except KeyError:
+        raise ValueError(f"layout must be one of {sorted(_LAYOUTS)}") from None
+
+
+def _signal_batch(audio_signal):
+    """-> (float32 C-contiguous (B, ns) array, was_1d).  Like the reference, >2-D is an error."""
+    x = np.asarray(audio_signal)
+    if x.ndim not in (1, 2):
+        raise ValueError("audio_signal must have shape (number_samples,) or (batch, number_samples)")
+    one = x.ndim == 1
+    x = np.ascontiguousarray(x.reshape(1, -1) if one else x, dtype=np.float32)
+    return x, one
+
+
+def _matrix_out(batch, rows, cols, dtype, layout, one):
+    """Host result buffer for a (rows, cols) = (bins, frames) matrix per clip, and the view to return."""
+    if layout == LAYOUT_FRAME_MAJOR:
+        mem = np.empty((batch, cols, rows), dtype=dtype)
+        view = np.swapaxes(mem, 1, 2)
+    else:
+        mem = np.empty((batch, rows, cols), dtype=dtype)
+        view = mem
+    return mem, (view[0] if one else view)
+
+
+def _stream_ptr(stream):
+    return stream.ptr if stream is not None else None
+
+
+# ------------------------------------------------------------------ STFT / ISTFT
+def stft(audio_signal, window_function, step_length, *, layout="frame_major", stream=None, out=None):
+    """Short-time Fourier transform -- drop-in for ``zaf.stft`` (zaf.py:45-141).
+
+    Returns the full two-sided spectrum of shape (window_length, number_times) [complex64];
+    centre padding floor(N/2), number of frames and tail padding follow zaf.py:99-121 exactly.
+    ``out=`` (host path only) supplies the result memory, e.g. a pinned buffer.
+    """
+    plan, w = _stft_plan(window_function, step_length)
+    lay = _layout_id(layout)
+    n = len(w)
+    if isinstance(audio_signal, DeviceArray):
+        x = audio_signal
+        if x.dtype != np.float32 or len(x.shape) not in (1, 2) or x.transposed:
+            raise ValueError("device input must be a float32 (ns,) or (B, ns) DeviceArray")
+        one = len(x.shape) == 1
+        batch, ns = (1, x.shape[0]) if one else x.shape
+        nt = stft_geometry(ns, n, step_length)[1]
+        mem_shape = (batch, nt, n) if lay == LAYOUT_FRAME_MAJOR else (batch, n, nt)
+        out = DeviceArray(mem_shape[1:] if one else mem_shape, np.complex64, transposed=lay == LAYOUT_FRAME_MAJOR)
+        _lib.check(_lib.lib().zafb_stft_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+                                            _stream_ptr(stream)))
+        return out
+    x, one = _signal_batch(audio_signal)
+    batch, ns = x.shape
+    nt = stft_geometry(ns, n, step_length)[1]
+    if out is None:
+        mem, view = _matrix_out(batch, n, nt, np.complex64, lay, one)
+    else:  # caller-provided (e.g. pinned) result memory in the chosen layout
+        want = (batch, nt, n) if lay == LAYOUT_FRAME_MAJOR else (batch, n, nt)
+        if out.dtype != np.complex64 or not out.flags.c_contiguous or out.size != int(np.prod(want)):
+            raise ValueError(f"out must be a C-contiguous complex64 array with {want} elements")
+        mem = out.reshape(want)
+        view = np.swapaxes(mem, 1, 2) if lay == LAYOUT_FRAME_MAJOR else mem
+        view = view[0] if one else view
+    _lib.check(_lib.lib().zafb_stft_host_f32(plan, x.ctypes.data, batch, ns, ns, mem.ctypes.data, lay))
+    return view
+
+
+def _spec_memory(audio_stft, dtype):
+    """Find the memory layout of a (..., bins, frames) host array without copying if possible."""
+    a = np.asarray(audio_stft)
+    if a.ndim not in (2, 3):
+        raise ValueError("expected shape (bins, frames) or (batch, bins, frames)")
+    one = a.ndim == 2
+    if one:
+        a = a[None]
+    if a.dtype != dtype:
+        a = a.astype(dtype)
+    t = np.swapaxes(a, 1, 2)
+    if t.flags.c_contiguous and not a.flags.c_contiguous:
+        return t, LAYOUT_FRAME_MAJOR, one, a.shape
+    return np.ascontiguousarray(a), LAYOUT_BIN_MAJOR, one, a.shape
+
+
+def istft(audio_stft, window_function, step_length, *, stream=None):
+    """Inverse STFT by constant overlap-add -- drop-in for ``zaf.istft`` (zaf.py:144-243).
+
+    Output length nt*hop - (N - hop); only the real part of the inverse transform is kept, no
+    synthesis window, division by sum(w[0:N:hop]) -- all as in the reference (including its
+    N-hop trim, which makes the round trip an identity only for hop = N/2).
+    """
+    plan, w = _stft_plan(window_function, step_length)
+    n = len(w)
+    if isinstance(audio_stft, DeviceArray):
+        s = audio_stft
+        if s.dtype != np.complex64 or len(s.shape) not in (2, 3):
+            raise ValueError("device input must be a complex64 (N, nt) or (B, N, nt) DeviceArray")
+        one = len(s.shape) == 2
+        shape = s.shape
+        batch = 1 if one else shape[0]
+        if shape[-2] != n:
+            raise ValueError(f"audio_stft has {shape[-2]} bins but the window has {n} samples")
+        nt = shape[-1]
+        length = istft_geometry(n, nt, step_length)[2]
+        out = DeviceArray((length,) if one else (batch, length), np.float32)
+        lay = LAYOUT_FRAME_MAJOR if s.transposed else LAYOUT_BIN_MAJOR
+        _lib.check(_lib.lib().zafb_istft_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), length,
+                                             _stream_ptr(stream)))
+        return out
+    mem, lay, one, shape = _spec_memory(audio_stft, np.complex64)
+    batch, bins, nt = shape
+    if bins != n:
+        raise ValueError(f"audio_stft has {bins} bins but the window has {n} samples")
+    length = istft_geometry(n, nt, step_length)[2]
+    y = np.empty((batch, length), dtype=np.float32)
+    _lib.check(_lib.lib().zafb_istft_host_f32(plan, mem.ctypes.data, batch, nt, lay, y.ctypes.data, length))
+    return y[0] if one else y
+
+
+# ------------------------------------------------------------------ helpers for device-side one-shot calls
+def _run_on_device(x_host, out_mem, call):
+    """H2D -> call(x_dev_ptr, out_dev_ptr) -> D2H for the transforms without a host-pipelined entry point."""
+    ensure_init()
+    xd = to_device(x_host)
+    od = DeviceArray(out_mem.shape, out_mem.dtype)
+    try:
+        call(C.c_void_p(xd.ptr), C.c_void_p(od.ptr))
+        od.to_host(out=out_mem)
+    finally:
+        xd.free()
+        od.free()
+
+
+# ------------------------------------------------------------------ MDCT / IMDCT
+def _mdct_plan(window_function):
+    w = _window64(window_function)
+    if len(w) % 2:
+        raise ValueError("window_function must have an even length (zaf.py:1071 fails to broadcast otherwise)")
+    return _mdct_plans.get(("mdct", len(w), w.tobytes()), w.ctypes.data, len(w)), w
+
+
+def mdct(audio_signal, window_function, *, layout="frame_major", stream=None):
+    """Modified discrete cosine transform -- drop-in for ``zaf.mdct`` (zaf.py:984-1075).
+    Returns (window_length/2, number_times) float32."""
+    plan, w = _mdct_plan(window_function)
+    lay = _layout_id(layout)
+    n = len(w)
+    if isinstance(audio_signal, DeviceArray):
+        x = audio_signal
+        one = len(x.shape) == 1
+        batch, ns = (1, x.shape[0]) if one else x.shape
+        m, nt, _ = mdct_geometry(ns, n)
+        mem_shape = (batch, nt, m) if lay == LAYOUT_FRAME_MAJOR else (batch, m, nt)
+        out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
+        _lib.check(_lib.lib().zafb_mdct_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+                                            _stream_ptr(stream)))
+        return out
+    x, one = _signal_batch(audio_signal)
+    batch, ns = x.shape
+    m, nt, _ = mdct_geometry(ns, n)
+    mem, view = _matrix_out(batch, m, nt, np.float32, lay, one)
+    _run_on_device(x, mem, lambda xd, od: _lib.check(
+        _lib.lib().zafb_mdct_f32(plan, xd, batch, ns, ns, od, lay, None)))
+    return view
+
+
+def imdct(audio_mdct, window_function, *, stream=None):
+    """Inverse MDCT with TDAC overlap-add -- drop-in for ``zaf.imdct`` (zaf.py:1078-1184).
+    Output length M*(nt-1)-1 (the reference's ``[M : -M-1]`` slice)."""
+    plan, w = _mdct_plan(window_function)
+    n = len(w)
+    if isinstance(audio_mdct, DeviceArray):
+        s = audio_mdct
+        one = len(s.shape) == 2
+        shape = s.shape
+        batch = 1 if one else shape[0]
+        if shape[-2] * 2 != n:
+            raise ValueError("audio_mdct rows must equal window_length/2")
+        nt = shape[-1]
+        length = imdct_geometry(n // 2, nt)[1]
+        out = DeviceArray((length,) if one else (batch, length), np.float32)
+        lay = LAYOUT_FRAME_MAJOR if s.transposed else LAYOUT_BIN_MAJOR
+        _lib.check(_lib.lib().zafb_imdct_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), length,
+                                             _stream_ptr(stream)))
+        return out
+    mem, lay, one, shape = _spec_memory(audio_mdct, np.float32)
+    batch, bins, nt = shape
+    if bins * 2 != n:
+        raise ValueError("audio_mdct rows must equal window_length/2")
+    length = imdct_geometry(bins, nt)[1]
+    y = np.empty((batch, length), dtype=np.float32)
+    _run_on_device(mem, y, lambda xd, od: _lib.check(
+        _lib.lib().zafb_imdct_f32(plan, xd, batch, nt, lay, od, length, None)))
+    return y[0] if one else y
+
+
+# ------------------------------------------------------------------ DCT / DST
+def _dct_like(audio_signal, kind, dtype_code):
+    if dtype_code not in (1, 2, 3, 4):
+        return None  # the reference falls through its if/elif chain and returns None (zaf.py:759-839)
+    if isinstance(audio_signal, DeviceArray):
+        x = audio_signal
+        one = len(x.shape) == 1
+        batch, n = (1, x.shape[0]) if one else x.shape
+        plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
+        out = DeviceArray(x.shape, np.float32)
+        _lib.check(_lib.lib().zafb_dct_f32(plan, C.c_void_p(x.ptr), batch, n, C.c_void_p(out.ptr), n, None))
+        return out
+    x, one = _signal_batch(audio_signal)
+    batch, n = x.shape
+    plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
+    out = np.empty((batch, n), dtype=np.float32)
+    _run_on_device(x, out, lambda xd, od: _lib.check(_lib.lib().zafb_dct_f32(plan, xd, batch, n, od, n, None)))
+    return out[0] if one else out
+
+
+def dct(audio_signal, dct_type):
+    """Orthonormal DCT-I/II/III/IV -- drop-in for ``zaf.dct`` (zaf.py:703-839).  A 2-D input is a
+    batch of vectors (extension).  Unknown types return None like the reference."""
+    return _dct_like(audio_signal, 0, dct_type)
+
+
+def dst(audio_signal, dst_type):
+    """Orthonormal DST-I/II/III/IV -- drop-in for ``zaf.dst`` (zaf.py:842-981)."""
+    return _dct_like(audio_signal, 1, dst_type)
+
+
+# ------------------------------------------------------------------ mel spectrogram / MFCC
+def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients):
+    w = _window64(window_function)
+    fb = mel_filterbank.toarray() if hasattr(mel_filterbank, "toarray") else np.asarray(mel_filterbank)  # zaf.py:373
+    fb = np.ascontiguousarray(fb, dtype=np.float64)
+    if fb.ndim != 2 or fb.shape[1] != len(w) // 2:
+        raise ValueError(f"mel_filterbank must have shape (number_mels, window_length/2 = {len(w) // 2})")
+    key = ("mel", len(w), int(step_length), int(number_coefficients), w.tobytes(), fb.tobytes())
+    plan = _mel_plans.get(key, w.ctypes.data, len(w), int(step_length), fb.ctypes.data, fb.shape[0],
+                          int(number_coefficients))
+    return plan, w, fb.shape[0]
+
+
+def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, ncoef, rows_of, layout, stream):
+    plan, w, n_mels = _mel_plan(window_function, step_length, mel_filterbank, ncoef)
+    lay = _layout_id(layout)
+    rows = rows_of(n_mels)
+    if isinstance(audio_signal, DeviceArray):
+        x = audio_signal
+        one = len(x.shape) == 1
+        batch, ns = (1, x.shape[0]) if one else x.shape
+        nt = stft_geometry(ns, len(w), step_length)[1]
+        mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
+        out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
+        _lib.check(getattr(_lib.lib(), fn)(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+                                           _stream_ptr(stream)))
+        return out
+    x, one = _signal_batch(audio_signal)
+    batch, ns = x.shape
+    nt = stft_geometry(ns, len(w), step_length)[1]
+    mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
+    _run_on_device(x, mem, lambda xd, od: _lib.check(
+        getattr(_lib.lib(), fn)(plan, xd, batch, ns, ns, od, lay, None)))
+    return view
+
+
+def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *, layout="frame_major", stream=None):
+    """Mel spectrogram -- drop-in for ``zaf.melspectrogram`` (zaf.py:324-375): filterbank times the
+    magnitude of STFT rows 1..N/2 (no DC, with Nyquist).  Returns (number_mels, number_times)."""
+    return _mel_like("zafb_melspectrogram_f32", audio_signal, window_function, step_length, mel_filterbank, 0,
+                     lambda n_mels: n_mels, layout, stream)
+
+
+def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coefficients, *,
+         layout="frame_major", stream=None):
+    """MFCCs -- drop-in for ``zaf.mfcc`` (zaf.py:378-454): orthonormal DCT-II over the mel axis of
+    ln(filterbank @ |STFT|^2 + eps), rows 1..number_coefficients.  Returns (number_coefficients, number_times)."""
+    ncoef = int(number_coefficients)
+    return _mel_like("zafb_mfcc_f32", audio_signal, window_function, step_length, mel_filterbank, ncoef,
+                     lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream)
+
+
+# ------------------------------------------------------------------ CQT
+def _cqt_plan(cqt_kernel, step):
+    import scipy.sparse
+
+    k = scipy.sparse.csr_matrix(cqt_kernel)
+    k.sort_indices()
+    data = np.ascontiguousarray(k.data, dtype=np.complex128)
+    indptr = np.ascontiguousarray(k.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(k.indices, dtype=np.int32)
+    nf, fft_length = k.shape
+    key = ("cqt", nf, fft_length, int(step), data.tobytes(), indices.tobytes(), indptr.tobytes())
+    plan = _cqt_plans.get(key, nf, fft_length, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, int(step))
+    return plan, nf, fft_length
+
+
+def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resolution, cqt_kernel, layout, stream):
+    step = round(sampling_frequency / time_resolution)  # zaf.py:603 (Python round-half-even)
+    plan, nf, fft_length = _cqt_plan(cqt_kernel, step)
+    lay = _layout_id(layout)
+    rows = octave_resolution if octave_resolution else nf
+    if isinstance(audio_signal, DeviceArray):
+        x = audio_signal
+        one = len(x.shape) == 1
+        batch, ns = (1, x.shape[0]) if one else x.shape
+        nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
+        mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
+        out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
+        _lib.check(_lib.lib().zafb_cqt_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, int(octave_resolution),
+                                           C.c_void_p(out.ptr), lay, _stream_ptr(stream)))
+        return out
+    x, one = _signal_batch(audio_signal)
+    batch, ns = x.shape
+    nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
+    mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
+    _run_on_device(x, mem, lambda xd, od: _lib.check(
+        _lib.lib().zafb_cqt_f32(plan, xd, batch, ns, ns, int(octave_resolution), od, lay, None)))
+    return view
+
+
+def cqtspectrogram(audio_signal, sampling_frequency, time_resolution, cqt_kernel, *, layout="frame_major",
+                   stream=None):
+    """Constant-Q spectrogram -- drop-in for ``zaf.cqtspectrogram`` (zaf.py:562-635).
+    Returns (number_frequencies, number_times) float32."""
+    return _cqt_like(audio_signal, sampling_frequency, time_resolution, 0, cqt_kernel, layout, stream)
+
+
+def cqtchromagram(audio_signal, sampling_frequency, time_resolution, octave_resolution, cqt_kernel, *,
+                  layout="frame_major", stream=None):
+    """CQT chromagram -- drop-in for ``zaf.cqtchromagram`` (zaf.py:638-700): rows i::octave_resolution
+    of the CQT spectrogram summed.  Returns (octave_resolution, number_times) float32."""
+    return _cqt_like(audio_signal, sampling_frequency, time_resolution, int(octave_resolution), cqt_kernel, layout,
+                     stream)

@@ -1,0 +1,112 @@
+"""ctypes binding of libzafb200.so (the C ABI declared in include/zafb200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzafb200.so")
+
+OK, E_BADARG, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NCCL = 0, -1, -2, -3, -4, -5
+LAYOUT_FRAME_MAJOR, LAYOUT_BIN_MAJOR = 0, 1
+
+_i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
+_pi64 = C.POINTER(C.c_int64)
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes).  Mirrors include/zafb200.h one to one (tests/test_abi.py checks it).
+PROTOTYPES = {
+    "zafb_last_error": (C.c_char_p, []),
+    "zafb_version": (C.c_char_p, []),
+    "zafb_device_count": (_int, [C.POINTER(_int)]),
+    "zafb_init": (_int, [_int]),
+    "zafb_device_info": (_int, [_int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_sz), C.c_char_p, _sz]),
+    "zafb_malloc": (_int, [_pvp, _sz]),
+    "zafb_free": (_int, [_vp]),
+    "zafb_host_alloc": (_int, [_pvp, _sz]),
+    "zafb_host_free": (_int, [_vp]),
+    "zafb_memcpy_h2d": (_int, [_vp, _vp, _sz, _vp]),
+    "zafb_memcpy_d2h": (_int, [_vp, _vp, _sz, _vp]),
+    "zafb_memcpy_d2d": (_int, [_vp, _vp, _sz, _vp]),
+    "zafb_memset": (_int, [_vp, _int, _sz, _vp]),
+    "zafb_stream_create": (_int, [_pvp]),
+    "zafb_stream_destroy": (_int, [_vp]),
+    "zafb_stream_sync": (_int, [_vp]),
+    "zafb_device_sync": (_int, []),
+    "zafb_event_create": (_int, [_pvp]),
+    "zafb_event_destroy": (_int, [_vp]),
+    "zafb_event_record": (_int, [_vp, _vp]),
+    "zafb_event_sync": (_int, [_vp]),
+    "zafb_event_elapsed_ms": (_int, [_vp, _vp, C.POINTER(C.c_float)]),
+    "zafb_launch_count": (_i64, []),
+    "zafb_stft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
+    "zafb_istft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
+    "zafb_mdct_geometry": (_int, [_i64, _i64, _pi64, _pi64, _pi64]),
+    "zafb_imdct_geometry": (_int, [_i64, _i64, _pi64, _pi64]),
+    "zafb_cqt_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
+    "zafb_stft_plan_create": (_int, [_pvp, _vp, _i64, _i64]),
+    "zafb_stft_plan_destroy": (_int, [_vp]),
+    "zafb_stft_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_istft_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp]),
+    "zafb_stft_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
+    "zafb_istft_host_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64]),
+    "zafb_mdct_plan_create": (_int, [_pvp, _vp, _i64]),
+    "zafb_mdct_plan_destroy": (_int, [_vp]),
+    "zafb_mdct_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_imdct_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp]),
+    "zafb_dct_plan_create": (_int, [_pvp, _int, _int, _i64]),
+    "zafb_dct_plan_destroy": (_int, [_vp]),
+    "zafb_dct_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "zafb_mel_plan_create": (_int, [_pvp, _vp, _i64, _i64, _vp, _i64, _i64]),
+    "zafb_mel_plan_destroy": (_int, [_vp]),
+    "zafb_melspectrogram_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_mfcc_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_cqt_plan_create": (_int, [_pvp, _i64, _i64, _vp, _vp, _vp, _i64]),
+    "zafb_cqt_plan_destroy": (_int, [_vp]),
+    "zafb_cqt_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp]),
+}
+# not part of the public header: test hooks
+_PRIVATE = {
+    "zafb_stft_plan_force_kernel": (_int, [_vp, _int]),
+}
+
+_lib = None
+
+
+class ZafbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libzafb200.so once.  Raises if it has not been built -- by design there is no
+    NumPy/CPU substitute behind these functions."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZafbError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in {**PROTOTYPES, **_PRIVATE}.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc == OK:
+        return
+    msg = lib().zafb_last_error().decode("utf-8", "replace")
+    if rc == E_BADARG:
+        raise ValueError(msg)
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == E_NOMEM:
+        raise MemoryError(msg)
+    raise ZafbError(f"libzafb200 error {rc}: {msg}")

@@ -1,0 +1,254 @@
+// Runtime plumbing of libzafb200: device, memory, streams, events, error strings, and the
+// bit-exact integer bookkeeping of the reference's framing (no device needed for the latter).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace zafb {
+
+std::string& last_error_ref() {
+    static thread_local std::string msg;
+    return msg;
+}
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+std::atomic<int64_t> g_launches{0};
+
+int upload_f32(float** dev, const double* host, size_t n) {
+    std::vector<float> tmp(n ? n : 1);
+    for (size_t i = 0; i < n; ++i) tmp[i] = static_cast<float>(host[i]);
+    ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), (n ? n : 1) * sizeof(float)));
+    ZAFB_CUDA(cudaMemcpy(*dev, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    return ZAFB_OK;
+}
+
+int upload_c32(float2** dev, const double* host_ri, size_t n) {
+    std::vector<float2> tmp(n ? n : 1);
+    for (size_t i = 0; i < n; ++i)
+        tmp[i] = make_float2(static_cast<float>(host_ri[2 * i]), static_cast<float>(host_ri[2 * i + 1]));
+    ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), (n ? n : 1) * sizeof(float2)));
+    ZAFB_CUDA(cudaMemcpy(*dev, tmp.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    return ZAFB_OK;
+}
+
+int upload_twiddles(float2** dev, int64_t n, int64_t count) {
+    std::vector<double> t(2 * static_cast<size_t>(count > 0 ? count : 1));
+    const double pi = 3.14159265358979323846264338327950288;
+    for (int64_t i = 0; i < count; ++i) {
+        const double a = -2.0 * pi * static_cast<double>(i % n) / static_cast<double>(n);
+        t[2 * i] = std::cos(a);
+        t[2 * i + 1] = std::sin(a);
+    }
+    return upload_c32(dev, t.data(), static_cast<size_t>(count));
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached = n;
+    return n;
+}
+
+}  // namespace zafb
+
+using namespace zafb;
+
+extern "C" {
+
+const char* zafb_last_error(void) { return last_error_ref().c_str(); }
+const char* zafb_version(void) { return "zafb200 0.1 (sm_100a)"; }
+
+int zafb_device_count(int* count) {
+    ZAFB_REQUIRE(count != nullptr, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(ZAFB_E_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return ZAFB_OK;
+}
+
+int zafb_init(int device) {
+    ZAFB_CUDA(cudaSetDevice(device));
+    ZAFB_CUDA(cudaFree(nullptr));
+    int major = 0;
+    ZAFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10)
+        return fail(ZAFB_E_UNSUPPORTED, "device %d has compute capability %d.x; this library is sm_100a only",
+                    device, major);
+    return ZAFB_OK;
+}
+
+int zafb_device_info(int device, int* sm, int* cc_major, int* cc_minor, size_t* total_mem, char* name,
+                     size_t name_len) {
+    cudaDeviceProp p;
+    ZAFB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm) *sm = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    if (name && name_len) {
+        strncpy(name, p.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return ZAFB_OK;
+}
+
+int zafb_malloc(void** p, size_t bytes) {
+    ZAFB_REQUIRE(p != nullptr, "dev_ptr is NULL");
+    ZAFB_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    return ZAFB_OK;
+}
+int zafb_free(void* p) {
+    ZAFB_CUDA(cudaFree(p));
+    return ZAFB_OK;
+}
+int zafb_host_alloc(void** p, size_t bytes) {
+    ZAFB_REQUIRE(p != nullptr, "host_ptr is NULL");
+    ZAFB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return ZAFB_OK;
+}
+int zafb_host_free(void* p) {
+    ZAFB_CUDA(cudaFreeHost(p));
+    return ZAFB_OK;
+}
+int zafb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    ZAFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return ZAFB_OK;
+}
+int zafb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    ZAFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return ZAFB_OK;
+}
+int zafb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    ZAFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return ZAFB_OK;
+}
+int zafb_memset(void* p, int value, size_t bytes, void* stream) {
+    ZAFB_CUDA(cudaMemsetAsync(p, value, bytes, static_cast<cudaStream_t>(stream)));
+    return ZAFB_OK;
+}
+
+int zafb_stream_create(void** s) {
+    ZAFB_REQUIRE(s != nullptr, "stream is NULL");
+    cudaStream_t st;
+    ZAFB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *s = st;
+    return ZAFB_OK;
+}
+int zafb_stream_destroy(void* s) {
+    ZAFB_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(s)));
+    return ZAFB_OK;
+}
+int zafb_stream_sync(void* s) {
+    ZAFB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(s)));
+    return ZAFB_OK;
+}
+int zafb_device_sync(void) {
+    ZAFB_CUDA(cudaDeviceSynchronize());
+    return ZAFB_OK;
+}
+int zafb_event_create(void** e) {
+    ZAFB_REQUIRE(e != nullptr, "event is NULL");
+    cudaEvent_t ev;
+    ZAFB_CUDA(cudaEventCreate(&ev));
+    *e = ev;
+    return ZAFB_OK;
+}
+int zafb_event_destroy(void* e) {
+    ZAFB_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(e)));
+    return ZAFB_OK;
+}
+int zafb_event_record(void* e, void* s) {
+    ZAFB_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(e), static_cast<cudaStream_t>(s)));
+    return ZAFB_OK;
+}
+int zafb_event_sync(void* e) {
+    ZAFB_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(e)));
+    return ZAFB_OK;
+}
+int zafb_event_elapsed_ms(void* a, void* b, float* ms) {
+    ZAFB_REQUIRE(ms != nullptr, "ms is NULL");
+    ZAFB_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+    return ZAFB_OK;
+}
+int64_t zafb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------ integer bookkeeping
+// The reference computes these with Python floats (true division + ceil/floor); IEEE double
+// division followed by ceil()/floor() is the same operation, so the results are bit-identical.
+int zafb_stft_geometry(int64_t ns, int64_t n, int64_t hop, int64_t* pad, int64_t* nt, int64_t* tail) {
+    ZAFB_REQUIRE(ns >= 0 && n >= 1 && hop >= 1, "stft geometry: need ns >= 0, window_length >= 1, step_length >= 1");
+    const int64_t p = n / 2;                                                       // zaf.py:99
+    const int64_t t =
+        static_cast<int64_t>(std::ceil(static_cast<double>((ns + 2 * p) - n) / static_cast<double>(hop))) + 1;  // :102-109
+    if (pad) *pad = p;
+    if (nt) *nt = t;
+    if (tail) *tail = (t * hop + (n - hop) - p) - ns;                              // :116-121
+    return ZAFB_OK;
+}
+
+int zafb_istft_geometry(int64_t n, int64_t nt, int64_t hop, int64_t* ola, int64_t* trim, int64_t* out_len) {
+    ZAFB_REQUIRE(n >= 1 && nt >= 0 && hop >= 1, "istft geometry: need window_length >= 1, nt >= 0, step_length >= 1");
+    const int64_t total = nt * hop + (n - hop);                                    // zaf.py:217
+    const int64_t tr = n - hop;                                                    // :236-238
+    // Python slice semantics of [tr : total - tr] (negative stop counts from the end, empty if reversed)
+    int64_t stop = total - tr;
+    int64_t start = tr;
+    if (start < 0) start = start + total < 0 ? 0 : start + total;
+    if (stop < 0) stop = stop + total < 0 ? 0 : stop + total;
+    if (start > total) start = total;
+    if (stop > total) stop = total;
+    if (ola) *ola = total;
+    if (trim) *trim = start;  // == N - hop whenever hop <= N
+    if (out_len) *out_len = stop > start ? stop - start : 0;
+    return ZAFB_OK;
+}
+
+int zafb_mdct_geometry(int64_t ns, int64_t n, int64_t* half, int64_t* nt, int64_t* tail) {
+    ZAFB_REQUIRE(ns >= 0 && n >= 2, "mdct geometry: need ns >= 0 and window_length >= 2");
+    const int64_t m = n / 2;                                                       // zaf.py:1029-1030
+    const int64_t t = static_cast<int64_t>(std::ceil(static_cast<double>(ns) / static_cast<double>(m))) + 1;  // :1033
+    if (half) *half = m;
+    if (nt) *nt = t;
+    if (tail) *tail = (t + 1) * m - ns;                                            // :1038
+    return ZAFB_OK;
+}
+
+int zafb_imdct_geometry(int64_t m, int64_t nt, int64_t* ola, int64_t* out_len) {
+    ZAFB_REQUIRE(m >= 1 && nt >= 0, "imdct geometry: need number_frequencies >= 1, nt >= 0");
+    const int64_t total = m * (nt + 1);                                            // zaf.py:1132
+    const int64_t len = total - 2 * m - 1;                                         // [M : -M-1], :1182
+    if (ola) *ola = total;
+    if (out_len) *out_len = len > 0 ? len : 0;
+    return ZAFB_OK;
+}
+
+int zafb_cqt_geometry(int64_t ns, int64_t step, int64_t fft_length, int64_t* nt, int64_t* front, int64_t* back) {
+    ZAFB_REQUIRE(ns >= 0 && step >= 1 && fft_length >= 1, "cqt geometry: need ns >= 0, step >= 1, fft_length >= 1");
+    ZAFB_REQUIRE(fft_length >= step, "cqt geometry: step_length %lld exceeds fft_length %lld (np.pad would reject the negative pad, zaf.py:612)",
+                 (long long)step, (long long)fft_length);
+    if (nt) *nt = static_cast<int64_t>(std::floor(static_cast<double>(ns) / static_cast<double>(step)));   // zaf.py:606
+    if (front) *front = static_cast<int64_t>(std::ceil(static_cast<double>(fft_length - step) / 2.0));     // :615
+    if (back) *back = static_cast<int64_t>(std::floor(static_cast<double>(fft_length - step) / 2.0));      // :616
+    return ZAFB_OK;
+}
+
+}  // extern "C"

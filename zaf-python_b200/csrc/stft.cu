@@ -1,0 +1,544 @@
+// STFT / ISTFT kernels (zaf.py:45-141, 144-243).
+//
+//   stft2048_warp_kernel  the north-star path: N = 2048, one warp per frame.  The frame's 2048 real
+//                         samples are read as 1024 complex points straight into registers
+//                         (coalesced 8-byte loads), windowed, transformed by two in-register
+//                         radix-32 FFTs with one shared-memory transpose between them (four-step
+//                         1024 = 32 x 32), unpacked to the real-input spectrum with warp shuffles
+//                         and stored as the full two-sided spectrum with coalesced streaming stores.
+//   stft_generic_kernel   any power-of-two N >= 2: one CTA per frame, Stockham FFT of N/2 complex
+//                         points in shared memory, either output layout.
+//   stft_dft_kernel       any other N (the reference accepts every N): direct O(N^2) DFT.
+//   istft_tile_kernel     overlap-add in gather form: a CTA owns a tile of output samples, inverse
+//                         transforms every frame that touches it in increasing frame order (the
+//                         reference's summation order, zaf.py:227-233) and writes each sample once:
+//                         no atomics, bit-reproducible.
+#include <cmath>
+#include <type_traits>
+#include <vector>
+
+#include "fft_core.cuh"
+
+namespace zafb {}
+using namespace zafb;
+
+struct zafb_stft_plan {
+    int64_t n = 0, hop = 0;
+    int log2n = -1;          // -1 if n is not a power of two
+    float* d_window = nullptr;      // n floats: fp32(window)
+    float2* d_window_half = nullptr;  // n/2 float2: 0.5 * window pairs (power-of-two n only)
+    float2* d_tw_half = nullptr;    // W_{n/2}^t, t < n/2
+    float2* d_tw_full = nullptr;    // W_n^t, t < n
+    float2* d_tw_4step = nullptr;   // n == 2048: W_1024^{k1*n2} at [k1*32 + n2]
+    double gain = 1.0;              // sum(w[0:N:hop]) accumulated like Python's builtin sum (zaf.py:241)
+    int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
+};
+
+namespace {
+
+constexpr int kMaxDynSmem = 200 * 1024;
+
+// ------------------------------------------------------------------------------------------
+// N = 2048: one warp per frame
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 8;
+constexpr int kRowPad = 33;  // float2 row pitch of the 32x32 transpose buffer (conflict-free)
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
+                     const float2* __restrict__ win_half, const float2* __restrict__ tw4,
+                     const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames) {
+    extern __shared__ float2 smem[];
+    float2* s_win = smem;          // 1024: (0.5 w[2n], 0.5 w[2n+1])
+    float2* s_tw = smem + 1024;    // 1024: W_1024^{k1*n2} at [k1*32+n2]
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    float2* s_buf = smem + 2048 + warp * (32 * kRowPad);
+
+    for (int i = tid; i < 1024; i += kWarpsPerCta * 32) {
+        s_win[i] = win_half[i];
+        s_tw[i] = tw4[i];
+    }
+    const float2 c_lane = tw_full[lane];  // W_2048^lane
+    __syncthreads();
+
+    for (int64_t f = int64_t(blockIdx.x) * kWarpsPerCta + warp; f < total_frames;
+         f += int64_t(gridDim.x) * kWarpsPerCta) {
+        const int64_t clip = f / nt;
+        const int64_t j = f - clip * nt;
+        const int64_t start = j * hop - 1024;  // first sample of the frame (may be < 0)
+        const float* xc = x + clip * clip_stride;
+
+        float2 v[32];
+        if (start >= 0 && start + 2048 <= ns) {
+            const float2* p = reinterpret_cast<const float2*>(xc + start) + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = __ldg(p + 32 * r);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int64_t s = start + 2 * (lane + 32 * r);
+                v[r].x = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
+                v[r].y = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float2 w = s_win[lane + 32 * r];
+            v[r].x *= w.x;
+            v[r].y *= w.y;
+        }
+
+        // step 1: 32-point FFT over n1 (register index); thread = n2
+        fft_reg<32>(v);
+        // step 2+3: twiddle W_1024^{k1 n2}, transpose through shared memory
+        static_for<0, 32>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            float2 y = v[bitrev(k1, 5)];
+            if constexpr (k1 > 0) y = cmul(y, s_tw[k1 * 32 + lane]);
+            s_buf[k1 * kRowPad + lane] = y;
+        });
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = s_buf[lane * kRowPad + n2];
+        __syncwarp();
+        // step 4: 32-point FFT over n2; thread = k1, Z[k1 + 32 k2] = v[bitrev(k2)]
+        fft_reg<32>(v);
+
+        // real-input unpack: X[k] = E + w_k O, X[k+1024] = E - w_k O with
+        //   E = Z[k] + conj(Z[1024-k]),  O = -i (Z[k] - conj(Z[1024-k]))   (the 1/2 is in the window)
+        float2* o = out + f * 2048 + lane;
+        const int src = (32 - lane) & 31;
+        static_for<0, 32>([&](auto k2c) {
+            constexpr int k2 = decltype(k2c)::value;
+            const float2 z = v[bitrev(k2, 5)];
+            const float2 mine = v[bitrev(31 - k2, 5)];
+            float2 p;
+            p.x = __shfl_sync(0xffffffffu, mine.x, src);
+            p.y = __shfl_sync(0xffffffffu, mine.y, src);
+            if (lane == 0) p = v[bitrev((32 - k2) & 31, 5)];
+            const float2 e = make_float2(z.x + p.x, z.y - p.y);
+            const float2 od = make_float2(z.y + p.y, p.x - z.x);
+            const float2 w = mul_tw<k2, 64>(c_lane);
+            const float2 t = cmul(w, od);
+            st_stream(o + 32 * k2, cadd(e, t));
+            st_stream(o + 1024 + 32 * k2, csub(e, t));
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic power-of-two N: one CTA per frame (grid-stride), Stockham FFT in shared memory
+// ------------------------------------------------------------------------------------------
+__global__ void stft_generic_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
+                                    int64_t hop, int log2n, const float* __restrict__ window,
+                                    const float2* __restrict__ tw_half, const float2* __restrict__ tw_full,
+                                    float2* __restrict__ out, int layout, int64_t total_frames) {
+    extern __shared__ float2 smem[];
+    const int n = 1 << log2n;
+    const int m = n >> 1;
+    float2* a = smem;
+    float2* b = smem + m;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * hop - m;
+        const float* xc = x + clip * clip_stride;
+        for (int i = tid; i < m; i += nth) {
+            const int64_t s = start + 2 * i;
+            const float x0 = (s >= 0 && s < ns) ? xc[s] : 0.f;
+            const float x1 = (s + 1 >= 0 && s + 1 < ns) ? xc[s + 1] : 0.f;
+            a[i] = make_float2(x0 * window[2 * i], x1 * window[2 * i + 1]);
+        }
+        __syncthreads();
+        const float2* z = block_fft(a, b, tw_half, log2n - 1, tid, nth);
+        for (int k = tid; k < m; k += nth) {
+            const float2 zk = z[k];
+            const float2 zp = z[(m - k) & (m - 1)];
+            const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+            const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+            const float2 t = cmul(tw_full[k], od);
+            const float2 lo = cadd(e, t), hi = csub(e, t);
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) {
+                out[f * n + k] = lo;
+                out[f * n + m + k] = hi;
+            } else {
+                out[(clip * n + k) * nt + j] = lo;
+                out[(clip * n + m + k) * nt + j] = hi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// any N: direct DFT, one CTA per frame
+__global__ void stft_dft_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
+                                int64_t hop, int n, const float* __restrict__ window,
+                                const float2* __restrict__ tw_full, float2* __restrict__ out, int layout,
+                                int64_t total_frames) {
+    extern __shared__ float2 smem[];
+    float* fr = reinterpret_cast<float*>(smem);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int pad = n / 2;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * hop - pad;
+        const float* xc = x + clip * clip_stride;
+        for (int i = tid; i < n; i += nth) {
+            const int64_t s = start + i;
+            fr[i] = (s >= 0 && s < ns) ? xc[s] * window[i] : 0.f;
+        }
+        __syncthreads();
+        for (int k = tid; k < n; k += nth) {
+            float re = 0.f, im = 0.f;
+            int idx = 0;
+            for (int i = 0; i < n; ++i) {
+                const float2 w = tw_full[idx];
+                re = fmaf(fr[i], w.x, re);
+                im = fmaf(fr[i], w.y, im);
+                idx += k;
+                if (idx >= n) idx -= n;
+            }
+            const float2 v = make_float2(re, im);
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n + k] = v;
+            else out[(clip * n + k) * nt + j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ISTFT: gather-form overlap-add, one CTA per (clip, tile of output samples)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {
+    int64_t q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+}
+
+// log2n >= 0: power-of-two path (full-size complex FFT of conj(X)); log2n < 0: direct inverse DFT.
+__global__ void istft_tile_kernel(const float2* __restrict__ spec, int64_t nt, int64_t hop, int n, int log2n,
+                                  int layout, const float2* __restrict__ tw_full, float scale,
+                                  int64_t tile, int64_t tiles_per_clip, int64_t ola_len, int64_t out_start,
+                                  int64_t out_len, float* __restrict__ y, int64_t y_stride) {
+    extern __shared__ float2 smem[];
+    float2* a = smem;
+    float2* b = smem + n;
+    float* acc = reinterpret_cast<float*>(smem + 2 * n);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t clip = blockIdx.x / tiles_per_clip;
+    const int64_t t = blockIdx.x - clip * tiles_per_clip;
+    const int64_t p0 = out_start + t * tile;  // OLA coordinates of the tile
+    int64_t p1 = p0 + tile;
+    if (p1 > out_start + out_len) p1 = out_start + out_len;
+    for (int64_t i = tid; i < tile; i += nth) acc[i] = 0.f;
+    int64_t j_lo = floor_div(p0 - n, hop) + 1;
+    if (j_lo < 0) j_lo = 0;
+    int64_t j_hi = floor_div(p1 - 1, hop);
+    if (j_hi > nt - 1) j_hi = nt - 1;
+    __syncthreads();
+    for (int64_t j = j_lo; j <= j_hi; ++j) {
+        for (int k = tid; k < n; k += nth) {
+            const float2 v = (layout == ZAFB_LAYOUT_FRAME_MAJOR) ? spec[(clip * nt + j) * n + k]
+                                                                 : spec[(clip * n + k) * nt + j];
+            a[k] = cconj(v);
+        }
+        __syncthreads();
+        const float2* res;
+        if (log2n >= 0) {
+            res = block_fft(a, b, tw_full, log2n, tid, nth);
+        } else {
+            for (int i = tid; i < n; i += nth) {
+                float re = 0.f;
+                int idx = 0;
+                for (int k = 0; k < n; ++k) {
+                    const float2 w = tw_full[idx];
+                    re += a[k].x * w.x - a[k].y * w.y;
+                    idx += i;
+                    if (idx >= n) idx -= n;
+                }
+                b[i] = make_float2(re, 0.f);
+            }
+            __syncthreads();
+            res = b;
+        }
+        const int64_t base = j * hop;
+        for (int i = tid; i < n; i += nth) {
+            const int64_t p = base + i;
+            if (p >= p0 && p < p1) acc[p - p0] += res[i].x;
+        }
+        __syncthreads();
+    }
+    float* yc = y + clip * y_stride;
+    for (int64_t p = p0 + tid; p < p1; p += nth) yc[p - out_start] = acc[p - p0] * scale;
+    (void)ola_len;
+}
+
+bool g_attr_done = false;
+int set_kernel_attrs() {
+    if (g_attr_done) return ZAFB_OK;
+    ZAFB_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    g_attr_done = true;
+    return ZAFB_OK;
+}
+
+int fft_threads(int points) {  // threads for a block FFT of `points` complex points
+    int t = points / 4;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zafb_stft_plan_create(zafb_stft_plan** out, const double* window, int64_t n, int64_t hop) {
+    ZAFB_REQUIRE(out != nullptr && window != nullptr, "plan/window is NULL");
+    ZAFB_REQUIRE(n >= 1 && hop >= 1, "window_length and step_length must be >= 1");
+    if (n > (1 << 20)) return fail(ZAFB_E_UNSUPPORTED, "window_length %lld too large", (long long)n);
+    zafb_stft_plan* p = new zafb_stft_plan();
+    p->n = n;
+    p->hop = hop;
+    p->log2n = (is_pow2(n) && n >= 2) ? ilog2(n) : -1;
+    int rc = upload_f32(&p->d_window, window, n);
+    if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, n, n);
+    if (rc == ZAFB_OK && p->log2n >= 1) {
+        std::vector<double> half(n);
+        for (int64_t i = 0; i < n; ++i) half[i] = 0.5 * window[i];
+        float* tmp = nullptr;
+        rc = upload_f32(&tmp, half.data(), n);
+        p->d_window_half = reinterpret_cast<float2*>(tmp);
+        if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
+    }
+    if (rc == ZAFB_OK && n == 2048) {
+        // W_1024^{k1*n2} laid out [k1][n2]
+        std::vector<double> t(2 * 1024);
+        const double pi = 3.14159265358979323846264338327950288;
+        for (int k1 = 0; k1 < 32; ++k1)
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % 1024) / 1024.0;
+                t[2 * (k1 * 32 + n2)] = std::cos(a);
+                t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
+            }
+        rc = upload_c32(&p->d_tw_4step, t.data(), 1024);
+    }
+    // COLA gain exactly as the reference: Python's builtin sum over float64 (zaf.py:241)
+    double g = 0.0;
+    for (int64_t i = 0; i < n; i += hop) g += window[i];
+    p->gain = g;
+    if (rc != ZAFB_OK) {
+        zafb_stft_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return ZAFB_OK;
+}
+
+int zafb_stft_plan_destroy(zafb_stft_plan* p) {
+    if (!p) return ZAFB_OK;
+    cudaFree(p->d_window);
+    cudaFree(p->d_window_half);
+    cudaFree(p->d_tw_half);
+    cudaFree(p->d_tw_full);
+    cudaFree(p->d_tw_4step);
+    delete p;
+    return ZAFB_OK;
+}
+
+// test hook: 0 = auto, 1 = generic kernels only, 2 = require the warp kernel
+int zafb_stft_plan_force_kernel(zafb_stft_plan* p, int which) {
+    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 2, "bad plan / kernel id");
+    p->force_kernel = which;
+    return ZAFB_OK;
+}
+
+int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                  float* out, int layout, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0, "n_clips and ns must be >= 0");
+    ZAFB_REQUIRE(clip_stride >= ns, "clip_stride %lld < ns %lld", (long long)clip_stride, (long long)ns);
+    ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0 || n_clips == 0), "x/out is NULL");
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    int64_t nt = 0;
+    zafb_stft_geometry(ns, p->n, p->hop, nullptr, &nt, nullptr);
+    const int64_t total = n_clips * nt;
+    if (total == 0) return ZAFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int sms = sm_count();
+    float2* o = reinterpret_cast<float2*>(out);
+
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (clip_stride % 2 == 0) && (p->hop % 2 == 0);
+    const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
+    if (p->force_kernel == 2 && !warp_ok)
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, frame-major layout, even hop/stride, 8-byte aligned x");
+    if (warp_ok && p->force_kernel != 1) {
+        const size_t smem = (2048 + kWarpsPerCta * 32 * kRowPad) * sizeof(float2);
+        int64_t ctas = ceil_div(total, kWarpsPerCta);
+        const int64_t resident = int64_t(sms) * 2;
+        if (ctas > resident) ctas = resident;
+        stft2048_warp_kernel<<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+            x, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, o, total);
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    }
+    const int64_t grid = total < int64_t(sms) * 32 ? total : int64_t(sms) * 32;
+    if (p->log2n >= 1) {
+        const int m = int(p->n / 2);
+        const size_t smem = size_t(p->n) * sizeof(float2);
+        if (smem > size_t(kMaxDynSmem))
+            return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
+        stft_generic_kernel<<<static_cast<unsigned>(grid), fft_threads(m), smem, st>>>(
+            x, ns, clip_stride, nt, p->hop, p->log2n, p->d_window, p->d_tw_half, p->d_tw_full, o, layout, total);
+    } else {
+        const size_t smem = size_t(p->n) * sizeof(float) + 16;
+        if (smem > size_t(kMaxDynSmem))
+            return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
+        int th = int(p->n) < 256 ? ((int(p->n) + 31) / 32) * 32 : 256;
+        stft_dft_kernel<<<static_cast<unsigned>(grid), th, smem, st>>>(x, ns, clip_stride, nt, p->hop, int(p->n),
+                                                                        p->d_window, p->d_tw_full, o, layout, total);
+    }
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                   int64_t y_stride, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "n_clips and nt must be >= 0");
+    ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    int64_t ola = 0, start = 0, len = 0;
+    zafb_istft_geometry(p->n, nt, p->hop, &ola, &start, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride %lld < output length %lld", (long long)y_stride, (long long)len);
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
+    const int n = int(p->n);
+    // tile: about 4 windows of output, bounded by shared memory (2 n float2 + tile floats)
+    const size_t fft_bytes = size_t(2) * n * sizeof(float2);
+    if (fft_bytes + 4096 > size_t(kMaxDynSmem))
+        return fail(ZAFB_E_UNSUPPORTED, "istft: window_length %d needs %zu B of shared memory", n, fft_bytes);
+    int64_t tile = 4 * int64_t(n);
+    const int64_t max_tile = int64_t((kMaxDynSmem - fft_bytes) / sizeof(float));
+    if (tile > max_tile) tile = max_tile;
+    if (tile > len) tile = len;
+    const int64_t tiles = ceil_div(len, tile);
+    const size_t smem = fft_bytes + size_t(tile) * sizeof(float);
+    const float scale = static_cast<float>(1.0 / (double(n) * p->gain));
+    const int64_t blocks = n_clips * tiles;
+    if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "istft: too many tiles (%lld)", (long long)blocks);
+    istft_tile_kernel<<<static_cast<unsigned>(blocks), fft_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(spec), nt, p->hop, n, p->log2n >= 1 ? p->log2n : (n == 1 ? 0 : -1), layout,
+        p->d_tw_full, scale, tile, tiles, ola, start, len, y, y_stride);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer pipelines
+namespace {
+struct HostPipe {
+    static constexpr int kStreams = 3;
+    cudaStream_t st[kStreams] = {};
+    void* d_in[kStreams] = {};
+    void* d_out[kStreams] = {};
+    ~HostPipe() {
+        for (int i = 0; i < kStreams; ++i) {
+            if (st[i]) cudaStreamDestroy(st[i]);
+            cudaFree(d_in[i]);
+            cudaFree(d_out[i]);
+        }
+    }
+    int init(size_t in_bytes, size_t out_bytes) {
+        for (int i = 0; i < kStreams; ++i) {
+            ZAFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            ZAFB_CUDA(cudaMalloc(&d_in[i], in_bytes ? in_bytes : 1));
+            ZAFB_CUDA(cudaMalloc(&d_out[i], out_bytes ? out_bytes : 1));
+        }
+        return ZAFB_OK;
+    }
+};
+constexpr size_t kChunkBytes = size_t(256) << 20;  // device output bytes per pipeline stage
+}  // namespace
+
+int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                       float* out, int layout) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    int64_t nt = 0;
+    zafb_stft_geometry(ns, p->n, p->hop, nullptr, &nt, nullptr);
+    if (n_clips == 0) return ZAFB_OK;
+    const size_t out_clip = size_t(nt) * p->n * sizeof(float2);
+    // device-side clip pitch: even number of samples so the float2 fast path stays aligned
+    const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    int64_t per = int64_t(kChunkBytes / (out_clip ? out_clip : 1));
+    if (per < 1) per = 1;
+    if (per > n_clips) per = n_clips;
+    HostPipe pipe;
+    int rc = pipe.init(size_t(per) * (dpitch ? dpitch : 2) * sizeof(float), size_t(per) * out_clip);
+    if (rc != ZAFB_OK) return rc;
+    int s = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += per, s = (s + 1) % HostPipe::kStreams) {
+        const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
+        if (ns > 0)
+            ZAFB_CUDA(cudaMemcpy2DAsync(pipe.d_in[s], size_t(dpitch) * sizeof(float), x + c0 * clip_stride,
+                                        size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(nc),
+                                        cudaMemcpyHostToDevice, pipe.st[s]));
+        rc = zafb_stft_f32(p, static_cast<const float*>(pipe.d_in[s]), nc, ns, dpitch,
+                           static_cast<float*>(pipe.d_out[s]), layout, pipe.st[s]);
+        if (rc != ZAFB_OK) return rc;
+        ZAFB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out) + size_t(c0) * out_clip, pipe.d_out[s],
+                                  size_t(nc) * out_clip, cudaMemcpyDeviceToHost, pipe.st[s]));
+    }
+    for (int i = 0; i < HostPipe::kStreams; ++i) ZAFB_CUDA(cudaStreamSynchronize(pipe.st[i]));
+    return ZAFB_OK;
+}
+
+int zafb_istft_host_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                        int64_t y_stride) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "bad batch geometry");
+    int64_t len = 0;
+    zafb_istft_geometry(p->n, nt, p->hop, nullptr, nullptr, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride too small");
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    const size_t in_clip = size_t(nt) * p->n * sizeof(float2);
+    int64_t per = int64_t(kChunkBytes / (in_clip ? in_clip : 1));
+    if (per < 1) per = 1;
+    if (per > n_clips) per = n_clips;
+    HostPipe pipe;
+    int rc = pipe.init(size_t(per) * in_clip, size_t(per) * len * sizeof(float));
+    if (rc != ZAFB_OK) return rc;
+    int s = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += per, s = (s + 1) % HostPipe::kStreams) {
+        const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
+        ZAFB_CUDA(cudaMemcpyAsync(pipe.d_in[s], reinterpret_cast<const char*>(spec) + size_t(c0) * in_clip,
+                                  size_t(nc) * in_clip, cudaMemcpyHostToDevice, pipe.st[s]));
+        rc = zafb_istft_f32(p, static_cast<const float*>(pipe.d_in[s]), nc, nt, layout,
+                            static_cast<float*>(pipe.d_out[s]), len, pipe.st[s]);
+        if (rc != ZAFB_OK) return rc;
+        ZAFB_CUDA(cudaMemcpy2DAsync(y + c0 * y_stride, size_t(y_stride) * sizeof(float), pipe.d_out[s],
+                                    size_t(len) * sizeof(float), size_t(len) * sizeof(float), size_t(nc),
+                                    cudaMemcpyDeviceToHost, pipe.st[s]));
+    }
+    for (int i = 0; i < HostPipe::kStreams; ++i) ZAFB_CUDA(cudaStreamSynchronize(pipe.st[i]));
+    return ZAFB_OK;
+}
+
+}  // extern "C"
