@@ -1,0 +1,192 @@
+"""GPU parity tests for mdct/imdct, dct/dst, melspectrogram/mfcc, cqtspectrogram/cqtchromagram.
+Checker = golden vectors of the unmodified reference + the float64 oracle.  Same metric as test_gpu_stft."""
+import numpy as np
+import pytest
+import scipy.sparse
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def assert_parity(got, ref, tol=TOL):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    mx, l2 = oracle.parity_metrics(got, ref)
+    assert mx <= tol and l2 <= tol, (mx, l2)
+
+
+# ------------------------------------------------------------------------------- MDCT / IMDCT
+def test_mdct_imdct_golden(zaf_gpu, golden):
+    g = golden("mdct")
+    for case in g.cases():
+        x, w = g.get(case, "x").astype(np.float32), g.get(case, "w")
+        ref = g.get(case, "mdct")
+        for layout in ("frame_major", "bin_major"):
+            got = zaf_gpu.mdct(x, w, layout=layout)
+            assert got.dtype == np.float32
+            assert_parity(got, ref)
+        y_ref = g.get(case, "imdct")
+        assert_parity(zaf_gpu.imdct(np.ascontiguousarray(ref.astype(np.float32)), w), y_ref)
+        assert_parity(zaf_gpu.imdct(np.ascontiguousarray(ref.T.astype(np.float32)).T, w), y_ref)
+
+
+@pytest.mark.parametrize("n,ns", [(2048, 44100), (2048, 1323000), (1024, 3000), (256, 1000), (64, 320), (64, 0), (8, 50),
+                                  (4, 9), (2, 7), (100, 1000), (6, 40), (1000, 5000), (4096, 20000)])
+def test_mdct_imdct_vs_oracle(zaf_gpu, n, ns):
+    rng = np.random.default_rng(n + ns)
+    x = rng.uniform(-1, 1, ns).astype(np.float32)
+    w = oracle.kbd_window(n) if n >= 64 and n % 4 == 0 else oracle.sine_window(n)
+    ref = oracle.mdct(x, w)
+    got = zaf_gpu.mdct(x, w)
+    assert_parity(got, ref)
+    y_ref = oracle.imdct(ref, w)
+    y = zaf_gpu.imdct(got, w)
+    assert y.shape == y_ref.shape == (max(0, (n // 2) * (ref.shape[1] - 1) - 1),)
+    assert_parity(y, y_ref)
+    # TDAC: perfect reconstruction of the input (zaf.py:1098-1109)
+    m = min(len(y), ns)
+    if m:
+        assert np.max(np.abs(y[:m] - x[:m])) <= 2e-5
+
+
+def test_mdct_errors_and_batch(zaf_gpu):
+    with pytest.raises(ValueError):
+        zaf_gpu.mdct(np.zeros(100, np.float32), np.ones(255))
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (4, 30000)).astype(np.float32)
+    w = oracle.kbd_window(2048)
+    batch = zaf_gpu.mdct(x, w)
+    for c in range(4):
+        assert np.array_equal(batch[c], zaf_gpu.mdct(x[c], w))
+    xd = zaf_gpu.to_device(x)
+    md = zaf_gpu.mdct(xd, w)
+    yd = zaf_gpu.imdct(md, w)
+    y = yd.to_host()
+    assert np.max(np.abs(y[:, :30000] - x)) <= 2e-5
+
+
+# ------------------------------------------------------------------------------- DCT / DST
+def test_dct_dst_golden(zaf_gpu, golden):
+    g = golden("dctdst")
+    for case in g.cases():
+        x = g.get(case, "x").astype(np.float32)
+        for t in (1, 2, 3, 4):
+            assert_parity(zaf_gpu.dct(x, t), g.get(case, f"dct{t}"))
+            assert_parity(zaf_gpu.dst(x, t), g.get(case, f"dst{t}"))
+    assert zaf_gpu.dct(np.ones(8, np.float32), 5) is None and zaf_gpu.dst(np.ones(8, np.float32), 0) is None
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 16, 31, 64, 100, 256, 1024, 2048, 4096])
+def test_dct_dst_vs_oracle_fft_and_direct(zaf_gpu, n):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (3, n)).astype(np.float32)
+    lib = zaf_gpu._lib.lib()
+    for kind, fn, ofn in ((0, zaf_gpu.dct, oracle.dct), (1, zaf_gpu.dst, oracle.dst)):
+        for t in (1, 2, 3, 4):
+            got = fn(x, t)
+            for c in range(3):
+                assert_parity(got[c], ofn(x[c], t))
+            # the table-driven direct kernel must agree as well
+            plan = zaf_gpu._dct_plans.get((kind, t, n), kind, t, n)
+            zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, 1))
+            try:
+                got_d = fn(x, t)
+            finally:
+                lib.zafb_dct_plan_force_direct(plan, 0)
+            for c in range(3):
+                assert_parity(got_d[c], ofn(x[c], t))
+
+
+def test_dst_inverse_pairs(zaf_gpu):
+    x = np.random.default_rng(5).uniform(-1, 1, 1024).astype(np.float32)
+    assert np.max(np.abs(zaf_gpu.dst(zaf_gpu.dst(x, 1), 1) - x)) <= 1e-5
+    assert np.max(np.abs(zaf_gpu.dst(zaf_gpu.dst(x, 2), 3) - x)) <= 1e-5
+    assert np.max(np.abs(zaf_gpu.dst(zaf_gpu.dst(x, 4), 4) - x)) <= 1e-5
+    assert np.max(np.abs(zaf_gpu.dct(zaf_gpu.dct(x, 2), 3) - x)) <= 1e-5
+    assert np.max(np.abs(zaf_gpu.dct(zaf_gpu.dct(x, 1), 1) - x)) <= 1e-5
+
+
+# ------------------------------------------------------------------------------- mel / mfcc
+def test_mel_mfcc_golden(zaf_gpu, golden):
+    g = golden("mel")
+    for case in g.cases():
+        x, w, hop = g.get(case, "x").astype(np.float32), g.get(case, "w"), int(g.get(case, "hop"))
+        fb = zaf_gpu.melfilterbank(int(g.get(case, "fs")), len(w), int(g.get(case, "nmel")))
+        ncoef = int(g.get(case, "ncoef"))
+        ref_mel, ref_mfcc = g.get(case, "mel"), g.get(case, "mfcc")
+        for layout in ("frame_major", "bin_major"):
+            got = zaf_gpu.melspectrogram(x, w, hop, fb, layout=layout)
+            assert got.shape == ref_mel.shape
+            if case == "silent":
+                assert np.max(np.abs(got)) == 0.0
+            else:
+                assert_parity(got, ref_mel)
+            got = zaf_gpu.mfcc(x, w, hop, fb, ncoef, layout=layout)
+            assert got.shape == ref_mfcc.shape
+            if case == "silent":
+                assert np.max(np.abs(got)) <= 1e-4  # log(eps) is constant -> every kept coefficient is ~0
+            else:
+                assert_parity(got, ref_mfcc)
+
+
+def test_mel_mfcc_cfg3_batch_vs_oracle(zaf_gpu):
+    """BASELINE cfg 3 shape (5 s @ 16 kHz, N=1024, hop=256, 128 mel, 40 coefficients), a few clips."""
+    rng = np.random.default_rng(20261017 + 3)
+    x = rng.uniform(-1, 1, (6, 80000)).astype(np.float32)
+    w = oracle.hamming_periodic(1024)
+    fb = zaf_gpu.melfilterbank(16000, 1024, 128)
+    mel = zaf_gpu.melspectrogram(x, w, 256, fb)
+    cep = zaf_gpu.mfcc(x, w, 256, fb, 40)
+    assert mel.shape == (6, 128, 314) and cep.shape == (6, 40, 314)
+    dense = fb.toarray()
+    for c in (0, 5):
+        assert_parity(mel[c], oracle.melspectrogram(x[c], w, 256, dense))
+        assert_parity(cep[c], oracle.mfcc(x[c], w, 256, dense, 40))
+    # dense (non-banded) operator and more coefficients than mel rows - 1
+    dense_fb = np.abs(rng.standard_normal((10, 512)))
+    assert_parity(zaf_gpu.melspectrogram(x[0], w, 256, dense_fb), oracle.melspectrogram(x[0], w, 256, dense_fb))
+    got = zaf_gpu.mfcc(x[0], w, 256, dense_fb, 40)
+    ref = oracle.mfcc(x[0], w, 256, dense_fb, 40)
+    assert got.shape == ref.shape == (9, 314)
+    assert_parity(got, ref)
+
+
+# ------------------------------------------------------------------------------- CQT
+def _kernel(g, tag):
+    shape = tuple(int(s) for s in g.get(tag, "kernel_shape"))
+    return scipy.sparse.csr_matrix(
+        (g.get(tag, "kernel_data"), g.get(tag, "kernel_indices"), g.get(tag, "kernel_indptr")), shape=shape)
+
+
+def test_cqt_golden(zaf_gpu, golden):
+    g = golden("cqt")
+    for tag in g.cases():
+        fs, res, _, _ = g.get(tag, "params")
+        k = _kernel(g, tag)
+        x = g.get(tag, "x").astype(np.float32)
+        tr = int(g.get(tag, "time_resolution"))
+        for layout in ("frame_major", "bin_major"):
+            assert_parity(zaf_gpu.cqtspectrogram(x, int(fs), tr, k, layout=layout), g.get(tag, "spec"))
+            assert_parity(zaf_gpu.cqtchromagram(x, int(fs), tr, int(res), k, layout=layout), g.get(tag, "chroma"))
+
+
+def test_cqt_small_kernels_vs_oracle(zaf_gpu):
+    """Smaller FFT lengths (odd and even log2), columns in the upper half of the spectrum, complex weights."""
+    rng = np.random.default_rng(9)
+    for fs, res, fmin, fmax, tr in ((8000, 6, 220.0, 1760.0, 50), (4000, 4, 200.0, 1600.0, 40), (16000, 12, 440.0, 3520.0, 25)):
+        k = zaf_gpu.cqtkernel(fs, res, fmin, fmax)
+        x = rng.uniform(-1, 1, (2, fs)).astype(np.float32)
+        got = zaf_gpu.cqtspectrogram(x, fs, tr, k)
+        for c in range(2):
+            assert_parity(got[c], oracle.cqtspectrogram(x[c], fs, tr, k))
+    # an arbitrary complex banded operator, bands crossing L/2
+    L, nf = 1024, 5
+    dense = np.zeros((nf, L), complex)
+    for r in range(nf):
+        lo = 400 + 40 * r
+        dense[r, lo:lo + 150] = rng.standard_normal(150) + 1j * rng.standard_normal(150)
+    dense[0, 0] = 1.0
+    x = rng.uniform(-1, 1, 6000).astype(np.float32)
+    k = scipy.sparse.csr_matrix(dense)
+    assert_parity(zaf_gpu.cqtspectrogram(x, 8000, 100, k), oracle.cqtspectrogram(x, 8000, 100, k))

@@ -72,6 +72,7 @@ PROTOTYPES = {
 # not part of the public header: test hooks
 _PRIVATE = {
     "zafb_stft_plan_force_kernel": (_int, [_vp, _int]),
+    "zafb_dct_plan_force_direct": (_int, [_vp, _int]),
 }
 
 _lib = None

@@ -1,0 +1,278 @@
+// cqtspectrogram / cqtchromagram (zaf.py:562-635, 638-700).
+//
+// Per frame the reference computes abs(K * fft(x[i : i + L])) with K the sparse (n_freqs, L) CQT kernel.
+// One CTA per frame:
+//   1. the L real samples (zero-padded by predication, zaf.py:612-620) are loaded as L/2 complex points into
+//      shared memory (128 KB at L = 32 768);
+//   2. in-place radix-4 (+ one radix-2) decimation-in-frequency FFT -- in place because two 128 KB ping-pong
+//      buffers do not fit; the result is left in digit-reversed order and read through pos();
+//   3. each kernel row is one contiguous band (true for every kernel zaf.cqtkernel builds; gaps inside a band
+//      are packed as zeros): one warp per row walks its band, unpacking the real-input spectrum bin on the fly
+//      (X[c] = E + W_L^c O) and accumulating K[r, c] * X[c]; columns above L/2 use X[c] = conj(X[L - c]);
+//   4. magnitude, optional chroma fold (rows i :: octave_resolution summed), store.
+#include <cmath>
+#include <vector>
+
+#include "fft_core.cuh"
+
+using namespace zafb;
+
+struct zafb_cqt_plan {
+    int64_t n_freqs = 0, fft_length = 0, step = 0;
+    int log2m = 0;                 // M = fft_length / 2 complex points
+    float2* d_tw_fft = nullptr;    // W_M^t, t < M
+    float2* d_tw_full = nullptr;   // W_L^t, t <= M
+    int* d_band_lo = nullptr;
+    int* d_band_len = nullptr;
+    int* d_band_off = nullptr;
+    float2* d_weights = nullptr;   // packed complex bands
+    int64_t packed = 0;
+};
+
+namespace {
+
+constexpr int kMaxDynSmem = 220 * 1024;
+constexpr int kThreads = 1024;
+
+// position of frequency k after the in-place DIF passes (radix 4 ... 4 [2])
+__device__ __forceinline__ int dif_pos(int k, int log2m) {
+    int pos = 0;
+    int rem = log2m;
+    while (rem >= 2) {
+        rem -= 2;
+        pos += (k & 3) << rem;
+        k >>= 2;
+    }
+    if (rem == 1) pos += (k & 1);
+    return pos;
+}
+
+__device__ __forceinline__ void fft_inplace_dif(float2* z, const float2* __restrict__ tw, int log2m, int tid, int nth) {
+    const int M = 1 << log2m;
+    int span_log = log2m;
+    while (span_log >= 2) {
+        const int quarter = 1 << (span_log - 2);
+        const int tshift = log2m - span_log;  // W_S^t = W_M^{t << tshift}
+        for (int t = tid; t < (M >> 2); t += nth) {
+            const int i = t & (quarter - 1);
+            const int base = ((t - i) << 2) + i;
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = z[base + q * quarter];
+            fft_reg<4>(v);  // bit-reversed: X[q] = v[bitrev(q, 2)]
+            z[base] = v[0];
+            if (i == 0) {
+                z[base + quarter] = v[2];
+                z[base + 2 * quarter] = v[1];
+                z[base + 3 * quarter] = v[3];
+            } else {
+                z[base + quarter] = cmul(v[2], tw[(i) << tshift]);
+                z[base + 2 * quarter] = cmul(v[1], tw[(2 * i) << tshift]);
+                z[base + 3 * quarter] = cmul(v[3], tw[(3 * i) << tshift]);
+            }
+        }
+        __syncthreads();
+        span_log -= 2;
+    }
+    if (span_log == 1) {
+        for (int t = tid; t < (M >> 1); t += nth) {
+            const float2 p = z[2 * t], q = z[2 * t + 1];
+            z[2 * t] = cadd(p, q);
+            z[2 * t + 1] = csub(p, q);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cqt_frame_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
+                 int log2m, const float2* __restrict__ tw_fft, const float2* __restrict__ tw_full,
+                 const int* __restrict__ band_lo, const int* __restrict__ band_len, const int* __restrict__ band_off,
+                 const float2* __restrict__ weights, int n_freqs, int octave, float* __restrict__ out, int layout,
+                 int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    const int M = 1 << log2m;
+    const int L = M << 1;
+    float2* z = smem2;
+    float* q = reinterpret_cast<float*>(smem2 + M);  // n_freqs magnitudes
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * step - front;
+        const float* xc = x + clip * clip_stride;
+        for (int i = tid; i < M; i += nth) {
+            const int64_t s = start + 2 * i;
+            const float x0 = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
+            const float x1 = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
+            z[i] = make_float2(x0, x1);
+        }
+        __syncthreads();
+        fft_inplace_dif(z, tw_fft, log2m, tid, nth);
+        const float2 z0 = z[0];
+        for (int r = warp; r < n_freqs; r += nwarps) {
+            const int lo = band_lo[r], len = band_len[r];
+            const float2* w = weights + band_off[r];
+            float ar = 0.f, ai = 0.f;
+            for (int c = lane; c < len; c += 32) {
+                int col = lo + c;
+                const bool mirror = col > M;
+                const int k = mirror ? L - col : col;
+                float2 X;
+                if (k == M) {
+                    X = make_float2(z0.x - z0.y, 0.f);
+                } else if (k == 0) {
+                    X = make_float2(z0.x + z0.y, 0.f);
+                } else {
+                    const float2 zk = z[dif_pos(k, log2m)];
+                    const float2 zp = z[dif_pos(M - k, log2m)];
+                    const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+                    const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+                    X = cadd(e, cmul(__ldg(tw_full + k), od));
+                }
+                if (mirror) X.y = -X.y;
+                const float2 kv = __ldg(w + c);
+                ar += kv.x * X.x - kv.y * X.y;
+                ai += kv.x * X.y + kv.y * X.x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+            }
+            if (lane == 0) q[r] = sqrtf(ar * ar + ai * ai);
+        }
+        __syncthreads();
+        if (octave > 0) {
+            for (int i = tid; i < octave; i += nth) {
+                float acc = 0.f;
+                for (int r = i; r < n_freqs; r += octave) acc += q[r];  // zaf.py:693-698
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * octave + i] = acc;
+                else out[(clip * octave + i) * nt + j] = acc;
+            }
+        } else {
+            for (int r = tid; r < n_freqs; r += nth) {
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_freqs + r] = q[r];
+                else out[(clip * int64_t(n_freqs) + r) * nt + j] = q[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+bool g_attr_done = false;
+int set_kernel_attrs() {
+    if (g_attr_done) return ZAFB_OK;
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    g_attr_done = true;
+    return ZAFB_OK;
+}
+
+template <class T>
+int upload_vec(T** dev, const std::vector<T>& v) {
+    ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), (v.size() ? v.size() : 1) * sizeof(T)));
+    ZAFB_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ZAFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_length, const int32_t* indptr,
+                         const int32_t* indices, const double* data_ri, int64_t step) {
+    ZAFB_REQUIRE(out != nullptr && indptr != nullptr, "plan/indptr is NULL");
+    ZAFB_REQUIRE(n_freqs >= 1 && fft_length >= 2 && step >= 1, "bad cqt plan parameters");
+    if (!is_pow2(fft_length) || fft_length < 4)
+        return fail(ZAFB_E_UNSUPPORTED, "cqt: fft_length %lld is not a power of two >= 4", (long long)fft_length);
+    const int64_t m = fft_length / 2;
+    if (size_t(m) * sizeof(float2) + size_t(n_freqs) * sizeof(float) + 64 > size_t(kMaxDynSmem))
+        return fail(ZAFB_E_UNSUPPORTED, "cqt: fft_length %lld does not fit in shared memory", (long long)fft_length);
+    ZAFB_REQUIRE(fft_length >= step, "cqt: step_length %lld exceeds fft_length %lld", (long long)step, (long long)fft_length);
+    zafb_cqt_plan* p = new zafb_cqt_plan();
+    p->n_freqs = n_freqs;
+    p->fft_length = fft_length;
+    p->step = step;
+    p->log2m = ilog2(m);
+    std::vector<int> lo(n_freqs, 0), len(n_freqs, 0), off(n_freqs, 0);
+    std::vector<float2> w;
+    for (int64_t r = 0; r < n_freqs; ++r) {
+        const int b = indptr[r], e = indptr[r + 1];
+        off[r] = int(w.size());
+        if (e <= b) continue;
+        int cmin = indices[b], cmax = indices[b];
+        for (int i = b; i < e; ++i) {
+            if (indices[i] < 0 || indices[i] >= fft_length) {
+                delete p;
+                return fail(ZAFB_E_BADARG, "cqt: column index %d out of range", indices[i]);
+            }
+            cmin = indices[i] < cmin ? indices[i] : cmin;
+            cmax = indices[i] > cmax ? indices[i] : cmax;
+        }
+        lo[r] = cmin;
+        len[r] = cmax - cmin + 1;
+        const size_t base = w.size();
+        w.resize(base + size_t(len[r]), make_float2(0.f, 0.f));
+        for (int i = b; i < e; ++i)  // duplicates are summed, like scipy's CSR mat-vec
+        {
+            float2& dst = w[base + size_t(indices[i] - cmin)];
+            dst.x += static_cast<float>(data_ri[2 * i]);
+            dst.y += static_cast<float>(data_ri[2 * i + 1]);
+        }
+    }
+    p->packed = int64_t(w.size());
+    int rc = upload_twiddles(&p->d_tw_fft, m, m);
+    if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, fft_length, m + 1);
+    if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
+    if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_len, len);
+    if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
+    if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
+    if (rc != ZAFB_OK) {
+        zafb_cqt_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return ZAFB_OK;
+}
+
+int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
+    if (!p) return ZAFB_OK;
+    cudaFree(p->d_tw_fft);
+    cudaFree(p->d_tw_full);
+    cudaFree(p->d_band_lo);
+    cudaFree(p->d_band_len);
+    cudaFree(p->d_band_off);
+    cudaFree(p->d_weights);
+    delete p;
+    return ZAFB_OK;
+}
+
+int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                 int64_t octave_resolution, float* out, int layout, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
+    ZAFB_REQUIRE(octave_resolution >= 0 && octave_resolution <= p->n_freqs, "bad octave_resolution");
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    int64_t nt = 0, front = 0;
+    rc = zafb_cqt_geometry(ns, p->step, p->fft_length, &nt, &front, nullptr);
+    if (rc != ZAFB_OK) return rc;
+    const int64_t total = n_clips * nt;
+    if (total == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && x != nullptr, "x/out is NULL");
+    const int64_t m = p->fft_length / 2;
+    const size_t smem = size_t(m) * sizeof(float2) + size_t(p->n_freqs) * sizeof(float) + 64;
+    int th = int(m / 4);
+    if (th < 64) th = 64;
+    if (th > kThreads) th = kThreads;
+    const int64_t resident = int64_t(sm_count()) * (smem > 100 * 1024 ? 1 : 2);
+    const int64_t grid = total < resident ? total : resident;
+    cqt_frame_kernel<<<unsigned(grid), th, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, ns, clip_stride, nt, p->step, front, p->log2m, p->d_tw_fft, p->d_tw_full, p->d_band_lo, p->d_band_len,
+        p->d_band_off, p->d_weights, int(p->n_freqs), int(octave_resolution), out, layout, total);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+}  // extern "C"

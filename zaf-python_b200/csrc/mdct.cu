@@ -1,0 +1,311 @@
+// MDCT / IMDCT kernels (zaf.py:984-1075, 1078-1184).
+//
+// Both directions are a DCT-IV of size M = N/2 computed through an M/2-point complex FFT:
+//     t[m] = (v[2m] + i v[M-1-2m]) e^{-i pi m / M},   y = FFT_{M/2}(t) . e^{-i pi (m + 1/4) / M},
+//     DCT4(v)[2m] = Re y[m],   DCT4(v)[M-1-2m] = -Im y[m]
+// MDCT :  X[:, j] = DCT4(fold(w . frame_j)),  fold(u) = [ -c_r - d , a - b_r ]   (u = [a b c d], _r = reversed)
+// IMDCT:  (p, q) = halves of DCT4(X[:, j]);  frame_j = (2/M) w . [ q, -q_r, -p_r, -p ];  y = TDAC overlap-add.
+// (Identities checked against the reference's pre/post-twiddle formulation in tests/ and SURVEY.md 8a.)
+//
+//   mdct_generic_kernel   one CTA per frame, Stockham FFT in shared memory, power-of-two M >= 2.
+//   mdct_direct_kernel    any even N: direct O(M N) cosine sum (table lookup), the reference accepts any even N.
+//   imdct_tile_kernel     one CTA per run of consecutive hop-blocks; every output sample is the sum of exactly
+//                         two frames (h-1 and h), computed in that order and written once -- no atomics.
+#include <cmath>
+#include <vector>
+
+#include "fft_core.cuh"
+
+using namespace zafb;
+
+struct zafb_mdct_plan {
+    int64_t n = 0, m = 0;
+    int log2m = -1;               // power-of-two M only
+    float* d_window = nullptr;    // n floats
+    float2* d_tw_fft = nullptr;   // W_{M/2}^t, t < M/2
+    float2* d_pre = nullptr;      // e^{-i pi m / M}, m < M/2
+    float2* d_post = nullptr;     // e^{-i pi (m + 1/4) / M}, m < M/2
+    float* d_cos = nullptr;       // direct path: cos(2 pi t / (8M)), t < 8M
+};
+
+namespace {
+
+constexpr int kMaxDynSmem = 200 * 1024;
+
+// DCT-IV of the M values in v (shared) -> out (shared, M floats).  a/b: M/2 float2 scratch each.
+__device__ __forceinline__ void dct4_block(const float* v, float* out, float2* a, float2* b,
+                                           const float2* __restrict__ tw_fft, const float2* __restrict__ pre,
+                                           const float2* __restrict__ post, int log2m, int tid, int nth) {
+    const int m_len = 1 << log2m;
+    const int h = m_len >> 1;
+    for (int m = tid; m < h; m += nth) a[m] = cmul(make_float2(v[2 * m], v[m_len - 1 - 2 * m]), pre[m]);
+    __syncthreads();
+    const float2* y = block_fft(a, b, tw_fft, log2m - 1, tid, nth);
+    for (int m = tid; m < h; m += nth) {
+        const float2 r = cmul(y[m], post[m]);
+        out[2 * m] = r.x;
+        out[m_len - 1 - 2 * m] = -r.y;
+    }
+    __syncthreads();
+}
+
+__global__ void mdct_generic_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
+                                    int log2m, const float* __restrict__ window, const float2* __restrict__ tw_fft,
+                                    const float2* __restrict__ pre, const float2* __restrict__ post,
+                                    float* __restrict__ out, int layout, int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    const int m_len = 1 << log2m, h = m_len >> 1;
+    float2* a = smem2;
+    float2* b = smem2 + h;
+    float* v = reinterpret_cast<float*>(smem2 + 2 * h);
+    float* res = v + m_len;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = (j - 1) * m_len;  // frame j covers original samples [(j-1)M, (j+1)M)
+        const float* xc = x + clip * clip_stride;
+        auto u = [&](int i) -> float {           // windowed sample i of the 2M-long frame
+            const int64_t s = start + i;
+            return (s >= 0 && s < ns) ? xc[s] * window[i] : 0.f;
+        };
+        for (int i = tid; i < h; i += nth) {
+            v[i] = -u(3 * h - 1 - i) - u(3 * h + i);      // -c_r - d
+            v[h + i] = u(i) - u(m_len - 1 - i);           //  a - b_r
+        }
+        __syncthreads();
+        dct4_block(v, res, a, b, tw_fft, pre, post, log2m, tid, nth);
+        for (int k = tid; k < m_len; k += nth) {
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * m_len + k] = res[k];
+            else out[(clip * m_len + k) * nt + j] = res[k];
+        }
+        __syncthreads();
+    }
+}
+
+// any even N: X[k] = sum_n u[n] cos(pi/M (n + 1/2 + M/2)(k + 1/2)) = cos(2 pi (2n+1+M)(2k+1) / (8M))
+__global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int m_len,
+                                   const float* __restrict__ window, const float* __restrict__ costab,
+                                   float* __restrict__ out, int layout, int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    float* u = reinterpret_cast<float*>(smem2);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int n = 2 * m_len, period = 8 * m_len;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = (j - 1) * m_len;
+        const float* xc = x + clip * clip_stride;
+        for (int i = tid; i < n; i += nth) {
+            const int64_t s = start + i;
+            u[i] = (s >= 0 && s < ns) ? xc[s] * window[i] : 0.f;
+        }
+        __syncthreads();
+        for (int k = tid; k < m_len; k += nth) {
+            const int kk = 2 * k + 1;
+            int idx = int((int64_t(1 + m_len) * kk) % period);
+            const int step = (2 * kk) % period;
+            float acc = 0.f;
+            for (int i = 0; i < n; ++i) {
+                acc = fmaf(u[i], costab[idx], acc);
+                idx += step;
+                if (idx >= period) idx -= period;
+            }
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * m_len + k] = acc;
+            else out[(clip * m_len + k) * nt + j] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// IMDCT.  Output sample p (OLA coordinates, hop-block h = p / M) = second half of frame h-1 + first half of frame h.
+// The reference keeps OLA[M : M*nt - 1]: hop-blocks 1 .. nt-1, last sample dropped (zaf.py:1182).
+// One CTA owns hop-blocks [h0, h1) of one clip and walks frames h0-1 .. h1-1, carrying the second half.
+__global__ void imdct_tile_kernel(const float* __restrict__ spec, int64_t nt, int m_len, int log2m, int layout,
+                                  const float* __restrict__ window, const float2* __restrict__ tw_fft,
+                                  const float2* __restrict__ pre, const float2* __restrict__ post,
+                                  const float* __restrict__ costab, int64_t blocks_per_tile, int64_t tiles_per_clip,
+                                  int64_t out_len, float* __restrict__ y, int64_t y_stride) {
+    extern __shared__ float2 smem2[];
+    const int h = m_len >> 1;
+    float2* a = smem2;
+    float2* b = smem2 + (h > 0 ? h : 1);
+    float* v = reinterpret_cast<float*>(smem2 + 2 * (h > 0 ? h : 1));
+    float* res = v + m_len;           // DCT-IV result (p | q), or the whole 2M block on the direct path
+    float* carry = res + 2 * m_len;   // second half of the previous frame, already scaled and windowed
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t clip = blockIdx.x / tiles_per_clip;
+    const int64_t tile = blockIdx.x - clip * tiles_per_clip;
+    const int64_t h0 = 1 + tile * blocks_per_tile;
+    int64_t h1 = h0 + blocks_per_tile;
+    if (h1 > nt) h1 = nt;
+    const float scale = 2.0f / float(m_len);
+    float* yc = y + clip * y_stride;
+    for (int64_t j = h0 - 1; j < h1; ++j) {
+        for (int k = tid; k < m_len; k += nth)
+            v[k] = (layout == ZAFB_LAYOUT_FRAME_MAJOR) ? spec[(clip * nt + j) * m_len + k] : spec[(clip * m_len + k) * nt + j];
+        __syncthreads();
+        if (log2m >= 1) {
+            dct4_block(v, res, a, b, tw_fft, pre, post, log2m, tid, nth);
+        } else {  // any M: the 2M-long block directly, cos(pi/M (n+1/2+M/2)(k+1/2)) = costab[((2n+1+M)(2k+1)) mod 8M]
+            const int period = 8 * m_len;
+            for (int i = tid; i < 2 * m_len; i += nth) {
+                const int nn = 2 * i + 1 + m_len;
+                int idx = nn % period;
+                const int step = (2 * nn) % period;
+                float acc = 0.f;
+                for (int k = 0; k < m_len; ++k) {
+                    acc = fmaf(v[k], costab[idx], acc);
+                    idx += step;
+                    if (idx >= period) idx -= period;
+                }
+                res[i] = acc;
+            }
+            __syncthreads();
+        }
+        // power-of-two path: block = [ q, -q_r, -p_r, -p ] with p = res[0:h], q = res[h:M]:
+        //   first half  (n < M):        n < h ? q[n] : -q[M-1-(n-h)]
+        //   second half (n' = n-M < M): n' < h ? -p[h-1-n'] : -p[n'-h]
+        const bool folded = log2m >= 1;
+        if (j >= h0) {
+            const int64_t base = j * m_len - m_len;  // output index of OLA sample j*M (trim = M)
+            for (int i = tid; i < m_len; i += nth) {
+                const float first = folded ? ((i < h) ? res[h + i] : -res[m_len - 1 - (i - h)]) : res[i];
+                const int64_t o = base + i;
+                if (o < out_len) yc[o] = carry[i] + scale * window[i] * first;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < m_len; i += nth) {
+            const float second = folded ? ((i < h) ? -res[h - 1 - i] : -res[i - h]) : res[m_len + i];
+            carry[i] = scale * window[m_len + i] * second;
+        }
+        __syncthreads();
+    }
+}
+
+bool g_attr_done = false;
+int set_kernel_attrs() {
+    if (g_attr_done) return ZAFB_OK;
+    ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mdct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(imdct_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    g_attr_done = true;
+    return ZAFB_OK;
+}
+
+int threads_for(int points) {
+    int t = points / 4;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zafb_mdct_plan_create(zafb_mdct_plan** out, const double* window, int64_t n) {
+    ZAFB_REQUIRE(out != nullptr && window != nullptr, "plan/window is NULL");
+    ZAFB_REQUIRE(n >= 2 && n % 2 == 0, "mdct: window_length must be even and >= 2 (got %lld)", (long long)n);
+    if (n > (1 << 16)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window_length %lld too large", (long long)n);
+    zafb_mdct_plan* p = new zafb_mdct_plan();
+    p->n = n;
+    p->m = n / 2;
+    p->log2m = (is_pow2(p->m) && p->m >= 2) ? ilog2(p->m) : -1;
+    const double pi = 3.14159265358979323846264338327950288;
+    int rc = upload_f32(&p->d_window, window, n);
+    if (rc == ZAFB_OK && p->log2m >= 1) {
+        const int64_t h = p->m / 2;
+        std::vector<double> pre(2 * h), post(2 * h);
+        for (int64_t m = 0; m < h; ++m) {
+            pre[2 * m] = std::cos(-pi * double(m) / double(p->m));
+            pre[2 * m + 1] = std::sin(-pi * double(m) / double(p->m));
+            post[2 * m] = std::cos(-pi * (double(m) + 0.25) / double(p->m));
+            post[2 * m + 1] = std::sin(-pi * (double(m) + 0.25) / double(p->m));
+        }
+        rc = upload_c32(&p->d_pre, pre.data(), h);
+        if (rc == ZAFB_OK) rc = upload_c32(&p->d_post, post.data(), h);
+        if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_fft, h, h);
+    } else if (rc == ZAFB_OK) {
+        std::vector<double> c(8 * p->m);
+        for (int64_t t = 0; t < 8 * p->m; ++t) c[t] = std::cos(2.0 * pi * double(t) / double(8 * p->m));
+        rc = upload_f32(&p->d_cos, c.data(), c.size());
+    }
+    if (rc != ZAFB_OK) {
+        zafb_mdct_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return ZAFB_OK;
+}
+
+int zafb_mdct_plan_destroy(zafb_mdct_plan* p) {
+    if (!p) return ZAFB_OK;
+    cudaFree(p->d_window);
+    cudaFree(p->d_tw_fft);
+    cudaFree(p->d_pre);
+    cudaFree(p->d_post);
+    cudaFree(p->d_cos);
+    delete p;
+    return ZAFB_OK;
+}
+
+int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                  float* out, int layout, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    int64_t nt = 0;
+    zafb_mdct_geometry(ns, p->n, nullptr, &nt, nullptr);
+    const int64_t total = n_clips * nt;
+    if (total == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    const int64_t grid = total < int64_t(sm_count()) * 32 ? total : int64_t(sm_count()) * 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int m = int(p->m);
+    if (p->log2m >= 1) {
+        const size_t smem = size_t(m) * sizeof(float2) + 2 * size_t(m) * sizeof(float);
+        if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
+        mdct_generic_kernel<<<unsigned(grid), threads_for(m / 2), smem, st>>>(x, ns, clip_stride, nt, p->log2m, p->d_window,
+                                                                              p->d_tw_fft, p->d_pre, p->d_post, out, layout, total);
+    } else {
+        const size_t smem = size_t(2 * m) * sizeof(float) + 16;
+        if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
+        int th = m < 256 ? ((m + 31) / 32) * 32 : 256;
+        mdct_direct_kernel<<<unsigned(grid), th, smem, st>>>(x, ns, clip_stride, nt, m, p->d_window, p->d_cos, out, layout, total);
+    }
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                   int64_t y_stride, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "bad batch geometry");
+    ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    int64_t len = 0;
+    zafb_imdct_geometry(p->m, nt, nullptr, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride %lld < output length %lld", (long long)y_stride, (long long)len);
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
+    const int m = int(p->m);
+    const int64_t hop_blocks = nt - 1;  // hop-blocks 1 .. nt-1 are written
+    int64_t per_tile = 16;
+    if (per_tile > hop_blocks) per_tile = hop_blocks;
+    const int64_t tiles = ceil_div(hop_blocks, per_tile);
+    const int h = m / 2 > 0 ? m / 2 : 1;
+    const size_t smem = size_t(2 * h) * sizeof(float2) + 4 * size_t(m) * sizeof(float) + 16;
+    if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "imdct: window too large for shared memory");
+    const int64_t blocks = n_clips * tiles;
+    if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "imdct: too many tiles");
+    imdct_tile_kernel<<<unsigned(blocks), threads_for(m / 2), smem, static_cast<cudaStream_t>(stream)>>>(
+        spec, nt, m, p->log2m, layout, p->d_window, p->d_tw_fft, p->d_pre, p->d_post, p->d_cos, per_tile, tiles, len, y,
+        y_stride);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+}  // extern "C"
