@@ -29,6 +29,7 @@ from ._device import (DeviceArray, Event, PinnedArray, Stream, device_count, emp
                       launch_count, synchronize, to_device)
 from ._lib import LAYOUT_BIN_MAJOR, LAYOUT_FRAME_MAJOR, ZafbError  # noqa: F401
 from ._operators import cqtkernel, melfilterbank  # noqa: F401
+from ._shard import shard_range  # noqa: F401
 
 __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",

@@ -85,10 +85,17 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
                 if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_mels + r] = acc;
                 else out[(clip * n_mels + r) * nt + j] = acc;
             } else {
-                mel[r] = logf(acc + 2.220446049250313e-16f);  // np.finfo(float).eps, zaf.py:445
+                mel[r] = acc + 2.220446049250313e-16f;  // np.finfo(float).eps, zaf.py:445
             }
         }
         if (mode == 1) {
+            __syncthreads();
+            // ln(mel_r) - ln(mel_0) instead of ln(mel_r): rows k >= 1 of the DCT-II matrix sum to zero, so the
+            // constant drops out exactly, and the log of a ratio keeps ~1e-7 absolute accuracy where the log
+            // itself (values ~10) only has ~1e-6 in fp32.
+            const float ref0 = mel[0];
+            __syncthreads();
+            for (int r = tid; r < n_mels; r += nth) mel[r] = logf(mel[r] / ref0);
             __syncthreads();
             for (int i = tid; i < n_coef; i += nth) {
                 const float* d = dct + int64_t(i) * n_mels;
