@@ -1,0 +1,219 @@
+#!/usr/bin/env python
+"""Device-resident timing of every BASELINE.json config, one JSON line each.
+
+bench.py carries the headline metric (cfg 2 forward STFT).  This script times the other transforms
+of the hot path on their BASELINE shapes with inputs already in HBM, CUDA events on the launching
+stream, and reports algorithmic bytes / launch duration against the measured HBM peak.
+
+    python scripts/bench_configs.py [--only stft,istft,mdct,imdct,mel,mfcc,cqt,dct] [--scale 1.0] [--out FILE]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import zaf_python_b200 as zaf  # noqa: E402
+
+
+def peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def hamming_periodic(n):
+    return 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(n) / n)
+
+
+def kbd(n, alpha=5.0):
+    k = np.kaiser(n // 2 + 1, np.pi * alpha)
+    half = np.sqrt(np.cumsum(k[: n // 2]) / np.sum(k))
+    return np.concatenate([half, half[::-1]])
+
+
+def device_batch(clips, ns, seed, distinct=32):
+    """(clips, ns) float32 on the device, built from `distinct` seeded clips tiled over the batch."""
+    rng = np.random.default_rng(seed)
+    distinct = min(distinct, clips)
+    host = rng.uniform(-1, 1, (distinct, ns)).astype(np.float32)
+    d = zaf.empty((clips, ns), np.float32)
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    for c0 in range(0, clips, distinct):
+        n = min(distinct, clips - c0)
+        zaf._lib.check(lib.zafb_memcpy_h2d(C.c_void_p(d.ptr + c0 * ns * 4), host.ctypes.data, n * ns * 4, None))
+    zaf.synchronize()
+    return d, host
+
+
+def timeit(fn, steps, warmup=3):
+    stream = zaf.Stream()
+    out = None
+    for _ in range(warmup):
+        out = fn(stream)
+    stream.synchronize()
+    e0, e1 = zaf.Event(), zaf.Event()
+    l0 = zaf.launch_count()
+    e0.record(stream)
+    for _ in range(steps):
+        o = fn(stream)
+        if o is not None and o is not out and hasattr(o, "free"):
+            o.free()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_ms(e1) / steps, out, (zaf.launch_count() - l0) // steps
+
+
+def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
+    gbs = algo_bytes / (ms * 1e-3) / 1e9
+    return {"transform": name, "config": cfg, "units": frames, "unit": unit, "ms_per_step": ms,
+            "units_per_sec": frames / (ms * 1e-3), "algorithmic_bytes": int(algo_bytes), "achieved_gbs": gbs,
+            "hbm_peak_gbs": peak(), "hbm_frac": gbs / peak(), "launches_per_step": int(launches), "note": note}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="stft,istft,mdct,imdct,mel,mfcc,cqt,dct")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    zaf.init(0)
+    out_lines = []
+
+    def emit(d):
+        out_lines.append(d)
+        print(json.dumps(d), flush=True)
+
+    # ---- cfg 2: stft + istft, 1024 clips x 10 s @ 48 kHz, N = 2048, hop = 512
+    if only & {"stft", "istft"}:
+        clips, ns, n, hop = max(1, int(1024 * args.scale)), 480000, 2048, 512
+        w = hamming_periodic(n)
+        xd, _ = device_batch(clips, ns, 20261017 + 2)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        spec = zaf.empty((clips, nt, n), np.complex64)
+        spec.transposed = True
+        plan, _ = zaf._stft_plan(w, hop)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        cfg = f"cfg2: {clips} clips x 10 s @ 48 kHz, N=2048 hop=512"
+
+        def f_stft(stream):
+            zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 0, stream.ptr))
+
+        ms, _, nl = timeit(f_stft, args.steps)
+        if "stft" in only:
+            emit(line("stft", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * n * 8, nl))
+        if "istft" in only:
+            ylen = zaf.istft_geometry(n, nt, hop)[2]
+            yd = zaf.empty((clips, ylen), np.float32)
+
+            def f_istft(stream):
+                zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, stream.ptr))
+
+            ms, _, nl = timeit(f_istft, args.steps)
+            emit(line("istft", cfg, clips * nt, "frames", ms, clips * nt * n * 8 + clips * ylen * 4, nl))
+            yd.free()
+        xd.free()
+        spec.free()
+
+    # ---- cfg 4: mdct + imdct, 2048 clips x 30 s @ 44.1 kHz, KBD N = 2048
+    if only & {"mdct", "imdct"}:
+        clips, ns, n = max(1, int(2048 * args.scale)), 1323000, 2048
+        w = kbd(n)
+        xd, _ = device_batch(clips, ns, 20261017 + 4)
+        m, nt, _ = zaf.mdct_geometry(ns, n)
+        plan, _ = zaf._mdct_plan(w)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        spec = zaf.empty((clips, nt, m), np.float32)
+        cfg = f"cfg4: {clips} clips x 30 s @ 44.1 kHz, KBD N=2048"
+
+        def f_mdct(stream):
+            zaf._lib.check(lib.zafb_mdct_f32(plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 0, stream.ptr))
+
+        ms, _, nl = timeit(f_mdct, args.steps)
+        if "mdct" in only:
+            emit(line("mdct", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * m * 4, nl))
+        if "imdct" in only:
+            ylen = zaf.imdct_geometry(m, nt)[1]
+            pitch = (ylen + 1) & ~1
+            yd = zaf.empty((clips, pitch), np.float32)
+
+            def f_imdct(stream):
+                zaf._lib.check(lib.zafb_imdct_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), pitch, stream.ptr))
+
+            ms, _, nl = timeit(f_imdct, args.steps)
+            emit(line("imdct", cfg, clips * nt, "frames", ms, clips * nt * m * 4 + clips * ylen * 4, nl))
+            yd.free()
+        xd.free()
+        spec.free()
+
+    # ---- cfg 3: melspectrogram + mfcc, 4096 clips x 5 s @ 16 kHz, N = 1024, hop = 256, 128 mels, 40 coefficients
+    if only & {"mel", "mfcc"}:
+        clips, ns, n, hop, fs = max(1, int(4096 * args.scale)), 80000, 1024, 256, 16000
+        w = hamming_periodic(n)
+        fb = zaf.melfilterbank(fs, n, 128)
+        xd, _ = device_batch(clips, ns, 20261017 + 3)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        cfg = f"cfg3: {clips} clips x 5 s @ 16 kHz, N=1024 hop=256, 128 mels, 40 coeffs"
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        plan_mel, _, _ = zaf._mel_plan(w, hop, fb, 0)
+        plan_mfcc, _, _ = zaf._mel_plan(w, hop, fb, 40)
+        od = zaf.empty((clips, nt, 128), np.float32)
+        if "mel" in only:
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_melspectrogram_f32(
+                plan_mel, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+            emit(line("melspectrogram", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 128 * 4, nl,
+                      "FP32/shared-memory bound, not HBM (SURVEY 8d)"))
+        if "mfcc" in only:
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_mfcc_f32(
+                plan_mfcc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+            emit(line("mfcc", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
+                      "FP32/shared-memory bound, not HBM (SURVEY 8d)"))
+        xd.free()
+
+    # ---- cfg 5: cqtspectrogram, 512 clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8, 25 frames/s
+    if "cqt" in only:
+        clips, ns, fs = max(1, int(512 * args.scale)), 882000, 44100
+        kern = zaf.cqtkernel(fs, 12, 32.70319566257483, 4186.009044809578)
+        xd, _ = device_batch(clips, ns, 20261017 + 5)
+        step, nt, _, _ = zaf.cqt_geometry(ns, fs, 25, kern.shape[1])
+        cfg = f"cfg5: {clips} clips x 20 s @ 44.1 kHz, 84 bins, L={kern.shape[1]}, step={step}"
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        plan_cqt, nf, _ = zaf._cqt_plan(kern, step)
+        od = zaf.empty((clips, nt, nf), np.float32)
+        ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_cqt_f32(
+            plan_cqt, C.c_void_p(xd.ptr), clips, ns, ns, 0, C.c_void_p(od.ptr), 0, s.ptr)), max(3, args.steps // 3))
+        emit(line("cqtspectrogram", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * kern.shape[0] * 4, nl,
+                  "FP32/shared-memory bound: 32768-point FFT per frame (SURVEY 8d)"))
+        xd.free()
+
+    # ---- dct / dst: 2^20 vectors of 1024 samples (the reference's example length)
+    if "dct" in only:
+        batch, n = max(1, int((1 << 20) * args.scale)), 1024
+        xd, _ = device_batch(batch, n, 20261017 + 6, distinct=4096)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        od = zaf.empty((batch, n), np.float32)
+        for kind, name in ((0, "dct"), (1, "dst")):
+            for t in (1, 2, 3, 4):
+                plan = zaf._dct_plans.get((kind, t, n), kind, t, n)
+                ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_dct_f32(
+                    plan, C.c_void_p(xd.ptr), batch, n, C.c_void_p(od.ptr), n, s.ptr)), max(3, args.steps // 3))
+                emit(line(f"{name}-{t}", f"{batch} vectors x {n}", batch, "vectors", ms, batch * n * 8, nl))
+        xd.free()
+
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        with open(args.out, "w") as f:
+            for d in out_lines:
+                f.write(json.dumps(d) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,43 @@ def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force):
             assert_parity(got[c], oracle.stft(x[c], w, hop))
 
 
+@pytest.mark.parametrize("force", [1, 2])
+@pytest.mark.parametrize("hop", [256, 512, 1024])
+def test_istft_2048_kernels_agree_with_oracle(zaf_gpu, force, hop):
+    """The warp-per-run overlap-add kernel (2) and the generic tile kernel (1) on the same
+    NON-Hermitian spectra (the reference keeps Re(ifft) of whatever it is given, zaf.py:223);
+    97 frames per clip so that a clip is split into several runs."""
+    rng = np.random.default_rng(20261017 + hop)
+    n, nt, clips = 2048, 97, 3
+    spec = (rng.standard_normal((clips, nt, n)) + 1j * rng.standard_normal((clips, nt, n))).astype(np.complex64)
+    w = oracle.hamming_periodic(n)
+    plan, _ = zaf_gpu._stft_plan(w, hop)
+    zaf_gpu._lib.check(zaf_gpu._lib.lib().zafb_stft_plan_force_kernel(plan, force))
+    try:
+        got = zaf_gpu.istft(np.swapaxes(spec, 1, 2), w, hop)  # frame-major memory, (clips, N, nt) view
+        one = zaf_gpu.istft(np.swapaxes(spec, 1, 2)[1], w, hop)
+    finally:
+        zaf_gpu._lib.lib().zafb_stft_plan_force_kernel(plan, 0)
+    assert got.shape == (clips, nt * hop - (n - hop))
+    for c in range(clips):
+        assert_parity(got[c], oracle.istft(spec[c].T.astype(np.complex128), w, hop))
+    assert np.array_equal(one, got[1])  # bitwise: a clip's result does not depend on the batch around it
+
+
+def test_istft_2048_short_inputs(zaf_gpu):
+    """nt < N/hop gives an empty signal, nt == N/hop exactly one hop-block (zaf.py:236-238)."""
+    rng = np.random.default_rng(5)
+    n, hop = 2048, 512
+    w = oracle.hamming_periodic(n)
+    for nt in (1, 3, 4, 5, 9):
+        spec = (rng.standard_normal((n, nt)) + 1j * rng.standard_normal((n, nt))).astype(np.complex64)
+        ref = oracle.istft(spec.astype(np.complex128), w, hop)
+        got = zaf_gpu.istft(np.ascontiguousarray(spec.T).T, w, hop)
+        assert got.shape == ref.shape
+        if ref.size:
+            assert_parity(got, ref)
+
+
 @pytest.mark.parametrize("n,hop,ns", [(2048, 512, 48000), (2048, 1024, 480000), (1024, 256, 80000), (512, 128, 5000),
                                       (256, 64, 1000), (64, 16, 0), (128, 32, 37), (4096, 1024, 30000), (8, 2, 50),
                                       (2, 1, 9), (2048, 300, 9000), (2048, 511, 9000), (1024, 1024, 4000)])

@@ -10,6 +10,8 @@
 // All functions are __host__ __device__ so tests/host/fft_core_test.cu can check them on the CPU.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace zafb {
@@ -74,6 +76,97 @@ ZAFB_HD int stockham_schedule(int log2m, int* radix) {
 }
 
 #ifdef __CUDACC__
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// ---------------------------------------------------------------- one warp, 1024 complex points
+// Four-step FFT 1024 = 32 x 32 by ONE warp.  In: v[r] = x[lane + 32 r].  Out: X[lane + 32 k2] is
+// v[bitrev(k2, 5)] (same element-to-thread map as the input, register order bit-reversed).
+//   tw4[k1 * 32 + n2] = W_1024^{k1 n2} (shared memory).
+// SPLIT = false: `buf` is a 32 x kFft1024Pitch float2 tile, one 64-bit transpose.
+// SPLIT = true : `buf` is a 32 x kFft1024Pitch float tile, the real and imaginary parts are
+//                transposed one after the other (half the shared memory, twice the instructions).
+constexpr int kFft1024Pitch = 33;  // row pitch of the transpose tile (conflict-free)
+
+template <bool SPLIT>
+__device__ __forceinline__ void warp_fft1024(float2 (&v)[32], const float2* __restrict__ tw4, void* buf, int lane) {
+    fft_reg<32>(v);  // over n1 (register index); thread = n2
+    if constexpr (!SPLIT) {
+        float2* s = static_cast<float2*>(buf);
+        static_for<0, 32>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            float2 y = v[bitrev(k1, 5)];
+            if constexpr (k1 > 0) y = cmul(y, tw4[k1 * 32 + lane]);
+            s[k1 * kFft1024Pitch + lane] = y;
+        });
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = s[lane * kFft1024Pitch + n2];
+        __syncwarp();
+    } else {
+        float* s = static_cast<float*>(buf);
+        float im[32];
+        static_for<0, 32>([&](auto k1c) {
+            constexpr int k1 = decltype(k1c)::value;
+            float2 y = v[bitrev(k1, 5)];
+            if constexpr (k1 > 0) y = cmul(y, tw4[k1 * 32 + lane]);
+            s[k1 * kFft1024Pitch + lane] = y.x;
+            im[k1] = y.y;
+        });
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2].x = s[lane * kFft1024Pitch + n2];
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) s[k1 * kFft1024Pitch + lane] = im[k1];
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2].y = s[lane * kFft1024Pitch + n2];
+        __syncwarp();
+    }
+    fft_reg<32>(v);  // over n2; thread = k1
+}
+
+// ---------------------------------------------------------------- one warp, 512 complex points
+// Four-step FFT 512 = 16 x 32 by ONE warp.  In: v[r] = x[lane + 32 r], r < 16.  Out: X[lane + 32 k]
+// is v[bitrev(k, 4)].  tw[k1 * 32 + n2] = W_512^{k1 n2} (shared memory, 16 x 32); buf: 16 x
+// kFft1024Pitch float2.  Step 1: FFT-16 over the register index.  Step 2: the 16 FFT-32 over n2
+// are shared by lane pairs (k1, parity): each lane does the radix-2 butterfly for its output
+// parity while reading its row back from the transpose tile, then an FFT-16 in registers.
+__device__ __forceinline__ void warp_fft512(float2 (&v)[16], const float2* __restrict__ tw, float2* buf, int lane) {
+    fft_reg<16>(v);
+    static_for<0, 16>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        float2 y = v[bitrev(k1, 4)];
+        if constexpr (k1 > 0) y = cmul(y, tw[k1 * 32 + lane]);
+        buf[k1 * kFft1024Pitch + lane] = y;
+    });
+    __syncwarp();
+    const float2* row = buf + (lane & 15) * kFft1024Pitch;
+    const bool odd = lane >= 16;
+    const float sgn = odd ? -1.f : 1.f;
+    static_for<0, 16>([&](auto nc) {
+        constexpr int n2 = decltype(nc)::value;
+        const float2 a = row[n2];
+        const float2 b = row[n2 + 16];
+        const float2 d = make_float2(fmaf(sgn, b.x, a.x), fmaf(sgn, b.y, a.y));
+        if constexpr (n2 == 0) {
+            v[n2] = d;
+        } else {
+            const float wr = odd ? Tw<n2, 32>::re : 1.f;
+            const float wi = odd ? Tw<n2, 32>::im : 0.f;
+            v[n2] = make_float2(d.x * wr - d.y * wi, d.x * wi + d.y * wr);
+        }
+    });
+    __syncwarp();
+    fft_reg<16>(v);
+}
+
 // Whole-block M-point FFT in shared memory (ping-pong between a and b).  Every thread of the
 // group [0, nthreads) calls it with its tid; a leading __syncthreads() is the caller's job
 // (data in `a` must be visible).  Returns the buffer that holds the result; ends with a barrier.

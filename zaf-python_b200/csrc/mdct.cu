@@ -11,7 +11,9 @@
 //   mdct_direct_kernel    any even N: direct O(M N) cosine sum (table lookup), the reference accepts any even N.
 //   imdct_tile_kernel     one CTA per run of consecutive hop-blocks; every output sample is the sum of exactly
 //                         two frames (h-1 and h), computed in that order and written once -- no atomics.
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -26,11 +28,14 @@ struct zafb_mdct_plan {
     float2* d_pre = nullptr;      // e^{-i pi m / M}, m < M/2
     float2* d_post = nullptr;     // e^{-i pi (m + 1/4) / M}, m < M/2
     float* d_cos = nullptr;       // direct path: cos(2 pi t / (8M)), t < 8M
+    float2* d_tw_4step = nullptr; // n == 2048: W_512^{k1*n2} at [k1*32 + n2], k1 < 16
+    int force_kernel = 0;         // 0 auto, 1 generic, 2 warp (tests)
 };
 
 namespace {
 
 constexpr int kMaxDynSmem = 200 * 1024;
+constexpr int kMdctCtasPerSm = 2;
 
 // DCT-IV of the M values in v (shared) -> out (shared, M floats).  a/b: M/2 float2 scratch each.
 __device__ __forceinline__ void dct4_block(const float* v, float* out, float2* a, float2* b,
@@ -116,6 +121,177 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// N = 2048 (M = 1024): one warp per frame, everything in registers except one transpose.
+//
+// With the windowed frame u viewed as 1024 pairs P[p] = (u[2p], u[2p+1]) the DCT-IV input
+// t[m] = (v[2m] + i v[M-1-2m]) pre[m] of the folded block v = [-c_r - d, a - b_r] needs, for m < 256,
+//     P[768+m], P[767-m], P[255-m], P[256+m]
+// and t[511-m] needs exactly the same four pairs.  A lane therefore loads 4 x 8 coalesced pairs,
+// forms t[m] for its own m = lane + 32 r (r < 8) and hands the raw value of t[511-m] to lane
+// 31 - lane (register 15 - r) with one xor-31 shuffle.  After the 512-point FFT the outputs
+// X[2k] = Re Y[k], X[1023-2k] = -Im Y[k] are regrouped into pairs (X[2P], X[2P+1]) with the same
+// shuffle, so loads and stores are all full 256-byte warp transactions.
+// (Index maps validated in float64 against the closed form of zaf.py:1047-1073.)
+// ------------------------------------------------------------------------------------------
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float2 ld_pair(const float* __restrict__ xc, int64_t start, int p, int64_t ns, bool inside) {
+    if (inside) return __ldg(reinterpret_cast<const float2*>(xc + start) + p);
+    const int64_t s = start + 2 * p;
+    float2 r;
+    r.x = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
+    r.y = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
+    return r;
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 2)
+mdct2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
+                     const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
+                     const float2* __restrict__ pre, const float2* __restrict__ post, float* __restrict__ out,
+                     int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    float2* s_win = smem2;         // 1024 pairs of the window
+    float2* s_tw = smem2 + 1024;   // 512: W_512^{k1 n2}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* s_buf = smem2 + 1536 + warp * (16 * kFft1024Pitch);
+    for (int i = tid; i < 1024; i += kWarps * 32) s_win[i] = win_pairs[i];
+    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
+    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane
+    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M}
+    __syncthreads();
+
+    for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = (j - 1) * 1024;  // frame j covers original samples [(j-1)M, (j+1)M)
+        const float* xc = x + clip * clip_stride;
+        const bool inside = start >= 0 && start + 2048 <= ns;
+
+        float2 v[16];
+        static_for<0, 8>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const int m = lane + 32 * r;
+            float2 p1 = ld_pair(xc, start, 768 + m, ns, inside);
+            float2 p2 = ld_pair(xc, start, 767 - m, ns, inside);
+            float2 p3 = ld_pair(xc, start, 255 - m, ns, inside);
+            float2 p4 = ld_pair(xc, start, 256 + m, ns, inside);
+            const float2 w1 = s_win[768 + m], w2 = s_win[767 - m], w3 = s_win[255 - m], w4 = s_win[256 + m];
+            p1.x *= w1.x; p1.y *= w1.y;
+            p2.x *= w2.x; p2.y *= w2.y;
+            p3.x *= w3.x; p3.y *= w3.y;
+            p4.x *= w4.x; p4.y *= w4.y;
+            v[r] = make_float2(-p2.y - p1.x, p3.y - p4.x);               // raw t[m]
+            const float2 other = make_float2(p3.x - p4.y, -p2.x - p1.y);  // raw t[511 - m], belongs to lane 31 - lane
+            v[15 - r].x = __shfl_xor_sync(0xffffffffu, other.x, 31);
+            v[15 - r].y = __shfl_xor_sync(0xffffffffu, other.y, 31);
+        });
+        static_for<0, 16>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            v[r] = cmul(v[r], mul_tw<r, 64>(c_lane));
+        });
+
+        warp_fft512(v, s_tw, s_buf, lane);  // Y[lane + 32 k] = v[bitrev(k, 4)]
+
+        static_for<0, 16>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            v[bitrev(k, 4)] = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(p_lane));
+        });
+        float2* o = reinterpret_cast<float2*>(out + f * 1024) + lane;
+        static_for<0, 16>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(15 - k, 4)].y, 31);
+            __stcs(o + 32 * k, make_float2(v[bitrev(k, 4)].x, -im));
+        });
+    }
+}
+
+// IMDCT, N = 2048: one warp per run of consecutive hop-blocks of one clip; the second half of the
+// previous frame (already scaled and windowed) is carried in registers, so every output sample is
+// carry (frame h-1) + first half (frame h), written once.  A run re-reads the one frame before it.
+__global__ void __launch_bounds__(kWarps * 32, 2)
+imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __restrict__ win_pairs,
+                      const float2* __restrict__ tw4, const float2* __restrict__ pre,
+                      const float2* __restrict__ post, int64_t runs_per_clip, int run_len, int64_t total_runs,
+                      int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned) {
+    extern __shared__ float2 smem2[];
+    float2* s_win = smem2;
+    float2* s_tw = smem2 + 1024;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* s_buf = smem2 + 1536 + warp * (16 * kFft1024Pitch);
+    for (int i = tid; i < 1024; i += kWarps * 32) s_win[i] = win_pairs[i];
+    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
+    const float2 c_lane = pre[lane];
+    const float2 p_lane = post[lane];
+    __syncthreads();
+    constexpr float kScale = 2.0f / 1024.0f;
+
+    for (int64_t task = int64_t(blockIdx.x) * kWarps + warp; task < total_runs; task += int64_t(gridDim.x) * kWarps) {
+        const int64_t clip = task / runs_per_clip;
+        const int64_t run = task - clip * runs_per_clip;
+        const int64_t h0 = 1 + run * run_len;
+        int64_t h1 = h0 + run_len;
+        if (h1 > nt) h1 = nt;
+        float* yc = y + clip * y_stride;
+        float2 carry[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) carry[i] = make_float2(0.f, 0.f);
+
+        for (int64_t j = h0 - 1; j < h1; ++j) {
+            const float2* X = reinterpret_cast<const float2*>(spec + (clip * nt + j) * 1024) + lane;
+            float2 xp[16], v[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) xp[r] = __ldg(X + 32 * r);
+            static_for<0, 16>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float im = __shfl_xor_sync(0xffffffffu, xp[15 - r].y, 31);  // X[1023 - 2m]
+                v[r] = cmul(make_float2(xp[r].x, im), mul_tw<r, 64>(c_lane));
+            });
+
+            warp_fft512(v, s_tw, s_buf, lane);
+
+            // A[k] = res[2k] = Re(Y post), B[k] = res[1023 - 2k] = -Im(Y post), k = lane + 32 kap
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const float2 t = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(p_lane));
+                v[bitrev(k, 4)] = make_float2(t.x, -t.y);
+            });
+            const bool emit = j >= h0;
+            const int64_t base = (j - 1) * 1024;  // output index of OLA sample j*M (trim = M)
+            static_for<0, 16>([&](auto rc) {
+                constexpr int rho = decltype(rc)::value;
+                constexpr int own = rho < 8 ? rho + 8 : rho - 8;   // register (kap) of this lane's value
+                constexpr int oth = rho < 8 ? 7 - rho : 23 - rho;  // register of lane 31 - lane's value
+                const float2 mine = v[bitrev(own, 4)];
+                float2 part;
+                part.x = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, 4)].x, 31);
+                part.y = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, 4)].y, 31);
+                float2 first, second;
+                if constexpr (rho < 8) {
+                    first = make_float2(mine.x, part.y);     // ( A[P+256],  B[255-P])
+                    second = make_float2(-mine.y, -part.x);  // (-B[P+256], -A[255-P])
+                } else {
+                    first = make_float2(-mine.y, -part.x);   // (-B[P-256], -A[767-P])
+                    second = make_float2(-mine.x, -part.y);  // (-A[P-256], -B[767-P])
+                }
+                const int P = lane + 32 * rho;
+                const float2 w1 = s_win[P], w2 = s_win[512 + P];
+                if (emit) {
+                    const float2 o = make_float2(fmaf(kScale * w1.x, first.x, carry[rho].x),
+                                                 fmaf(kScale * w1.y, first.y, carry[rho].y));
+                    const int64_t idx = base + 2 * P;
+                    if (y_aligned && idx + 1 < out_len) {
+                        __stcs(reinterpret_cast<float2*>(yc + idx), o);
+                    } else {
+                        if (idx < out_len) yc[idx] = o.x;
+                        if (idx + 1 < out_len) yc[idx + 1] = o.y;
+                    }
+                }
+                carry[rho] = make_float2(kScale * w2.x * second.x, kScale * w2.y * second.y);
+            });
+        }
+    }
+}
+
 // IMDCT.  Output sample p (OLA coordinates, hop-block h = p / M) = second half of frame h-1 + first half of frame h.
 // The reference keeps OLA[M : M*nt - 1]: hop-blocks 1 .. nt-1, last sample dropped (zaf.py:1182).
 // One CTA owns hop-blocks [h0, h1) of one clip and walks frames h0-1 .. h1-1, carrying the second half.
@@ -185,6 +361,8 @@ __global__ void imdct_tile_kernel(const float* __restrict__ spec, int64_t nt, in
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
+    ZAFB_CUDA(cudaFuncSetAttribute(mdct2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(imdct2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(imdct_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -225,6 +403,16 @@ int zafb_mdct_plan_create(zafb_mdct_plan** out, const double* window, int64_t n)
         rc = upload_c32(&p->d_pre, pre.data(), h);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_post, post.data(), h);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_fft, h, h);
+        if (rc == ZAFB_OK && n == 2048) {  // W_512^{k1*n2} laid out [k1][n2] for the warp kernels
+            std::vector<double> t(2 * 512);
+            for (int k1 = 0; k1 < 16; ++k1)
+                for (int n2 = 0; n2 < 32; ++n2) {
+                    const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+                    t[2 * (k1 * 32 + n2)] = std::cos(a);
+                    t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
+                }
+            rc = upload_c32(&p->d_tw_4step, t.data(), 512);
+        }
     } else if (rc == ZAFB_OK) {
         std::vector<double> c(8 * p->m);
         for (int64_t t = 0; t < 8 * p->m; ++t) c[t] = std::cos(2.0 * pi * double(t) / double(8 * p->m));
@@ -245,7 +433,15 @@ int zafb_mdct_plan_destroy(zafb_mdct_plan* p) {
     cudaFree(p->d_pre);
     cudaFree(p->d_post);
     cudaFree(p->d_cos);
+    cudaFree(p->d_tw_4step);
     delete p;
+    return ZAFB_OK;
+}
+
+// test hook: 0 = auto, 1 = generic kernels only, 2 = require the warp kernels
+int zafb_mdct_plan_force_kernel(zafb_mdct_plan* p, int which) {
+    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 2, "bad plan / kernel id");
+    p->force_kernel = which;
     return ZAFB_OK;
 }
 
@@ -264,6 +460,23 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     const int64_t grid = total < int64_t(sm_count()) * 32 ? total : int64_t(sm_count()) * 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int m = int(p->m);
+    {
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && clip_stride % 2 == 0 &&
+                             reinterpret_cast<uintptr_t>(out) % 8 == 0;
+        const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
+        if (p->force_kernel == 2 && !warp_ok)
+            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N=2048, frame-major layout, even clip_stride, 8-byte aligned x/out");
+        if (warp_ok && p->force_kernel != 1) {
+            const size_t smem = (1536 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            int64_t ctas = ceil_div(total, kWarps);
+            if (ctas > int64_t(sm_count()) * kMdctCtasPerSm) ctas = int64_t(sm_count()) * kMdctCtasPerSm;
+            mdct2048_warp_kernel<<<unsigned(ctas), kWarps * 32, smem, st>>>(
+                x, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
+                out, total);
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        }
+    }
     if (p->log2m >= 1) {
         const size_t smem = size_t(m) * sizeof(float2) + 2 * size_t(m) * sizeof(float);
         if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
@@ -292,6 +505,35 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     if (n_clips == 0 || len == 0) return ZAFB_OK;
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
+    {
+        const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
+        if (p->force_kernel == 2 && !warp_ok)
+            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N=2048, frame-major layout, 8-byte aligned spectra");
+        if (warp_ok && p->force_kernel != 1) {
+            const int64_t nblocks = nt - 1;
+            const int64_t resident_warps = int64_t(sm_count()) * kMdctCtasPerSm * kWarps;
+            int64_t best_len = nblocks, best_cost = INT64_MAX;
+            for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
+                const int64_t runs = n_clips * ceil_div(nblocks, l);
+                const int64_t cost = ceil_div(runs, resident_warps) * (l + 1);
+                if (cost < best_cost || (cost == best_cost && l > best_len)) {
+                    best_cost = cost;
+                    best_len = l;
+                }
+            }
+            const int64_t runs_per_clip = ceil_div(nblocks, best_len);
+            const int64_t total = n_clips * runs_per_clip;
+            int64_t ctas = ceil_div(total, kWarps);
+            if (ctas > int64_t(sm_count()) * kMdctCtasPerSm) ctas = int64_t(sm_count()) * kMdctCtasPerSm;
+            const size_t smem = (1536 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            const int y_aligned = (reinterpret_cast<uintptr_t>(y) % 8 == 0 && y_stride % 2 == 0) ? 1 : 0;
+            imdct2048_warp_kernel<<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+                spec, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
+                int(best_len), total, len, y, y_stride, y_aligned);
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        }
+    }
     const int64_t hop_blocks = nt - 1;  // hop-blocks 1 .. nt-1 are written
     int64_t per_tile = 16;
     if (per_tile > hop_blocks) per_tile = hop_blocks;

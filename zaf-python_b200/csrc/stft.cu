@@ -13,7 +13,9 @@
 //                         transforms every frame that touches it in increasing frame order (the
 //                         reference's summation order, zaf.py:227-233) and writes each sample once:
 //                         no atomics, bit-reproducible.
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <type_traits>
 #include <vector>
 
@@ -42,15 +44,6 @@ constexpr int kMaxDynSmem = 200 * 1024;
 // N = 2048: one warp per frame
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = 8;
-constexpr int kRowPad = 33;  // float2 row pitch of the 32x32 transpose buffer (conflict-free)
-
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
 
 __device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
 
@@ -64,7 +57,7 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    float2* s_buf = smem + 2048 + warp * (32 * kRowPad);
+    float2* s_buf = smem + 2048 + warp * (32 * kFft1024Pitch);
 
     for (int i = tid; i < 1024; i += kWarpsPerCta * 32) {
         s_win[i] = win_half[i];
@@ -100,21 +93,7 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
             v[r].y *= w.y;
         }
 
-        // step 1: 32-point FFT over n1 (register index); thread = n2
-        fft_reg<32>(v);
-        // step 2+3: twiddle W_1024^{k1 n2}, transpose through shared memory
-        static_for<0, 32>([&](auto k1c) {
-            constexpr int k1 = decltype(k1c)::value;
-            float2 y = v[bitrev(k1, 5)];
-            if constexpr (k1 > 0) y = cmul(y, s_tw[k1 * 32 + lane]);
-            s_buf[k1 * kRowPad + lane] = y;
-        });
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) v[n2] = s_buf[lane * kRowPad + n2];
-        __syncwarp();
-        // step 4: 32-point FFT over n2; thread = k1, Z[k1 + 32 k2] = v[bitrev(k2)]
-        fft_reg<32>(v);
+        warp_fft1024<false>(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2)]
 
         // real-input unpack: X[k] = E + w_k O, X[k+1024] = E - w_k O with
         //   E = Z[k] + conj(Z[1024-k]),  O = -i (Z[k] - conj(Z[1024-k]))   (the 1/2 is in the window)
@@ -135,6 +114,109 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
             st_stream(o + 32 * k2, cadd(e, t));
             st_stream(o + 1024 + 32 * k2, csub(e, t));
         });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ISTFT, N = 2048, hop = 2048 / R (R = 2, 4, 8), frame-major spectra: one warp per RUN of
+// consecutive output hop-blocks of one clip.
+//
+// Frame j adds its part q (samples [q hop, (q+1) hop)) into hop-block j + q of the overlap-add
+// signal (zaf.py:227-233); block h is complete once frame h has been added.  A warp walks the
+// frames of its run in increasing order, keeps the R - 1 unfinished blocks in a private
+// shared-memory ring, and writes every finished block once: no atomics, no inter-warp
+// synchronisation, and the summation order of every output sample is the reference's (frames
+// h-R+1, ..., h).  A run re-reads the R - 1 frames before its first block (warm-up).
+//
+// Per frame: Re(ifft(X)) for an arbitrary (not necessarily Hermitian) X is the c2r transform of
+// H[k] = (X[k] + conj(X[N-k])) / 2; it is packed into ONE 1024-point complex FFT,
+//   Z[k] = E[k] + i O[k],  E = H[k] + H[k+1024],  O = (H[k] - H[k+1024]) conj(W_2048^k),
+//   y[2n] + i y[2n+1] = conj(FFT_1024(conj(Z)))[n] / (2 N)        (validated in float64).
+// ------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+istft2048_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
+                      const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
+                      int64_t total_runs, float* __restrict__ y, int64_t y_stride) {
+    constexpr int HOP = 2048 / R;
+    constexpr int K = 32 / R;            // registers (float2) per part
+    constexpr int SLOTS = R - 1;
+    constexpr int RING = SLOTS * (HOP / 2);  // float2 per warp
+    extern __shared__ float2 smem[];
+    float2* s_tw = smem;  // 1024
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    float2* s_ring = smem + 1024 + warp * RING;
+    float* s_buf = reinterpret_cast<float*>(smem + 1024 + kWarpsPerCta * RING) + warp * (32 * kFft1024Pitch);
+
+    for (int i = tid; i < 1024; i += kWarpsPerCta * 32) s_tw[i] = tw4[i];
+    const float2 c_lane = tw_full[lane];  // W_2048^lane
+    __syncthreads();
+
+    for (int64_t task = int64_t(blockIdx.x) * kWarpsPerCta + warp; task < total_runs;
+         task += int64_t(gridDim.x) * kWarpsPerCta) {
+        const int64_t clip = task / runs_per_clip;
+        const int64_t run = task - clip * runs_per_clip;
+        const int64_t h_begin = (R - 1) + run * run_len;  // first finished block of the run (OLA coordinates)
+        int64_t h_end = h_begin + run_len;
+        if (h_end > nt) h_end = nt;
+        for (int i = lane; i < RING; i += 32) s_ring[i] = make_float2(0.f, 0.f);
+        __syncwarp();
+        float* yc = y + clip * y_stride;
+        int slot0 = int((h_begin - (R - 1)) % SLOTS);  // ring slot of block j
+
+        for (int64_t j = h_begin - (R - 1); j < h_end; ++j) {
+            const float2* X = spec + (clip * nt + j) * 2048;
+            float2 v[32];
+            // r and 31 - r back to back: the mirrored loads (c, d) of one hit the lines the direct
+            // loads (a, b) of the other have just brought into L1
+            static_for<0, 32>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                constexpr int r = (t % 2 == 0) ? t / 2 : 31 - t / 2;
+                const int k = lane + 32 * r;
+                const float2 a = __ldg(X + k);
+                const float2 b = __ldg(X + 1024 + k);
+                const float2 c = __ldg(X + 1024 - k);
+                const float2 d = __ldg(X + ((2048 - k) & 2047));
+                const float2 h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
+                const float2 h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + 1024]
+                const float2 e = cadd(h0, h1);
+                const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, 64>(c_lane));
+                // conj(Z) = conj(e + i o)
+                v[r] = make_float2(e.x - o.y, -(e.y + o.x));
+            });
+
+            warp_fft1024<true>(v, s_tw, s_buf, lane);  // conj(z[lane + 32 k2]) = v[bitrev(k2)]
+
+            static_for<0, 32>([&](auto k2c) {
+                constexpr int k2 = decltype(k2c)::value;
+                constexpr int q = k2 / K;   // part of the frame
+                constexpr int i = k2 % K;
+                const float2 z = make_float2(v[bitrev(k2, 5)].x, -v[bitrev(k2, 5)].y);
+                if constexpr (q == 0) {
+                    float2 acc = z;
+                    if constexpr (R > 1) {
+                        const float2 prev = s_ring[slot0 * (HOP / 2) + lane + 32 * i];
+                        acc = make_float2(prev.x + z.x, prev.y + z.y);
+                    }
+                    if (j >= h_begin) {
+                        float2* dst = reinterpret_cast<float2*>(yc + (j - (R - 1)) * HOP) + lane + 32 * i;
+                        *dst = make_float2(acc.x * scale, acc.y * scale);
+                    }
+                } else if constexpr (q == R - 1) {
+                    s_ring[slot0 * (HOP / 2) + lane + 32 * i] = z;  // block j + R - 1 starts in the slot block j left
+                } else {
+                    int s = slot0 + q;
+                    if (s >= SLOTS) s -= SLOTS;
+                    float2* cell = s_ring + s * (HOP / 2) + lane + 32 * i;
+                    const float2 prev = *cell;
+                    *cell = make_float2(prev.x + z.x, prev.y + z.y);
+                }
+            });
+            slot0 = (slot0 + 1 == SLOTS) ? 0 : slot0 + 1;
+        }
+        __syncwarp();
     }
 }
 
@@ -289,10 +371,42 @@ bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
+    return ZAFB_OK;
+}
+
+template <int R>
+int launch_istft2048(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
+                     int64_t y_stride, cudaStream_t st) {
+    const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
+    const int64_t resident_warps = int64_t(sm_count()) * 2 * kWarpsPerCta;
+    // run length: minimise (runs per warp) x (frames per run, warm-up included)
+    int64_t best_len = nblocks, best_cost = INT64_MAX;
+    for (int64_t len = nblocks < 8 ? nblocks : 8; len <= nblocks && len <= 1024; ++len) {
+        const int64_t runs = n_clips * ceil_div(nblocks, len);
+        const int64_t cost = ceil_div(runs, resident_warps) * (len + R - 1);
+        if (cost < best_cost || (cost == best_cost && len > best_len)) {
+            best_cost = cost;
+            best_len = len;
+        }
+    }
+    const int64_t runs_per_clip = ceil_div(nblocks, best_len);
+    const int64_t total = n_clips * runs_per_clip;
+    int64_t ctas = ceil_div(total, kWarpsPerCta);
+    if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+    constexpr int HOP = 2048 / R;
+    const size_t smem = 1024 * sizeof(float2) + size_t(kWarpsPerCta) * ((R - 1) * (HOP / 2) * sizeof(float2) +
+                                                                        32 * kFft1024Pitch * sizeof(float));
+    const float scale = static_cast<float>(1.0 / (2.0 * 2048.0 * p->gain));
+    istft2048_warp_kernel<R><<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+        spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride);
+    ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
 
@@ -389,7 +503,7 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     if (p->force_kernel == 2 && !warp_ok)
         return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, frame-major layout, even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
-        const size_t smem = (2048 + kWarpsPerCta * 32 * kRowPad) * sizeof(float2);
+        const size_t smem = (2048 + kWarpsPerCta * 32 * kFft1024Pitch) * sizeof(float2);
         int64_t ctas = ceil_div(total, kWarpsPerCta);
         const int64_t resident = int64_t(sms) * 2;
         if (ctas > resident) ctas = resident;
@@ -431,6 +545,22 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     if (n_clips == 0 || len == 0) return ZAFB_OK;
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int n = int(p->n);
+    {
+        const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
+                             y_stride % 2 == 0;
+        const bool warp_ok = n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned &&
+                             (p->hop == 256 || p->hop == 512 || p->hop == 1024);
+        if (p->force_kernel == 2 && !warp_ok)
+            return fail(ZAFB_E_UNSUPPORTED,
+                        "istft warp kernel needs N=2048, hop in {256,512,1024}, frame-major layout, even y_stride");
+        if (warp_ok && p->force_kernel != 1) {
+            const float2* s2 = reinterpret_cast<const float2*>(spec);
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            if (p->hop == 1024) return launch_istft2048<2>(p, s2, n_clips, nt, y, y_stride, st);
+            if (p->hop == 512) return launch_istft2048<4>(p, s2, n_clips, nt, y, y_stride, st);
+            return launch_istft2048<8>(p, s2, n_clips, nt, y, y_stride, st);
+        }
+    }
     // tile: about 4 windows of output, bounded by shared memory (2 n float2 + tile floats)
     const size_t fft_bytes = size_t(2) * n * sizeof(float2);
     if (fft_bytes + 4096 > size_t(kMaxDynSmem))
