@@ -50,6 +50,36 @@ def test_mdct_imdct_vs_oracle(zaf_gpu, n, ns):
         assert np.max(np.abs(y[:m] - x[:m])) <= 2e-5
 
 
+@pytest.mark.parametrize("force", [1, 2])
+def test_mdct_imdct_2048_kernels_agree_with_oracle(zaf_gpu, force):
+    """The warp-per-frame MDCT / warp-per-run IMDCT kernels (2) and the generic kernels (1) on the
+    same batch: odd and even clip lengths, clips long enough to be split into several runs."""
+    rng = np.random.default_rng(20261017 + 4)
+    w = oracle.kbd_window(2048)
+    lib = zaf_gpu._lib.lib()
+    plan, _ = zaf_gpu._mdct_plan(w)
+    for ns in (100001, 65536, 1000):
+        x = rng.uniform(-1, 1, (3, ns)).astype(np.float32)
+        zaf_gpu._lib.check(lib.zafb_mdct_plan_force_kernel(plan, force))
+        try:
+            got = zaf_gpu.mdct(x, w)
+            back = zaf_gpu.imdct(got, w)
+            xd = zaf_gpu.to_device(x if ns % 2 == 0 else np.pad(x, ((0, 0), (0, 1))))
+            if ns % 2:
+                xd.cols = ns
+            back_dev = zaf_gpu.imdct(zaf_gpu.mdct(xd, w), w)
+        finally:
+            lib.zafb_mdct_plan_force_kernel(plan, 0)
+        for c in range(3):
+            ref = oracle.mdct(x[c], w)
+            assert_parity(got[c], ref)
+            assert_parity(back[c], oracle.imdct(ref, w))
+        assert back.shape[1] == 1024 * (got.shape[2] - 1) - 1
+        m = min(back.shape[1], ns)
+        assert np.max(np.abs(back[:, :m] - x[:, :m])) <= 2e-5  # TDAC
+        assert np.array_equal(back_dev.to_host(), back)
+
+
 def test_mdct_errors_and_batch(zaf_gpu):
     with pytest.raises(ValueError):
         zaf_gpu.mdct(np.zeros(100, np.float32), np.ones(255))

@@ -133,6 +133,17 @@ def _signal_batch(audio_signal):
     return x, one
 
 
+def _even_pitch(x):
+    """(batch, ns) float32 -> (array whose rows start at even element offsets, pitch).  The vectorised
+    kernels need 8-byte aligned rows; an odd ns gets one padding column (never read as signal)."""
+    ns = x.shape[1]
+    if ns % 2 == 0 or x.shape[0] == 1:
+        return x, max(ns, 1) if x.shape[0] == 1 else ns
+    padded = np.zeros((x.shape[0], ns + 1), dtype=x.dtype)
+    padded[:, :ns] = x
+    return padded, ns + 1
+
+
 def _matrix_out(batch, rows, cols, dtype, layout, one):
     """Host result buffer for a (rows, cols) = (bins, frames) matrix per clip, and the view to return."""
     if layout == LAYOUT_FRAME_MAJOR:
@@ -142,6 +153,10 @@ def _matrix_out(batch, rows, cols, dtype, layout, one):
         mem = np.empty((batch, rows, cols), dtype=dtype)
         view = mem
     return mem, (view[0] if one else view)
+
+
+def _even(n):
+    return (int(n) + 1) & ~1
 
 
 def _stream_ptr(stream):
@@ -168,7 +183,7 @@ def stft(audio_signal, window_function, step_length, *, layout="frame_major", st
         nt = stft_geometry(ns, n, step_length)[1]
         mem_shape = (batch, nt, n) if lay == LAYOUT_FRAME_MAJOR else (batch, n, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.complex64, transposed=lay == LAYOUT_FRAME_MAJOR)
-        _lib.check(_lib.lib().zafb_stft_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+        _lib.check(_lib.lib().zafb_stft_f32(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, C.c_void_p(out.ptr), lay,
                                             _stream_ptr(stream)))
         return out
     x, one = _signal_batch(audio_signal)
@@ -273,15 +288,16 @@ def mdct(audio_signal, window_function, *, layout="frame_major", stream=None):
         m, nt, _ = mdct_geometry(ns, n)
         mem_shape = (batch, nt, m) if lay == LAYOUT_FRAME_MAJOR else (batch, m, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
-        _lib.check(_lib.lib().zafb_mdct_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+        _lib.check(_lib.lib().zafb_mdct_f32(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, C.c_void_p(out.ptr), lay,
                                             _stream_ptr(stream)))
         return out
     x, one = _signal_batch(audio_signal)
     batch, ns = x.shape
     m, nt, _ = mdct_geometry(ns, n)
     mem, view = _matrix_out(batch, m, nt, np.float32, lay, one)
+    x, pitch = _even_pitch(x)
     _run_on_device(x, mem, lambda xd, od: _lib.check(
-        _lib.lib().zafb_mdct_f32(plan, xd, batch, ns, ns, od, lay, None)))
+        _lib.lib().zafb_mdct_f32(plan, xd, batch, ns, pitch, od, lay, None)))
     return view
 
 
@@ -299,9 +315,10 @@ def imdct(audio_mdct, window_function, *, stream=None):
             raise ValueError("audio_mdct rows must equal window_length/2")
         nt = shape[-1]
         length = imdct_geometry(n // 2, nt)[1]
-        out = DeviceArray((length,) if one else (batch, length), np.float32)
+        pitch = _even(length)  # the reference's odd length M(nt-1)-1 would misalign every other row
+        out = DeviceArray((pitch,) if one else (batch, pitch), np.float32, cols=length)
         lay = LAYOUT_FRAME_MAJOR if s.transposed else LAYOUT_BIN_MAJOR
-        _lib.check(_lib.lib().zafb_imdct_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), length,
+        _lib.check(_lib.lib().zafb_imdct_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), pitch,
                                              _stream_ptr(stream)))
         return out
     mem, lay, one, shape = _spec_memory(audio_mdct, np.float32)
@@ -309,9 +326,11 @@ def imdct(audio_mdct, window_function, *, stream=None):
     if bins * 2 != n:
         raise ValueError("audio_mdct rows must equal window_length/2")
     length = imdct_geometry(bins, nt)[1]
-    y = np.empty((batch, length), dtype=np.float32)
+    pitch = _even(length)
+    y = np.empty((batch, pitch), dtype=np.float32)
     _run_on_device(mem, y, lambda xd, od: _lib.check(
-        _lib.lib().zafb_imdct_f32(plan, xd, batch, nt, lay, od, length, None)))
+        _lib.lib().zafb_imdct_f32(plan, xd, batch, nt, lay, od, pitch, None)))
+    y = y[:, :length]
     return y[0] if one else y
 
 
@@ -325,7 +344,7 @@ def _dct_like(audio_signal, kind, dtype_code):
         batch, n = (1, x.shape[0]) if one else x.shape
         plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
         out = DeviceArray(x.shape, np.float32)
-        _lib.check(_lib.lib().zafb_dct_f32(plan, C.c_void_p(x.ptr), batch, n, C.c_void_p(out.ptr), n, None))
+        _lib.check(_lib.lib().zafb_dct_f32(plan, C.c_void_p(x.ptr), batch, x.pitch, C.c_void_p(out.ptr), n, None))
         return out
     x, one = _signal_batch(audio_signal)
     batch, n = x.shape
@@ -370,15 +389,16 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
         nt = stft_geometry(ns, len(w), step_length)[1]
         mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
-        _lib.check(getattr(_lib.lib(), fn)(plan, C.c_void_p(x.ptr), batch, ns, ns, C.c_void_p(out.ptr), lay,
+        _lib.check(getattr(_lib.lib(), fn)(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, C.c_void_p(out.ptr), lay,
                                            _stream_ptr(stream)))
         return out
     x, one = _signal_batch(audio_signal)
     batch, ns = x.shape
     nt = stft_geometry(ns, len(w), step_length)[1]
     mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
+    x, pitch = _even_pitch(x)
     _run_on_device(x, mem, lambda xd, od: _lib.check(
-        getattr(_lib.lib(), fn)(plan, xd, batch, ns, ns, od, lay, None)))
+        getattr(_lib.lib(), fn)(plan, xd, batch, ns, pitch, od, lay, None)))
     return view
 
 
@@ -425,15 +445,16 @@ def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resoluti
         nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
         mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
-        _lib.check(_lib.lib().zafb_cqt_f32(plan, C.c_void_p(x.ptr), batch, ns, ns, int(octave_resolution),
+        _lib.check(_lib.lib().zafb_cqt_f32(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, int(octave_resolution),
                                            C.c_void_p(out.ptr), lay, _stream_ptr(stream)))
         return out
     x, one = _signal_batch(audio_signal)
     batch, ns = x.shape
     nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
     mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
+    x, pitch = _even_pitch(x)
     _run_on_device(x, mem, lambda xd, od: _lib.check(
-        _lib.lib().zafb_cqt_f32(plan, xd, batch, ns, ns, int(octave_resolution), od, lay, None)))
+        _lib.lib().zafb_cqt_f32(plan, xd, batch, ns, pitch, int(octave_resolution), od, lay, None)))
     return view
 
 

@@ -42,9 +42,11 @@ class DeviceArray:
     """A typed, shaped view of a device allocation.  ``strides_view`` records whether the logical
     array is the transpose of the last two axes of the memory (frame-major transforms)."""
 
-    def __init__(self, shape, dtype, ptr=None, owner=None, transposed=False):
+    def __init__(self, shape, dtype, ptr=None, owner=None, transposed=False, cols=None):
         ensure_init()
         self.mem_shape = tuple(int(s) for s in shape)  # shape of the memory, C order
+        # rows padded to an aligned pitch: the logical last axis has `cols` <= mem_shape[-1] elements
+        self.cols = None if cols is None or int(cols) == self.mem_shape[-1] else int(cols)
         self.dtype = np.dtype(dtype)
         self.transposed = bool(transposed)
         self.nbytes = int(np.prod(self.mem_shape, dtype=np.int64)) * self.dtype.itemsize
@@ -62,7 +64,14 @@ class DeviceArray:
     def shape(self):
         if self.transposed:
             return self.mem_shape[:-2] + (self.mem_shape[-1], self.mem_shape[-2])
+        if self.cols is not None:
+            return self.mem_shape[:-1] + (self.cols,)
         return self.mem_shape
+
+    @property
+    def pitch(self):
+        """Elements between consecutive rows of the memory (>= the logical row length)."""
+        return self.mem_shape[-1]
 
     def free(self):
         if self._owns and self.ptr:
@@ -83,10 +92,12 @@ class DeviceArray:
                                               stream.ptr if stream else None))
         if stream is None:
             synchronize()
-        return np.swapaxes(host, -1, -2) if self.transposed else host
+        if self.transposed:
+            return np.swapaxes(host, -1, -2)
+        return host[..., :self.cols] if self.cols is not None else host
 
     def __repr__(self):
-        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, transposed={self.transposed})"
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, transposed={self.transposed}, pitch={self.pitch})"
 
 
 def to_device(array, dtype=None, stream=None) -> DeviceArray:

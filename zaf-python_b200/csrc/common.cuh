@@ -52,6 +52,8 @@ int upload_c32(float2** dev, const double* host_ri, size_t n);
 // W_n^t = exp(-2 pi i t / n), t in [0, count), generated in float64.
 int upload_twiddles(float2** dev, int64_t n, int64_t count);
 int sm_count();
+// tuning switch read from the environment (experiments only; the default is the shipped path)
+int env_flag(const char* name, int dflt);
 
 // ---------------------------------------------------------------- complex helpers
 #define ZAFB_HD __host__ __device__ __forceinline__

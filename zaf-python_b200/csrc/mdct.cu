@@ -35,7 +35,6 @@ struct zafb_mdct_plan {
 namespace {
 
 constexpr int kMaxDynSmem = 200 * 1024;
-constexpr int kMdctCtasPerSm = 2;
 
 // DCT-IV of the M values in v (shared) -> out (shared, M floats).  a/b: M/2 float2 scratch each.
 __device__ __forceinline__ void dct4_block(const float* v, float* out, float2* a, float2* b,
@@ -136,50 +135,71 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = 8;
 
-__device__ __forceinline__ float2 ld_pair(const float* __restrict__ xc, int64_t start, int p, int64_t ns, bool inside) {
-    if (inside) return __ldg(reinterpret_cast<const float2*>(xc + start) + p);
-    const int64_t s = start + 2 * p;
-    float2 r;
-    r.x = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
-    r.y = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
-    return r;
+constexpr int kWarpSmemF2 = 1024 + 512;  // window pairs, W_512 four-step table
+
+__device__ __forceinline__ void load_tables(float2* smem, const float2* __restrict__ win_pairs,
+                                            const float2* __restrict__ tw4, int tid) {
+    for (int i = tid; i < 1024; i += kWarps * 32) smem[i] = win_pairs[i];
+    for (int i = tid; i < 512; i += kWarps * 32) smem[1024 + i] = tw4[i];
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 2)
+template <int OCC>
+__global__ void __launch_bounds__(kWarps * 32, OCC)
 mdct2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
                      const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
                      const float2* __restrict__ pre, const float2* __restrict__ post, float* __restrict__ out,
                      int64_t total_frames) {
     extern __shared__ float2 smem2[];
-    float2* s_win = smem2;         // 1024 pairs of the window
-    float2* s_tw = smem2 + 1024;   // 512: W_512^{k1 n2}
+    const float2* s_win = smem2;          // 1024 pairs of the window
+    const float2* s_tw = smem2 + 1024;    // 512: W_512^{k1 n2}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = smem2 + 1536 + warp * (16 * kFft1024Pitch);
-    for (int i = tid; i < 1024; i += kWarps * 32) s_win[i] = win_pairs[i];
-    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
-    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane
-    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M}
+    float2* s_buf = smem2 + kWarpSmemF2 + warp * (16 * kFft1024Pitch);
+    load_tables(smem2, win_pairs, tw4, tid);
+    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane; pre[lane + 32 r] = c_lane W_64^r
+    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M};       post[lane + 32 k] = p_lane W_64^k
     __syncthreads();
 
     for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
         const int64_t clip = f / nt, j = f - clip * nt;
         const int64_t start = (j - 1) * 1024;  // frame j covers original samples [(j-1)M, (j+1)M)
         const float* xc = x + clip * clip_stride;
-        const bool inside = start >= 0 && start + 2048 <= ns;
 
+        // pairs 768+m, 767-m, 255-m, 256+m for m = lane + 32 r, r < 8
+        float2 pr[8][4];
+        if (start >= 0 && start + 2048 <= ns) {
+            const float2* fp = reinterpret_cast<const float2*>(xc + start);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int m = lane + 32 * r;
+                pr[r][0] = __ldg(fp + 768 + m);
+                pr[r][1] = __ldg(fp + 767 - m);
+                pr[r][2] = __ldg(fp + 255 - m);
+                pr[r][3] = __ldg(fp + 256 + m);
+            }
+        } else {
+            auto ld = [&](int p) {
+                const int64_t s0 = start + 2 * p;
+                return make_float2((s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f,
+                                   (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f);
+            };
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int m = lane + 32 * r;
+                pr[r][0] = ld(768 + m);
+                pr[r][1] = ld(767 - m);
+                pr[r][2] = ld(255 - m);
+                pr[r][3] = ld(256 + m);
+            }
+        }
         float2 v[16];
         static_for<0, 8>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const int m = lane + 32 * r;
-            float2 p1 = ld_pair(xc, start, 768 + m, ns, inside);
-            float2 p2 = ld_pair(xc, start, 767 - m, ns, inside);
-            float2 p3 = ld_pair(xc, start, 255 - m, ns, inside);
-            float2 p4 = ld_pair(xc, start, 256 + m, ns, inside);
             const float2 w1 = s_win[768 + m], w2 = s_win[767 - m], w3 = s_win[255 - m], w4 = s_win[256 + m];
-            p1.x *= w1.x; p1.y *= w1.y;
-            p2.x *= w2.x; p2.y *= w2.y;
-            p3.x *= w3.x; p3.y *= w3.y;
-            p4.x *= w4.x; p4.y *= w4.y;
+            const float2 p1 = make_float2(pr[r][0].x * w1.x, pr[r][0].y * w1.y);
+            const float2 p2 = make_float2(pr[r][1].x * w2.x, pr[r][1].y * w2.y);
+            const float2 p3 = make_float2(pr[r][2].x * w3.x, pr[r][2].y * w3.y);
+            const float2 p4 = make_float2(pr[r][3].x * w4.x, pr[r][3].y * w4.y);
             v[r] = make_float2(-p2.y - p1.x, p3.y - p4.x);               // raw t[m]
             const float2 other = make_float2(p3.x - p4.y, -p2.x - p1.y);  // raw t[511 - m], belongs to lane 31 - lane
             v[15 - r].x = __shfl_xor_sync(0xffffffffu, other.x, 31);
@@ -208,20 +228,20 @@ mdct2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
 // IMDCT, N = 2048: one warp per run of consecutive hop-blocks of one clip; the second half of the
 // previous frame (already scaled and windowed) is carried in registers, so every output sample is
 // carry (frame h-1) + first half (frame h), written once.  A run re-reads the one frame before it.
-__global__ void __launch_bounds__(kWarps * 32, 2)
+template <int OCC>
+__global__ void __launch_bounds__(kWarps * 32, OCC)
 imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __restrict__ win_pairs,
                       const float2* __restrict__ tw4, const float2* __restrict__ pre,
                       const float2* __restrict__ post, int64_t runs_per_clip, int run_len, int64_t total_runs,
                       int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned) {
     extern __shared__ float2 smem2[];
-    float2* s_win = smem2;
-    float2* s_tw = smem2 + 1024;
+    const float2* s_win = smem2;
+    const float2* s_tw = smem2 + 1024;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = smem2 + 1536 + warp * (16 * kFft1024Pitch);
-    for (int i = tid; i < 1024; i += kWarps * 32) s_win[i] = win_pairs[i];
-    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
-    const float2 c_lane = pre[lane];
-    const float2 p_lane = post[lane];
+    float2* s_buf = smem2 + kWarpSmemF2 + warp * (16 * kFft1024Pitch);
+    load_tables(smem2, win_pairs, tw4, tid);
+    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane; pre[lane + 32 r] = c_lane W_64^r
+    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M};       post[lane + 32 k] = p_lane W_64^k
     __syncthreads();
     constexpr float kScale = 2.0f / 1024.0f;
 
@@ -361,8 +381,8 @@ __global__ void imdct_tile_kernel(const float* __restrict__ spec, int64_t nt, in
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
-    ZAFB_CUDA(cudaFuncSetAttribute(mdct2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(imdct2048_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mdct2048_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(imdct2048_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(imdct_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -461,16 +481,18 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int m = int(p->m);
     {
-        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && clip_stride % 2 == 0 &&
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
                              reinterpret_cast<uintptr_t>(out) % 8 == 0;
         const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
         if (p->force_kernel == 2 && !warp_ok)
             return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N=2048, frame-major layout, even clip_stride, 8-byte aligned x/out");
         if (warp_ok && p->force_kernel != 1) {
-            const size_t smem = (1536 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
+            constexpr int occ = 3;
             int64_t ctas = ceil_div(total, kWarps);
-            if (ctas > int64_t(sm_count()) * kMdctCtasPerSm) ctas = int64_t(sm_count()) * kMdctCtasPerSm;
-            mdct2048_warp_kernel<<<unsigned(ctas), kWarps * 32, smem, st>>>(
+            if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
+            mdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
                 x, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
                 out, total);
             ZAFB_LAUNCH_CHECK();
@@ -511,7 +533,8 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
             return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N=2048, frame-major layout, 8-byte aligned spectra");
         if (warp_ok && p->force_kernel != 1) {
             const int64_t nblocks = nt - 1;
-            const int64_t resident_warps = int64_t(sm_count()) * kMdctCtasPerSm * kWarps;
+            constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
+            const int64_t resident_warps = int64_t(sm_count()) * occ * kWarps;
             int64_t best_len = nblocks, best_cost = INT64_MAX;
             for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
                 const int64_t runs = n_clips * ceil_div(nblocks, l);
@@ -524,10 +547,10 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
             const int64_t runs_per_clip = ceil_div(nblocks, best_len);
             const int64_t total = n_clips * runs_per_clip;
             int64_t ctas = ceil_div(total, kWarps);
-            if (ctas > int64_t(sm_count()) * kMdctCtasPerSm) ctas = int64_t(sm_count()) * kMdctCtasPerSm;
-            const size_t smem = (1536 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
-            const int y_aligned = (reinterpret_cast<uintptr_t>(y) % 8 == 0 && y_stride % 2 == 0) ? 1 : 0;
-            imdct2048_warp_kernel<<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
+            const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            const int y_aligned = (reinterpret_cast<uintptr_t>(y) % 8 == 0 && (n_clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
+            imdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                 spec, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
                 int(best_len), total, len, y, y_stride, y_aligned);
             ZAFB_LAUNCH_CHECK();

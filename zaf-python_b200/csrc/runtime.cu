@@ -1,6 +1,7 @@
 // Runtime plumbing of libzafb200: device, memory, streams, events, error strings, and the
 // bit-exact integer bookkeeping of the reference's framing (no device needed for the latter).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,11 @@ int upload_twiddles(float2** dev, int64_t n, int64_t count) {
         t[2 * i + 1] = std::sin(a);
     }
     return upload_c32(dev, t.data(), static_cast<size_t>(count));
+}
+
+int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
 }
 
 int sm_count() {

@@ -498,7 +498,7 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     const int sms = sm_count();
     float2* o = reinterpret_cast<float2*>(out);
 
-    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (clip_stride % 2 == 0) && (p->hop % 2 == 0);
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
     const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
     if (p->force_kernel == 2 && !warp_ok)
         return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, frame-major layout, even hop/stride, 8-byte aligned x");
@@ -547,7 +547,7 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     const int n = int(p->n);
     {
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
-                             y_stride % 2 == 0;
+                             (n_clips <= 1 || y_stride % 2 == 0);
         const bool warp_ok = n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned &&
                              (p->hop == 256 || p->hop == 512 || p->hop == 1024);
         if (p->force_kernel == 2 && !warp_ok)
