@@ -182,6 +182,40 @@ def test_mel_mfcc_cfg3_batch_vs_oracle(zaf_gpu):
     assert_parity(got, ref)
 
 
+@pytest.mark.parametrize("force", [1, 2])
+@pytest.mark.parametrize("n_mels,ncoef,fs", [(128, 40, 16000), (40, 13, 16000), (77, 60, 44100), (100, 99, 22050), (1, 1, 16000)])
+def test_mel_mfcc_1024_kernels_agree_with_oracle(zaf_gpu, force, n_mels, ncoef, fs):
+    """Warp-per-frame kernel (2) and generic kernel (1) for N = 1024: row counts that are not
+    multiples of 32, odd row counts (middle row of the DCT symmetry), more coefficients than 32."""
+    rng = np.random.default_rng(n_mels * 1000 + ncoef)
+    x = rng.uniform(-1, 1, (3, 20001)).astype(np.float32)
+    x[2, 5000:9000] = 0.0  # a stretch of digital silence inside a clip
+    w = oracle.hamming_periodic(1024)
+    fb = zaf_gpu.melfilterbank(fs, 1024, n_mels)
+    dense = fb.toarray()
+    lib = zaf_gpu._lib.lib()
+    for hop in (256, 512):
+        plans = [zaf_gpu._mel_plan(w, hop, fb, 0)[0], zaf_gpu._mel_plan(w, hop, fb, ncoef)[0]]
+        for p in plans:
+            zaf_gpu._lib.check(lib.zafb_mel_plan_force_kernel(p, force))
+        try:
+            mel = zaf_gpu.melspectrogram(x, w, hop, fb)
+            if force == 2 and min(ncoef, n_mels - 1) > 64:  # outside the warp kernel's envelope: must refuse, not guess
+                with pytest.raises(NotImplementedError):
+                    zaf_gpu.mfcc(x, w, hop, fb, ncoef)
+                lib.zafb_mel_plan_force_kernel(plans[1], 0)
+            cep = zaf_gpu.mfcc(x, w, hop, fb, ncoef)
+        finally:
+            for p in plans:
+                lib.zafb_mel_plan_force_kernel(p, 0)
+        for c in range(3):
+            assert_parity(mel[c], oracle.melspectrogram(x[c], w, hop, dense))
+            ref = oracle.mfcc(x[c], w, hop, dense, ncoef)
+            assert cep[c].shape == ref.shape
+            if ref.size:
+                assert_parity(cep[c], ref)
+
+
 # ------------------------------------------------------------------------------- CQT
 def _kernel(g, tag):
     shape = tuple(int(s) for s in g.get(tag, "kernel_shape"))

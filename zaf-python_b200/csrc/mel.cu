@@ -7,6 +7,7 @@
 // creation into one contiguous band per row [first non-zero column, last non-zero column]: 882 weights
 // instead of 65 536 at BASELINE cfg 3.
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -25,6 +26,18 @@ struct zafb_mel_plan {
     float* d_weights = nullptr;
     float* d_dct = nullptr;        // n_coef x n_mels, rows 1..n_coef of the orthonormal DCT-II matrix
     int64_t nnz_packed = 0;
+    // N = 1024 warp kernel: mel rows r = lane + 32 g (g < 4) belong to lane `lane`
+    bool warp_ok = false;
+    int grp_len[4] = {0, 0, 0, 0};  // longest band of each row group
+    int grp_off[4] = {0, 0, 0, 0};  // offset of the group's [c][lane] weight block in d_wt
+    float* d_wt = nullptr;          // zero-padded band weights, [g][c][lane]
+    float2* d_tw_4step = nullptr;   // W_512^{k1 n2}, [k1][n2]
+    float2* d_tw_n = nullptr;       // W_1024^t, t < 32
+    int* d_lo = nullptr;            // first column of row lane + 32 g, at [g * 32 + lane]
+    float* d_dh = nullptr;          // DCT-II half table, float4 at [(m / 4) * coef_pad + i] = D[i + 1][4 (m / 4) .. +3]
+    int coef_pad = 0;               // n_coef rounded up to 32
+    int half_mels = 0;              // ceil(n_mels / 2)
+    int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
 };
 
 namespace {
@@ -115,10 +128,166 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// N = 1024 (BASELINE cfg 3): one warp per frame, no block-level synchronisation.
+//   load 512 sample pairs (coalesced 8-byte loads) * window pairs held in REGISTERS (they are the
+//   same for every frame a lane processes) -> warp_fft512 -> real-input unpack with one xor-style
+//   shuffle per bin -> |X|^2 (or |X|) of bins 1..512 into the warp's shared-memory tile ->
+//   banded filterbank, lane l owning mel rows l, l+32, l+64, l+96 (weights zero-padded per row
+//   group, [g][c][lane] so the weight loads are conflict-free) -> melspectrogram rows, or
+//   ln ratio -> DCT-II through its even/odd symmetry  C[k] = sum_{m < n/2} D[k][m] (L[m] +- L[n-1-m])
+//   with lane l owning coefficients l and l + 32.
+// ------------------------------------------------------------------------------------------
+constexpr int kWarps = 8;
+constexpr int kMelWarpTile = 16 * kFft1024Pitch;  // float2 per warp: FFT transpose tile, then spectrum / log-mel scratch
+
+template <int MODE>  // 0 melspectrogram, 1 mfcc
+__global__ void __launch_bounds__(kWarps * 32, 2)
+mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
+                    const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
+                    const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
+                    int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
+                    int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    float2* s_tw = smem2;                                    // 512: W_512^{k1 n2}
+    float* s_wt = reinterpret_cast<float*>(smem2 + 512);     // wt_total floats
+    float4* s_dh = reinterpret_cast<float4*>(s_wt + ((wt_total + 3) & ~3));  // (half_mels/4 rounded up) * coef_pad float4
+    const int dh_count = MODE == 1 ? ((half_mels + 3) / 4) * coef_pad : 0;
+    float2* s_warp = reinterpret_cast<float2*>(s_dh + dh_count);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* s_buf = s_warp + warp * kMelWarpTile;
+    float* s_spec = reinterpret_cast<float*>(s_buf);         // 512 floats (+ slack) once the FFT is done
+    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
+    for (int i = tid; i < wt_total; i += kWarps * 32) s_wt[i] = wt[i];
+    for (int i = tid; i < dh_count; i += kWarps * 32) s_dh[i] = dh[i];
+    float2 win[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const float2 w = win_pairs[lane + 32 * r];
+        win[r] = make_float2(0.5f * w.x, 0.5f * w.y);  // the 1/2 of the real-input split, exact in fp32
+    }
+    const float2 c_lane = tw_full[lane];  // W_1024^lane
+    int lo[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) lo[g] = lo_tab[g * 32 + lane];
+    const int glen[4] = {grp_len.x, grp_len.y, grp_len.z, grp_len.w};
+    const int goff[4] = {grp_off.x, grp_off.y, grp_off.z, grp_off.w};
+    __syncthreads();
+
+    for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * hop - 512;
+        const float* xc = x + clip * clip_stride;
+        float2 v[16];
+        if (start >= 0 && start + 1024 <= ns) {
+            const float2* fp = reinterpret_cast<const float2*>(xc + start) + lane;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = __ldg(fp + 32 * r);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int64_t s0 = start + 2 * (lane + 32 * r);
+                v[r].x = (s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f;
+                v[r].y = (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            v[r].x *= win[r].x;
+            v[r].y *= win[r].y;
+        }
+        warp_fft512(v, s_tw, s_buf, lane);  // Z[lane + 32 k] = v[bitrev(k, 4)]
+
+        // X[k] = E + W_1024^k O,  E = Z[k] + conj(Z[512-k]),  O = -i (Z[k] - conj(Z[512-k])),  k = lane + 32 kap;
+        // column c = k - 1 (zaf.py:370 drops DC, keeps Nyquist); lane 0 / kap 0 produces the Nyquist bin instead of DC.
+        const int src = (32 - lane) & 31;
+        static_for<0, 16>([&](auto kc) {
+            constexpr int kap = decltype(kc)::value;
+            const float2 z = v[bitrev(kap, 4)];
+            const float2 mine = v[bitrev(15 - kap, 4)];
+            float2 pz;
+            pz.x = __shfl_sync(0xffffffffu, mine.x, src);
+            pz.y = __shfl_sync(0xffffffffu, mine.y, src);
+            if (lane == 0) pz = v[bitrev((16 - kap) & 15, 4)];
+            const float2 e = make_float2(z.x + pz.x, z.y - pz.y);
+            const float2 od = make_float2(z.y + pz.y, pz.x - z.x);
+            const float2 t = cmul(mul_tw<kap, 32>(c_lane), od);
+            float2 xk = cadd(e, t);
+            if (kap == 0 && lane == 0) xk = csub(e, t);  // X[512] = E[0] - O[0]
+            const float pw = xk.x * xk.x + xk.y * xk.y;
+            const int col = (kap == 0 && lane == 0) ? 511 : lane + 32 * kap - 1;
+            s_spec[col] = MODE == 0 ? sqrtf(pw) : pw;
+        });
+        __syncwarp();
+
+        float mel[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float* w = s_wt + goff[g] + lane;
+            const float* sp = s_spec + lo[g];
+            const int len = glen[g];
+            float acc = 0.f;
+            for (int c = 0; c < len; ++c) acc = fmaf(w[32 * c], sp[c], acc);
+            mel[g] = acc;
+        }
+        __syncwarp();  // every lane is done reading the spectrum
+
+        if constexpr (MODE == 0) {
+            float* o = out + f * n_mels;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (lane + 32 * g < n_mels) o[lane + 32 * g] = mel[g];
+        } else {
+            // ln(mel_r + eps) - ln(mel_0 + eps): rows k >= 1 of the DCT-II matrix sum to zero, so the constant drops
+            // out exactly, and the log of a ratio keeps fp32 absolute accuracy where the log itself does not.
+            const float ref0 = __shfl_sync(0xffffffffu, mel[0], 0) + 2.220446049250313e-16f;
+            float* s_log = s_spec;            // n_mels floats
+            float* s_sym = s_spec + 128;      // S[m] at [m], A[m] at [64 + m], m < half_mels <= 64
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (lane + 32 * g < n_mels) s_log[lane + 32 * g] = logf((mel[g] + 2.220446049250313e-16f) / ref0);
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = lane + 32 * h;
+                float sv = 0.f, av = 0.f;
+                if (m < half_mels) {
+                    const int mm = n_mels - 1 - m;
+                    const float a = s_log[m], b = (mm != m) ? s_log[mm] : 0.f;
+                    sv = a + b;
+                    av = (mm != m) ? a - b : 0.f;
+                }
+                s_sym[m] = sv;
+                s_sym[64 + m] = av;
+            }
+            __syncwarp();
+            const int quads = (half_mels + 3) >> 2;
+            for (int i0 = 0; i0 < n_coef; i0 += 32) {
+                const int i = i0 + lane;                       // coefficient row k = i + 1
+                const float4* sa = reinterpret_cast<const float4*>(s_sym + ((i & 1) ? 0 : 64));  // k even -> S, k odd -> A
+                const float4* d = s_dh + i;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int q = 0; q < quads; ++q) {
+                    const float4 s4 = sa[q];
+                    const float4 d4 = d[q * coef_pad];
+                    acc0 = fmaf(d4.x, s4.x, acc0);
+                    acc1 = fmaf(d4.y, s4.y, acc1);
+                    acc0 = fmaf(d4.z, s4.z, acc0);
+                    acc1 = fmaf(d4.w, s4.w, acc1);
+                }
+                if (i < n_coef) out[f * n_coef + i] = acc0 + acc1;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -143,6 +312,31 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
     const int64_t rows = mode == 0 ? p->n_mels : p->n_coef;
     if (total == 0 || rows == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    {
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
+        const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
+        if (p->force_kernel == 2 && !ok)
+            return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N=1024, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
+        if (ok && p->force_kernel != 1) {
+            const int wt_total = p->grp_off[3] + 32 * p->grp_len[3];
+            const int dh_count = mode == 1 ? ((p->half_mels + 3) / 4) * p->coef_pad : 0;
+            const size_t smem = 512 * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) + size_t(dh_count) * sizeof(float4) +
+                                size_t(kWarps) * kMelWarpTile * sizeof(float2);
+            if (smem <= size_t(kMaxDynSmem) / 2) {
+                int64_t ctas = ceil_div(total, kWarps);
+                if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+                const int4 gl = make_int4(p->grp_len[0], p->grp_len[1], p->grp_len[2], p->grp_len[3]);
+                const int4 go = make_int4(p->grp_off[0], p->grp_off[1], p->grp_off[2], p->grp_off[3]);
+                auto kern = mode == 0 ? mel1024_warp_kernel<0> : mel1024_warp_kernel<1>;
+                kern<<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+                    x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
+                    p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
+                    int(p->n_coef), p->coef_pad, out, total);
+                ZAFB_LAUNCH_CHECK();
+                return ZAFB_OK;
+            }
+        }
+    }
     const int m = int(p->n / 2);
     const size_t smem = size_t(p->n) * sizeof(float2) + size_t(m + p->n_mels) * sizeof(float) + 16;
     if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mel: window_length %lld too large", (long long)p->n);
@@ -208,11 +402,63 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct, d);
+    if (rc == ZAFB_OK && n == 1024 && n_mels <= 128 && p->n_coef <= 64) {
+        // row groups of 32 rows, zero-padded to the longest band of the group; the band start is clamped so that
+        // lo + grp_len never leaves the 512-column spectrum (the padding weights are zero)
+        std::vector<int> lo4(128, 0);
+        std::vector<float> wt;
+        for (int g = 0; g < 4; ++g) {
+            int longest = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int64_t r = l + 32 * g;
+                if (r < n_mels && len[r] > longest) longest = len[r];
+            }
+            p->grp_len[g] = longest;
+            p->grp_off[g] = int(wt.size());
+            wt.resize(wt.size() + size_t(32) * longest, 0.f);
+            for (int l = 0; l < 32; ++l) {
+                const int64_t r = l + 32 * g;
+                if (r >= n_mels || len[r] == 0) continue;
+                int start = lo[r];
+                if (start + longest > int(cols)) start = int(cols) - longest;  // shift left, pad in front
+                lo4[g * 32 + l] = start;
+                for (int c = 0; c < len[r]; ++c) wt[p->grp_off[g] + 32 * (lo[r] - start + c) + l] = w[off[r] + c];
+            }
+        }
+        p->half_mels = int((n_mels + 1) / 2);
+        p->coef_pad = int((p->n_coef + 31) / 32 * 32);
+        const int quads = (p->half_mels + 3) / 4;
+        std::vector<float> dh(size_t(quads) * (p->coef_pad ? p->coef_pad : 32) * 4, 0.f);
+        for (int64_t i = 0; i < p->n_coef; ++i)
+            for (int64_t mm = 0; mm < p->half_mels; ++mm)
+                dh[((mm / 4) * p->coef_pad + i) * 4 + (mm % 4)] = static_cast<float>(
+                    std::sqrt(2.0 / double(n_mels)) * std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels)));
+        std::vector<double> t4(2 * 512);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+                t4[2 * (k1 * 32 + n2)] = std::cos(a);
+                t4[2 * (k1 * 32 + n2) + 1] = std::sin(a);
+            }
+        rc = upload_c32(&p->d_tw_4step, t4.data(), 512);
+        if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_n, 1024, 32);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_wt, wt);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_lo, lo4);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_dh, dh);
+        p->warp_ok = rc == ZAFB_OK;
+    }
     if (rc != ZAFB_OK) {
         zafb_mel_plan_destroy(p);
         return rc;
     }
     *out = p;
+    return ZAFB_OK;
+}
+
+// test hook: 0 = auto, 1 = generic kernel only, 2 = require the warp kernel
+int zafb_mel_plan_force_kernel(zafb_mel_plan* p, int which) {
+    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 2, "bad plan / kernel id");
+    p->force_kernel = which;
     return ZAFB_OK;
 }
 
@@ -226,6 +472,11 @@ int zafb_mel_plan_destroy(zafb_mel_plan* p) {
     cudaFree(p->d_band_off);
     cudaFree(p->d_weights);
     cudaFree(p->d_dct);
+    cudaFree(p->d_tw_4step);
+    cudaFree(p->d_tw_n);
+    cudaFree(p->d_wt);
+    cudaFree(p->d_lo);
+    cudaFree(p->d_dh);
     delete p;
     return ZAFB_OK;
 }
