@@ -235,6 +235,47 @@ def test_cqt_golden(zaf_gpu, golden):
             assert_parity(zaf_gpu.cqtchromagram(x, int(fs), tr, int(res), k, layout=layout), g.get(tag, "chroma"))
 
 
+@pytest.mark.parametrize("force", [1, 2])
+def test_cqt_32768_kernels_agree_with_oracle(zaf_gpu, force):
+    """Register-FFT kernel (2) and generic kernel (1) at fft_length 32768 (BASELINE cfg 5 kernel): odd clip
+    length (unaligned rows), edge frames that need zero padding, chroma fold, a mirrored band and the Nyquist column."""
+    rng = np.random.default_rng(20261017 + 5)
+    fs = 44100
+    k = zaf_gpu.cqtkernel(fs, 12, 32.70319566257483, 4186.009044809578)
+    assert k.shape == (84, 32768)
+    x = rng.uniform(-1, 1, (2, 30001)).astype(np.float32)
+    lib = zaf_gpu._lib.lib()
+    step = round(fs / 25)
+    plan = zaf_gpu._cqt_plan(k, step)[0]
+    zaf_gpu._lib.check(lib.zafb_cqt_plan_force_kernel(plan, force))
+    try:
+        spec = zaf_gpu.cqtspectrogram(x, fs, 25, k)
+        chroma = zaf_gpu.cqtchromagram(x, fs, 25, 12, k)
+        spec_c = zaf_gpu.cqtspectrogram(x[0], fs, 25, k, layout="bin_major")
+    finally:
+        lib.zafb_cqt_plan_force_kernel(plan, 0)
+    for c in range(2):
+        ref = oracle.cqtspectrogram(x[c], fs, 25, k)
+        assert_parity(spec[c], ref)
+        assert_parity(chroma[c], oracle.cqtchromagram(x[c], fs, 25, 12, k))
+    assert np.array_equal(spec_c, spec[0]) and spec_c.flags.c_contiguous
+    # arbitrary complex operator: DC column, Nyquist column, a band across L/2 and one in the mirrored half
+    L = 32768
+    dense = scipy.sparse.lil_matrix((4, L), dtype=complex)
+    dense[0, 0:40] = rng.standard_normal(40) + 1j * rng.standard_normal(40)
+    dense[1, L // 2 - 30:L // 2 + 30] = rng.standard_normal(60) + 1j * rng.standard_normal(60)
+    dense[2, L - 500:L - 400] = rng.standard_normal(100)
+    dense[3, 8000:8400] = 1j * rng.standard_normal(400)
+    kk = scipy.sparse.csr_matrix(dense)
+    plan = zaf_gpu._cqt_plan(kk, 4410)[0]
+    zaf_gpu._lib.check(lib.zafb_cqt_plan_force_kernel(plan, force))
+    try:
+        got = zaf_gpu.cqtspectrogram(x[1], fs, 10, kk)
+    finally:
+        lib.zafb_cqt_plan_force_kernel(plan, 0)
+    assert_parity(got, oracle.cqtspectrogram(x[1], fs, 10, kk))
+
+
 def test_cqt_small_kernels_vs_oracle(zaf_gpu):
     """Smaller FFT lengths (odd and even log2), columns in the upper half of the spectrum, complex weights."""
     rng = np.random.default_rng(9)

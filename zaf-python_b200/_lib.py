@@ -75,6 +75,7 @@ _PRIVATE = {
     "zafb_dct_plan_force_direct": (_int, [_vp, _int]),
     "zafb_mdct_plan_force_kernel": (_int, [_vp, _int]),
     "zafb_mel_plan_force_kernel": (_int, [_vp, _int]),
+    "zafb_cqt_plan_force_kernel": (_int, [_vp, _int]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 //      (X[c] = E + W_L^c O) and accumulating K[r, c] * X[c]; columns above L/2 use X[c] = conj(X[L - c]);
 //   4. magnitude, optional chroma fold (rows i :: octave_resolution summed), store.
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "fft_core.cuh"
@@ -27,6 +28,11 @@ struct zafb_cqt_plan {
     int* d_band_off = nullptr;
     float2* d_weights = nullptr;   // packed complex bands
     int64_t packed = 0;
+    // L = 32768 register-FFT kernel
+    float2* d_t1 = nullptr;        // W_16384^{il q} at [q * 32 + il], il < 32, q < 32
+    float2* d_t2 = nullptr;        // W_512^{ih q}  at [q * 16 + ih], ih < 16, q < 32
+    int pair_lo = 0, pair_hi = -1; // range of min(k, M - k) over every column any band touches
+    int force_kernel = 0;          // 0 auto, 1 generic, 2 register-FFT kernel (tests)
 };
 
 namespace {
@@ -160,10 +166,164 @@ cqt_frame_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// L = 32768 (M = 16384 complex points; BASELINE cfg 5 and the reference's example kernel):
+// one CTA of 512 threads per frame, the FFT in THREE in-place passes 16384 = 32 x 32 x 16 with
+// the radix-32 / radix-16 butterflies held in registers (fft_reg), instead of seven radix-4
+// passes through shared memory.
+//   pass 1  thread t owns x[t + 512 q], q < 32, loaded straight from global memory (coalesced
+//           8-byte loads) -> FFT-32 -> twiddle W_M^{t k1} = T1[k1][lane] T2[k1][warp] -> z
+//   pass 2  32 blocks of 512: thread (b, i) owns z[512 b + i + 16 q] -> FFT-32 -> W_512^{i k2}
+//   pass 3  1024 blocks of 16 contiguous points -> FFT-16
+// Frequency k = k1 + 32 k2 + 1024 k3 ends at position 512 k1 + 16 k2 + k3.  Every address goes
+// through the XOR swizzle a ^ ((a >> 4) & 15), which makes all three passes bank-conflict free.
+// Then the real-input split is applied IN PLACE to the bins some band needs (pairs k, M - k),
+// and one warp per kernel row accumulates its band.
+// ------------------------------------------------------------------------------------------
+constexpr int kRegThreads = 512;
+constexpr int kRegM = 16384;
+
+__device__ __forceinline__ int swz(int a) { return a ^ ((a >> 4) & 15); }
+__device__ __forceinline__ int reg_pos(int k) { return swz(((k & 31) << 9) | (((k >> 5) & 31) << 4) | (k >> 10)); }
+
+__global__ void __launch_bounds__(kRegThreads, 1)
+cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
+                const float2* __restrict__ t1, const float2* __restrict__ t2, const float2* __restrict__ tw_full,
+                const int* __restrict__ band_lo, const int* __restrict__ band_len, const int* __restrict__ band_off,
+                const float2* __restrict__ weights, int n_freqs, int octave, int pair_lo, int pair_hi,
+                float* __restrict__ out, int layout, int64_t total_frames) {
+    extern __shared__ float2 smem2[];
+    constexpr int M = kRegM, L = 2 * kRegM;
+    float2* z = smem2;
+    float2* s_t1 = smem2 + M;        // 1024
+    float2* s_t2 = s_t1 + 1024;      // 512
+    float* q = reinterpret_cast<float*>(s_t2 + 512);  // n_freqs magnitudes
+    __shared__ float s_nyq;          // X[M]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 1024; i += kRegThreads) s_t1[i] = t1[i];
+    for (int i = tid; i < 512; i += kRegThreads) s_t2[i] = t2[i];
+    __syncthreads();
+    const int ts = tid ^ ((tid >> 4) & 15);  // swizzled low part of pass-1 addresses
+    const int b2 = tid >> 4, i2 = tid & 15;  // pass 2: block, offset
+
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * step - front;
+        const float* xc = x + clip * clip_stride;
+        float2 v[32];
+        // ---- pass 1
+        if (start >= 0 && start + L <= ns && ((reinterpret_cast<uintptr_t>(xc + start) & 7) == 0)) {
+            const float2* fp = reinterpret_cast<const float2*>(xc + start) + tid;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = __ldg(fp + 512 * r);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int64_t s0 = start + 2 * (tid + 512 * r);
+                v[r].x = (s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f;
+                v[r].y = (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f;
+            }
+        }
+        fft_reg<32>(v);
+        static_for<0, 32>([&](auto kc) {
+            constexpr int k1 = decltype(kc)::value;
+            float2 y = v[bitrev(k1, 5)];
+            if constexpr (k1 > 0) y = cmul(cmul(y, s_t1[k1 * 32 + lane]), s_t2[k1 * 16 + warp]);
+            z[512 * k1 + ts] = y;
+        });
+        __syncthreads();
+        // ---- pass 2
+        {
+            float2* zb = z + 512 * b2;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = zb[16 * r + (i2 ^ (r & 15))];
+            fft_reg<32>(v);
+            static_for<0, 32>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                float2 y = v[bitrev(k2, 5)];
+                if constexpr (k2 > 0) y = cmul(y, s_t2[k2 * 16 + i2]);
+                zb[16 * k2 + (i2 ^ (k2 & 15))] = y;
+            });
+        }
+        __syncthreads();
+        // ---- pass 3
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int blk = tid + 512 * h;
+            float2* zb = z + 16 * blk;
+            const int sw = blk & 15;
+            float2 u[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) u[r] = zb[r ^ sw];
+            fft_reg<16>(u);
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k3 = decltype(kc)::value;
+                zb[k3 ^ sw] = u[bitrev(k3, 4)];
+            });
+        }
+        __syncthreads();
+        // ---- real-input split, in place, for the pairs (k, M - k) some band needs
+        for (int k = pair_lo + tid; k <= pair_hi; k += kRegThreads) {
+            if (k == 0) {
+                const float2 z0 = z[0];
+                z[0] = make_float2(z0.x + z0.y, 0.f);
+                s_nyq = z0.x - z0.y;
+            } else {
+                const int pk = reg_pos(k), pm = reg_pos(M - k);
+                const float2 zk = z[pk], zp = z[pm];
+                const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+                const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+                const float2 t = cmul(__ldg(tw_full + k), od);
+                z[pk] = cadd(e, t);                                   // X[k]
+                if (pm != pk) z[pm] = make_float2(e.x - t.x, t.y - e.y);  // X[M - k] = conj(E - W O)
+            }
+        }
+        __syncthreads();
+        // ---- banded kernel rows, one warp per row
+        for (int r = warp; r < n_freqs; r += kRegThreads / 32) {
+            const int lo = band_lo[r], len = band_len[r];
+            const float2* w = weights + band_off[r];
+            float ar = 0.f, ai = 0.f;
+            for (int c = lane; c < len; c += 32) {
+                const int col = lo + c;
+                const bool mirror = col > M;
+                const int k = mirror ? L - col : col;
+                float2 X = (k == M) ? make_float2(s_nyq, 0.f) : z[reg_pos(k)];
+                if (mirror) X.y = -X.y;
+                const float2 kv = __ldg(w + c);
+                ar += kv.x * X.x - kv.y * X.y;
+                ai += kv.x * X.y + kv.y * X.x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+            }
+            if (lane == 0) q[r] = sqrtf(ar * ar + ai * ai);
+        }
+        __syncthreads();
+        if (octave > 0) {
+            for (int i = tid; i < octave; i += kRegThreads) {
+                float acc = 0.f;
+                for (int r = i; r < n_freqs; r += octave) acc += q[r];  // zaf.py:693-698
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * octave + i] = acc;
+                else out[(clip * octave + i) * nt + j] = acc;
+            }
+        } else {
+            for (int r = tid; r < n_freqs; r += kRegThreads) {
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_freqs + r] = q[r];
+                else out[(clip * int64_t(n_freqs) + r) * nt + j] = q[r];
+            }
+        }
+        // the next frame's pass 1 only writes z after its own loads; q[] is rewritten after two more barriers
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(cqt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -221,7 +381,38 @@ int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_lengt
         }
     }
     p->packed = int64_t(w.size());
+    {   // which pairs (k, M - k) of the half spectrum the bands touch
+        int plo = int(m), phi = -1;
+        for (int64_t r = 0; r < n_freqs; ++r)
+            for (int c = 0; c < len[r]; ++c) {
+                const int64_t col = lo[r] + c;
+                const int64_t k = col > m ? fft_length - col : col;
+                const int pr = int(k < m - k ? k : m - k);
+                plo = pr < plo ? pr : plo;
+                phi = pr > phi ? pr : phi;
+            }
+        p->pair_lo = plo;
+        p->pair_hi = phi;
+    }
     int rc = upload_twiddles(&p->d_tw_fft, m, m);
+    if (rc == ZAFB_OK && fft_length == 32768) {
+        const double pi = 3.14159265358979323846264338327950288;
+        std::vector<double> a(2 * 1024), b(2 * 512);
+        for (int q = 0; q < 32; ++q) {
+            for (int il = 0; il < 32; ++il) {
+                const double ang = -2.0 * pi * double(il * q) / 16384.0;
+                a[2 * (q * 32 + il)] = std::cos(ang);
+                a[2 * (q * 32 + il) + 1] = std::sin(ang);
+            }
+            for (int ih = 0; ih < 16; ++ih) {
+                const double ang = -2.0 * pi * double((ih * q) % 512) / 512.0;
+                b[2 * (q * 16 + ih)] = std::cos(ang);
+                b[2 * (q * 16 + ih) + 1] = std::sin(ang);
+            }
+        }
+        rc = upload_c32(&p->d_t1, a.data(), 1024);
+        if (rc == ZAFB_OK) rc = upload_c32(&p->d_t2, b.data(), 512);
+    }
     if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, fft_length, m + 1);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_len, len);
@@ -243,7 +434,16 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
     cudaFree(p->d_band_len);
     cudaFree(p->d_band_off);
     cudaFree(p->d_weights);
+    cudaFree(p->d_t1);
+    cudaFree(p->d_t2);
     delete p;
+    return ZAFB_OK;
+}
+
+// test hook: 0 = auto, 1 = generic kernel only, 2 = require the register-FFT kernel
+int zafb_cqt_plan_force_kernel(zafb_cqt_plan* p, int which) {
+    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 2, "bad plan / kernel id");
+    p->force_kernel = which;
     return ZAFB_OK;
 }
 
@@ -262,6 +462,20 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
     if (total == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && x != nullptr, "x/out is NULL");
     const int64_t m = p->fft_length / 2;
+    {
+        const size_t smem_reg = size_t(kRegM + 1536) * sizeof(float2) + size_t(p->n_freqs) * sizeof(float) + 64;
+        const bool ok = p->fft_length == 32768 && p->d_t1 != nullptr && smem_reg <= size_t(kMaxDynSmem);
+        if (p->force_kernel == 2 && !ok) return fail(ZAFB_E_UNSUPPORTED, "cqt register-FFT kernel needs fft_length 32768");
+        if (ok && p->force_kernel != 1) {
+            const int64_t grid = total < int64_t(sm_count()) ? total : int64_t(sm_count());
+            cqt32768_kernel<<<unsigned(grid), kRegThreads, smem_reg, static_cast<cudaStream_t>(stream)>>>(
+                x, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo, p->d_band_len,
+                p->d_band_off, p->d_weights, int(p->n_freqs), int(octave_resolution), p->pair_lo, p->pair_hi, out, layout,
+                total);
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        }
+    }
     const size_t smem = size_t(m) * sizeof(float2) + size_t(p->n_freqs) * sizeof(float) + 64;
     int th = int(m / 4);
     if (th < 64) th = 64;
