@@ -168,23 +168,23 @@ cqt_frame_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
 
 // ------------------------------------------------------------------------------------------
 // L = 32768 (M = 16384 complex points; BASELINE cfg 5 and the reference's example kernel):
-// one CTA of 512 threads per frame, the FFT in THREE in-place passes 16384 = 32 x 32 x 16 with
-// the radix-32 / radix-16 butterflies held in registers (fft_reg), instead of seven radix-4
-// passes through shared memory.
-//   pass 1  thread t owns x[t + 512 q], q < 32, loaded straight from global memory (coalesced
-//           8-byte loads) -> FFT-32 -> twiddle W_M^{t k1} = T1[k1][lane] T2[k1][warp] -> z
-//   pass 2  32 blocks of 512: thread (b, i) owns z[512 b + i + 16 q] -> FFT-32 -> W_512^{i k2}
-//   pass 3  1024 blocks of 16 contiguous points -> FFT-16
-// Frequency k = k1 + 32 k2 + 1024 k3 ends at position 512 k1 + 16 k2 + k3.  Every address goes
-// through the XOR swizzle a ^ ((a >> 4) & 15), which makes all three passes bank-conflict free.
+// one CTA of 512 threads per frame, the FFT in THREE in-place decimation-in-time passes
+// 16384 = 16 x 32 x 32 with the radix-16 / radix-32 butterflies held in registers (fft_reg),
+// instead of seven radix-4 passes through shared memory.  With n = a + 32 b + 1024 c and
+// k = kc + 16 kb + 512 ka:
+//   pass 1  thread (a, b) loads x[a + 32 b + 1024 c], c < 16, straight from global memory
+//           (coalesced 8-byte loads), FFT-16 over c -> S1[a][b][kc]           at 512 a + 16 b  + kc
+//   pass 2  thread (a, kc): S1[a][b][kc] W_512^{b kc}, FFT-32 over b -> S2     at 512 a + 16 kb + kc
+//   pass 3  thread j = 16 kb + kc: S2[a][j] W_M^{a j}, FFT-32 over a -> X[k]   at 512 ka + j = k
+// so the spectrum ends in NATURAL order.  Every address has its low four bits XOR-ed with bits
+// 4..7 and 9..12 (swz), which makes all three passes and the consumers bank-conflict free.
 // Then the real-input split is applied IN PLACE to the bins some band needs (pairs k, M - k),
 // and one warp per kernel row accumulates its band.
 // ------------------------------------------------------------------------------------------
 constexpr int kRegThreads = 512;
 constexpr int kRegM = 16384;
 
-__device__ __forceinline__ int swz(int a) { return a ^ ((a >> 4) & 15); }
-__device__ __forceinline__ int reg_pos(int k) { return swz(((k & 31) << 9) | (((k >> 5) & 31) << 4) | (k >> 10)); }
+__device__ __forceinline__ int swz(int a) { return a ^ (((a >> 4) ^ (a >> 9)) & 15); }
 
 __global__ void __launch_bounds__(kRegThreads, 1)
 cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
@@ -195,70 +195,80 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     extern __shared__ float2 smem2[];
     constexpr int M = kRegM, L = 2 * kRegM;
     float2* z = smem2;
-    float2* s_t1 = smem2 + M;        // 1024
-    float2* s_t2 = s_t1 + 1024;      // 512
+    float2* s_t1 = smem2 + M;        // 1024: W_M^{il r} at [r * 32 + il]
+    float2* s_t2 = s_t1 + 1024;      // 512:  W_512^{ih r} at [r * 16 + ih]
     float* q = reinterpret_cast<float*>(s_t2 + 512);  // n_freqs magnitudes
     __shared__ float s_nyq;          // X[M]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += kRegThreads) s_t1[i] = t1[i];
     for (int i = tid; i < 512; i += kRegThreads) s_t2[i] = t2[i];
     __syncthreads();
-    const int ts = tid ^ ((tid >> 4) & 15);  // swizzled low part of pass-1 addresses
-    const int b2 = tid >> 4, i2 = tid & 15;  // pass 2: block, offset
+    const int a2 = tid >> 4, c2 = tid & 15;  // pass 2: a, kc
 
     for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
         const int64_t clip = f / nt, j = f - clip * nt;
         const int64_t start = j * step - front;
         const float* xc = x + clip * clip_stride;
-        float2 v[32];
-        // ---- pass 1
-        if (start >= 0 && start + L <= ns && ((reinterpret_cast<uintptr_t>(xc + start) & 7) == 0)) {
-            const float2* fp = reinterpret_cast<const float2*>(xc + start) + tid;
+        const bool fast = start >= 0 && start + L <= ns && ((reinterpret_cast<uintptr_t>(xc + start) & 7) == 0);
+        // ---- pass 1: two (a, b) items per thread, t' = a + 32 b = tid + 512 h
 #pragma unroll
-            for (int r = 0; r < 32; ++r) v[r] = __ldg(fp + 512 * r);
-        } else {
+        for (int h = 0; h < 2; ++h) {
+            const int tp = tid + 512 * h;
+            float2 u[16];
+            if (fast) {
+                const float2* fp = reinterpret_cast<const float2*>(xc + start) + tp;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                const int64_t s0 = start + 2 * (tid + 512 * r);
-                v[r].x = (s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f;
-                v[r].y = (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f;
+                for (int c = 0; c < 16; ++c) u[c] = __ldg(fp + 1024 * c);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int64_t s0 = start + 2 * (tp + 1024 * c);
+                    u[c].x = (s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f;
+                    u[c].y = (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f;
+                }
             }
-        }
-        fft_reg<32>(v);
-        static_for<0, 32>([&](auto kc) {
-            constexpr int k1 = decltype(kc)::value;
-            float2 y = v[bitrev(k1, 5)];
-            if constexpr (k1 > 0) y = cmul(cmul(y, s_t1[k1 * 32 + lane]), s_t2[k1 * 16 + warp]);
-            z[512 * k1 + ts] = y;
-        });
-        __syncthreads();
-        // ---- pass 2
-        {
-            float2* zb = z + 512 * b2;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) v[r] = zb[16 * r + (i2 ^ (r & 15))];
-            fft_reg<32>(v);
-            static_for<0, 32>([&](auto kc) {
-                constexpr int k2 = decltype(kc)::value;
-                float2 y = v[bitrev(k2, 5)];
-                if constexpr (k2 > 0) y = cmul(y, s_t2[k2 * 16 + i2]);
-                zb[16 * k2 + (i2 ^ (k2 & 15))] = y;
+            fft_reg<16>(u);
+            const int a = tp & 31, b = tp >> 5;
+            float2* zb = z + 512 * a + 16 * b;
+            const int sw = (a ^ b) & 15;
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                zb[k ^ sw] = u[bitrev(k, 4)];
             });
         }
         __syncthreads();
-        // ---- pass 3
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int blk = tid + 512 * h;
-            float2* zb = z + 16 * blk;
-            const int sw = blk & 15;
-            float2 u[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) u[r] = zb[r ^ sw];
-            fft_reg<16>(u);
-            static_for<0, 16>([&](auto kc) {
-                constexpr int k3 = decltype(kc)::value;
-                zb[k3 ^ sw] = u[bitrev(k3, 4)];
+        float2 v[32];
+        // ---- pass 2: thread (a, kc), FFT-32 over b
+        {
+            float2* zb = z + 512 * a2;
+            const int sw = c2 ^ (a2 & 15);
+            static_for<0, 32>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float2 y = zb[16 * r + (sw ^ (r & 15))];
+                if constexpr (r > 0) v[r] = cmul(y, s_t2[r * 16 + c2]);
+                else v[r] = y;
+            });
+            fft_reg<32>(v);
+            static_for<0, 32>([&](auto kc) {
+                constexpr int kb = decltype(kc)::value;
+                zb[16 * kb + (sw ^ (kb & 15))] = v[bitrev(kb, 5)];
+            });
+        }
+        __syncthreads();
+        // ---- pass 3: thread j = tid, FFT-32 over a; twiddle W_M^{a j} = W_M^{a lane} W_512^{a warp}
+        {
+            const int sw = (tid ^ (tid >> 4)) & 15;   // kc ^ (kb & 15)
+            const int hi = tid & ~15;
+            static_for<0, 32>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float2 y = z[512 * r + hi + (sw ^ (r & 15))];
+                if constexpr (r > 0) v[r] = cmul(cmul(y, s_t1[r * 32 + lane]), s_t2[r * 16 + warp]);
+                else v[r] = y;
+            });
+            fft_reg<32>(v);
+            static_for<0, 32>([&](auto kc) {
+                constexpr int ka = decltype(kc)::value;
+                z[512 * ka + hi + (sw ^ (ka & 15))] = v[bitrev(ka, 5)];
             });
         }
         __syncthreads();
@@ -269,12 +279,12 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 z[0] = make_float2(z0.x + z0.y, 0.f);
                 s_nyq = z0.x - z0.y;
             } else {
-                const int pk = reg_pos(k), pm = reg_pos(M - k);
+                const int pk = swz(k), pm = swz(M - k);
                 const float2 zk = z[pk], zp = z[pm];
                 const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
                 const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
                 const float2 t = cmul(__ldg(tw_full + k), od);
-                z[pk] = cadd(e, t);                                   // X[k]
+                z[pk] = cadd(e, t);                                       // X[k]
                 if (pm != pk) z[pm] = make_float2(e.x - t.x, t.y - e.y);  // X[M - k] = conj(E - W O)
             }
         }
@@ -288,7 +298,7 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 const int col = lo + c;
                 const bool mirror = col > M;
                 const int k = mirror ? L - col : col;
-                float2 X = (k == M) ? make_float2(s_nyq, 0.f) : z[reg_pos(k)];
+                float2 X = (k == M) ? make_float2(s_nyq, 0.f) : z[swz(k)];
                 if (mirror) X.y = -X.y;
                 const float2 kv = __ldg(w + c);
                 ar += kv.x * X.x - kv.y * X.y;
@@ -315,7 +325,7 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 else out[(clip * int64_t(n_freqs) + r) * nt + j] = q[r];
             }
         }
-        // the next frame's pass 1 only writes z after its own loads; q[] is rewritten after two more barriers
+        // the next frame's pass 1 only writes z, which nobody reads any more; q[] is rewritten after four more barriers
     }
 }
 
