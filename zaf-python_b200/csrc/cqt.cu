@@ -10,6 +10,7 @@
 //      are packed as zeros): one warp per row walks its band, unpacking the real-input spectrum bin on the fly
 //      (X[c] = E + W_L^c O) and accumulating K[r, c] * X[c]; columns above L/2 use X[c] = conj(X[L - c]);
 //   4. magnitude, optional chroma fold (rows i :: octave_resolution summed), store.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -32,6 +33,11 @@ struct zafb_cqt_plan {
     float2* d_t1 = nullptr;        // W_16384^{il q} at [q * 32 + il], il < 32, q < 32
     float2* d_t2 = nullptr;        // W_512^{ih q}  at [q * 16 + ih], ih < 16, q < 32
     int pair_lo = 0, pair_hi = -1; // range of min(k, M - k) over every column any band touches
+    bool real_weights = false;     // every imaginary part is below fp32 resolution of the row's real parts
+    float* d_weights_re = nullptr; // real parts only (same packing as d_weights)
+    int* d_sched = nullptr;        // rows sorted by decreasing band length, dealt to the 16 warps longest-first
+    int* d_sched_cnt = nullptr;    // rows per warp
+    int sched_stride = 0;
     int force_kernel = 0;          // 0 auto, 1 generic, 2 register-FFT kernel (tests)
 };
 
@@ -190,18 +196,27 @@ __global__ void __launch_bounds__(kRegThreads, 1)
 cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
                 const float2* __restrict__ t1, const float2* __restrict__ t2, const float2* __restrict__ tw_full,
                 const int* __restrict__ band_lo, const int* __restrict__ band_len, const int* __restrict__ band_off,
-                const float2* __restrict__ weights, int n_freqs, int octave, int pair_lo, int pair_hi,
-                float* __restrict__ out, int layout, int64_t total_frames) {
+                const float2* __restrict__ weights, const float* __restrict__ weights_re, int packed, int smem_weights,
+                int smem_split_tw, const int* __restrict__ sched, const int* __restrict__ sched_cnt, int sched_stride,
+                int n_freqs, int octave, int pair_lo, int pair_hi, float* __restrict__ out, int layout,
+                int64_t total_frames) {
     extern __shared__ float2 smem2[];
     constexpr int M = kRegM, L = 2 * kRegM;
     float2* z = smem2;
     float2* s_t1 = smem2 + M;        // 1024: W_M^{il r} at [r * 32 + il]
     float2* s_t2 = s_t1 + 1024;      // 512:  W_512^{ih r} at [r * 16 + ih]
-    float* q = reinterpret_cast<float*>(s_t2 + 512);  // n_freqs magnitudes
+    float* q = reinterpret_cast<float*>(s_t2 + 512);  // n_freqs magnitudes (rounded up to an even count)
+    float2* s_split = reinterpret_cast<float2*>(q + ((n_freqs + 1) & ~1));  // W_L^k, k in [pair_lo, pair_hi]
+    float* s_w = reinterpret_cast<float*>(s_split + (smem_split_tw ? pair_hi - pair_lo + 1 : 0));  // real band weights
     __shared__ float s_nyq;          // X[M]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 1024; i += kRegThreads) s_t1[i] = t1[i];
     for (int i = tid; i < 512; i += kRegThreads) s_t2[i] = t2[i];
+    if (smem_split_tw)
+        for (int i = tid; i <= pair_hi - pair_lo; i += kRegThreads) s_split[i] = tw_full[pair_lo + i];
+    if (smem_weights)
+        for (int i = tid; i < packed; i += kRegThreads) s_w[i] = weights_re[i];
+    const int my_rows = sched_cnt[warp];
     __syncthreads();
     const int a2 = tid >> 4, c2 = tid & 15;  // pass 2: a, kc
 
@@ -283,26 +298,49 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 const float2 zk = z[pk], zp = z[pm];
                 const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
                 const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
-                const float2 t = cmul(__ldg(tw_full + k), od);
+                const float2 t = cmul(smem_split_tw ? s_split[k - pair_lo] : __ldg(tw_full + k), od);
                 z[pk] = cadd(e, t);                                       // X[k]
                 if (pm != pk) z[pm] = make_float2(e.x - t.x, t.y - e.y);  // X[M - k] = conj(E - W O)
             }
         }
         __syncthreads();
-        // ---- banded kernel rows, one warp per row
-        for (int r = warp; r < n_freqs; r += kRegThreads / 32) {
+        // ---- banded kernel rows, one warp per row; rows are dealt to the warps longest-first at plan time
+        for (int it = 0; it < my_rows; ++it) {
+            const int r = sched[warp * sched_stride + it];
             const int lo = band_lo[r], len = band_len[r];
-            const float2* w = weights + band_off[r];
             float ar = 0.f, ai = 0.f;
-            for (int c = lane; c < len; c += 32) {
-                const int col = lo + c;
-                const bool mirror = col > M;
-                const int k = mirror ? L - col : col;
-                float2 X = (k == M) ? make_float2(s_nyq, 0.f) : z[swz(k)];
-                if (mirror) X.y = -X.y;
-                const float2 kv = __ldg(w + c);
-                ar += kv.x * X.x - kv.y * X.y;
-                ai += kv.x * X.y + kv.y * X.x;
+            if (smem_weights && lo + len <= M) {  // real weights in shared memory, no mirrored columns
+                const float* w = s_w + band_off[r];
+                float br = 0.f, bi = 0.f;
+                int c = lane;
+                for (; c + 32 < len; c += 64) {
+                    const float2 X0 = z[swz(lo + c)], X1 = z[swz(lo + c + 32)];
+                    const float w0 = w[c], w1 = w[c + 32];
+                    ar = fmaf(w0, X0.x, ar);
+                    ai = fmaf(w0, X0.y, ai);
+                    br = fmaf(w1, X1.x, br);
+                    bi = fmaf(w1, X1.y, bi);
+                }
+                if (c < len) {
+                    const float2 X0 = z[swz(lo + c)];
+                    const float w0 = w[c];
+                    ar = fmaf(w0, X0.x, ar);
+                    ai = fmaf(w0, X0.y, ai);
+                }
+                ar += br;
+                ai += bi;
+            } else {
+                const float2* w = weights + band_off[r];
+                for (int c = lane; c < len; c += 32) {
+                    const int col = lo + c;
+                    const bool mirror = col > M;
+                    const int k = mirror ? L - col : col;
+                    float2 X = (k == M) ? make_float2(s_nyq, 0.f) : z[swz(k)];
+                    if (mirror) X.y = -X.y;
+                    const float2 kv = __ldg(w + c);
+                    ar += kv.x * X.x - kv.y * X.y;
+                    ai += kv.x * X.y + kv.y * X.x;
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -422,6 +460,43 @@ int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_lengt
         }
         rc = upload_c32(&p->d_t1, a.data(), 1024);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_t2, b.data(), 512);
+        // real kernel?  (zaf.cqtkernel's rows are real to 1e-16: centred temporal kernels, zaf.py:515-557.)  An imaginary
+        // part below 2^-40 of the row's largest real part cannot change an fp32 accumulation, so it is dropped.
+        bool real = true;
+        std::vector<float> wre(w.size());
+        for (int64_t r = 0; r < n_freqs && real; ++r) {
+            float mx = 0.f;
+            for (int c = 0; c < len[r]; ++c) mx = std::fmax(mx, std::fabs(w[off[r] + c].x));
+            for (int c = 0; c < len[r]; ++c)
+                if (std::fabs(w[off[r] + c].y) > mx * 9.1e-13f) real = false;
+        }
+        for (size_t i = 0; i < w.size(); ++i) wre[i] = w[i].x;
+        p->real_weights = real;
+        if (rc == ZAFB_OK && real) rc = upload_vec(&p->d_weights_re, wre);
+        // longest-processing-time-first deal of the rows to the 16 warps
+        constexpr int kW = kRegThreads / 32;
+        std::vector<int> order(n_freqs);
+        for (int64_t r = 0; r < n_freqs; ++r) order[r] = int(r);
+        std::stable_sort(order.begin(), order.end(), [&](int x1, int x2) { return len[x1] > len[x2]; });
+        std::vector<std::vector<int>> lists(kW);
+        std::vector<int64_t> load(kW, 0);
+        for (int r : order) {
+            int best = 0;
+            for (int wv = 1; wv < kW; ++wv)
+                if (load[wv] < load[best]) best = wv;
+            lists[best].push_back(r);
+            load[best] += (len[r] + 31) / 32 + 1;  // iterations + the reduction
+        }
+        size_t longest = 1;
+        for (auto& l : lists) longest = l.size() > longest ? l.size() : longest;
+        std::vector<int> sched(kW * longest, 0), cnt(kW, 0);
+        for (int wv = 0; wv < kW; ++wv) {
+            cnt[wv] = int(lists[wv].size());
+            for (size_t i = 0; i < lists[wv].size(); ++i) sched[wv * longest + i] = lists[wv][i];
+        }
+        p->sched_stride = int(longest);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_sched, sched);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_sched_cnt, cnt);
     }
     if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, fft_length, m + 1);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
@@ -446,6 +521,9 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
     cudaFree(p->d_weights);
     cudaFree(p->d_t1);
     cudaFree(p->d_t2);
+    cudaFree(p->d_weights_re);
+    cudaFree(p->d_sched);
+    cudaFree(p->d_sched_cnt);
     delete p;
     return ZAFB_OK;
 }
@@ -473,14 +551,26 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
     ZAFB_REQUIRE(out != nullptr && x != nullptr, "x/out is NULL");
     const int64_t m = p->fft_length / 2;
     {
-        const size_t smem_reg = size_t(kRegM + 1536) * sizeof(float2) + size_t(p->n_freqs) * sizeof(float) + 64;
-        const bool ok = p->fft_length == 32768 && p->d_t1 != nullptr && smem_reg <= size_t(kMaxDynSmem);
+        size_t smem_reg = size_t(kRegM + 1536) * sizeof(float2) + size_t((p->n_freqs + 1) & ~int64_t(1)) * sizeof(float) + 64;
+        const bool ok = p->fft_length == 32768 && p->d_t1 != nullptr && p->d_sched != nullptr && smem_reg <= size_t(kMaxDynSmem);
+        // optional shared-memory residents, in order of benefit: the real band weights, the split twiddles
+        int smem_weights = 0, smem_split = 0;
+        const size_t split_bytes = p->pair_hi >= p->pair_lo ? size_t(p->pair_hi - p->pair_lo + 1) * sizeof(float2) : 0;
+        if (ok && split_bytes && smem_reg + split_bytes <= size_t(kMaxDynSmem)) {
+            smem_split = 1;
+            smem_reg += split_bytes;
+        }
+        if (ok && p->real_weights && smem_reg + size_t(p->packed) * sizeof(float) <= size_t(kMaxDynSmem)) {
+            smem_weights = 1;
+            smem_reg += size_t(p->packed) * sizeof(float);
+        }
         if (p->force_kernel == 2 && !ok) return fail(ZAFB_E_UNSUPPORTED, "cqt register-FFT kernel needs fft_length 32768");
         if (ok && p->force_kernel != 1) {
             const int64_t grid = total < int64_t(sm_count()) ? total : int64_t(sm_count());
             cqt32768_kernel<<<unsigned(grid), kRegThreads, smem_reg, static_cast<cudaStream_t>(stream)>>>(
                 x, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo, p->d_band_len,
-                p->d_band_off, p->d_weights, int(p->n_freqs), int(octave_resolution), p->pair_lo, p->pair_hi, out, layout,
+                p->d_band_off, p->d_weights, p->d_weights_re, int(p->packed), smem_weights, smem_split, p->d_sched,
+                p->d_sched_cnt, p->sched_stride, int(p->n_freqs), int(octave_resolution), p->pair_lo, p->pair_hi, out, layout,
                 total);
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
