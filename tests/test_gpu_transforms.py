@@ -128,6 +128,36 @@ def test_dct_dst_vs_oracle_fft_and_direct(zaf_gpu, n):
                 assert_parity(got_d[c], ofn(x[c], t))
 
 
+@pytest.mark.parametrize("n", [16, 100, 257, 1000, 1024, 2048])
+def test_dct_dst_tensor_core_matrix_path(zaf_gpu, n):
+    """Types I (any N) and non-power-of-two N of every type go through the tcgen05 3xTF32 GEMM against the
+    closed-form matrix; batch sizes that are not multiples of the 128-row tile, strided input."""
+    rng = np.random.default_rng(1000 + n)
+    lib = zaf_gpu._lib.lib()
+    for batch in (130, 9):
+        x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        for kind, fn, ofn in ((0, zaf_gpu.dct, oracle.dct), (1, zaf_gpu.dst, oracle.dst)):
+            for t in (1, 2, 3, 4):
+                fft_path = t >= 2 and n & (n - 1) == 0
+                plan = zaf_gpu._dct_plans.get((kind, t, n), kind, t, n)
+                if fft_path:  # the matrix path does not exist there and must say so
+                    zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, 2))
+                    try:
+                        with pytest.raises(NotImplementedError):
+                            fn(x, t)
+                    finally:
+                        lib.zafb_dct_plan_force_direct(plan, 0)
+                    continue
+                zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, 2))
+                try:
+                    got = fn(x, t)
+                finally:
+                    lib.zafb_dct_plan_force_direct(plan, 0)
+                for c in (0, batch // 2, batch - 1):
+                    assert_parity(got[c], ofn(x[c], t))
+                assert np.array_equal(got, fn(x, t))  # the default route for batch >= 8 is the same path
+
+
 def test_dst_inverse_pairs(zaf_gpu):
     x = np.random.default_rng(5).uniform(-1, 1, 1024).astype(np.float32)
     assert np.max(np.abs(zaf_gpu.dst(zaf_gpu.dst(x, 1), 1) - x)) <= 1e-5

@@ -19,9 +19,11 @@
 //   dct_direct_kernel  everything else (types I, whose natural FFT lengths 2(N-1) / 2(N+1) are not powers of two,
 //                      and non-power-of-two N): the trigonometric sum itself, table-driven, exact index arithmetic.
 #include <cmath>
+#include <cstdint>
 #include <vector>
 
 #include "fft_core.cuh"
+#include "gemm_tc.cuh"
 
 using namespace zafb;
 
@@ -37,7 +39,11 @@ struct zafb_dct_plan {
     float2* d_tw_fft = nullptr;   // W_{N/2}^t
     float2* d_tw_a = nullptr;     // per-type twiddles (see kernels)
     float2* d_tw_b = nullptr;
-    int force_direct = 0;
+    int force_direct = 0;         // test hook: 1 = direct kernel, 2 = require the tensor-core matrix path
+    // matrix path (types I and non-power-of-two N): out = x . Mat^T on the tensor cores, Mat[k][n] in hi/lo TF32 halves
+    float* d_mat_hi = nullptr;
+    float* d_mat_lo = nullptr;
+    int64_t ldk = 0;              // row pitch of the matrix and of the split input (n rounded up to 4)
 };
 
 namespace {
@@ -284,6 +290,25 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_a, ta.data(), ta.size() / 2);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_b, tb.data(), tb.size() / 2);
     }
+    // matrix path for everything the FFT path does not cover: Mat[k][m] = s_out[k] s_in[m] T[(a(m) b(k)) mod P]
+    if (rc == ZAFB_OK && p->log2n < 2 && n >= 16 && n <= 8192) {
+        p->ldk = (n + 3) & ~int64_t(3);
+        std::vector<double> mat(size_t(n) * p->ldk, 0.0);
+        for (int64_t k = 0; k < n; ++k) {
+            const int64_t b = p->b0 + int64_t(p->db) * k;
+            for (int64_t m = 0; m < n; ++m) {
+                const int64_t a = p->a0 + int64_t(p->da) * m;
+                mat[k * p->ldk + m] = sout[k] * sin_[m] * tab[(a * b) % p->period];
+            }
+        }
+        std::vector<float> hi(mat.size()), lo(mat.size());
+        split_tf32_host(mat.data(), mat.size(), hi.data(), lo.data());
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p->d_mat_hi), hi.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_mat_lo), lo.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_mat_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_mat_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "dct: uploading the transform matrix failed: %s", cudaGetErrorString(e));
+    }
     if (rc != ZAFB_OK) {
         zafb_dct_plan_destroy(p);
         return rc;
@@ -300,11 +325,13 @@ int zafb_dct_plan_destroy(zafb_dct_plan* p) {
     cudaFree(p->d_tw_fft);
     cudaFree(p->d_tw_a);
     cudaFree(p->d_tw_b);
+    cudaFree(p->d_mat_hi);
+    cudaFree(p->d_mat_lo);
     delete p;
     return ZAFB_OK;
 }
 
-// test hook: 1 = always use the direct kernel
+// test hook: 1 = always use the direct kernel, 2 = require the tensor-core matrix path
 int zafb_dct_plan_force_direct(zafb_dct_plan* p, int on) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
     p->force_direct = on;
@@ -322,6 +349,29 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
     const int n = int(p->n);
     const int64_t grid = batch < int64_t(sm_count()) * 16 ? batch : int64_t(sm_count()) * 16;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool mat_ok = p->d_mat_hi != nullptr && reinterpret_cast<uintptr_t>(out) % 4 == 0;
+    if (p->force_direct == 2 && !mat_ok)
+        return fail(ZAFB_E_UNSUPPORTED, "dct: no tensor-core matrix path for this plan (power-of-two types II-IV use the FFT)");
+    if (mat_ok && (p->force_direct == 2 || (p->force_direct == 0 && batch >= 8))) {
+        // split the input into TF32 halves in a stream-ordered scratch buffer, then one 3xTF32 GEMM
+        static bool pool_ready = false;
+        if (!pool_ready) {  // keep the stream-ordered scratch in the pool between calls instead of returning it to the OS
+            int dev = 0;
+            cudaMemPool_t pool;
+            uint64_t keep = UINT64_MAX;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_ready = true;
+        }
+        float* ws = nullptr;
+        const size_t half = size_t(batch) * size_t(p->ldk);
+        ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * half * sizeof(float), st));
+        rc = split_tf32(x, batch, n, stride, ws, ws + half, p->ldk, st);
+        if (rc == ZAFB_OK)
+            rc = gemm3xtf32(ws, ws + half, p->ldk, p->d_mat_hi, p->d_mat_lo, p->ldk, out, out_stride, batch, n, n, st);
+        cudaFreeAsync(ws, st);
+        return rc;
+    }
     if (p->log2n >= 2 && !p->force_direct) {
         int flags = 0;
         if (p->kind == 1) flags = (p->type == 2) ? (2 | 4) : (1 | 8);

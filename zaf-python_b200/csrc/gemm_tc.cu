@@ -1,0 +1,352 @@
+// Dense contraction on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+//     C[M x N] = A[M x K] . B[N x K]^T          (A, B K-major, C row-major)
+//
+// used where the hot path really is a dense matrix product:
+//   * dct / dst of types whose natural FFT length is not a power of two (types I at N = 2^k are
+//     real FFTs of length 2(N-1) = 2.3.11.31 / 2(N+1) = 2.5^2.41 at N = 1024, zaf.py:770-771,
+//     907-910): batch x closed-form orthonormal matrix (hard part 8b);
+//   * the mel filterbank / CQT-kernel application in isolation.
+//
+// Precision: a single TF32 product (10-bit mantissa) misses the 1e-5 parity bar by 20x
+// (SURVEY.md section 7.3), so every operand is split x = hi + lo with hi = tf32(x),
+// lo = tf32(x - hi) and the kernel accumulates  A_hi B_hi + A_hi B_lo + A_lo B_hi  in the fp32
+// TMEM accumulator ("3xTF32"; the dropped lo.lo term is 2^-22 relative).  The tensor core adds
+// into its accumulator with truncation, an error that grows linearly with the length of the
+// accumulation chain (measured: 1.0e-5 of max|C| at K = 1000 in one chain), so K is cut into chunks
+// of 128: each chunk is accumulated in one of two TMEM buffers and the epilogue warps add the
+// chunks in registers with round-to-nearest fp32 while the next chunk is being multiplied.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 4   TMA producer: per 32-column K block, four cp.async.bulk.tensor loads (A_hi, A_lo,
+//            B_hi, B_lo tiles, 128-byte swizzle) into a 3-stage shared-memory ring, mbarrier
+//            complete_tx signalling;
+//   warp 5   allocates TMEM (2 x BN columns), then ONE thread issues
+//            tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8): 4 K-steps x 3 products
+//            per stage; tcgen05.commit frees the stage and, every 4 stages, publishes the chunk;
+//   warps 0-3 epilogue: per chunk tcgen05.ld (32 lanes x 32 columns per warp) -> running sums in
+//            registers -> release the TMEM buffer; after the last chunk, registers -> global.
+#include <cuda.h>
+
+#include <cstdint>
+#include <mutex>
+#include <vector>
+
+#include "gemm_tc.cuh"
+
+namespace zafb {
+namespace {
+
+constexpr int kBM = 128;       // UMMA M
+constexpr int kBK = 32;        // fp32 elements per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;      // tf32: 32 bytes per instruction
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr int kChunkKb = 4;    // K blocks per accumulation chain (128 elements of K)
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO 1 << 16 | SBO 64 << 32 | version 1 << 46 | SWIZZLE_128B 2 << 61)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+
+template <int BN>
+struct Smem {
+    static constexpr int kATile = kBM * kBK * 4;  // 16 KB
+    static constexpr int kBTile = BN * kBK * 4;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;
+    static constexpr int kBars = kStages * kStage;          // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    static constexpr int kTmemPtr = kBars + 8 * (2 * kStages + 4);
+    static constexpr int kTotal = kTmemPtr + 16 + 1024;     // + slack to align the base to 1024 bytes
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                  const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                  float* __restrict__ C, int64_t M, int64_t N, int64_t K, int64_t ldc) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_full = base + S::kBars, bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + S::kTmemPtr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+    const int num_kb = int((K + kBK - 1) / kBK);
+    const int num_chunks = (num_kb + kChunkKb - 1) / kChunkKb;
+    constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers (a power of two >= 32)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {  // ===== TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages, it = kb / kStages;
+                mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+                const uint32_t st = base + s * S::kStage;
+                mbar_expect_tx(bar_full + 8 * s, S::kStage);
+                tma_load_2d(st, &tm_ahi, bar_full + 8 * s, kb * kBK, m_blk * kBM);
+                tma_load_2d(st + S::kATile, &tm_alo, bar_full + 8 * s, kb * kBK, m_blk * kBM);
+                tma_load_2d(st + 2 * S::kATile, &tm_bhi, bar_full + 8 * s, kb * kBK, n_blk * BN);
+                tma_load_2d(st + 2 * S::kATile + S::kBTile, &tm_blo, bar_full + 8 * s, kb * kBK, n_blk * BN);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {  // ===== MMA issuer
+            // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages, it = kb / kStages;
+                const int chunk = kb / kChunkKb, buf = chunk & 1;
+                if (kb % kChunkKb == 0) {  // a new accumulation chain: its TMEM buffer must have been drained
+                    mbar_wait(bar_tempty + 8 * buf, ((chunk >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(bar_full + 8 * s, it & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * S::kStage;
+                const uint32_t acc = tmem_acc + uint32_t(buf * BN);
+                const uint64_t a_hi = umma_desc_k_sw128(st), a_lo = umma_desc_k_sw128(st + S::kATile);
+                const uint64_t b_hi = umma_desc_k_sw128(st + 2 * S::kATile), b_lo = umma_desc_k_sw128(st + 2 * S::kATile + S::kBTile);
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint64_t adv = uint64_t((k * kUmmaK * 4) >> 4);  // +32 bytes inside the swizzle row
+                    umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, ((kb % kChunkKb) | k) != 0);
+                    umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                }
+                umma_commit(bar_empty + 8 * s);  // the stage is free once these MMAs have read it
+                if (kb % kChunkKb == kChunkKb - 1 || kb == num_kb - 1) umma_commit(bar_tfull + 8 * buf);  // chunk complete
+            }
+        }
+    } else {  // ===== epilogue: warp w owns TMEM lanes [32 w, 32 w + 32) = rows of the tile
+        float sum[BN];
+#pragma unroll
+        for (int i = 0; i < BN; ++i) sum[i] = 0.f;
+        for (int chunk = 0; chunk < num_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(bar_tfull + 8 * buf, (chunk >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_acc + (uint32_t(32 * warp) << 16) + uint32_t(buf * BN + c0), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[c0 + i] += v[i];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * buf) : "memory");
+        }
+        const int64_t row = int64_t(m_blk) * kBM + 32 * warp + lane;
+        if (row < M) {
+            float* crow = C + row * ldc + int64_t(n_blk) * BN;
+            const int64_t ncol = N - int64_t(n_blk) * BN;
+            if ((ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ncol >= BN) {
+#pragma unroll
+                for (int i = 0; i < BN; i += 4)
+                    *reinterpret_cast<float4*>(crow + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < BN; ++i)
+                    if (i < ncol) crow[i] = sum[i];
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc(tmem_acc, kTmemCols);
+    }
+}
+
+// hi = tf32(x) (round to nearest), lo = tf32(x - hi)
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ldx, float* __restrict__ hi,
+                                  float* __restrict__ lo, int64_t ld_out) {
+    const int64_t total = rows * ld_out;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / ld_out, c = i - r * ld_out;
+        const float v = c < cols ? x[r * ldx + c] : 0.f;
+        uint32_t h, l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hv = __uint_as_float(h);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hv));
+        hi[i] = hv;
+        lo[i] = __uint_as_float(l);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// rows x cols fp32 matrix, row pitch ld elements, box = 32 columns x box_rows rows, 128-byte swizzle, zero fill
+int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ZAFB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(ld) * sizeof(float)};
+    const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZAFB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %lld x %lld matrix, pitch %lld",
+                                       int(r), (long long)rows, (long long)cols, (long long)ld);
+    return ZAFB_OK;
+}
+
+template <int BN>
+int launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, float* c,
+           int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
+        attr = true;
+    }
+    CUtensorMap ma, mal, mb, mbl;
+    int rc = make_map(&ma, a_hi, M, K, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mal, a_lo, M, K, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mb, b_hi, N, K, ldb, BN);
+    if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, N, K, ldb, BN);
+    if (rc != ZAFB_OK) return rc;
+    const dim3 grid(unsigned((N + BN - 1) / BN), unsigned((M + kBM - 1) / kBM));
+    gemm3xtf32_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(ma, mal, mb, mbl, c, M, N, K, ldc);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+}  // namespace
+
+int split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo, int64_t ld_out, cudaStream_t st) {
+    if (rows * ld_out == 0) return ZAFB_OK;
+    int64_t blocks = (rows * ld_out + 255) / 256;
+    const int64_t cap = int64_t(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    split_tf32_kernel<<<unsigned(blocks), 256, 0, st>>>(x, rows, cols, ldx, hi, lo, ld_out);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+void split_tf32_host(const double* x, size_t n, float* hi, float* lo) {
+    auto rna = [](float v) {
+        uint32_t u;
+        memcpy(&u, &v, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;  // round half away on the 13 dropped bits, like cvt.rna.tf32.f32
+        float r;
+        memcpy(&r, &u, 4);
+        return r;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        const float h = rna(static_cast<float>(x[i]));
+        hi[i] = h;
+        lo[i] = rna(static_cast<float>(x[i] - double(h)));
+    }
+}
+
+int gemm3xtf32(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, float* c,
+               int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+    ZAFB_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm: bad shape");
+    if (M == 0 || N == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "gemm: operand row pitches must be multiples of 4 elements (TMA: 16-byte strides)");
+    ZAFB_REQUIRE(reinterpret_cast<uintptr_t>(a_hi) % 16 == 0 && reinterpret_cast<uintptr_t>(a_lo) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(b_hi) % 16 == 0 && reinterpret_cast<uintptr_t>(b_lo) % 16 == 0,
+                 "gemm: operands must be 16-byte aligned");
+    ZAFB_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31), "gemm: dimension too large");
+    if (N > 64) return launch<128>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);
+    return launch<64>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);
+}
+
+}  // namespace zafb

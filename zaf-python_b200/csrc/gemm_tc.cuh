@@ -1,0 +1,21 @@
+// fp32-accurate dense contraction on the tcgen05 tensor cores (3xTF32); see gemm_tc.cu.
+#pragma once
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace zafb {
+
+// hi = tf32(x), lo = tf32(x - hi) of a rows x cols matrix (row pitch ldx) into two matrices of pitch
+// ld_out >= cols (a multiple of 4; the padding columns are written as zeros).
+int split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo, int64_t ld_out, cudaStream_t st);
+// the same split for a host-side float64 table (constant operators: rounded once from float64)
+void split_tf32_host(const double* x, size_t n, float* hi, float* lo);
+
+// C[M x N] (row pitch ldc) = A[M x K] . B[N x K]^T with A = a_hi + a_lo, B = b_hi + b_lo (K-major, pitches lda / ldb
+// multiples of 4 elements, 16-byte aligned).  Asynchronous on `st`.
+int gemm3xtf32(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, float* c,
+               int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st);
+
+}  // namespace zafb
