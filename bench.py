@@ -41,57 +41,113 @@ def hamming_periodic(n):
 
 
 # ----------------------------------------------------------------------------- CPU baseline
+CPU_CLIPS_PER_CORE = 12  # ~0.9 core-seconds each: 16 cores -> ~14 core-seconds of CPU work per sample
+
+
 def _cpu_worker(args):
     seed, clips = args
     import oracle  # the CPU port of the reference algorithm: checker / baseline only
 
     rng = np.random.default_rng(seed)
     w = hamming_periodic(N_WIN)
+    xs = [rng.uniform(-1, 1, NS).astype(np.float32) for _ in range(clips)]  # inputs resident before timing
     frames = 0
-    for _ in range(clips):
-        x = rng.uniform(-1, 1, NS).astype(np.float32)
+    t0 = time.perf_counter()
+    for x in xs:
         frames += oracle.stft(x, w, HOP).shape[1]
-    return frames
+    return frames, time.perf_counter() - t0
 
 
-def cpu_baseline(clips_per_core=2, cores=None):
+def cpu_baseline(clips_per_core=CPU_CLIPS_PER_CORE, cores=None):
     """Time the oracle's port of zaf.stft (same operation sequence as zaf.py:95-141: Python framing
-    loop + float64 pocketfft c2c) on all host cores over a bounded sample of the cfg-2 workload."""
+    loop + float64 pocketfft c2c) on all host cores over a bounded sample of the cfg-2 workload.
+    Every process transforms its own clips; the duration is the slowest process's compute time."""
     cores = cores or len(os.sched_getaffinity(0))
     jobs = [(SEED + 1000 + i, clips_per_core) for i in range(cores)]
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 0)] * cores)  # start the workers / import numpy
-        t0 = time.perf_counter()
-        frames = sum(pool.map(_cpu_worker, jobs))
-        dt = time.perf_counter() - t0
+        pool.map(_cpu_worker, [(0, 1)] * cores)  # start the workers, import numpy, warm pocketfft
+        res = pool.map(_cpu_worker, jobs)
+    frames = sum(r[0] for r in res)
+    dt = max(r[1] for r in res)
     return {
         "value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
         "sample": f"{cores * clips_per_core} clips x {SECONDS} s @ {FS} Hz of the {CLIPS}-clip batch "
-                  f"({frames} frames, {dt:.2f} s wall, {cores} processes, float64 NumPy pocketfft)",
+                  f"({frames} frames, {dt:.2f} s wall = {sum(r[1] for r in res):.1f} core-seconds, {cores} processes, "
+                  f"float64 NumPy pocketfft)",
     }, dt
 
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread
+    (nvidia_ml_py, every ~2 ms), falling back to `nvidia-smi -lms` if NVML cannot be loaded."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            self.idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        except (ValueError, IndexError):
+            self.idx = gpu_index
+        self.samples = []  # (time, sm_mhz, reasons bitmask)
+        self.smax = None
+        self._stop = threading.Event()
+        self._thread = None
         self.proc = None
+        self.f = None
+
+    def _poll(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((time.time(), float(mhz), int(why)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, args=(nv, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self, t_begin, t_end):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0, "source": None}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            inside = [s for s in self.samples if t_begin <= s[0] <= t_end]
+            if not inside:  # a region shorter than one polling period: take the closest samples
+                inside = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t_begin + t_end)))[:3]
+            mask = 0
+            for s in inside:
+                mask |= s[2]
+            if inside:
+                out.update(sm_mhz=float(np.median([s[1] for s in inside])), samples=len(inside), source="nvml",
+                           reasons=sorted(n for b, n in self.REASONS.items() if mask & b))
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -122,7 +178,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), samples=len(sm), source="nvidia-smi")
         out["reasons"] = sorted(reasons)
         return out
 
@@ -189,11 +245,12 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     cores = len(os.sched_getaffinity(0))
+    per_core = max(1, args.cpu_clips_per_core)
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_baseline(1, cores)
     vals, times = [], []
     for _ in range(args.steps):
-        cb, dt = cpu_baseline(2, cores)
+        cb, dt = cpu_baseline(per_core, cores)
         vals.append(cb["value"])
         times.append(dt)
     value = float(np.mean(vals))
@@ -204,7 +261,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE cfg 2: zaf.stft per clip, 10 s @ 48 kHz, Hamming 2048, hop 512 "
                                "(each step = a bounded sample of the 1024-clip batch)",
-                   "window_length": N_WIN, "step_length": HOP, "clips_per_step": 2 * cores},
+                   "window_length": N_WIN, "step_length": HOP, "clips_per_step": per_core * cores},
         "cpu_baseline": cb, "gpu_launches": 0,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -214,7 +271,7 @@ def run_ours(args):
     dist = Dist(args.gpus)
     cb = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
-        cb, _ = cpu_baseline(2)  # before any CUDA call (fork-safe)
+        cb, _ = cpu_baseline(max(1, args.cpu_clips_per_core))  # before any CUDA call (fork-safe)
 
     import zaf_python_b200 as zaf
 
@@ -351,14 +408,18 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 200; 5 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS, help="clips per GPU (BASELINE cfg 2: 1024)")
     ap.add_argument("--e2e-clips", type=int, default=CLIPS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cpu-clips-per-core", type=int, default=CPU_CLIPS_PER_CORE,
+                    help="size of the bounded CPU sample (clips per host core)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 200
     if args.impl == "reference":
         run_reference(args)
     else:
