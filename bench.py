@@ -267,6 +267,42 @@ def run_reference(args):
     }))
 
 
+def split_merge_leg(zaf, dist, xd, w, nt, clips, stream, reps=3):
+    """scatter (NCCL) -> local STFT -> gather (NCCL) of ONE cfg-2 batch held by rank 0; device-timed, max over ranks."""
+    ids = [zaf.dist.make_unique_id() if dist.rank == 0 else None]
+    dist.td.broadcast_object_list(ids, src=0)
+    comm = zaf.dist.Communicator(dist.rank, dist.world, ids[0])
+    lo, hi = comm.shard_range(clips)
+    shard = zaf.empty((hi - lo, NS), np.float32)
+    full = zaf.empty((clips, nt, N_WIN), np.complex64) if dist.rank == 0 else None
+    spec_buf = zaf.empty((hi - lo, nt, N_WIN), np.complex64)
+    e0, e1, e2, e3 = zaf.Event(), zaf.Event(), zaf.Event(), zaf.Event()
+    best = None
+    for _ in range(reps + 1):  # first pass = warm-up (NCCL channel set-up)
+        dist.barrier()
+        e0.record(stream)
+        comm.scatter(xd if dist.rank == 0 else None, clips, (NS,), np.float32, stream=stream, out=shard)
+        e1.record(stream)
+        spec = zaf.stft(shard, w, HOP, stream=stream, out=spec_buf)
+        e2.record(stream)
+        comm.gather(spec, clips, stream=stream, out=full)
+        e3.record(stream)
+        e3.synchronize()
+        t = [dist.max(e0.elapsed_ms(e1)), dist.max(e1.elapsed_ms(e2)), dist.max(e2.elapsed_ms(e3)), dist.max(e0.elapsed_ms(e3))]
+        if best is None or t[3] < best[3]:
+            best = t
+    comm.close()
+    shard.free()
+    spec_buf.free()
+    if full is not None:
+        full.free()
+    return {"scaling": "strong", "global_clips": clips, "scatter_ms": best[0], "stft_ms": best[1], "gather_ms": best[2],
+            "total_ms": best[3], "frames_per_sec": clips * nt / (best[3] * 1e-3),
+            "scatter_bytes": int(clips * NS * 4 * (dist.world - 1) / dist.world),
+            "gather_bytes": int(clips * nt * N_WIN * 8 * (dist.world - 1) / dist.world),
+            "note": "rank 0 holds the batch; grouped ncclSend/ncclRecv over NVLink; best of %d" % reps}
+
+
 def run_ours(args):
     dist = Dist(args.gpus)
     cb = None
@@ -381,6 +417,14 @@ def run_ours(args):
     except (MemoryError, RuntimeError) as exc:  # e.g. not enough pinnable host memory
         e2e = {"value": None, "unit": "frames/s", "error": str(exc)[:200]}
 
+    # N > 1: the batch split / merge leg (strong scaling): rank 0 holds the whole cfg-2 batch in HBM, scatters the
+    # clips over NCCL, every rank transforms its shard, the spectra are gathered back on rank 0
+    if dist.world > 1 and not args.no_split_merge:
+        try:
+            extra["split_merge"] = split_merge_leg(zaf, dist, xd, w, nt, clips, stream)
+        except Exception as exc:  # noqa: BLE001 -- the headline number does not depend on this leg
+            extra["split_merge"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if dist.rank == 0:
         algo_bytes = clips * NS * 4 + frames * N_WIN * 8
         peak, peak_src = measured_peak()
@@ -415,6 +459,7 @@ def main():
     ap.add_argument("--e2e-clips", type=int, default=CLIPS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-split-merge", action="store_true", help="N > 1: skip the NCCL split/merge leg")
     ap.add_argument("--cpu-clips-per-core", type=int, default=CPU_CLIPS_PER_CORE,
                     help="size of the bounded CPU sample (clips per host core)")
     args = ap.parse_args()

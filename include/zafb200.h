@@ -54,6 +54,7 @@ const char* zafb_last_error(void);
 const char* zafb_version(void);
 int zafb_device_count(int* count);
 int zafb_init(int device);              /* cudaSetDevice + context warm-up            */
+int zafb_shutdown(void);                /* release the host-pipeline streams/buffers   */
 int zafb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* total_mem, char* name, size_t name_len);
 
@@ -130,6 +131,12 @@ int zafb_mdct_f32(const zafb_mdct_plan* plan, const float* x, int64_t n_clips, i
 int zafb_imdct_f32(const zafb_mdct_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
                    int layout, float* y, int64_t y_stride, void* stream);
 
+/* Host-buffer versions of the two calls above (same chunked pipeline as zafb_stft_host_f32). */
+int zafb_mdct_host_f32(const zafb_mdct_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
+                       int64_t clip_stride, float* out_host, int layout);
+int zafb_imdct_host_f32(const zafb_mdct_plan* plan, const float* spec_host, int64_t n_clips,
+                        int64_t nt, int layout, float* y_host, int64_t y_stride);
+
 /* ---------------------------------------------------------------- DCT / DST
  * zaf.dct (zaf.py:759-839) / zaf.dst (zaf.py:901-981): orthonormal types 1..4 of `batch`
  * vectors of length n (vector b at x + b*stride).  kind: 0 = DCT, 1 = DST. */
@@ -138,6 +145,9 @@ int zafb_dct_plan_create(zafb_dct_plan** plan, int kind, int type, int64_t n);
 int zafb_dct_plan_destroy(zafb_dct_plan* plan);
 int zafb_dct_f32(const zafb_dct_plan* plan, const float* x, int64_t batch, int64_t stride,
                  float* out, int64_t out_stride, void* stream);
+
+int zafb_dct_host_f32(const zafb_dct_plan* plan, const float* x_host, int64_t batch, int64_t stride,
+                      float* out_host, int64_t out_stride);
 
 /* ----------------------------------------------------- mel spectrogram / MFCC
  * The filterbank is passed dense row-major (n_mels x N/2, float64) -- the wrapper calls
@@ -155,6 +165,11 @@ int zafb_melspectrogram_f32(const zafb_mel_plan* plan, const float* x, int64_t n
 int zafb_mfcc_f32(const zafb_mel_plan* plan, const float* x, int64_t n_clips, int64_t ns,
                   int64_t clip_stride, float* out, int layout, void* stream);
 
+int zafb_melspectrogram_host_f32(const zafb_mel_plan* plan, const float* x_host, int64_t n_clips,
+                                 int64_t ns, int64_t clip_stride, float* out_host, int layout);
+int zafb_mfcc_host_f32(const zafb_mel_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
+                       int64_t clip_stride, float* out_host, int layout);
+
 /* ------------------------------------------------------- CQT spectrogram/chroma
  * The kernel is passed as CSR (complex128 data as interleaved doubles), i.e. the
  * scipy.sparse.csr_matrix zaf.cqtkernel returns (zaf.py:554-557). */
@@ -169,6 +184,31 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* plan);
 int zafb_cqt_f32(const zafb_cqt_plan* plan, const float* x, int64_t n_clips, int64_t ns,
                  int64_t clip_stride, int64_t octave_resolution, float* out, int layout,
                  void* stream);
+
+int zafb_cqt_host_f32(const zafb_cqt_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
+                      int64_t clip_stride, int64_t octave_resolution, float* out_host, int layout);
+
+/* ------------------------------------------------- multi-GPU batch split / merge
+ * One process per GPU.  The reference has no distributed code; clips are
+ * independent, so the only collectives on the path move a batch: rows (a clip, or one clip's
+ * spectrogram; opaque byte strings) are split from / merged on a root rank over NCCL (NVLink 5 /
+ * NVSwitch).  Rank r of R owns rows [floor(r n / R), floor((r+1) n / R)).  NCCL is loaded with
+ * dlopen at the first call; every pointer is a DEVICE pointer, transfers are stream-ordered. */
+typedef struct zafb_comm zafb_comm;
+int zafb_dist_shard_range(int64_t n_rows, int rank, int world, int64_t* begin, int64_t* end);
+int zafb_dist_nccl_version(int* version);
+int zafb_dist_unique_id(void* id128);                 /* rank 0: 128-byte NCCL id to hand to its peers */
+int zafb_dist_init(zafb_comm** comm, const void* id128, int rank, int world); /* after zafb_init(device) */
+int zafb_dist_destroy(zafb_comm* comm);
+int zafb_dist_rank(const zafb_comm* comm, int* rank, int* world);
+int zafb_dist_broadcast(zafb_comm* comm, void* buf, size_t bytes, int root, void* stream);
+int zafb_dist_scatter_rows(zafb_comm* comm, const void* src_root, void* dst, int64_t n_rows,
+                           int64_t row_bytes, int root, void* stream);
+int zafb_dist_gather_rows(zafb_comm* comm, const void* src, void* dst_root, int64_t n_rows,
+                          int64_t row_bytes, int root, void* stream);
+int zafb_dist_allgather_rows(zafb_comm* comm, const void* src, void* dst, int64_t n_rows,
+                             int64_t row_bytes, void* stream);
+int zafb_dist_max_f64(zafb_comm* comm, double* value, void* stream);  /* max over ranks, synchronises */
 
 #ifdef __cplusplus
 }

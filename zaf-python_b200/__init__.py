@@ -29,13 +29,14 @@ from ._device import (DeviceArray, Event, PinnedArray, Stream, device_count, emp
                       launch_count, synchronize, to_device)
 from ._lib import LAYOUT_BIN_MAJOR, LAYOUT_FRAME_MAJOR, ZafbError  # noqa: F401
 from ._operators import cqtkernel, melfilterbank  # noqa: F401
-from ._shard import shard_range  # noqa: F401
+from . import _dist as dist  # noqa: F401
+from ._dist import shard_range  # noqa: F401
 
 __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
     "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
     "to_device", "empty", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count",
-    "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry",
+    "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry", "dist", "shard_range",
 ]
 
 _LAYOUTS = {"frame_major": LAYOUT_FRAME_MAJOR, "bin_major": LAYOUT_BIN_MAJOR}
@@ -133,17 +134,6 @@ def _signal_batch(audio_signal):
     return x, one
 
 
-def _even_pitch(x):
-    """(batch, ns) float32 -> (array whose rows start at even element offsets, pitch).  The vectorised
-    kernels need 8-byte aligned rows; an odd ns gets one padding column (never read as signal)."""
-    ns = x.shape[1]
-    if ns % 2 == 0 or x.shape[0] == 1:
-        return x, max(ns, 1) if x.shape[0] == 1 else ns
-    padded = np.zeros((x.shape[0], ns + 1), dtype=x.dtype)
-    padded[:, :ns] = x
-    return padded, ns + 1
-
-
 def _matrix_out(batch, rows, cols, dtype, layout, one):
     """Host result buffer for a (rows, cols) = (bins, frames) matrix per clip, and the view to return."""
     if layout == LAYOUT_FRAME_MAJOR:
@@ -169,7 +159,8 @@ def stft(audio_signal, window_function, step_length, *, layout="frame_major", st
 
     Returns the full two-sided spectrum of shape (window_length, number_times) [complex64];
     centre padding floor(N/2), number of frames and tail padding follow zaf.py:99-121 exactly.
-    ``out=`` (host path only) supplies the result memory, e.g. a pinned buffer.
+    ``out=`` supplies the result memory: a NumPy array (e.g. pinned) on the host path, a DeviceArray
+    on the device path.
     """
     plan, w = _stft_plan(window_function, step_length)
     lay = _layout_id(layout)
@@ -182,7 +173,13 @@ def stft(audio_signal, window_function, step_length, *, layout="frame_major", st
         batch, ns = (1, x.shape[0]) if one else x.shape
         nt = stft_geometry(ns, n, step_length)[1]
         mem_shape = (batch, nt, n) if lay == LAYOUT_FRAME_MAJOR else (batch, n, nt)
-        out = DeviceArray(mem_shape[1:] if one else mem_shape, np.complex64, transposed=lay == LAYOUT_FRAME_MAJOR)
+        if out is None:
+            out = DeviceArray(mem_shape[1:] if one else mem_shape, np.complex64, transposed=lay == LAYOUT_FRAME_MAJOR)
+        elif not isinstance(out, DeviceArray) or out.dtype != np.complex64 or out.nbytes != 8 * batch * nt * n:
+            raise ValueError(f"out must be a complex64 DeviceArray with {batch * nt * n} elements")
+        else:  # caller-provided device memory, viewed in the requested layout
+            out = DeviceArray(mem_shape[1:] if one else mem_shape, np.complex64, ptr=out.ptr, owner=out,
+                              transposed=lay == LAYOUT_FRAME_MAJOR)
         _lib.check(_lib.lib().zafb_stft_f32(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, C.c_void_p(out.ptr), lay,
                                             _stream_ptr(stream)))
         return out
@@ -253,20 +250,6 @@ def istft(audio_stft, window_function, step_length, *, stream=None):
     return y[0] if one else y
 
 
-# ------------------------------------------------------------------ helpers for device-side one-shot calls
-def _run_on_device(x_host, out_mem, call):
-    """H2D -> call(x_dev_ptr, out_dev_ptr) -> D2H for the transforms without a host-pipelined entry point."""
-    ensure_init()
-    xd = to_device(x_host)
-    od = DeviceArray(out_mem.shape, out_mem.dtype)
-    try:
-        call(C.c_void_p(xd.ptr), C.c_void_p(od.ptr))
-        od.to_host(out=out_mem)
-    finally:
-        xd.free()
-        od.free()
-
-
 # ------------------------------------------------------------------ MDCT / IMDCT
 def _mdct_plan(window_function):
     w = _window64(window_function)
@@ -295,9 +278,8 @@ def mdct(audio_signal, window_function, *, layout="frame_major", stream=None):
     batch, ns = x.shape
     m, nt, _ = mdct_geometry(ns, n)
     mem, view = _matrix_out(batch, m, nt, np.float32, lay, one)
-    x, pitch = _even_pitch(x)
-    _run_on_device(x, mem, lambda xd, od: _lib.check(
-        _lib.lib().zafb_mdct_f32(plan, xd, batch, ns, pitch, od, lay, None)))
+    ensure_init()
+    _lib.check(_lib.lib().zafb_mdct_host_f32(plan, x.ctypes.data, batch, ns, ns, mem.ctypes.data, lay))
     return view
 
 
@@ -326,11 +308,9 @@ def imdct(audio_mdct, window_function, *, stream=None):
     if bins * 2 != n:
         raise ValueError("audio_mdct rows must equal window_length/2")
     length = imdct_geometry(bins, nt)[1]
-    pitch = _even(length)
-    y = np.empty((batch, pitch), dtype=np.float32)
-    _run_on_device(mem, y, lambda xd, od: _lib.check(
-        _lib.lib().zafb_imdct_f32(plan, xd, batch, nt, lay, od, pitch, None)))
-    y = y[:, :length]
+    y = np.empty((batch, length), dtype=np.float32)
+    ensure_init()
+    _lib.check(_lib.lib().zafb_imdct_host_f32(plan, mem.ctypes.data, batch, nt, lay, y.ctypes.data, length))
     return y[0] if one else y
 
 
@@ -350,7 +330,7 @@ def _dct_like(audio_signal, kind, dtype_code):
     batch, n = x.shape
     plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
     out = np.empty((batch, n), dtype=np.float32)
-    _run_on_device(x, out, lambda xd, od: _lib.check(_lib.lib().zafb_dct_f32(plan, xd, batch, n, od, n, None)))
+    _lib.check(_lib.lib().zafb_dct_host_f32(plan, x.ctypes.data, batch, n, out.ctypes.data, n))
     return out[0] if one else out
 
 
@@ -396,9 +376,7 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
     batch, ns = x.shape
     nt = stft_geometry(ns, len(w), step_length)[1]
     mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
-    x, pitch = _even_pitch(x)
-    _run_on_device(x, mem, lambda xd, od: _lib.check(
-        getattr(_lib.lib(), fn)(plan, xd, batch, ns, pitch, od, lay, None)))
+    _lib.check(getattr(_lib.lib(), fn.replace("_f32", "_host_f32"))(plan, x.ctypes.data, batch, ns, ns, mem.ctypes.data, lay))
     return view
 
 
@@ -452,9 +430,8 @@ def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resoluti
     batch, ns = x.shape
     nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
     mem, view = _matrix_out(batch, rows, nt, np.float32, lay, one)
-    x, pitch = _even_pitch(x)
-    _run_on_device(x, mem, lambda xd, od: _lib.check(
-        _lib.lib().zafb_cqt_f32(plan, xd, batch, ns, pitch, int(octave_resolution), od, lay, None)))
+    _lib.check(_lib.lib().zafb_cqt_host_f32(plan, x.ctypes.data, batch, ns, ns, int(octave_resolution), mem.ctypes.data,
+                                            lay))
     return view
 
 

@@ -24,6 +24,7 @@ PROTOTYPES = {
     "zafb_version": (C.c_char_p, []),
     "zafb_device_count": (_int, [C.POINTER(_int)]),
     "zafb_init": (_int, [_int]),
+    "zafb_shutdown": (_int, []),
     "zafb_device_info": (_int, [_int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_sz), C.c_char_p, _sz]),
     "zafb_malloc": (_int, [_pvp, _sz]),
     "zafb_free": (_int, [_vp]),
@@ -58,16 +59,33 @@ PROTOTYPES = {
     "zafb_mdct_plan_destroy": (_int, [_vp]),
     "zafb_mdct_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_imdct_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp]),
+    "zafb_mdct_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
+    "zafb_imdct_host_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64]),
     "zafb_dct_plan_create": (_int, [_pvp, _int, _int, _i64]),
     "zafb_dct_plan_destroy": (_int, [_vp]),
     "zafb_dct_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "zafb_dct_host_f32": (_int, [_vp, _vp, _i64, _i64, _vp, _i64]),
     "zafb_mel_plan_create": (_int, [_pvp, _vp, _i64, _i64, _vp, _i64, _i64]),
     "zafb_mel_plan_destroy": (_int, [_vp]),
     "zafb_melspectrogram_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_mfcc_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_melspectrogram_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
+    "zafb_mfcc_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
     "zafb_cqt_plan_create": (_int, [_pvp, _i64, _i64, _vp, _vp, _vp, _i64]),
     "zafb_cqt_plan_destroy": (_int, [_vp]),
     "zafb_cqt_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp]),
+    "zafb_cqt_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int]),
+    "zafb_dist_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
+    "zafb_dist_nccl_version": (_int, [C.POINTER(_int)]),
+    "zafb_dist_unique_id": (_int, [_vp]),
+    "zafb_dist_init": (_int, [_pvp, _vp, _int, _int]),
+    "zafb_dist_destroy": (_int, [_vp]),
+    "zafb_dist_rank": (_int, [_vp, C.POINTER(_int), C.POINTER(_int)]),
+    "zafb_dist_broadcast": (_int, [_vp, _vp, _sz, _int, _vp]),
+    "zafb_dist_scatter_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "zafb_dist_gather_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
+    "zafb_dist_allgather_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "zafb_dist_max_f64": (_int, [_vp, C.POINTER(C.c_double), _vp]),
 }
 # not part of the public header: test hooks
 _PRIVATE = {

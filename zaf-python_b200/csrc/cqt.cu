@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "host_pipe.cuh"
 
 using namespace zafb;
 
@@ -587,6 +588,27 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
         p->d_band_off, p->d_weights, int(p->n_freqs), int(octave_resolution), out, layout, total);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
+}
+
+int zafb_cqt_host_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                      int64_t octave_resolution, float* out, int layout) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    ZAFB_REQUIRE(octave_resolution >= 0 && octave_resolution <= p->n_freqs, "bad octave_resolution");
+    int64_t nt = 0;
+    int rc = zafb_cqt_geometry(ns, p->step, p->fft_length, &nt, nullptr, nullptr);
+    if (rc != ZAFB_OK) return rc;
+    if (n_clips == 0 || nt == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && x != nullptr, "x/out is NULL");
+    const int64_t rows = octave_resolution > 0 ? octave_resolution : p->n_freqs;
+    const size_t out_clip = size_t(nt) * size_t(rows) * sizeof(float);
+    const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    return run_host_pipeline(x, size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(dpitch) * sizeof(float),
+                             out, out_clip, out_clip, out_clip, n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return zafb_cqt_f32(p, static_cast<const float*>(d_in), nc, ns, dpitch, octave_resolution,
+                                                     static_cast<float*>(d_out), layout, st);
+                             });
 }
 
 }  // extern "C"

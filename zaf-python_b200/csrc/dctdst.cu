@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "host_pipe.cuh"
 #include "gemm_tc.cuh"
 
 using namespace zafb;
@@ -389,6 +390,21 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
     }
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
+}
+
+int zafb_dct_host_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t stride, float* out,
+                      int64_t out_stride) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(batch >= 0 && stride >= p->n && out_stride >= p->n, "bad batch geometry");
+    if (batch == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(x != nullptr && out != nullptr, "x/out is NULL");
+    const int64_t dpitch = (p->n + 3) & ~int64_t(3);  // 16-byte aligned rows on the device
+    return run_host_pipeline(x, size_t(stride) * sizeof(float), size_t(p->n) * sizeof(float), size_t(dpitch) * sizeof(float), out,
+                             size_t(out_stride) * sizeof(float), size_t(p->n) * sizeof(float), size_t(dpitch) * sizeof(float),
+                             batch, [&](void* d_in, void* d_out, int64_t, int64_t nb, cudaStream_t st) {
+                                 return zafb_dct_f32(p, static_cast<const float*>(d_in), nb, dpitch,
+                                                     static_cast<float*>(d_out), dpitch, st);
+                             });
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "host_pipe.cuh"
 
 using namespace zafb;
 
@@ -571,6 +572,45 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
         y_stride);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer pipelines
+int zafb_mdct_host_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                       float* out, int layout) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    int64_t nt = 0;
+    zafb_mdct_geometry(ns, p->n, nullptr, &nt, nullptr);
+    if (n_clips == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    const size_t out_clip = size_t(nt) * p->m * sizeof(float);
+    const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    return run_host_pipeline(x, size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(dpitch) * sizeof(float),
+                             out, out_clip, out_clip, out_clip, n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return zafb_mdct_f32(p, static_cast<const float*>(d_in), nc, ns, dpitch,
+                                                      static_cast<float*>(d_out), layout, st);
+                             });
+}
+
+int zafb_imdct_host_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                        int64_t y_stride) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "bad batch geometry");
+    int64_t len = 0;
+    zafb_imdct_geometry(p->m, nt, nullptr, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride too small");
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
+    const size_t in_clip = size_t(nt) * p->m * sizeof(float);
+    // the reference's odd output length M(nt-1)-1 would misalign every other row: even device pitch
+    const int64_t dpitch = (len + 1) & ~int64_t(1);
+    return run_host_pipeline(spec, in_clip, in_clip, in_clip, y, size_t(y_stride) * sizeof(float), size_t(len) * sizeof(float),
+                             size_t(dpitch) * sizeof(float), n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return zafb_imdct_f32(p, static_cast<const float*>(d_in), nc, nt, layout,
+                                                       static_cast<float*>(d_out), dpitch, st);
+                             });
 }
 
 }  // extern "C"

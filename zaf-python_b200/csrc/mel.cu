@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "host_pipe.cuh"
 
 using namespace zafb;
 
@@ -489,6 +490,35 @@ int zafb_melspectrogram_f32(const zafb_mel_plan* p, const float* x, int64_t n_cl
 int zafb_mfcc_f32(const zafb_mel_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, float* out,
                   int layout, void* stream) {
     return launch(p, 1, x, n_clips, ns, clip_stride, out, layout, stream);
+}
+
+static int mel_host(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                    float* out, int layout) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    int64_t nt = 0;
+    zafb_stft_geometry(ns, p->n, p->hop, nullptr, &nt, nullptr);
+    if (n_clips == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    const int64_t rows = mode == 0 ? p->n_mels : p->n_coef;
+    const size_t out_clip = size_t(nt) * size_t(rows) * sizeof(float);
+    const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    return run_host_pipeline(x, size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(dpitch) * sizeof(float),
+                             out, out_clip, out_clip, out_clip, n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return launch(p, mode, static_cast<const float*>(d_in), nc, ns, dpitch,
+                                               static_cast<float*>(d_out), layout, st);
+                             });
+}
+
+int zafb_melspectrogram_host_f32(const zafb_mel_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                                 float* out, int layout) {
+    return mel_host(p, 0, x, n_clips, ns, clip_stride, out, layout);
+}
+
+int zafb_mfcc_host_f32(const zafb_mel_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, float* out,
+                       int layout) {
+    return mel_host(p, 1, x, n_clips, ns, clip_stride, out, layout);
 }
 
 }  // extern "C"

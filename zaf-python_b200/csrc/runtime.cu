@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_pipe.cuh"
 
 namespace zafb {
 
@@ -69,6 +70,63 @@ int sm_count() {
     return n;
 }
 
+// ------------------------------------------------------------------ host-buffer pipeline state
+HostPipe& host_pipe() {
+    static HostPipe hp;
+    return hp;
+}
+
+size_t host_pipe_chunk_bytes() {
+    int mb = env_flag("ZAFB_PIPE_CHUNK_MB", 64);
+    if (mb < 1) mb = 1;
+    return size_t(mb) << 20;
+}
+
+void HostPipe::release() {
+    for (int i = 0; i < kStages; ++i) {
+        if (st[i]) cudaStreamDestroy(st[i]);
+        cudaFree(d_in[i]);
+        cudaFree(d_out[i]);
+        st[i] = nullptr;
+        d_in[i] = d_out[i] = nullptr;
+    }
+    in_cap = out_cap = 0;
+    device = -1;
+}
+
+int HostPipe::ensure(size_t in_bytes, size_t out_bytes) {
+    int dev = 0;
+    ZAFB_CUDA(cudaGetDevice(&dev));
+    if (dev != device) {  // first use, or the process switched devices
+        if (device >= 0) {
+            cudaSetDevice(device);
+            release();
+            cudaSetDevice(dev);
+        }
+        for (int i = 0; i < kStages; ++i) ZAFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        device = dev;
+    }
+    if (in_bytes > in_cap) {
+        for (int i = 0; i < kStages; ++i) {
+            cudaFree(d_in[i]);
+            d_in[i] = nullptr;
+        }
+        in_cap = 0;
+        for (int i = 0; i < kStages; ++i) ZAFB_CUDA(cudaMalloc(&d_in[i], in_bytes));
+        in_cap = in_bytes;
+    }
+    if (out_bytes > out_cap) {
+        for (int i = 0; i < kStages; ++i) {
+            cudaFree(d_out[i]);
+            d_out[i] = nullptr;
+        }
+        out_cap = 0;
+        for (int i = 0; i < kStages; ++i) ZAFB_CUDA(cudaMalloc(&d_out[i], out_bytes));
+        out_cap = out_bytes;
+    }
+    return ZAFB_OK;
+}
+
 }  // namespace zafb
 
 using namespace zafb;
@@ -99,6 +157,13 @@ int zafb_init(int device) {
     if (major != 10)
         return fail(ZAFB_E_UNSUPPORTED, "device %d has compute capability %d.x; this library is sm_100a only",
                     device, major);
+    return ZAFB_OK;
+}
+
+int zafb_shutdown(void) {
+    HostPipe& hp = host_pipe();
+    std::lock_guard<std::mutex> lock(hp.mu);
+    hp.release();
     return ZAFB_OK;
 }
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "host_pipe.cuh"
 
 namespace zafb {}
 using namespace zafb;
@@ -582,31 +583,6 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
-namespace {
-struct HostPipe {
-    static constexpr int kStreams = 3;
-    cudaStream_t st[kStreams] = {};
-    void* d_in[kStreams] = {};
-    void* d_out[kStreams] = {};
-    ~HostPipe() {
-        for (int i = 0; i < kStreams; ++i) {
-            if (st[i]) cudaStreamDestroy(st[i]);
-            cudaFree(d_in[i]);
-            cudaFree(d_out[i]);
-        }
-    }
-    int init(size_t in_bytes, size_t out_bytes) {
-        for (int i = 0; i < kStreams; ++i) {
-            ZAFB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-            ZAFB_CUDA(cudaMalloc(&d_in[i], in_bytes ? in_bytes : 1));
-            ZAFB_CUDA(cudaMalloc(&d_out[i], out_bytes ? out_bytes : 1));
-        }
-        return ZAFB_OK;
-    }
-};
-constexpr size_t kChunkBytes = size_t(256) << 20;  // device output bytes per pipeline stage
-}  // namespace
-
 int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
                        float* out, int layout) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
@@ -614,30 +590,16 @@ int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     int64_t nt = 0;
     zafb_stft_geometry(ns, p->n, p->hop, nullptr, &nt, nullptr);
     if (n_clips == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
     const size_t out_clip = size_t(nt) * p->n * sizeof(float2);
     // device-side clip pitch: even number of samples so the float2 fast path stays aligned
     const int64_t dpitch = (ns + 1) & ~int64_t(1);
-    int64_t per = int64_t(kChunkBytes / (out_clip ? out_clip : 1));
-    if (per < 1) per = 1;
-    if (per > n_clips) per = n_clips;
-    HostPipe pipe;
-    int rc = pipe.init(size_t(per) * (dpitch ? dpitch : 2) * sizeof(float), size_t(per) * out_clip);
-    if (rc != ZAFB_OK) return rc;
-    int s = 0;
-    for (int64_t c0 = 0; c0 < n_clips; c0 += per, s = (s + 1) % HostPipe::kStreams) {
-        const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
-        if (ns > 0)
-            ZAFB_CUDA(cudaMemcpy2DAsync(pipe.d_in[s], size_t(dpitch) * sizeof(float), x + c0 * clip_stride,
-                                        size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(nc),
-                                        cudaMemcpyHostToDevice, pipe.st[s]));
-        rc = zafb_stft_f32(p, static_cast<const float*>(pipe.d_in[s]), nc, ns, dpitch,
-                           static_cast<float*>(pipe.d_out[s]), layout, pipe.st[s]);
-        if (rc != ZAFB_OK) return rc;
-        ZAFB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(out) + size_t(c0) * out_clip, pipe.d_out[s],
-                                  size_t(nc) * out_clip, cudaMemcpyDeviceToHost, pipe.st[s]));
-    }
-    for (int i = 0; i < HostPipe::kStreams; ++i) ZAFB_CUDA(cudaStreamSynchronize(pipe.st[i]));
-    return ZAFB_OK;
+    return run_host_pipeline(x, size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(dpitch) * sizeof(float),
+                             out, out_clip, out_clip, out_clip, n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return zafb_stft_f32(p, static_cast<const float*>(d_in), nc, ns, dpitch,
+                                                      static_cast<float*>(d_out), layout, st);
+                             });
 }
 
 int zafb_istft_host_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
@@ -648,27 +610,15 @@ int zafb_istft_host_f32(const zafb_stft_plan* p, const float* spec, int64_t n_cl
     zafb_istft_geometry(p->n, nt, p->hop, nullptr, nullptr, &len);
     ZAFB_REQUIRE(y_stride >= len, "y_stride too small");
     if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const size_t in_clip = size_t(nt) * p->n * sizeof(float2);
-    int64_t per = int64_t(kChunkBytes / (in_clip ? in_clip : 1));
-    if (per < 1) per = 1;
-    if (per > n_clips) per = n_clips;
-    HostPipe pipe;
-    int rc = pipe.init(size_t(per) * in_clip, size_t(per) * len * sizeof(float));
-    if (rc != ZAFB_OK) return rc;
-    int s = 0;
-    for (int64_t c0 = 0; c0 < n_clips; c0 += per, s = (s + 1) % HostPipe::kStreams) {
-        const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
-        ZAFB_CUDA(cudaMemcpyAsync(pipe.d_in[s], reinterpret_cast<const char*>(spec) + size_t(c0) * in_clip,
-                                  size_t(nc) * in_clip, cudaMemcpyHostToDevice, pipe.st[s]));
-        rc = zafb_istft_f32(p, static_cast<const float*>(pipe.d_in[s]), nc, nt, layout,
-                            static_cast<float*>(pipe.d_out[s]), len, pipe.st[s]);
-        if (rc != ZAFB_OK) return rc;
-        ZAFB_CUDA(cudaMemcpy2DAsync(y + c0 * y_stride, size_t(y_stride) * sizeof(float), pipe.d_out[s],
-                                    size_t(len) * sizeof(float), size_t(len) * sizeof(float), size_t(nc),
-                                    cudaMemcpyDeviceToHost, pipe.st[s]));
-    }
-    for (int i = 0; i < HostPipe::kStreams; ++i) ZAFB_CUDA(cudaStreamSynchronize(pipe.st[i]));
-    return ZAFB_OK;
+    const int64_t dpitch = (len + 1) & ~int64_t(1);
+    return run_host_pipeline(spec, in_clip, in_clip, in_clip, y, size_t(y_stride) * sizeof(float), size_t(len) * sizeof(float),
+                             size_t(dpitch) * sizeof(float), n_clips,
+                             [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
+                                 return zafb_istft_f32(p, static_cast<const float*>(d_in), nc, nt, layout,
+                                                       static_cast<float*>(d_out), dpitch, st);
+                             });
 }
 
 }  // extern "C"
