@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def assert_parity(got, ref, tol=TOL):
-    assert got.shape == ref.shape, (got.shape, ref.shape)
+def assert_parity(got, ref, tol=TOL, what=""):
+    assert got.shape == ref.shape, (got.shape, ref.shape, what)
     mx, l2 = oracle.parity_metrics(got, ref)
-    assert mx <= tol and l2 <= tol, (mx, l2)
+    assert mx <= tol and l2 <= tol, (mx, l2, what)
 
 
 # ------------------------------------------------------------------------------- MDCT / IMDCT
@@ -156,6 +156,31 @@ def test_dct_dst_tensor_core_matrix_path(zaf_gpu, n):
                 for c in (0, batch // 2, batch - 1):
                     assert_parity(got[c], ofn(x[c], t))
                 assert np.array_equal(got, fn(x, t))  # the default route for batch >= 8 is the same path
+
+
+def test_dct_dst_1024_warp_kernel(zaf_gpu):
+    """N = 1024, types II-IV: the one-warp-per-vector kernel (forced), the block FFT kernel (forced) and the default
+    route against the oracle; a batch that does not fill the last CTA; bit-identical results between calls."""
+    rng = np.random.default_rng(77)
+    lib = zaf_gpu._lib.lib()
+    batch = 2 * 148 * 8 + 13
+    x = rng.uniform(-1, 1, (batch, 1024)).astype(np.float32)
+    x[1] = 0.0
+    x[2, :] = 1.0
+    for kind, fn, ofn in ((0, zaf_gpu.dct, oracle.dct), (1, zaf_gpu.dst, oracle.dst)):
+        for t in (2, 3, 4):
+            plan = zaf_gpu._dct_plans.get((kind, t, 1024), kind, t, 1024)
+            res = {}
+            for force in (4, 3, 0):
+                zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, force))
+                try:
+                    res[force] = fn(x, t)
+                finally:
+                    lib.zafb_dct_plan_force_direct(plan, 0)
+                for c in (0, 1, 2, 3, batch // 2, batch - 1):
+                    assert_parity(res[force][c], ofn(x[c], t), what=f"kind {kind} type {t} force {force} vec {c}")
+            assert np.array_equal(res[4], res[0])  # the warp kernel is the default route
+            assert np.array_equal(fn(x[5], t), res[0][5])  # a single vector goes the same way
 
 
 def test_dst_inverse_pairs(zaf_gpu):

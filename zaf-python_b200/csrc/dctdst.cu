@@ -40,7 +40,9 @@ struct zafb_dct_plan {
     float2* d_tw_fft = nullptr;   // W_{N/2}^t
     float2* d_tw_a = nullptr;     // per-type twiddles (see kernels)
     float2* d_tw_b = nullptr;
-    int force_direct = 0;         // test hook: 1 = direct kernel, 2 = require the tensor-core matrix path
+    float2* d_tw_4step = nullptr; // n == 1024: W_512^{k1*n2} at [k1*32 + n2], k1 < 16 (warp kernel)
+    int force_direct = 0;         // test hook: 1 = direct kernel, 2 = require the tensor-core matrix path,
+                                  //            3 = block FFT kernel (no warp kernel), 4 = require the warp kernel
     // matrix path (types I and non-power-of-two N): out = x . Mat^T on the tensor cores, Mat[k][n] in hi/lo TF32 halves
     float* d_mat_hi = nullptr;
     float* d_mat_lo = nullptr;
@@ -192,11 +194,173 @@ __global__ void dct_fft_kernel(const float* __restrict__ x, int64_t batch, int64
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// N = 1024 (the reference's example length, zaf.py:726-753): one warp per vector, types II / III / IV
+// and their DST twins.  The 1024 real values are packed into ONE 512-point complex FFT held in the
+// registers of the warp (warp_fft512: two in-register radix-16 passes around one shared-memory
+// transpose); permutations, real-input split and twiddles are register renaming, xor-31 / mirror
+// shuffles and immediates.  Loads and stores are 8- or 16-byte coalesced, one pass over HBM.
+//   MODE 4  t[m] = (P[m].x + i P[511-m].y) e^{-i pi m/N},  P[p] = (x[2p], x[2p+1])   (same core as the MDCT kernel)
+//   MODE 2  Makhoul: z[q] = (x[4q], x[4q+2]), z[511-q] = (x[4q+3], x[4q+1]), q < 256;  V = real-input split of FFT(z);
+//           U_k = V_k e^{-i pi k/2N}:  X_k = s c_k Re U_k,  X_{N-k} = -s Im U_k,  X_{N/2} = s (Re Z_0 - Im Z_0)/sqrt2
+//   MODE 3  the exact inverse of MODE 2 (zaf.py:799-817 builds it from a 4N-point FFT instead)
+// DST twins: DST-II(x) = reverse(DCT-II((-1)^n x)), DST-III(x) = (-1)^k DCT-III(reverse x),
+// DST-IV(x) = (-1)^k DCT-IV(reverse x).   (All index maps validated in float64 against scipy's orthonormal transforms.)
+// ---------------------------------------------------------------------------------------------
+constexpr int kDctWarps = 8;
+
+template <int MODE, bool DST>
+__global__ void __launch_bounds__(kDctWarps * 32, 2)
+dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, const float2* __restrict__ tw4,
+                    const float2* __restrict__ tw_a, const float2* __restrict__ tw_b, float* __restrict__ out,
+                    int64_t out_stride) {
+    extern __shared__ float2 smem2[];
+    float2* s_tw = smem2;  // 512: W_512^{k1 n2}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* s_buf = smem2 + 512 + warp * (16 * kFft1024Pitch);
+    for (int i = tid; i < 512; i += kDctWarps * 32) s_tw[i] = tw4[i];
+    constexpr float kNorm = 0.04419417382415922f;   // sqrt(2 / 1024)
+    constexpr float kR2 = 0.70710678118654752f;
+    const float2 ta = tw_a[lane];
+    float2 tb = tw_b[lane];
+    if constexpr (MODE == 4) tb = cscale(tb, kNorm);                       // post twiddle carries sqrt(2/N)
+    if constexpr (MODE == 2) tb = lane == 0 ? make_float2(0.5f * kNorm, 0.f) : cscale(tb, 0.5f);  // s/2 e^{-i pi lane/2N}, no c_k
+    if constexpr (MODE == 3) tb = cscale(tb, 0.5f * kNorm);                // s/2 e^{+i pi lane/2N}
+    __syncthreads();
+    const int mirror = (32 - lane) & 31;
+
+    for (int64_t vec = int64_t(blockIdx.x) * kDctWarps + warp; vec < batch; vec += int64_t(gridDim.x) * kDctWarps) {
+        const float* xv = x + vec * stride;
+        float* ov = out + vec * out_stride;
+        float2 v[16];
+
+        if constexpr (MODE == 4) {
+            float2 xp[16];
+            const float2* P = reinterpret_cast<const float2*>(xv) + lane;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) xp[r] = __ldg(P + 32 * r);
+            static_for<0, 16>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float other = __shfl_xor_sync(0xffffffffu, xp[15 - r].y, 31);  // x[N-1-2m]
+                const float2 t = DST ? make_float2(other, xp[r].x) : make_float2(xp[r].x, other);
+                v[r] = cmul(t, mul_tw<r, 64>(ta));
+            });
+            warp_fft512(v, s_tw, s_buf, lane);
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                v[bitrev(k, 4)] = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(tb));
+            });
+            float2* o = reinterpret_cast<float2*>(ov) + lane;
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(15 - k, 4)].y, 31);
+                __stcs(o + 32 * k, make_float2(v[bitrev(k, 4)].x, DST ? im : -im));
+            });
+        } else if constexpr (MODE == 2) {
+            const float4* Q = reinterpret_cast<const float4*>(xv) + lane;
+            static_for<0, 8>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                float4 q = __ldg(Q + 32 * r);
+                if constexpr (DST) {  // (-1)^n x[n]
+                    q.y = -q.y;
+                    q.w = -q.w;
+                }
+                v[r] = make_float2(q.x, q.z);                                   // z[q]
+                v[15 - r].x = __shfl_xor_sync(0xffffffffu, q.w, 31);           // z[511 - q'] of lane 31 - lane
+                v[15 - r].y = __shfl_xor_sync(0xffffffffu, q.y, 31);
+            });
+            warp_fft512(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2, 4)]
+            static_for<0, 16>([&](auto kc) {
+                constexpr int k2 = decltype(kc)::value;
+                const float2 z = v[bitrev(k2, 4)];
+                const float2 mine = v[bitrev(15 - k2, 4)];
+                float2 p;
+                p.x = __shfl_sync(0xffffffffu, mine.x, mirror);
+                p.y = __shfl_sync(0xffffffffu, mine.y, mirror);
+                if (lane == 0) p = v[bitrev((16 - k2) & 15, 4)];
+                const float2 e = make_float2(z.x + p.x, z.y - p.y);
+                const float2 od = make_float2(z.y + p.y, p.x - z.x);
+                const float2 V = cadd(e, cmul(mul_tw<k2, 32>(ta), od));
+                const float2 U = cmul(V, mul_tw<k2, 128>(tb));
+                float lo = U.x, hi = -U.y;
+                const int k = lane + 32 * k2;
+                int ihi = 1024 - k;
+                if (k2 == 0 && lane == 0) {  // k = 0: X_0 carries c_0 = 1/sqrt2; the mirror slot holds X_{N/2}
+                    lo = tb.x * (e.x + od.x) * kR2;
+                    hi = tb.x * (e.x - od.x) * kR2;
+                    ihi = 512;
+                }
+                if constexpr (DST) {  // reversed output
+                    ov[1023 - k] = lo;
+                    ov[1023 - ihi] = hi;
+                } else {
+                    ov[k] = lo;
+                    ov[ihi] = hi;
+                }
+            });
+        } else {  // MODE 3
+            float xr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[i] = DST ? __ldg(xv + 1023 - lane - 32 * i) : __ldg(xv + lane + 32 * i);
+            // V_k = (C_k - i C_{N-k}) u_k (scaled by s/2), k = lane + 32 r
+            static_for<0, 16>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                float ck = xr[r];
+                float cn = __shfl_sync(0xffffffffu, xr[31 - r], mirror);
+                if (lane == 0) {
+                    cn = r == 0 ? 0.f : xr[(32 - r) & 31];
+                    if (r == 0) ck *= 1.41421356237309505f;  // C_0 = x_0 / c_0
+                }
+                v[r] = cmul(make_float2(ck, -cn), mul_tw<128 - r, 128>(tb));
+            });
+            float2 zin[16];
+            static_for<0, 16>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                float2 pv;
+                pv.x = __shfl_sync(0xffffffffu, v[15 - r].x, mirror);
+                pv.y = __shfl_sync(0xffffffffu, v[15 - r].y, mirror);
+                if (lane == 0) {
+                    if constexpr (r == 0) pv = make_float2(1.41421356237309505f * xr[16] * tb.x, 0.f);  // V_{N/2} is real
+                    else pv = v[16 - r];
+                }
+                const float2 e = make_float2(v[r].x + pv.x, v[r].y - pv.y);   // V_k + conj(V_{N/2-k})
+                const float2 d = make_float2(v[r].x - pv.x, v[r].y + pv.y);
+                const float2 o = cmul_conj(d, mul_tw<r, 32>(ta));
+                // Z = E + i O; the inverse FFT runs as conj(FFT(conj Z))
+                zin[r] = make_float2(e.x - o.y, -(e.y + o.x));
+            });
+            warp_fft512(zin, s_tw, s_buf, lane);  // conj(z[lane + 32 k2]) = zin[bitrev(k2, 4)]
+            float4* o4 = reinterpret_cast<float4*>(ov) + lane;
+            static_for<0, 8>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float2 own = zin[bitrev(r, 4)];
+                float2 oth;
+                oth.x = __shfl_xor_sync(0xffffffffu, zin[bitrev(15 - r, 4)].x, 31);
+                oth.y = __shfl_xor_sync(0xffffffffu, zin[bitrev(15 - r, 4)].y, 31);
+                // x[4q] = Re z[q], x[4q+1] = Im z[511-q], x[4q+2] = Im z[q], x[4q+3] = Re z[511-q]
+                float4 q = make_float4(own.x, -oth.y, -own.y, oth.x);
+                if constexpr (DST) {
+                    q.y = -q.y;
+                    q.w = -q.w;
+                }
+                __stcs(o4 + 32 * r, q);
+            });
+        }
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(dct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(dct_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -291,6 +455,16 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_a, ta.data(), ta.size() / 2);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_b, tb.data(), tb.size() / 2);
     }
+    if (rc == ZAFB_OK && p->log2n == 10) {  // W_512^{k1*n2} laid out [k1][n2] for the N = 1024 warp kernel
+        std::vector<double> t(2 * 512);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+                t[2 * (k1 * 32 + n2)] = std::cos(a);
+                t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
+            }
+        rc = upload_c32(&p->d_tw_4step, t.data(), 512);
+    }
     // matrix path for everything the FFT path does not cover: Mat[k][m] = s_out[k] s_in[m] T[(a(m) b(k)) mod P]
     if (rc == ZAFB_OK && p->log2n < 2 && n >= 16 && n <= 8192) {
         p->ldk = (n + 3) & ~int64_t(3);
@@ -328,6 +502,7 @@ int zafb_dct_plan_destroy(zafb_dct_plan* p) {
     cudaFree(p->d_tw_b);
     cudaFree(p->d_mat_hi);
     cudaFree(p->d_mat_lo);
+    cudaFree(p->d_tw_4step);
     delete p;
     return ZAFB_OK;
 }
@@ -373,7 +548,28 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
         cudaFreeAsync(ws, st);
         return rc;
     }
-    if (p->log2n >= 2 && !p->force_direct) {
+    {
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                             stride % 4 == 0 && out_stride % 4 == 0;
+        const bool warp_ok = p->d_tw_4step != nullptr && p->type >= 2 && aligned;
+        if (p->force_direct == 4 && !warp_ok)
+            return fail(ZAFB_E_UNSUPPORTED, "dct warp kernel needs N = 1024, type 2..4, 16-byte aligned rows");
+        if (warp_ok && (p->force_direct == 0 || p->force_direct == 4)) {
+            const size_t smem = (512 + kDctWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            int64_t ctas = ceil_div(batch, kDctWarps);
+            if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+            const unsigned g = unsigned(ctas), b = kDctWarps * 32;
+#define ZAFB_DCT_WARP(MODE, DST)                                                                                  \
+    dct1024_warp_kernel<MODE, DST><<<g, b, smem, st>>>(x, batch, stride, p->d_tw_4step, p->d_tw_a, p->d_tw_b, out, out_stride)
+            if (p->type == 2) { if (p->kind) ZAFB_DCT_WARP(2, true); else ZAFB_DCT_WARP(2, false); }
+            else if (p->type == 3) { if (p->kind) ZAFB_DCT_WARP(3, true); else ZAFB_DCT_WARP(3, false); }
+            else { if (p->kind) ZAFB_DCT_WARP(4, true); else ZAFB_DCT_WARP(4, false); }
+#undef ZAFB_DCT_WARP
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        }
+    }
+    if (p->log2n >= 2 && (p->force_direct == 0 || p->force_direct == 3)) {
         int flags = 0;
         if (p->kind == 1) flags = (p->type == 2) ? (2 | 4) : (1 | 8);
         const size_t smem = size_t(n) * sizeof(float2) + size_t(n) * sizeof(float);
