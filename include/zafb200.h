@@ -158,6 +158,12 @@ int zafb_mel_plan_create(zafb_mel_plan** plan, const double* window, int64_t win
                          int64_t step_length, const double* filterbank, int64_t n_mels,
                          int64_t n_coef);
 int zafb_mel_plan_destroy(zafb_mel_plan* plan);
+/* How the filterbank is applied.  FUSED (default): banded multiply-add inside the STFT kernel, the
+ * spectrum never reaches HBM.  TENSOR: the dense contraction of zaf.py:373/445 (np.matmul with the
+ * densified filterbank) on the tcgen05 tensor cores in 3xTF32 (window_length 1024 only). */
+#define ZAFB_MEL_ROUTE_FUSED 0
+#define ZAFB_MEL_ROUTE_TENSOR 1
+int zafb_mel_plan_set_route(zafb_mel_plan* plan, int route);
 /* zaf.melspectrogram (zaf.py:369-375): out n_clips * n_mels * nt float32 in `layout`. */
 int zafb_melspectrogram_f32(const zafb_mel_plan* plan, const float* x, int64_t n_clips, int64_t ns,
                             int64_t clip_stride, float* out, int layout, void* stream);

@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="stft,istft,mdct,imdct,mel,mfcc,cqt,dct")
+    ap.add_argument("--only", default="stft,istft,mdct,imdct,mel,mfcc,meltc,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -155,7 +155,7 @@ def main():
         spec.free()
 
     # ---- cfg 3: melspectrogram + mfcc, 4096 clips x 5 s @ 16 kHz, N = 1024, hop = 256, 128 mels, 40 coefficients
-    if only & {"mel", "mfcc"}:
+    if only & {"mel", "mfcc", "meltc"}:
         clips, ns, n, hop, fs = max(1, int(4096 * args.scale)), 80000, 1024, 256, 16000
         w = hamming_periodic(n)
         fb = zaf.melfilterbank(fs, n, 128)
@@ -176,6 +176,17 @@ def main():
                 plan_mfcc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
             emit(line("mfcc", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
                       "FP32/shared-memory bound, not HBM (SURVEY 8d)"))
+        if "meltc" in only:  # the dense tensor-core route of the same two transforms
+            plan_mel_tc, _, _ = zaf._mel_plan(w, hop, fb, 0, "tensor")
+            plan_mfcc_tc, _, _ = zaf._mel_plan(w, hop, fb, 40, "tensor")
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_melspectrogram_f32(
+                plan_mel_tc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+            emit(line("melspectrogram-tensor", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 128 * 4, nl,
+                      "dense 3xTF32 tcgen05 filterbank product, spectra staged through L2"))
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_mfcc_f32(
+                plan_mfcc_tc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+            emit(line("mfcc-tensor", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
+                      "dense 3xTF32 tcgen05 filterbank + DCT products"))
         xd.free()
 
     # ---- cfg 5: cqtspectrogram, 512 clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8, 25 frames/s

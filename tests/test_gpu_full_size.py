@@ -1,0 +1,117 @@
+"""BASELINE.json's full batch sizes on one B200, checked through size-independent properties
+(round trips, TDAC, inverse pairs, batch == tiled single clips) -- the oracle is too slow for these
+sizes; small-size parity against it lives in test_gpu_stft.py / test_gpu_transforms.py.
+Inputs are built on the device from 32 distinct seeded clips tiled over the batch."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+DISTINCT = 32
+
+
+def tiled_batch(zaf, clips, ns, seed):
+    rng = np.random.default_rng(seed)
+    host = rng.uniform(-1, 1, (DISTINCT, ns)).astype(np.float32)
+    d = zaf.empty((clips, ns), np.float32)
+    lib = zaf._lib.lib()
+    for c0 in range(0, clips, DISTINCT):
+        n = min(DISTINCT, clips - c0)
+        zaf._lib.check(lib.zafb_memcpy_h2d(C.c_void_p(d.ptr + c0 * ns * 4), host.ctypes.data, n * ns * 4, None))
+    zaf.synchronize()
+    return d, host
+
+
+def test_cfg2_stft_istft_full_batch(zaf_gpu):
+    """1024 clips x 10 s @ 48 kHz, N=2048 hop=512: 961 536 frames; the round trip reproduces the input
+    through the reference's own shift identity for EVERY clip, and clips that
+    share an input have bit-identical spectra wherever they sit in the batch."""
+    zaf = zaf_gpu
+    n, hop, ns, clips = 2048, 512, 480000, 1024
+    w = oracle.hamming_periodic(n)
+    xd, host = tiled_batch(zaf, clips, ns, 20261017 + 2)
+    sd = zaf.stft(xd, w, hop)
+    assert sd.shape == (clips, n, 939)
+    yd = zaf.istft(sd, w, hop)
+    y = yd.to_host()
+    assert y.shape == (clips, 939 * hop - (n - hop))
+    shift = (n - hop) - n // 2
+    m = min(y.shape[1], ns - shift)
+    worst = 0.0
+    for c0 in range(0, clips, DISTINCT):
+        worst = max(worst, float(np.max(np.abs(y[c0:c0 + DISTINCT, :m] - host[:, shift:shift + m]))))
+    assert worst <= 2e-5, worst
+    # bitwise: clip c and clip c + 32 k hold the same samples
+    lib = zaf._lib.lib()
+    a = np.empty((939, n), np.complex64)
+    b = np.empty((939, n), np.complex64)
+    for c, k in ((3, 31), (17, 8)):
+        zaf._lib.check(lib.zafb_memcpy_d2h(a.ctypes.data, C.c_void_p(sd.ptr + c * a.nbytes), a.nbytes, None))
+        zaf._lib.check(lib.zafb_memcpy_d2h(b.ctypes.data, C.c_void_p(sd.ptr + (c + DISTINCT * k) * a.nbytes), a.nbytes, None))
+        zaf.synchronize()
+        assert np.array_equal(a, b)
+    # one clip of the full batch against the oracle
+    mx, l2 = oracle.parity_metrics(a.T, oracle.stft(host[17], w, hop))
+    assert mx <= 1e-5 and l2 <= 1e-5
+
+
+def test_cfg4_mdct_imdct_full_batch_tdac(zaf_gpu):
+    """2048 clips x 30 s @ 44.1 kHz, KBD N=2048: 2 648 064 frames; TDAC perfect reconstruction
+    imdct(mdct(x))[:ns] == x on clips spread over the batch."""
+    zaf = zaf_gpu
+    n, ns, clips = 2048, 1323000, 2048
+    w = oracle.kbd_window(n)
+    xd, host = tiled_batch(zaf, clips, ns, 20261017 + 4)
+    md = zaf.mdct(xd, w)
+    assert md.shape == (clips, 1024, 1293)
+    yd = zaf.imdct(md, w)
+    assert yd.shape == (clips, 1024 * 1292 - 1)
+    lib = zaf._lib.lib()
+    row = np.empty(yd.pitch, np.float32)
+    for c in (0, 1, 777, 1500, 2047):
+        zaf._lib.check(lib.zafb_memcpy_d2h(row.ctypes.data, C.c_void_p(yd.ptr + c * yd.pitch * 4), yd.pitch * 4, None))
+        zaf.synchronize()
+        assert np.max(np.abs(row[:ns] - host[c % DISTINCT])) <= 2e-5
+    xd.free(), md.free(), yd.free()
+
+
+def test_cfg3_mel_mfcc_full_batch(zaf_gpu):
+    """4096 clips x 5 s @ 16 kHz: 1 286 144 frames; every clip equals the result of its 32-clip tile
+    (bitwise) and one tile matches the oracle."""
+    zaf = zaf_gpu
+    clips, ns, n, hop = 4096, 80000, 1024, 256
+    w = oracle.hamming_periodic(n)
+    fb = zaf.melfilterbank(16000, n, 128)
+    xd, host = tiled_batch(zaf, clips, ns, 20261017 + 3)
+    mel = zaf.melspectrogram(xd, w, hop, fb).to_host()
+    cep = zaf.mfcc(xd, w, hop, fb, 40).to_host()
+    assert mel.shape == (clips, 128, 314) and cep.shape == (clips, 40, 314)
+    for c0 in range(DISTINCT, clips, DISTINCT):
+        assert np.array_equal(mel[c0:c0 + DISTINCT], mel[:DISTINCT])
+        assert np.array_equal(cep[c0:c0 + DISTINCT], cep[:DISTINCT])
+    dense = fb.toarray()
+    for c in (0, 31):
+        mx, l2 = oracle.parity_metrics(mel[c], oracle.melspectrogram(host[c], w, hop, dense))
+        assert mx <= 1e-5 and l2 <= 1e-5
+        mx, l2 = oracle.parity_metrics(cep[c], oracle.mfcc(host[c], w, hop, dense, 40))
+        assert mx <= 1e-5 and l2 <= 1e-5
+
+
+def test_dct_dst_million_vectors_inverse_pairs(zaf_gpu):
+    """2^20 vectors x 1024: the orthonormal inverse pairs II <-> III and IV <-> IV of zaf.py:872-895 recover the input."""
+    zaf = zaf_gpu
+    batch, n = 1 << 20, 1024
+    xd, host = tiled_batch(zaf, batch, n, 20261017 + 6)
+    lib = zaf._lib.lib()
+    back = np.empty((DISTINCT, n), np.float32)
+    for fn, fwd, inv in ((zaf.dct, 2, 3), (zaf.dct, 4, 4), (zaf.dst, 2, 3), (zaf.dst, 4, 4)):
+        yd = fn(xd, fwd)
+        zd = fn(yd, inv)
+        for c0 in (0, batch // 2, batch - DISTINCT):
+            zaf._lib.check(lib.zafb_memcpy_d2h(back.ctypes.data, C.c_void_p(zd.ptr + c0 * n * 4), back.nbytes, None))
+            zaf.synchronize()
+            assert np.max(np.abs(back - host)) <= 1e-5
+        yd.free(), zd.free()

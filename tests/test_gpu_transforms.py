@@ -237,6 +237,31 @@ def test_mel_mfcc_cfg3_batch_vs_oracle(zaf_gpu):
     assert_parity(got, ref)
 
 
+@pytest.mark.parametrize("n_mels,ncoef,fs", [(128, 40, 16000), (40, 13, 16000), (77, 60, 44100), (5, 3, 16000)])
+def test_mel_mfcc_tensor_core_route(zaf_gpu, n_mels, ncoef, fs):
+    """route="tensor": the filterbank (and the MFCC DCT) as dense 3xTF32 products on the tcgen05 tensor cores.
+    Same parity bar as the fused route; frame counts that are not multiples of the 128-row tile; more clips than
+    one 16 384-frame chunk holds."""
+    rng = np.random.default_rng(4242 + n_mels)
+    w = oracle.hamming_periodic(1024)
+    fb = zaf_gpu.melfilterbank(fs, 1024, n_mels)
+    dense = fb.toarray()
+    for clips, ns, hop in ((3, 20001, 256), (70, 80000, 256), (2, 5000, 512)):
+        x = rng.uniform(-1, 1, (clips, ns)).astype(np.float32)
+        x[0, 1000:3000] = 0.0
+        mel = zaf_gpu.melspectrogram(x, w, hop, fb, route="tensor")
+        cep = zaf_gpu.mfcc(x, w, hop, fb, ncoef, route="tensor")
+        for c in sorted({0, clips // 2, clips - 1}):
+            assert_parity(mel[c], oracle.melspectrogram(x[c], w, hop, dense), what=f"mel clip {c}")
+            assert_parity(cep[c], oracle.mfcc(x[c], w, hop, dense, ncoef), what=f"mfcc clip {c}")
+        fused = zaf_gpu.melspectrogram(x, w, hop, fb)
+        assert oracle.parity_metrics(mel, fused)[0] <= 2e-6
+    with pytest.raises(NotImplementedError):  # the dense route exists for window_length 1024 only
+        zaf_gpu.melspectrogram(x[0], oracle.hamming_periodic(2048), 512, zaf_gpu.melfilterbank(fs, 2048, n_mels), route="tensor")
+    with pytest.raises(ValueError):
+        zaf_gpu.melspectrogram(x[0], w, 256, fb, route="nope")
+
+
 @pytest.mark.parametrize("force", [1, 2])
 @pytest.mark.parametrize("n_mels,ncoef,fs", [(128, 40, 16000), (40, 13, 16000), (77, 60, 44100), (100, 99, 22050), (1, 1, 16000)])
 def test_mel_mfcc_1024_kernels_agree_with_oracle(zaf_gpu, force, n_mels, ncoef, fs):

@@ -346,20 +346,28 @@ def dst(audio_signal, dst_type):
 
 
 # ------------------------------------------------------------------ mel spectrogram / MFCC
-def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients):
+_MEL_ROUTES = {"fused": 0, "tensor": 1}
+
+
+def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused"):
     w = _window64(window_function)
     fb = mel_filterbank.toarray() if hasattr(mel_filterbank, "toarray") else np.asarray(mel_filterbank)  # zaf.py:373
     fb = np.ascontiguousarray(fb, dtype=np.float64)
     if fb.ndim != 2 or fb.shape[1] != len(w) // 2:
         raise ValueError(f"mel_filterbank must have shape (number_mels, window_length/2 = {len(w) // 2})")
-    key = ("mel", len(w), int(step_length), int(number_coefficients), w.tobytes(), fb.tobytes())
+    if route not in _MEL_ROUTES:
+        raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
+    key = ("mel", len(w), int(step_length), int(number_coefficients), route, w.tobytes(), fb.tobytes())
+    fresh = key not in _mel_plans._d
     plan = _mel_plans.get(key, w.ctypes.data, len(w), int(step_length), fb.ctypes.data, fb.shape[0],
                           int(number_coefficients))
+    if fresh and route != "fused":
+        _lib.check(_lib.lib().zafb_mel_plan_set_route(plan, _MEL_ROUTES[route]))
     return plan, w, fb.shape[0]
 
 
-def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, ncoef, rows_of, layout, stream):
-    plan, w, n_mels = _mel_plan(window_function, step_length, mel_filterbank, ncoef)
+def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, ncoef, rows_of, layout, stream, route):
+    plan, w, n_mels = _mel_plan(window_function, step_length, mel_filterbank, ncoef, route)
     lay = _layout_id(layout)
     rows = rows_of(n_mels)
     if isinstance(audio_signal, DeviceArray):
@@ -380,20 +388,23 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
     return view
 
 
-def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *, layout="frame_major", stream=None):
+def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *, layout="frame_major", stream=None,
+                   route="fused"):
     """Mel spectrogram -- drop-in for ``zaf.melspectrogram`` (zaf.py:324-375): filterbank times the
-    magnitude of STFT rows 1..N/2 (no DC, with Nyquist).  Returns (number_mels, number_times)."""
+    magnitude of STFT rows 1..N/2 (no DC, with Nyquist).  Returns (number_mels, number_times).
+    ``route="tensor"`` applies the filterbank as the dense product of zaf.py:373 on the tcgen05 tensor
+    cores (3xTF32, window_length 1024); the default fuses the banded filterbank into the STFT kernel."""
     return _mel_like("zafb_melspectrogram_f32", audio_signal, window_function, step_length, mel_filterbank, 0,
-                     lambda n_mels: n_mels, layout, stream)
+                     lambda n_mels: n_mels, layout, stream, route)
 
 
 def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coefficients, *,
-         layout="frame_major", stream=None):
+         layout="frame_major", stream=None, route="fused"):
     """MFCCs -- drop-in for ``zaf.mfcc`` (zaf.py:378-454): orthonormal DCT-II over the mel axis of
     ln(filterbank @ |STFT|^2 + eps), rows 1..number_coefficients.  Returns (number_coefficients, number_times)."""
     ncoef = int(number_coefficients)
     return _mel_like("zafb_mfcc_f32", audio_signal, window_function, step_length, mel_filterbank, ncoef,
-                     lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream)
+                     lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream, route)
 
 
 # ------------------------------------------------------------------ CQT

@@ -6,11 +6,13 @@
 // The filterbank arrives dense (the wrapper's .toarray(), exactly like zaf.py:373) and is packed at plan
 // creation into one contiguous band per row [first non-zero column, last non-zero column]: 882 weights
 // instead of 65 536 at BASELINE cfg 3.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
 
 #include "fft_core.cuh"
+#include "gemm_tc.cuh"
 #include "host_pipe.cuh"
 
 using namespace zafb;
@@ -39,6 +41,13 @@ struct zafb_mel_plan {
     int coef_pad = 0;               // n_coef rounded up to 32
     int half_mels = 0;              // ceil(n_mels / 2)
     int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
+    // tensor-core route (ZAFB_MEL_ROUTE_TENSOR): the filterbank and the MFCC DCT rows as dense TF32 hi/lo operands
+    int route = 0;
+    float* d_fb_hi = nullptr;       // n_mels x (n/2)
+    float* d_fb_lo = nullptr;
+    float* d_dct_hi = nullptr;      // n_coef x ld_mel
+    float* d_dct_lo = nullptr;
+    int64_t ld_mel = 0;             // n_mels rounded up to 4
 };
 
 namespace {
@@ -142,13 +151,24 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
 constexpr int kWarps = 8;
 constexpr int kMelWarpTile = 16 * kFft1024Pitch;  // float2 per warp: FFT transpose tile, then spectrum / log-mel scratch
 
-template <int MODE>  // 0 melspectrogram, 1 mfcc
+__device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    lo = __uint_as_float(l);
+}
+
+// SPLIT = true: the kernel stops after the spectrum and writes |X| (MODE 0) or |X|^2 (MODE 1) of bins 1..512 as TF32
+// hi/lo halves to out / out_lo ([frame][512]) -- the A operand of the tensor-core filterbank product.
+template <int MODE, bool SPLIT = false>  // 0 melspectrogram, 1 mfcc
 __global__ void __launch_bounds__(kWarps * 32, 2)
 mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                     const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
                     const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
                     int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
-                    int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames) {
+                    int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames,
+                    float* __restrict__ out_lo = nullptr) {
     extern __shared__ float2 smem2[];
     float2* s_tw = smem2;                                    // 512: W_512^{k1 n2}
     float* s_wt = reinterpret_cast<float*>(smem2 + 512);     // wt_total floats
@@ -221,6 +241,18 @@ mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride
         });
         __syncwarp();
 
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float hi, lo_part;
+                split_tf32_dev(s_spec[lane + 32 * i], hi, lo_part);
+                out[f * 512 + lane + 32 * i] = hi;
+                out_lo[f * 512 + lane + 32 * i] = lo_part;
+            }
+            __syncwarp();
+            continue;
+        }
+
         float mel[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -283,12 +315,32 @@ mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride
     }
 }
 
+// tensor route, MFCC: ln((mel_r + eps) / (mel_0 + eps)) of a [frames][n_mels] matrix as TF32 hi/lo halves (pitch ld);
+// the common term ln(mel_0 + eps) drops out of DCT rows >= 1 exactly (their weights sum to zero).
+__global__ void mel_log_split_kernel(const float* __restrict__ mel, int64_t frames, int n_mels, int64_t ld,
+                                     float* __restrict__ hi, float* __restrict__ lo) {
+    const int64_t total = frames * ld;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t f = i / ld;
+        const int r = int(i - f * ld);
+        float h = 0.f, l = 0.f;
+        if (r < n_mels) {
+            const float ref0 = mel[f * n_mels] + 2.220446049250313e-16f;
+            split_tf32_dev(logf((mel[f * n_mels + r] + 2.220446049250313e-16f) / ref0), h, l);
+        }
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel1024_warp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel1024_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -298,6 +350,68 @@ int upload_vec(T** dev, const std::vector<T>& v) {
     ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), (v.size() ? v.size() : 1) * sizeof(T)));
     ZAFB_CUDA(cudaMemcpy(*dev, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return ZAFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core route (north star: "the mel filterbank matmul on tensor cores ... a dense contraction"):
+//   (1) mel1024_warp_kernel<MODE, true>  frames -> |X| or |X|^2 of bins 1..512, split into TF32 hi/lo halves
+//   (2) gemm3xtf32 (tcgen05 / TMEM / TMA): [frames x 512] . filterbank[n_mels x 512]^T -> mel [frames x n_mels]
+//   (3) MFCC only: log-ratio + split, then gemm3xtf32 with the DCT-II rows 1..n_coef
+// in chunks of 16 384 frames so that the 64 MB of split spectra stay in the 126 MB L2 between (1) and (2).
+// The fused banded-FMA kernel above does 74x fewer multiply-adds and never writes the spectrum; it is the
+// default and the faster one (DESIGN.md section 4.3 has both timings) -- this route is the dense form.
+// ------------------------------------------------------------------------------------------
+int launch_tensor(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                  int64_t nt, float* out, cudaStream_t st) {
+    static bool pool_ready = false;
+    if (!pool_ready) {  // keep the stream-ordered scratch in the pool between calls
+        int dev = 0;
+        cudaMemPool_t pool;
+        uint64_t keep = UINT64_MAX;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_ready = true;
+    }
+    const int64_t total = n_clips * nt;
+    const int64_t clips_per_chunk = std::max<int64_t>(1, 16384 / (nt > 0 ? nt : 1));
+    const int64_t chunk_frames = std::min(total, clips_per_chunk * nt);
+    const int64_t n_mels = p->n_mels, ld = p->ld_mel, n_coef = p->n_coef;
+    // scratch: spectra hi/lo, and for MFCC the mel matrix and its log hi/lo
+    auto round64 = [](size_t v) { return (v + 63) & ~size_t(63); };  // keep every segment 256-byte aligned (TMA: 16)
+    const size_t spec_f = round64(size_t(chunk_frames) * 512);
+    const size_t mel_f = mode == 1 ? round64(size_t(chunk_frames) * size_t(n_mels)) : 0;
+    const size_t log_f = mode == 1 ? round64(size_t(chunk_frames) * size_t(ld)) : 0;
+    float* ws = nullptr;
+    ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (2 * spec_f + mel_f + 2 * log_f) * sizeof(float), st));
+    float *spec_hi = ws, *spec_lo = ws + spec_f, *mel_buf = ws + 2 * spec_f, *log_hi = mel_buf + mel_f, *log_lo = log_hi + log_f;
+    const size_t smem = 512 * sizeof(float2) + 16 + size_t(kWarps) * kMelWarpTile * sizeof(float2);
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    int rc = ZAFB_OK;
+    for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += clips_per_chunk) {
+        const int64_t nc = std::min(clips_per_chunk, n_clips - c0);
+        const int64_t frames = nc * nt;
+        int64_t ctas = ceil_div(frames, kWarps);
+        if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+        auto kern = mode == 0 ? mel1024_warp_kernel<0, true> : mel1024_warp_kernel<1, true>;
+        kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(x + c0 * clip_stride, ns, clip_stride, nt, int(p->hop),
+                                                         reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
+                                                         p->d_wt, p->d_lo, zero4, zero4, 0, nullptr, int(n_mels), 0, 0, 0, spec_hi, frames,
+                                                         spec_lo);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        float* mel_out = mode == 0 ? out + c0 * nt * n_mels : mel_buf;
+        rc = gemm3xtf32(spec_hi, spec_lo, 512, p->d_fb_hi, p->d_fb_lo, 512, mel_out, n_mels, frames, n_mels, 512, st);
+        if (rc == ZAFB_OK && mode == 1) {
+            int64_t blocks = ceil_div(frames * ld, 256);
+            if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+            mel_log_split_kernel<<<unsigned(blocks), 256, 0, st>>>(mel_buf, frames, int(n_mels), ld, log_hi, log_lo);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            rc = gemm3xtf32(log_hi, log_lo, ld, p->d_dct_hi, p->d_dct_lo, ld, out + c0 * nt * n_coef, n_coef, frames, n_coef,
+                            n_mels, st);
+        }
+    }
+    cudaFreeAsync(ws, st);
+    if (rc == ZAFB_OK) ZAFB_CUDA(cudaGetLastError());
+    return rc;
 }
 
 int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, float* out,
@@ -318,6 +432,11 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
         if (p->force_kernel == 2 && !ok)
             return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N=1024, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
+        if (p->route == ZAFB_MEL_ROUTE_TENSOR) {
+            if (!ok || p->d_fb_hi == nullptr)
+                return fail(ZAFB_E_UNSUPPORTED, "mel tensor-core route needs N=1024, <=128 mels, frame-major layout, even hop/stride");
+            return launch_tensor(p, mode, x, n_clips, ns, clip_stride, nt, out, static_cast<cudaStream_t>(stream));
+        }
         if (ok && p->force_kernel != 1) {
             const int wt_total = p->grp_off[3] + 32 * p->grp_len[3];
             const int dh_count = mode == 1 ? ((p->half_mels + 3) / 4) * p->coef_pad : 0;
@@ -332,7 +451,7 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
                 kern<<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                     x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                     p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
-                    int(p->n_coef), p->coef_pad, out, total);
+                    int(p->n_coef), p->coef_pad, out, total, nullptr);
                 ZAFB_LAUNCH_CHECK();
                 return ZAFB_OK;
             }
@@ -447,6 +566,24 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
         if (rc == ZAFB_OK) rc = upload_vec(&p->d_lo, lo4);
         if (rc == ZAFB_OK) rc = upload_vec(&p->d_dh, dh);
         p->warp_ok = rc == ZAFB_OK;
+        if (rc == ZAFB_OK) {  // dense TF32 hi/lo operands of the tensor-core route
+            p->ld_mel = (n_mels + 3) & ~int64_t(3);
+            std::vector<float> hi(size_t(n_mels) * 512), lo(hi.size());
+            split_tf32_host(fb, hi.size(), hi.data(), lo.data());
+            rc = upload_vec(&p->d_fb_hi, hi);
+            if (rc == ZAFB_OK) rc = upload_vec(&p->d_fb_lo, lo);
+            if (rc == ZAFB_OK && p->n_coef > 0) {
+                std::vector<double> d(size_t(p->n_coef) * p->ld_mel, 0.0);
+                for (int64_t i = 0; i < p->n_coef; ++i)
+                    for (int64_t mm = 0; mm < n_mels; ++mm)
+                        d[i * p->ld_mel + mm] = std::sqrt(2.0 / double(n_mels)) *
+                                                std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels));
+                std::vector<float> dhi(d.size()), dlo(d.size());
+                split_tf32_host(d.data(), d.size(), dhi.data(), dlo.data());
+                rc = upload_vec(&p->d_dct_hi, dhi);
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct_lo, dlo);
+            }
+        }
     }
     if (rc != ZAFB_OK) {
         zafb_mel_plan_destroy(p);
@@ -463,8 +600,21 @@ int zafb_mel_plan_force_kernel(zafb_mel_plan* p, int which) {
     return ZAFB_OK;
 }
 
+int zafb_mel_plan_set_route(zafb_mel_plan* p, int route) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(route == ZAFB_MEL_ROUTE_FUSED || route == ZAFB_MEL_ROUTE_TENSOR, "bad route %d", route);
+    if (route == ZAFB_MEL_ROUTE_TENSOR && p->d_fb_hi == nullptr)
+        return fail(ZAFB_E_UNSUPPORTED, "mel tensor-core route needs window_length 1024 and <= 128 mel rows");
+    p->route = route;
+    return ZAFB_OK;
+}
+
 int zafb_mel_plan_destroy(zafb_mel_plan* p) {
     if (!p) return ZAFB_OK;
+    cudaFree(p->d_fb_hi);
+    cudaFree(p->d_fb_lo);
+    cudaFree(p->d_dct_hi);
+    cudaFree(p->d_dct_lo);
     cudaFree(p->d_window);
     cudaFree(p->d_tw_half);
     cudaFree(p->d_tw_full);
