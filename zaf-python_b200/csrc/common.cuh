@@ -69,6 +69,12 @@ ZAFB_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
 ZAFB_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 ZAFB_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
+#ifdef __CUDACC__
+// pull one 128-byte line towards L2 (no register, no scoreboard entry): used to fetch a warp's NEXT frame while it
+// transforms the current one
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // ---------------------------------------------------------------- compile-time trigonometry
 // constexpr sin/cos in double (argument reduced to [0, pi/4], Taylor to < 1e-17) so that every
 // in-register twiddle is an immediate operand rounded once from float64.

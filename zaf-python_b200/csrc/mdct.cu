@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kWarps * 32, OCC)
 imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __restrict__ win_pairs,
                       const float2* __restrict__ tw4, const float2* __restrict__ pre,
                       const float2* __restrict__ post, int64_t runs_per_clip, int run_len, int64_t total_runs,
-                      int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned) {
+                      int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned, int prefetch) {
     extern __shared__ float2 smem2[];
     const float2* s_win = smem2;
     const float2* s_tw = smem2 + 1024;
@@ -259,6 +259,7 @@ imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* 
 
         for (int64_t j = h0 - 1; j < h1; ++j) {
             const float2* X = reinterpret_cast<const float2*>(spec + (clip * nt + j) * 1024) + lane;
+            if (prefetch && j + 1 < h1) prefetch_l2(reinterpret_cast<const char*>(X - lane + 512) + lane * 128);  // next frame: 32 lines
             float2 xp[16], v[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) xp[r] = __ldg(X + 32 * r);
@@ -553,7 +554,7 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
             const int y_aligned = (reinterpret_cast<uintptr_t>(y) % 8 == 0 && (n_clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
             imdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                 spec, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
-                int(best_len), total, len, y, y_stride, y_aligned);
+                int(best_len), total, len, y, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         }
