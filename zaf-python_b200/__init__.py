@@ -24,7 +24,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _pinned
 from ._device import (DeviceArray, Event, PinnedArray, Stream, device_count, empty, ensure_init, init,  # noqa: F401
                       launch_count, synchronize, to_device)
 from ._lib import LAYOUT_BIN_MAJOR, LAYOUT_FRAME_MAJOR, ZafbError  # noqa: F401
@@ -137,10 +137,10 @@ def _signal_batch(audio_signal):
 def _matrix_out(batch, rows, cols, dtype, layout, one):
     """Host result buffer for a (rows, cols) = (bins, frames) matrix per clip, and the view to return."""
     if layout == LAYOUT_FRAME_MAJOR:
-        mem = np.empty((batch, cols, rows), dtype=dtype)
+        mem = _pinned.empty((batch, cols, rows), dtype)
         view = np.swapaxes(mem, 1, 2)
     else:
-        mem = np.empty((batch, rows, cols), dtype=dtype)
+        mem = _pinned.empty((batch, rows, cols), dtype)
         view = mem
     return mem, (view[0] if one else view)
 
@@ -245,7 +245,7 @@ def istft(audio_stft, window_function, step_length, *, stream=None):
     if bins != n:
         raise ValueError(f"audio_stft has {bins} bins but the window has {n} samples")
     length = istft_geometry(n, nt, step_length)[2]
-    y = np.empty((batch, length), dtype=np.float32)
+    y = _pinned.empty((batch, length), np.float32)
     _lib.check(_lib.lib().zafb_istft_host_f32(plan, mem.ctypes.data, batch, nt, lay, y.ctypes.data, length))
     return y[0] if one else y
 
@@ -308,8 +308,7 @@ def imdct(audio_mdct, window_function, *, stream=None):
     if bins * 2 != n:
         raise ValueError("audio_mdct rows must equal window_length/2")
     length = imdct_geometry(bins, nt)[1]
-    y = np.empty((batch, length), dtype=np.float32)
-    ensure_init()
+    y = _pinned.empty((batch, length), np.float32)
     _lib.check(_lib.lib().zafb_imdct_host_f32(plan, mem.ctypes.data, batch, nt, lay, y.ctypes.data, length))
     return y[0] if one else y
 
@@ -329,7 +328,7 @@ def _dct_like(audio_signal, kind, dtype_code):
     x, one = _signal_batch(audio_signal)
     batch, n = x.shape
     plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
-    out = np.empty((batch, n), dtype=np.float32)
+    out = _pinned.empty((batch, n), np.float32)
     _lib.check(_lib.lib().zafb_dct_host_f32(plan, x.ctypes.data, batch, n, out.ctypes.data, n))
     return out[0] if one else out
 
