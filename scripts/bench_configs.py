@@ -93,7 +93,7 @@ def main():
         print(json.dumps(d), flush=True)
 
     # ---- cfg 2: stft + istft, 1024 clips x 10 s @ 48 kHz, N = 2048, hop = 512
-    if only & {"stft", "istft"}:
+    if only & {"stft", "istft", "stftbin"}:
         clips, ns, n, hop = max(1, int(1024 * args.scale)), 480000, 2048, 512
         w = hamming_periodic(n)
         xd, _ = device_batch(clips, ns, 20261017 + 2)
@@ -110,6 +110,15 @@ def main():
         ms, _, nl = timeit(f_stft, args.steps)
         if "stft" in only:
             emit(line("stft", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * n * 8, nl))
+        if "stftbin" in only:  # the reference's C-order memory (bin-major)
+            def f_stft_bin(stream):
+                zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 1, stream.ptr))
+
+            ms, _, nl = timeit(f_stft_bin, max(2, args.steps // 5))
+            emit(line("stft-bin-major", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * n * 8, nl,
+                      "layout = BIN_MAJOR: [clip][bin][frame], the reference's C order"))
+            f_stft(stream=zaf.Stream())  # leave a frame-major spectrum behind for the istft leg
+            zaf.synchronize()
         if "istft" in only:
             ylen = zaf.istft_geometry(n, nt, hop)[2]
             yd = zaf.empty((clips, ylen), np.float32)

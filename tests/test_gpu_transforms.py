@@ -375,3 +375,38 @@ def test_cqt_small_kernels_vs_oracle(zaf_gpu):
     x = rng.uniform(-1, 1, 6000).astype(np.float32)
     k = scipy.sparse.csr_matrix(dense)
     assert_parity(zaf_gpu.cqtspectrogram(x, 8000, 100, k), oracle.cqtspectrogram(x, 8000, 100, k))
+
+
+# ------------------------------------------------------------------------------- layouts
+def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
+    """layout="bin_major" (the reference's C-order memory) on the sizes served by the warp kernels goes through a
+    tiled transpose: results must equal the frame-major ones bit for bit, in C-contiguous memory, also when the batch
+    is cut into several scratch chunks, and the inverse transforms must accept C-order input."""
+    monkeypatch.setenv("ZAFB_TRANSPOSE_CHUNK_MB", "1")
+    rng = np.random.default_rng(99)
+    x = rng.uniform(-1, 1, (5, 30011)).astype(np.float32)
+    w = oracle.hamming_periodic(2048)
+    a = zaf_gpu.stft(x, w, 512)
+    b = zaf_gpu.stft(x, w, 512, layout="bin_major")
+    assert b.flags.c_contiguous and not a.flags.c_contiguous and np.array_equal(a, b)
+    assert np.array_equal(zaf_gpu.istft(b, w, 512), zaf_gpu.istft(a, w, 512))
+    assert_parity(b[3], oracle.stft(x[3], w, 512))
+    wk = oracle.kbd_window(2048)
+    ma = zaf_gpu.mdct(x, wk)
+    mb = zaf_gpu.mdct(x, wk, layout="bin_major")
+    assert mb.flags.c_contiguous and np.array_equal(ma, mb)
+    assert np.array_equal(zaf_gpu.imdct(mb, wk), zaf_gpu.imdct(ma, wk))
+    w1 = oracle.hamming_periodic(1024)
+    fb = zaf_gpu.melfilterbank(16000, 1024, 128)
+    for route in ("fused", "tensor"):
+        assert np.array_equal(zaf_gpu.melspectrogram(x, w1, 256, fb, layout="bin_major", route=route),
+                              zaf_gpu.melspectrogram(x, w1, 256, fb, route=route))
+        assert np.array_equal(zaf_gpu.mfcc(x, w1, 256, fb, 40, layout="bin_major", route=route),
+                              zaf_gpu.mfcc(x, w1, 256, fb, 40, route=route))
+    # device-resident, one chunk (even clip pitch, so the same warp kernels serve it)
+    monkeypatch.delenv("ZAFB_TRANSPOSE_CHUNK_MB")
+    x2 = np.ascontiguousarray(x[:, :30010])
+    a2 = zaf_gpu.stft(x2, w, 512)
+    sd = zaf_gpu.stft(zaf_gpu.to_device(x2), w, 512, layout="bin_major")
+    assert not sd.transposed and np.array_equal(sd.to_host(), a2)
+    assert np.array_equal(zaf_gpu.istft(sd, w, 512).to_host(), zaf_gpu.istft(a2, w, 512))

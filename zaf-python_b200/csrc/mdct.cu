@@ -18,6 +18,7 @@
 
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
+#include "transpose.cuh"
 
 using namespace zafb;
 
@@ -485,20 +486,27 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
                              reinterpret_cast<uintptr_t>(out) % 8 == 0;
-        const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
+        const bool warp_ok = p->n == 2048 && aligned;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N=2048, frame-major layout, even clip_stride, 8-byte aligned x/out");
+            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N=2048, even clip_stride, 8-byte aligned x/out");
         if (warp_ok && p->force_kernel != 1) {
-            const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
-            // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
-            constexpr int occ = 3;
-            int64_t ctas = ceil_div(total, kWarps);
-            if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-            mdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
-                x, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
-                out, total);
-            ZAFB_LAUNCH_CHECK();
-            return ZAFB_OK;
+            auto run = [&](const float* xs, int64_t clips, float* dst) -> int {
+                const int64_t frames = clips * nt;
+                const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+                // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
+                constexpr int occ = 3;
+                int64_t ctas = ceil_div(frames, kWarps);
+                if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
+                mdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
+                    xs, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
+                    dst, frames);
+                ZAFB_LAUNCH_CHECK();
+                return ZAFB_OK;
+            };
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, out);
+            return bin_major_from_frame_major(out, n_clips, nt, int64_t(1024), st, [&](int64_t c0, int64_t n, float* scratch) {
+                return run(x + c0 * clip_stride, n, scratch);
+            });
         }
     }
     if (p->log2m >= 1) {
@@ -530,33 +538,40 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
     {
-        const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
+        const bool warp_ok = p->n == 2048 && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N=2048, frame-major layout, 8-byte aligned spectra");
+            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N=2048, 8-byte aligned spectra");
         if (warp_ok && p->force_kernel != 1) {
-            const int64_t nblocks = nt - 1;
-            constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
-            const int64_t resident_warps = int64_t(sm_count()) * occ * kWarps;
-            int64_t best_len = nblocks, best_cost = INT64_MAX;
-            for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
-                const int64_t runs = n_clips * ceil_div(nblocks, l);
-                const int64_t cost = ceil_div(runs, resident_warps) * (l + 1);
-                if (cost < best_cost || (cost == best_cost && l > best_len)) {
-                    best_cost = cost;
-                    best_len = l;
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            auto run = [&](const float* sp, int64_t clips, float* yy) -> int {
+                const int64_t nblocks = nt - 1;
+                constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
+                const int64_t resident_warps = int64_t(sm_count()) * occ * kWarps;
+                int64_t best_len = nblocks, best_cost = INT64_MAX;
+                for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
+                    const int64_t runs = clips * ceil_div(nblocks, l);
+                    const int64_t cost = ceil_div(runs, resident_warps) * (l + 1);
+                    if (cost < best_cost || (cost == best_cost && l > best_len)) {
+                        best_cost = cost;
+                        best_len = l;
+                    }
                 }
-            }
-            const int64_t runs_per_clip = ceil_div(nblocks, best_len);
-            const int64_t total = n_clips * runs_per_clip;
-            int64_t ctas = ceil_div(total, kWarps);
-            if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-            const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
-            const int y_aligned = (reinterpret_cast<uintptr_t>(y) % 8 == 0 && (n_clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
-            imdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-                spec, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
-                int(best_len), total, len, y, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));
-            ZAFB_LAUNCH_CHECK();
-            return ZAFB_OK;
+                const int64_t runs_per_clip = ceil_div(nblocks, best_len);
+                const int64_t total = clips * runs_per_clip;
+                int64_t ctas = ceil_div(total, kWarps);
+                if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
+                const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+                const int y_aligned = (reinterpret_cast<uintptr_t>(yy) % 8 == 0 && (clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
+                imdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
+                    sp, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
+                    int(best_len), total, len, yy, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));
+                ZAFB_LAUNCH_CHECK();
+                return ZAFB_OK;
+            };
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(spec, n_clips, y);
+            return frame_major_from_bin_major(spec, n_clips, nt, int64_t(1024), st, [&](int64_t c0, int64_t nc, const float* scratch) {
+                return run(scratch, nc, y + c0 * y_stride);
+            });
         }
     }
     const int64_t hop_blocks = nt - 1;  // hop-blocks 1 .. nt-1 are written

@@ -14,6 +14,7 @@
 #include "fft_core.cuh"
 #include "gemm_tc.cuh"
 #include "host_pipe.cuh"
+#include "transpose.cuh"
 
 using namespace zafb;
 
@@ -429,6 +430,14 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
+        if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->warp_ok && aligned && p->force_kernel != 1) {
+            // the reference's C-order memory: the frame-major kernels into scratch, then a tiled transpose
+            return bin_major_from_frame_major(out, n_clips, nt, rows, static_cast<cudaStream_t>(stream),
+                                              [&](int64_t c0, int64_t n, float* scratch) {
+                                                  return launch(p, mode, x + c0 * clip_stride, n, ns, clip_stride, scratch,
+                                                                ZAFB_LAYOUT_FRAME_MAJOR, stream);
+                                              });
+        }
         const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
         if (p->force_kernel == 2 && !ok)
             return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N=1024, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");

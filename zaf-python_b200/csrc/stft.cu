@@ -21,6 +21,7 @@
 
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
+#include "transpose.cuh"
 
 namespace zafb {}
 using namespace zafb;
@@ -611,23 +612,31 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     float2* o = reinterpret_cast<float2*>(out);
 
     const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
-    const bool warp_ok = p->n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
+    const bool warp_ok = p->n == 2048 && aligned;
     if (p->force_kernel == 2 && !warp_ok)
-        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, frame-major layout, even hop/stride, 8-byte aligned x");
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
-        const size_t smem = (2048 + kWarpsPerCta * 32 * kFft1024Pitch) * sizeof(float2);
-        int64_t ctas = ceil_div(total, kWarpsPerCta);
-        const int64_t resident = int64_t(sms) * 2;
-        if (ctas > resident) ctas = resident;
         // measured on cfg 2 (B200): direct streaming stores 3.09 ms, TMA bulk stores 3.13-3.20 ms, L2 prefetch of the
         // next frame +8 %: the defaults are the fastest combination, the switches stay for experiments
-        auto kern = env_flag("ZAFB_STFT_BULK", 0) && reinterpret_cast<uintptr_t>(out) % 16 == 0 ? stft2048_warp_kernel<true>
-                                                                                                 : stft2048_warp_kernel<false>;
-        kern<<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
-            x, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, o, total,
-            env_flag("ZAFB_STFT_PREFETCH", 0));
-        ZAFB_LAUNCH_CHECK();
-        return ZAFB_OK;
+        const int bulk = env_flag("ZAFB_STFT_BULK", 0), prefetch = env_flag("ZAFB_STFT_PREFETCH", 0);
+        auto run = [&](const float* xs, int64_t clips, float2* dst) -> int {
+            const int64_t frames = clips * nt;
+            const size_t smem = (2048 + kWarpsPerCta * 32 * kFft1024Pitch) * sizeof(float2);
+            int64_t ctas = ceil_div(frames, kWarpsPerCta);
+            const int64_t resident = int64_t(sms) * 2;
+            if (ctas > resident) ctas = resident;
+            auto kern = bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft2048_warp_kernel<true> : stft2048_warp_kernel<false>;
+            kern<<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+                xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
+                prefetch);
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        };
+        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
+        // the reference's C-order memory: frame-major into scratch, then a tiled transpose (transpose.cuh)
+        return bin_major_from_frame_major(o, n_clips, nt, int64_t(2048), st, [&](int64_t c0, int64_t n, float2* scratch) {
+            return run(x + c0 * clip_stride, n, scratch);
+        });
     }
     const int64_t grid = total < int64_t(sms) * 32 ? total : int64_t(sms) * 32;
     if (p->log2n >= 1) {
@@ -665,17 +674,21 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     {
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
                              (n_clips <= 1 || y_stride % 2 == 0);
-        const bool warp_ok = n == 2048 && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned &&
-                             (p->hop == 256 || p->hop == 512 || p->hop == 1024);
+        const bool warp_ok = n == 2048 && aligned && (p->hop == 256 || p->hop == 512 || p->hop == 1024);
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED,
-                        "istft warp kernel needs N=2048, hop in {256,512,1024}, frame-major layout, even y_stride");
+            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N=2048, hop in {256,512,1024}, even y_stride");
         if (warp_ok && p->force_kernel != 1) {
-            const float2* s2 = reinterpret_cast<const float2*>(spec);
             cudaStream_t st = static_cast<cudaStream_t>(stream);
-            if (p->hop == 1024) return launch_istft2048<2>(p, s2, n_clips, nt, y, y_stride, st);
-            if (p->hop == 512) return launch_istft2048<4>(p, s2, n_clips, nt, y, y_stride, st);
-            return launch_istft2048<8>(p, s2, n_clips, nt, y, y_stride, st);
+            auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
+                if (p->hop == 1024) return launch_istft2048<2>(p, s2, clips, nt, yy, y_stride, st);
+                if (p->hop == 512) return launch_istft2048<4>(p, s2, clips, nt, yy, y_stride, st);
+                return launch_istft2048<8>(p, s2, clips, nt, yy, y_stride, st);
+            };
+            const float2* s2 = reinterpret_cast<const float2*>(spec);
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y);
+            return frame_major_from_bin_major(s2, n_clips, nt, int64_t(2048), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
+                return run(scratch, nc, y + c0 * y_stride);
+            });
         }
     }
     // tile: about 4 windows of output, bounded by shared memory (2 n float2 + tile floats)
