@@ -215,6 +215,12 @@ int zafb_dist_gather_rows(zafb_comm* comm, const void* src, void* dst_root, int6
 int zafb_dist_allgather_rows(zafb_comm* comm, const void* src, void* dst, int64_t n_rows,
                              int64_t row_bytes, void* stream);
 int zafb_dist_max_f64(zafb_comm* comm, double* value, void* stream);  /* max over ranks, synchronises */
+/* Peer memory (CUDA IPC, same node): the root exports a cudaMalloc'ed buffer (the START of the
+ * allocation), peers map it and use the mapped address as the output pointer of any *_f32 entry
+ * point: the transform's own stores cross NVLink, no separate gather. */
+int zafb_dist_peer_export(const void* dev_ptr, void* handle64);
+int zafb_dist_peer_open(const void* handle64, void** mapped);
+int zafb_dist_peer_close(void* mapped);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,8 @@ S="--scale 0.125 --steps 2"
 full istft2048 istft2048 3 python scripts/bench_configs.py --only istft $S
 full mdct2048 '^mdct2048' 3 python scripts/bench_configs.py --only mdct $S
 full imdct2048 imdct2048 3 python scripts/bench_configs.py --only imdct $S
+full dct1024 dct1024_warp 3 python scripts/bench_configs.py --only dct $S
+full transpose transpose_tile 1 python scripts/bench_configs.py --only stftbin $S
 for k in ${EXTRA_KERNELS:-}; do
     full $k $k 2 python scripts/bench_configs.py --only ${EXTRA_ONLY:-mel,mfcc,cqt,dct} $S
 done

@@ -88,4 +88,4 @@ def test_two_rank_split_merge_bitwise(zaf_gpu, tmp_path):
     assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
     res = [json.load(open(f"{out}.{r}")) for r in range(2)]
     assert all(r["max"] == 2.0 and r["table_ok"] and r["allgather_bitwise"] for r in res), res
-    assert res[0]["gather_bitwise"] and res[0]["shape"] == [11, 2048, 48], res
+    assert res[0]["gather_bitwise"] and res[0]["direct_bitwise"] and res[0]["shape"] == [11, 2048, 48], res

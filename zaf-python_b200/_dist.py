@@ -168,6 +168,42 @@ class Communicator:
                                                        self._row_bytes(row_shape, shard.dtype), self._sp(stream)))
         return dst
 
+    # ------------------------------------------------------------------ peer memory
+    def map_from_root(self, array, shape, dtype, root: int = 0, transposed: bool = False) -> DeviceArray:
+        """Collective.  Every rank receives a DeviceArray of memory shape ``shape`` that ALIASES the root's
+        ``array`` (a whole ``zaf.empty`` / ``to_device`` allocation): the root gets ``array`` itself, the peers a CUDA-IPC
+        mapping of it.  Passing (a row range of) it as ``out=`` of a transform makes the kernel store its result
+        straight into the root's HBM over NVLink -- the merge needs no separate collective.  Release with ``unmap``."""
+        from ._device import to_device
+
+        handle = np.zeros(64, np.uint8)
+        if self.rank == root:
+            _lib.check(_lib.lib().zafb_dist_peer_export(C.c_void_p(array.ptr), handle.ctypes.data))
+        hd = to_device(handle)
+        self.broadcast(hd, root)
+        handle = hd.to_host()
+        hd.free()
+        if self.rank == root:
+            return array
+        mapped = C.c_void_p()
+        _lib.check(_lib.lib().zafb_dist_peer_open(handle.ctypes.data, C.byref(mapped)))
+        view = DeviceArray(shape, dtype, ptr=mapped.value, transposed=transposed)
+        view._peer_mapping = mapped.value
+        return view
+
+    def unmap(self, view: DeviceArray):
+        m = getattr(view, "_peer_mapping", None)
+        if m:
+            _lib.check(_lib.lib().zafb_dist_peer_close(C.c_void_p(m)))
+            view._peer_mapping = None
+
+    @staticmethod
+    def rows(array: DeviceArray, begin: int, end: int) -> DeviceArray:
+        """Non-owning view of rows [begin, end) of the leading axis of ``array``'s memory."""
+        row_bytes = int(np.prod(array.mem_shape[1:], dtype=np.int64)) * array.dtype.itemsize
+        return DeviceArray((end - begin,) + tuple(array.mem_shape[1:]), array.dtype, ptr=array.ptr + begin * row_bytes,
+                           owner=array, transposed=array.transposed)
+
     def max(self, value: float, stream=None) -> float:
         """Max over ranks of a host scalar (device-timed durations); synchronises the stream."""
         v = C.c_double(float(value))

@@ -87,6 +87,9 @@ PROTOTYPES = {
     "zafb_dist_gather_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "zafb_dist_allgather_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "zafb_dist_max_f64": (_int, [_vp, C.POINTER(C.c_double), _vp]),
+    "zafb_dist_peer_export": (_int, [_vp, _vp]),
+    "zafb_dist_peer_open": (_int, [_vp, _pvp]),
+    "zafb_dist_peer_close": (_int, [_vp]),
 }
 # not part of the public header: test hooks
 _PRIVATE = {

@@ -270,6 +270,34 @@ int zafb_dist_max_f64(zafb_comm* c, double* value, void* stream) {
     return ZAFB_OK;
 }
 
+// ------------------------------------------------------------------ peer memory (same node, one process per GPU)
+// The merge without a separate collective: the root exports its result buffer, every peer maps it
+// (CUDA IPC; NVLink peer access is enabled lazily by the driver) and passes the mapped address as the
+// OUTPUT pointer of its transform -- the kernel's own stores travel over NVLink / NVSwitch, so the
+// transfer overlaps the math frame by frame and the spectrum never touches the sender's HBM.
+int zafb_dist_peer_export(const void* dev_ptr, void* handle64) {
+    ZAFB_REQUIRE(dev_ptr != nullptr && handle64 != nullptr, "pointer/handle is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    ZAFB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle64, &h, sizeof(h));
+    return ZAFB_OK;
+}
+
+int zafb_dist_peer_open(const void* handle64, void** mapped) {
+    ZAFB_REQUIRE(handle64 != nullptr && mapped != nullptr, "handle/mapped is NULL");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    ZAFB_CUDA(cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    return ZAFB_OK;
+}
+
+int zafb_dist_peer_close(void* mapped) {
+    if (!mapped) return ZAFB_OK;
+    ZAFB_CUDA(cudaIpcCloseMemHandle(mapped));
+    return ZAFB_OK;
+}
+
 int zafb_dist_rank(const zafb_comm* c, int* rank, int* world) {
     ZAFB_REQUIRE(c != nullptr, "comm is NULL");
     if (rank) *rank = c->rank;
