@@ -64,8 +64,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // BULK = true: the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame (issued by
 // one lane, executed by the TMA engine) instead of 64 st.global per lane.
-template <bool BULK>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+template <bool BULK, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                      const float2* __restrict__ win_half, const float2* __restrict__ tw4,
                      const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int prefetch) {
@@ -77,22 +77,27 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
     const int warp = tid >> 5;
     float2* s_buf = smem + 2048 + warp * (32 * kFft1024Pitch);
 
-    for (int i = tid; i < 1024; i += kWarpsPerCta * 32) {
+    for (int i = tid; i < 1024; i += WARPS * 32) {
         s_win[i] = win_half[i];
         s_tw[i] = tw4[i];
     }
     const float2 c_lane = tw_full[lane];  // W_2048^lane
     __syncthreads();
 
-    for (int64_t f = int64_t(blockIdx.x) * kWarpsPerCta + warp; f < total_frames;
-         f += int64_t(gridDim.x) * kWarpsPerCta) {
+    // prefetch bit 1: each CTA sweeps its own contiguous range of frames instead of the grid-stride interleave
+    const bool ranged = (prefetch & 2) != 0;
+    const int64_t per_cta = (total_frames + gridDim.x - 1) / gridDim.x;
+    const int64_t f_begin = ranged ? int64_t(blockIdx.x) * per_cta + warp : int64_t(blockIdx.x) * WARPS + warp;
+    const int64_t f_end = ranged ? min(total_frames, (int64_t(blockIdx.x) + 1) * per_cta) : total_frames;
+    const int64_t f_step = ranged ? WARPS : int64_t(gridDim.x) * WARPS;
+    for (int64_t f = f_begin; f < f_end; f += f_step) {
         const int64_t clip = f / nt;
         const int64_t j = f - clip * nt;
         const int64_t start = j * hop - 1024;  // first sample of the frame (may be < 0)
         const float* xc = x + clip * clip_stride;
 
-        if (prefetch) {  // this warp's next frame (8 KB = 64 lines, 2 per lane) towards L2 while this one is transformed
-            const int64_t fn = f + int64_t(gridDim.x) * kWarpsPerCta;
+        if (prefetch & 1) {  // this warp's next frame (8 KB = 64 lines, 2 per lane) towards L2 while this one is transformed
+            const int64_t fn = f + int64_t(gridDim.x) * WARPS;
             if (fn < total_frames) {
                 const int64_t cn = fn / nt;
                 const int64_t sn = (fn - cn * nt) * hop - 1024;
@@ -481,8 +486,9 @@ __global__ void istft_tile_kernel(const float2* __restrict__ spec, int64_t nt, i
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
-    ZAFB_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(stft2048_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -621,12 +627,16 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
         const int bulk = env_flag("ZAFB_STFT_BULK", 0), prefetch = env_flag("ZAFB_STFT_PREFETCH", 0);
         auto run = [&](const float* xs, int64_t clips, float2* dst) -> int {
             const int64_t frames = clips * nt;
-            const size_t smem = (2048 + kWarpsPerCta * 32 * kFft1024Pitch) * sizeof(float2);
-            int64_t ctas = ceil_div(frames, kWarpsPerCta);
+            // warps per CTA (2 CTAs per SM), measured on cfg 2: 4 -> 3.40 ms, 6 -> 3.04, 8 -> 3.11, 10 (96 registers) -> 3.36:
+            // more frames in flight do not help, the write stream is the limit
+            const int warps = (!bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
+            const size_t smem = (2048 + warps * 32 * kFft1024Pitch) * sizeof(float2);
+            int64_t ctas = ceil_div(frames, warps);
             const int64_t resident = int64_t(sms) * 2;
             if (ctas > resident) ctas = resident;
-            auto kern = bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft2048_warp_kernel<true> : stft2048_warp_kernel<false>;
-            kern<<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+            auto kern = warps == 6 ? stft2048_warp_kernel<false, 6>
+                        : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft2048_warp_kernel<true, 8> : stft2048_warp_kernel<false, 8>);
+            kern<<<static_cast<unsigned>(ctas), warps * 32, smem, st>>>(
                 xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
                 prefetch);
             ZAFB_LAUNCH_CHECK();
