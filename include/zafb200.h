@@ -76,6 +76,10 @@ int zafb_event_destroy(void* event);
 int zafb_event_record(void* event, void* stream);
 int zafb_event_sync(void* event);
 int zafb_event_elapsed_ms(void* start, void* stop, float* ms);
+/* zaf.wavread's normalisation (zaf.py:1199-1202) on the device: interleaved (frame, channel) int16 PCM ->
+ * planar fp32 [channel][frame] (row pitch out_stride), x / 2^15 exactly; mono != 0 writes the channel mean instead. */
+int zafb_pcm16_to_f32(const int16_t* pcm_dev, int64_t frames, int channels, int mono, float* out_dev,
+                      int64_t out_stride, void* stream);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t zafb_launch_count(void);
 

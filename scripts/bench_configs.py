@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="stft,istft,mdct,imdct,mel,mfcc,meltc,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,mdct,imdct,mel,mfcc,meltc,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -91,6 +91,23 @@ def main():
     def emit(d):
         out_lines.append(d)
         print(json.dumps(d), flush=True)
+
+    # ---- cfg 1: the reference's own CPU-runnable case, ONE clip through the drop-in host call (wall clock, H2D + D2H inside)
+    if "cfg1" in only:
+        import time
+
+        ns, n, hop = 480000, 2048, 1024
+        w = hamming_periodic(n)
+        x = np.random.default_rng(20261017 + 1).uniform(-1, 1, ns).astype(np.float32)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        best = 1e9
+        for _ in range(30):
+            t0 = time.perf_counter()
+            spec = zaf.stft(x, w, hop)
+            best = min(best, time.perf_counter() - t0)
+        assert spec.shape == (n, nt)
+        emit(line("stft-cfg1-host-call", "cfg1: 1 clip x 10 s @ 48 kHz, N=2048 hop=1024, zaf.stft(x, w, hop) with NumPy in/out", nt,
+                  "frames", best * 1e3, ns * 4 + nt * n * 8, 1, "end-to-end latency of one drop-in call (best of 30), not a device-resident rate"))
 
     # ---- cfg 2: stft + istft, 1024 clips x 10 s @ 48 kHz, N = 2048, hop = 512
     if only & {"stft", "istft", "stftbin"}:
@@ -131,6 +148,26 @@ def main():
             yd.free()
         xd.free()
         spec.free()
+
+    # ---- cfg 3 shape through plain stft / istft (N = 1024, hop = 256): the second window length with warp kernels
+    if "stft1024" in only:
+        clips, ns, n, hop = max(1, int(4096 * args.scale)), 80000, 1024, 256
+        w = hamming_periodic(n)
+        xd, _ = device_batch(clips, ns, 20261017 + 3)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        spec = zaf.empty((clips, nt, n), np.complex64)
+        plan, _ = zaf._stft_plan(w, hop)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        cfg = f"cfg3 shape: {clips} clips x 5 s @ 16 kHz, N=1024 hop=256"
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_stft_f32(
+            plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 0, s.ptr)), args.steps)
+        emit(line("stft-1024", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * n * 8, nl))
+        ylen = zaf.istft_geometry(n, nt, hop)[2]
+        yd = zaf.empty((clips, ylen), np.float32)
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_istft_f32(
+            plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, s.ptr)), args.steps)
+        emit(line("istft-1024", cfg, clips * nt, "frames", ms, clips * nt * n * 8 + clips * ylen * 4, nl))
+        xd.free(), spec.free(), yd.free()
 
     # ---- cfg 4: mdct + imdct, 2048 clips x 30 s @ 44.1 kHz, KBD N = 2048
     if only & {"mdct", "imdct"}:

@@ -35,7 +35,7 @@ from ._dist import shard_range  # noqa: F401
 __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
     "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
-    "to_device", "empty", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count",
+    "to_device", "empty", "from_pcm16", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count",
     "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry", "dist", "shard_range",
 ]
 
@@ -74,6 +74,36 @@ def cqt_geometry(number_samples, sampling_frequency, time_resolution, fft_length
     round-half-to-even on the float quotient, as in the reference."""
     step = round(sampling_frequency / time_resolution)
     return (step,) + _geom("zafb_cqt_geometry", 3, number_samples, step, fft_length)
+
+
+# ------------------------------------------------------------------ PCM input
+def from_pcm16(pcm, *, mono=False, stream=None):
+    """int16 PCM, shape (number_samples,) or (number_samples, number_channels) as ``scipy.io.wavfile.read`` returns it,
+    to a float32 DeviceArray normalised like ``zaf.wavread`` (zaf.py:1199-1202: x / 2**15), converted ON the GPU so only
+    the 16-bit samples cross PCIe.  Result: (number_channels, number_samples) -- one clip per channel, ready for the
+    batched transforms -- or, with ``mono=True``, the channel mean (number_samples,) of the reference's examples."""
+    a = np.ascontiguousarray(pcm)
+    if a.dtype != np.int16 or a.ndim not in (1, 2):
+        raise ValueError("pcm must be an int16 array of shape (number_samples,) or (number_samples, number_channels)")
+    frames = a.shape[0]
+    channels = 1 if a.ndim == 1 else a.shape[1]
+    ensure_init()
+    raw = to_device(a.reshape(-1), stream=stream)
+    pitch = _even(frames)
+    if mono or a.ndim == 1:
+        out = DeviceArray((frames,), np.float32)
+    else:
+        out = DeviceArray((channels, pitch), np.float32, cols=frames)
+    try:
+        _lib.check(_lib.lib().zafb_pcm16_to_f32(C.c_void_p(raw.ptr), frames, channels, 1 if (mono or a.ndim == 1) else 0,
+                                                C.c_void_p(out.ptr), pitch, _stream_ptr(stream)))
+        if stream is None:
+            synchronize()
+        else:
+            stream.synchronize()
+    finally:
+        raw.free()
+    return out
 
 
 # ------------------------------------------------------------------ plan caches

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "zafb_event_record": (_int, [_vp, _vp]),
     "zafb_event_sync": (_int, [_vp]),
     "zafb_event_elapsed_ms": (_int, [_vp, _vp, C.POINTER(C.c_float)]),
+    "zafb_pcm16_to_f32": (_int, [_vp, _i64, _int, _int, _vp, _i64, _vp]),
     "zafb_launch_count": (_i64, []),
     "zafb_stft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
     "zafb_istft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),

@@ -70,6 +70,25 @@ int sm_count() {
     return n;
 }
 
+// ------------------------------------------------------------------ PCM input (zaf.py:1199-1202)
+// wavread normalises integer PCM by 2^(8 itemsize - 1); here that happens on the GPU so that only the 16-bit samples
+// cross PCIe: interleaved (frame, channel) int16 -> planar [channel][frame] fp32 (x / 32768 is exact in fp32), or the
+// channel mean (the reference examples' np.mean(audio_signal, 1)) when `mono` is set.
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ pcm, int64_t frames, int channels, int mono,
+                                    float* __restrict__ out, int64_t out_stride) {
+    const float scale = 1.0f / 32768.0f;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < frames; i += int64_t(gridDim.x) * blockDim.x) {
+        const int16_t* p = pcm + i * channels;
+        if (mono) {
+            float acc = 0.f;
+            for (int c = 0; c < channels; ++c) acc += float(p[c]) * scale;
+            out[i] = acc / float(channels);
+        } else {
+            for (int c = 0; c < channels; ++c) out[int64_t(c) * out_stride + i] = float(p[c]) * scale;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host-buffer pipeline state
 HostPipe& host_pipe() {
     static HostPipe hp;
@@ -164,6 +183,20 @@ int zafb_shutdown(void) {
     HostPipe& hp = host_pipe();
     std::lock_guard<std::mutex> lock(hp.mu);
     hp.release();
+    return ZAFB_OK;
+}
+
+int zafb_pcm16_to_f32(const int16_t* pcm_dev, int64_t frames, int channels, int mono, float* out_dev, int64_t out_stride,
+                      void* stream) {
+    ZAFB_REQUIRE(frames >= 0 && channels >= 1 && channels <= 64, "pcm: need frames >= 0 and 1..64 channels");
+    ZAFB_REQUIRE(mono || out_stride >= frames, "pcm: out_stride %lld < frames %lld", (long long)out_stride, (long long)frames);
+    if (frames == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(pcm_dev != nullptr && out_dev != nullptr, "pcm/out is NULL");
+    int64_t blocks = ceil_div(frames, 256);
+    if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+    pcm16_to_f32_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(pcm_dev, frames, channels, mono, out_dev,
+                                                                                       out_stride);
+    ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
 

@@ -33,7 +33,7 @@ struct zafb_stft_plan {
     float2* d_window_half = nullptr;  // n/2 float2: 0.5 * window pairs (power-of-two n only)
     float2* d_tw_half = nullptr;    // W_{n/2}^t, t < n/2
     float2* d_tw_full = nullptr;    // W_n^t, t < n
-    float2* d_tw_4step = nullptr;   // n == 2048: W_1024^{k1*n2} at [k1*32 + n2]
+    float2* d_tw_4step = nullptr;   // n == 2048 / 1024: W_{n/2}^{k1*n2} at [k1*32 + n2]
     double gain = 1.0;              // sum(w[0:N:hop]) accumulated like Python's builtin sum (zaf.py:241)
     int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
 };
@@ -62,79 +62,82 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// BULK = true: the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame (issued by
-// one lane, executed by the TMA engine) instead of 64 st.global per lane.
-template <bool BULK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
-stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
-                     const float2* __restrict__ win_half, const float2* __restrict__ tw4,
-                     const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int prefetch) {
+// One warp transforms M = N / 2 complex points held in its registers (REGS = M / 32 per lane): N = 2048 -> warp_fft1024,
+// N = 1024 -> warp_fft512.  In: v[r] = z[lane + 32 r].  Out: Z[lane + 32 k2] = v[bitrev(k2, log2 REGS)].
+template <int N>
+struct WarpGeom {
+    static_assert(N == 1024 || N == 2048, "warp kernels exist for window lengths 1024 and 2048");
+    static constexpr int M = N / 2;
+    static constexpr int REGS = M / 32;
+    static constexpr int LOGR = clog2(REGS);
+    static constexpr int TILE = REGS * kFft1024Pitch;  // float2 per warp: the transpose tile of the four-step FFT
+};
+
+template <int N>
+__device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2* __restrict__ tw4, float2* buf, int lane) {
+    if constexpr (N == 2048) warp_fft1024<false>(v, tw4, buf, lane);
+    else warp_fft512(v, tw4, buf, lane);
+}
+
+// N = 2048 or 1024, one warp per frame.
+// BULK = true (N = 2048 only): the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame
+// (issued by one lane, executed by the TMA engine) instead of 64 st.global per lane.
+template <int N, bool BULK, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, N == 1024 ? 3 : 2)
+stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
+                 const float2* __restrict__ win_half, const float2* __restrict__ tw4,
+                 const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames) {
+    using G = WarpGeom<N>;
+    constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
+    static_assert(!BULK || N == 2048, "the bulk-store variant is written for N = 2048");
     extern __shared__ __align__(128) float2 smem[];
-    float2* s_win = smem;          // 1024: (0.5 w[2n], 0.5 w[2n+1])
-    float2* s_tw = smem + 1024;    // 1024: W_1024^{k1*n2} at [k1*32+n2]
+    float2* s_win = smem;       // M: (0.5 w[2n], 0.5 w[2n+1])
+    float2* s_tw = smem + M;    // M: W_M^{k1*n2} at [k1*32+n2]
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    float2* s_buf = smem + 2048 + warp * (32 * kFft1024Pitch);
+    float2* s_buf = smem + 2 * M + warp * G::TILE;
 
-    for (int i = tid; i < 1024; i += WARPS * 32) {
+    for (int i = tid; i < M; i += WARPS * 32) {
         s_win[i] = win_half[i];
         s_tw[i] = tw4[i];
     }
-    const float2 c_lane = tw_full[lane];  // W_2048^lane
+    const float2 c_lane = tw_full[lane];  // W_N^lane
     __syncthreads();
 
-    // prefetch bit 1: each CTA sweeps its own contiguous range of frames instead of the grid-stride interleave
-    const bool ranged = (prefetch & 2) != 0;
-    const int64_t per_cta = (total_frames + gridDim.x - 1) / gridDim.x;
-    const int64_t f_begin = ranged ? int64_t(blockIdx.x) * per_cta + warp : int64_t(blockIdx.x) * WARPS + warp;
-    const int64_t f_end = ranged ? min(total_frames, (int64_t(blockIdx.x) + 1) * per_cta) : total_frames;
-    const int64_t f_step = ranged ? WARPS : int64_t(gridDim.x) * WARPS;
-    for (int64_t f = f_begin; f < f_end; f += f_step) {
+    for (int64_t f = int64_t(blockIdx.x) * WARPS + warp; f < total_frames; f += int64_t(gridDim.x) * WARPS) {
         const int64_t clip = f / nt;
         const int64_t j = f - clip * nt;
-        const int64_t start = j * hop - 1024;  // first sample of the frame (may be < 0)
+        const int64_t start = j * hop - M;  // first sample of the frame (may be < 0): centre padding floor(N/2), zaf.py:99
         const float* xc = x + clip * clip_stride;
 
-        if (prefetch & 1) {  // this warp's next frame (8 KB = 64 lines, 2 per lane) towards L2 while this one is transformed
-            const int64_t fn = f + int64_t(gridDim.x) * WARPS;
-            if (fn < total_frames) {
-                const int64_t cn = fn / nt;
-                const int64_t sn = (fn - cn * nt) * hop - 1024;
-                if (sn >= 0 && sn + 2048 <= ns) {
-                    const char* pn = reinterpret_cast<const char*>(x + cn * clip_stride + sn);
-                    prefetch_l2(pn + lane * 128);
-                    prefetch_l2(pn + (lane + 32) * 128);
-                }
-            }
-        }
-        float2 v[32];
-        if (start >= 0 && start + 2048 <= ns) {
+        float2 v[REGS];
+        if (start >= 0 && start + N <= ns) {
             const float2* p = reinterpret_cast<const float2*>(xc + start) + lane;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) v[r] = __ldg(p + 32 * r);
+            for (int r = 0; r < REGS; ++r) v[r] = __ldg(p + 32 * r);
         } else {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < REGS; ++r) {
                 const int64_t s = start + 2 * (lane + 32 * r);
                 v[r].x = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
                 v[r].y = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
             }
         }
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
+        for (int r = 0; r < REGS; ++r) {
             const float2 w = s_win[lane + 32 * r];
             v[r].x *= w.x;
             v[r].y *= w.y;
         }
 
-        warp_fft1024<false>(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2)]
+        warp_fft_half<N>(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2)]
 
-        // real-input unpack: X[k] = E + w_k O, X[k+1024] = E - w_k O with
-        //   E = Z[k] + conj(Z[1024-k]),  O = -i (Z[k] - conj(Z[1024-k]))   (the 1/2 is in the window)
-        // computed for k < 512 only; the other half of the two-sided spectrum is its conjugate mirror,
-        // X[1024-k] = conj(X[k+1024]) and X[2048-k] = conj(X[k]), stored by the same lane (a warp still writes
-        // 32 consecutive bins per instruction, in descending lane order).  k = 512 is its own mirror (lane 0).
+        // real-input unpack: X[k] = E + w_k O, X[k+M] = E - w_k O with
+        //   E = Z[k] + conj(Z[M-k]),  O = -i (Z[k] - conj(Z[M-k])),  w_k = W_N^k   (the 1/2 is in the window)
+        // computed for k < M/2 only; the other half of the two-sided spectrum is its conjugate mirror,
+        // X[M-k] = conj(X[k+M]) and X[N-k] = conj(X[k]), stored by the same lane (a warp still writes
+        // 32 consecutive bins per instruction, in descending lane order).  k = M/2 is its own mirror (lane 0).
         const int src = (32 - lane) & 31;
         if constexpr (BULK) {
             const float2 z512 = v[bitrev(16, 5)];
@@ -159,8 +162,6 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
             float2* q0 = s_buf;
             float2* q1 = s_buf + 512;
             float2* g = out + f * 2048;
-            if (lane == 0) bulk_wait_read<0>();  // (no-op here: kept for symmetry with the loop below)
-            __syncwarp();
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) q0[lane + 32 * k2] = v[bitrev(k2, 5)];
             fence_async_smem();
@@ -199,38 +200,38 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
             __syncwarp();
             continue;
         }
-        float2* o = out + f * 2048 + lane;
-        float2* om = out + f * 2048 + 1024 - lane;
-        static_for<0, 16>([&](auto k2c) {
+        float2* o = out + f * N + lane;
+        float2* om = out + f * N + M - lane;
+        static_for<0, REGS / 2>([&](auto k2c) {
             constexpr int k2 = decltype(k2c)::value;
-            const float2 z = v[bitrev(k2, 5)];
-            const float2 mine = v[bitrev(31 - k2, 5)];
+            const float2 z = v[bitrev(k2, LOGR)];
+            const float2 mine = v[bitrev(REGS - 1 - k2, LOGR)];
             float2 p;
             p.x = __shfl_sync(0xffffffffu, mine.x, src);
             p.y = __shfl_sync(0xffffffffu, mine.y, src);
-            if (lane == 0) p = v[bitrev((32 - k2) & 31, 5)];
+            if (lane == 0) p = v[bitrev((REGS - k2) & (REGS - 1), LOGR)];
             const float2 e = make_float2(z.x + p.x, z.y - p.y);
             const float2 od = make_float2(z.y + p.y, p.x - z.x);
-            const float2 w = mul_tw<k2, 64>(c_lane);
+            const float2 w = mul_tw<k2, N / 32>(c_lane);
             const float2 t = cmul(w, od);
             const float2 lo = cadd(e, t), hi = csub(e, t);
             st_stream(o + 32 * k2, lo);
-            st_stream(o + 1024 + 32 * k2, hi);
+            st_stream(o + M + 32 * k2, hi);
             if (k2 > 0 || lane != 0) {
                 st_stream(om - 32 * k2, cconj(hi));
-                st_stream(om + 1024 - 32 * k2, cconj(lo));
+                st_stream(om + M - 32 * k2, cconj(lo));
             }
         });
-        if (lane == 0) {  // k = 512: Z[512] pairs with itself, w = -i
-            const float2 z = v[bitrev(16, 5)];
-            st_stream(out + f * 2048 + 512, make_float2(2.f * z.x, -2.f * z.y));
-            st_stream(out + f * 2048 + 1536, make_float2(2.f * z.x, 2.f * z.y));
+        if (lane == 0) {  // k = M/2: Z[M/2] pairs with itself, w = -i
+            const float2 z = v[bitrev(REGS / 2, LOGR)];
+            st_stream(out + f * N + M / 2, make_float2(2.f * z.x, -2.f * z.y));
+            st_stream(out + f * N + M + M / 2, make_float2(2.f * z.x, 2.f * z.y));
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// ISTFT, N = 2048, hop = 2048 / R (R = 2, 4, 8), frame-major spectra: one warp per RUN of
+// ISTFT, N = 2048 or 1024, hop = N / R (R = 2, 4, 8), frame-major spectra: one warp per RUN of
 // consecutive output hop-blocks of one clip.
 //
 // Frame j adds its part q (samples [q hop, (q+1) hop)) into hop-block j + q of the overlap-add
@@ -245,25 +246,31 @@ stft2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
 //   Z[k] = E[k] + i O[k],  E = H[k] + H[k+1024],  O = (H[k] - H[k+1024]) conj(W_2048^k),
 //   y[2n] + i y[2n+1] = conj(FFT_1024(conj(Z)))[n] / (2 N)        (validated in float64).
 // ------------------------------------------------------------------------------------------
-template <int R>
+template <int N, int R>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
-istft2048_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
-                      const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
-                      int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
-    constexpr int HOP = 2048 / R;
-    constexpr int K = 32 / R;            // registers (float2) per part
+istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
+                  const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
+                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
+    using G = WarpGeom<N>;
+    constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
+    constexpr int HOP = N / R;
+    constexpr int K = REGS / R;          // registers (float2) per part
+    static_assert(K >= 1, "hop too small for this window length");
     constexpr int SLOTS = R - 1;
     constexpr int RING = SLOTS * (HOP / 2);  // float2 per warp
+    // transpose tile per warp: N = 2048 uses the split (float) tile of warp_fft1024<true>, N = 1024 the float2 tile of
+    // warp_fft512 -- REGS * pitch * 4 bytes * (N == 2048 ? 1 : 2) = the same 4224 bytes either way
+    constexpr int TILE_FLOATS = N == 2048 ? 32 * kFft1024Pitch : 2 * 16 * kFft1024Pitch;
     extern __shared__ float2 smem[];
-    float2* s_tw = smem;  // 1024
+    float2* s_tw = smem;  // M
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    float2* s_ring = smem + 1024 + warp * RING;
-    float* s_buf = reinterpret_cast<float*>(smem + 1024 + kWarpsPerCta * RING) + warp * (32 * kFft1024Pitch);
+    float2* s_ring = smem + M + warp * RING;
+    float* s_buf = reinterpret_cast<float*>(smem + M + kWarpsPerCta * RING) + warp * TILE_FLOATS;
 
-    for (int i = tid; i < 1024; i += kWarpsPerCta * 32) s_tw[i] = tw4[i];
-    const float2 c_lane = tw_full[lane];  // W_2048^lane
+    for (int i = tid; i < M; i += kWarpsPerCta * 32) s_tw[i] = tw4[i];
+    const float2 c_lane = tw_full[lane];  // W_N^lane
     __syncthreads();
 
     for (int64_t task = int64_t(blockIdx.x) * kWarpsPerCta + warp; task < total_runs;
@@ -279,37 +286,39 @@ istft2048_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2*
         int slot0 = int((h_begin - (R - 1)) % SLOTS);  // ring slot of block j
 
         for (int64_t j = h_begin - (R - 1); j < h_end; ++j) {
-            const float2* X = spec + (clip * nt + j) * 2048;
-            if (prefetch && j + 1 < h_end) {  // the next frame of this run: 16 KB = 128 lines, 4 per lane
+            const float2* X = spec + (clip * nt + j) * N;
+            if (prefetch && j + 1 < h_end) {  // the next frame of this run towards L2: N * 8 / 128 lines, N / 512 per lane
 #pragma unroll
-                for (int i = 0; i < 4; ++i) prefetch_l2(X + 2048 + (lane + 32 * i) * 16);
+                for (int i = 0; i < N / 512; ++i) prefetch_l2(X + N + (lane + 32 * i) * 16);
             }
-            float2 v[32];
-            // r and 31 - r back to back: the mirrored loads (c, d) of one hit the lines the direct
+            float2 v[REGS];
+            // r and REGS - 1 - r back to back: the mirrored loads (c, d) of one hit the lines the direct
             // loads (a, b) of the other have just brought into L1
-            static_for<0, 32>([&](auto tc) {
+            static_for<0, REGS>([&](auto tc) {
                 constexpr int t = decltype(tc)::value;
-                constexpr int r = (t % 2 == 0) ? t / 2 : 31 - t / 2;
+                constexpr int r = (t % 2 == 0) ? t / 2 : REGS - 1 - t / 2;
                 const int k = lane + 32 * r;
                 const float2 a = __ldg(X + k);
-                const float2 b = __ldg(X + 1024 + k);
-                const float2 c = __ldg(X + 1024 - k);
-                const float2 d = __ldg(X + ((2048 - k) & 2047));
+                const float2 b = __ldg(X + M + k);
+                const float2 c = __ldg(X + M - k);
+                const float2 d = __ldg(X + ((N - k) & (N - 1)));
                 const float2 h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
-                const float2 h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + 1024]
+                const float2 h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + M]
                 const float2 e = cadd(h0, h1);
-                const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, 64>(c_lane));
+                const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, N / 32>(c_lane));
                 // conj(Z) = conj(e + i o)
                 v[r] = make_float2(e.x - o.y, -(e.y + o.x));
             });
 
-            warp_fft1024<true>(v, s_tw, s_buf, lane);  // conj(z[lane + 32 k2]) = v[bitrev(k2)]
+            // conj(z[lane + 32 k2]) = v[bitrev(k2)]
+            if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, s_buf, lane);
+            else warp_fft512(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
 
-            static_for<0, 32>([&](auto k2c) {
+            static_for<0, REGS>([&](auto k2c) {
                 constexpr int k2 = decltype(k2c)::value;
                 constexpr int q = k2 / K;   // part of the frame
                 constexpr int i = k2 % K;
-                const float2 z = make_float2(v[bitrev(k2, 5)].x, -v[bitrev(k2, 5)].y);
+                const float2 z = make_float2(v[bitrev(k2, LOGR)].x, -v[bitrev(k2, LOGR)].y);
                 if constexpr (q == 0) {
                     float2 acc = z;
                     if constexpr (R > 1) {
@@ -486,12 +495,16 @@ __global__ void istft_tile_kernel(const float2* __restrict__ spec, int64_t nt, i
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
-    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(stft2048_warp_kernel<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(istft2048_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -499,9 +512,9 @@ int set_kernel_attrs() {
     return ZAFB_OK;
 }
 
-template <int R>
-int launch_istft2048(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                     int64_t y_stride, cudaStream_t st) {
+template <int N, int R>
+int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
+                      int64_t y_stride, cudaStream_t st) {
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
     const int64_t resident_warps = int64_t(sm_count()) * 2 * kWarpsPerCta;
     // run length: minimise (runs per warp) x (frames per run, warm-up included)
@@ -518,11 +531,11 @@ int launch_istft2048(const zafb_stft_plan* p, const float2* spec, int64_t n_clip
     const int64_t total = n_clips * runs_per_clip;
     int64_t ctas = ceil_div(total, kWarpsPerCta);
     if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
-    constexpr int HOP = 2048 / R;
-    const size_t smem = 1024 * sizeof(float2) + size_t(kWarpsPerCta) * ((R - 1) * (HOP / 2) * sizeof(float2) +
-                                                                        32 * kFft1024Pitch * sizeof(float));
-    const float scale = static_cast<float>(1.0 / (2.0 * 2048.0 * p->gain));
-    istft2048_warp_kernel<R><<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+    constexpr int HOP = N / R;
+    const size_t smem = (N / 2) * sizeof(float2) + size_t(kWarpsPerCta) * ((R - 1) * (HOP / 2) * sizeof(float2) +
+                                                                           32 * kFft1024Pitch * sizeof(float));
+    const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
+    istft_warp_kernel<N, R><<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
         env_flag("ZAFB_ISTFT_PREFETCH", 1));
     ZAFB_LAUNCH_CHECK();
@@ -558,17 +571,18 @@ int zafb_stft_plan_create(zafb_stft_plan** out, const double* window, int64_t n,
         p->d_window_half = reinterpret_cast<float2*>(tmp);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
     }
-    if (rc == ZAFB_OK && n == 2048) {
-        // W_1024^{k1*n2} laid out [k1][n2]
-        std::vector<double> t(2 * 1024);
+    if (rc == ZAFB_OK && (n == 2048 || n == 1024)) {
+        // four-step twiddles of the warp kernels: W_M^{k1*n2} laid out [k1][n2], M = n/2 = (M/32) x 32
+        const int64_t m = n / 2;
+        std::vector<double> t(2 * m);
         const double pi = 3.14159265358979323846264338327950288;
-        for (int k1 = 0; k1 < 32; ++k1)
-            for (int n2 = 0; n2 < 32; ++n2) {
-                const double a = -2.0 * pi * double((k1 * n2) % 1024) / 1024.0;
+        for (int64_t k1 = 0; k1 < m / 32; ++k1)
+            for (int64_t n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % m) / double(m);
                 t[2 * (k1 * 32 + n2)] = std::cos(a);
                 t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
             }
-        rc = upload_c32(&p->d_tw_4step, t.data(), 1024);
+        rc = upload_c32(&p->d_tw_4step, t.data(), m);
     }
     // COLA gain exactly as the reference: Python's builtin sum over float64 (zaf.py:241)
     double g = 0.0;
@@ -618,34 +632,34 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     float2* o = reinterpret_cast<float2*>(out);
 
     const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
-    const bool warp_ok = p->n == 2048 && aligned;
+    const bool warp_ok = (p->n == 2048 || p->n == 1024) && aligned;
     if (p->force_kernel == 2 && !warp_ok)
-        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N=2048, even hop/stride, 8-byte aligned x");
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 1024 or 2048, even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
-        // measured on cfg 2 (B200): direct streaming stores 3.09 ms, TMA bulk stores 3.13-3.20 ms, L2 prefetch of the
-        // next frame +8 %: the defaults are the fastest combination, the switches stay for experiments
-        const int bulk = env_flag("ZAFB_STFT_BULK", 0), prefetch = env_flag("ZAFB_STFT_PREFETCH", 0);
+        // measured on cfg 2 (B200), profiles/r01_stft_experiments.txt: direct streaming stores 3.04-3.11 ms, TMA bulk stores
+        // 3.13-3.20 ms; 6 warps per CTA 3.04, 8 -> 3.11, 10 -> 3.36, 4 -> 3.40.  The defaults are the fastest combination.
+        const int bulk = p->n == 2048 ? env_flag("ZAFB_STFT_BULK", 0) : 0;
+        const int n = int(p->n);
         auto run = [&](const float* xs, int64_t clips, float2* dst) -> int {
             const int64_t frames = clips * nt;
-            // warps per CTA (2 CTAs per SM), measured on cfg 2: 4 -> 3.40 ms, 6 -> 3.04, 8 -> 3.11, 10 (96 registers) -> 3.36:
-            // more frames in flight do not help, the write stream is the limit
-            const int warps = (!bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
-            const size_t smem = (2048 + warps * 32 * kFft1024Pitch) * sizeof(float2);
+            const int warps = (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
+            const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(frames, warps);
-            const int64_t resident = int64_t(sms) * 2;
+            const int64_t resident = int64_t(sms) * (n == 1024 ? 3 : 2);
             if (ctas > resident) ctas = resident;
-            auto kern = warps == 6 ? stft2048_warp_kernel<false, 6>
-                        : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft2048_warp_kernel<true, 8> : stft2048_warp_kernel<false, 8>);
+            auto kern = n == 1024 ? stft_warp_kernel<1024, false, 8>
+                        : warps == 6 ? stft_warp_kernel<2048, false, 6>
+                        : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft_warp_kernel<2048, true, 8>
+                                                                             : stft_warp_kernel<2048, false, 8>);
             kern<<<static_cast<unsigned>(ctas), warps * 32, smem, st>>>(
-                xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
-                prefetch);
+                xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames);
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         };
         if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
         // the reference's C-order memory: frame-major into scratch, then a tiled transpose (transpose.cuh)
-        return bin_major_from_frame_major(o, n_clips, nt, int64_t(2048), st, [&](int64_t c0, int64_t n, float2* scratch) {
-            return run(x + c0 * clip_stride, n, scratch);
+        return bin_major_from_frame_major(o, n_clips, nt, p->n, st, [&](int64_t c0, int64_t nc, float2* scratch) {
+            return run(x + c0 * clip_stride, nc, scratch);
         });
     }
     const int64_t grid = total < int64_t(sms) * 32 ? total : int64_t(sms) * 32;
@@ -684,19 +698,25 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     {
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
                              (n_clips <= 1 || y_stride % 2 == 0);
-        const bool warp_ok = n == 2048 && aligned && (p->hop == 256 || p->hop == 512 || p->hop == 1024);
+        const int64_t ratio = (p->hop > 0 && n % p->hop == 0) ? n / p->hop : 0;
+        const bool warp_ok = (n == 2048 || n == 1024) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N=2048, hop in {256,512,1024}, even y_stride");
+            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 1024 or 2048, hop = N/2, N/4 or N/8, even y_stride");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
-                if (p->hop == 1024) return launch_istft2048<2>(p, s2, clips, nt, yy, y_stride, st);
-                if (p->hop == 512) return launch_istft2048<4>(p, s2, clips, nt, yy, y_stride, st);
-                return launch_istft2048<8>(p, s2, clips, nt, yy, y_stride, st);
+                if (n == 2048) {
+                    if (ratio == 2) return launch_istft_warp<2048, 2>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 4) return launch_istft_warp<2048, 4>(p, s2, clips, nt, yy, y_stride, st);
+                    return launch_istft_warp<2048, 8>(p, s2, clips, nt, yy, y_stride, st);
+                }
+                if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st);
+                if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st);
+                return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st);
             };
             const float2* s2 = reinterpret_cast<const float2*>(spec);
             if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y);
-            return frame_major_from_bin_major(s2, n_clips, nt, int64_t(2048), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
+            return frame_major_from_bin_major(s2, n_clips, nt, int64_t(n), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
                 return run(scratch, nc, y + c0 * y_stride);
             });
         }
