@@ -16,7 +16,8 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
-        'dram__throughput.avg.pct_of_peak_sustained_elapsed']
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'launch__grid_size']
 seen = set()
 for r in rows[2:]:
     name = r[idx['Kernel Name']][:60]
