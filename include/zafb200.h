@@ -65,6 +65,9 @@ int zafb_host_free(void* host_ptr);
 int zafb_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes, void* stream);
 int zafb_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes, void* stream);
 int zafb_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+/* rows of width_bytes at different pitches; kind: 0 = host to device, 1 = device to host, 2 = device to device */
+int zafb_memcpy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                  size_t rows, int kind, void* stream);
 int zafb_memset(void* dev_ptr, int value, size_t bytes, void* stream);
 
 int zafb_stream_create(void** stream);

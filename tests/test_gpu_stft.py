@@ -296,3 +296,20 @@ def test_pcm16_input_path(zaf_gpu):
         assert_parity(spec[c], oracle.stft(ref[:, c], w, 512))
     with pytest.raises(ValueError):
         zaf_gpu.from_pcm16(pcm.astype(np.int32))
+
+
+def test_device_batches_with_odd_length_rows(zaf_gpu):
+    """to_device pads the row pitch of an odd-length batch to an even number of samples, so device-resident batches
+    run on the same vectorised kernels as the host path (bit-identical results), and to_host drops the padding."""
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (4, 30011)).astype(np.float32)
+    xd = zaf_gpu.to_device(x)
+    assert xd.shape == (4, 30011) and xd.pitch == 30012
+    assert np.array_equal(xd.to_host(), x)
+    w = oracle.hamming_periodic(2048)
+    assert np.array_equal(zaf_gpu.stft(xd, w, 512).to_host(), zaf_gpu.stft(x, w, 512))
+    wk = oracle.kbd_window(2048)
+    md = zaf_gpu.mdct(xd, wk)
+    assert np.array_equal(md.to_host(), zaf_gpu.mdct(x, wk))
+    back = zaf_gpu.imdct(md, wk)            # odd output length M(nt-1)-1: padded pitch again
+    assert np.array_equal(back.to_host(), zaf_gpu.imdct(zaf_gpu.mdct(x, wk), wk))

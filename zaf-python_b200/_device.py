@@ -87,9 +87,18 @@ class DeviceArray:
     def to_host(self, out=None, stream=None):
         """Copy to a NumPy array of the logical shape (a transposed *view* of the copied memory
         for frame-major results -- no data movement on the host)."""
+        sp = stream.ptr if stream else None
+        if self.cols is not None and out is None:  # padded rows: copy only the logical columns
+            host = np.empty(self.mem_shape[:-1] + (self.cols,), dtype=self.dtype)
+            rows = int(np.prod(self.mem_shape[:-1], dtype=np.int64))
+            item = self.dtype.itemsize
+            _lib.check(_lib.lib().zafb_memcpy2d(host.ctypes.data, self.cols * item, C.c_void_p(self.ptr),
+                                                self.mem_shape[-1] * item, self.cols * item, rows, 1, sp))
+            if stream is None:
+                synchronize()
+            return host
         host = np.empty(self.mem_shape, dtype=self.dtype) if out is None else out
-        _lib.check(_lib.lib().zafb_memcpy_d2h(host.ctypes.data, C.c_void_p(self.ptr), self.nbytes,
-                                              stream.ptr if stream else None))
+        _lib.check(_lib.lib().zafb_memcpy_d2h(host.ctypes.data, C.c_void_p(self.ptr), self.nbytes, sp))
         if stream is None:
             synchronize()
         if self.transposed:
@@ -101,7 +110,18 @@ class DeviceArray:
 
 
 def to_device(array, dtype=None, stream=None) -> DeviceArray:
+    """Host array -> DeviceArray.  A batch of float32 signals with an odd number of samples per row gets an even row
+    pitch on the device (one padding column, never read as signal) so that every row stays 8-byte aligned for the
+    vectorised kernels."""
     a = np.ascontiguousarray(array, dtype=dtype)
+    if a.ndim == 2 and a.dtype == np.float32 and a.shape[0] > 1 and a.shape[1] % 2 == 1:
+        pitch = a.shape[1] + 1
+        d = DeviceArray((a.shape[0], pitch), a.dtype, cols=a.shape[1])
+        _lib.check(_lib.lib().zafb_memcpy2d(C.c_void_p(d.ptr), pitch * 4, a.ctypes.data, a.shape[1] * 4, a.shape[1] * 4,
+                                            a.shape[0], 0, stream.ptr if stream else None))
+        if stream is None:
+            synchronize()
+        return d
     d = DeviceArray(a.shape, a.dtype)
     if a.nbytes:
         _lib.check(_lib.lib().zafb_memcpy_h2d(C.c_void_p(d.ptr), a.ctypes.data, a.nbytes,

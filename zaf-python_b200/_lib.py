@@ -33,6 +33,7 @@ PROTOTYPES = {
     "zafb_memcpy_h2d": (_int, [_vp, _vp, _sz, _vp]),
     "zafb_memcpy_d2h": (_int, [_vp, _vp, _sz, _vp]),
     "zafb_memcpy_d2d": (_int, [_vp, _vp, _sz, _vp]),
+    "zafb_memcpy2d": (_int, [_vp, _sz, _vp, _sz, _sz, _sz, _int, _vp]),
     "zafb_memset": (_int, [_vp, _int, _sz, _vp]),
     "zafb_stream_create": (_int, [_pvp]),
     "zafb_stream_destroy": (_int, [_vp]),

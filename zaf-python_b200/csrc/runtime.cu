@@ -245,6 +245,15 @@ int zafb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
     ZAFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return ZAFB_OK;
 }
+int zafb_memcpy2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, int kind,
+                  void* stream) {
+    ZAFB_REQUIRE(kind >= 0 && kind <= 2, "memcpy2d: kind must be 0 (host to device), 1 (device to host) or 2 (device to device)");
+    ZAFB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "memcpy2d: pitch smaller than the row width");
+    if (width_bytes == 0 || rows == 0) return ZAFB_OK;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    ZAFB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, k, static_cast<cudaStream_t>(stream)));
+    return ZAFB_OK;
+}
 int zafb_memset(void* p, int value, size_t bytes, void* stream) {
     ZAFB_CUDA(cudaMemsetAsync(p, value, bytes, static_cast<cudaStream_t>(stream)));
     return ZAFB_OK;
