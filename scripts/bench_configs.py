@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,mdct,imdct,mel,mfcc,meltc,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,mdct,imdct,mel,mfcc,meltc,mel2048,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -234,6 +234,26 @@ def main():
             emit(line("mfcc-tensor", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
                       "dense 3xTF32 tcgen05 filterbank + DCT products"))
         xd.free()
+
+    # ---- the reference's own mel / mfcc example (zaf.py:347-357, 402-418): 44.1 kHz, N = 2048, hop = N/2, 128 mels, 20 coefficients
+    if "mel2048" in only:
+        clips, ns, n, hop, fs = max(1, int(1024 * args.scale)), 441000, 2048, 1024, 44100
+        w = hamming_periodic(n)
+        fb = zaf.melfilterbank(fs, n, 128)
+        xd, _ = device_batch(clips, ns, 20261017 + 7)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        cfg = f"reference example: {clips} clips x 10 s @ 44.1 kHz, N=2048 hop=1024, 128 mels, 20 coeffs"
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        plan_mel, _, _ = zaf._mel_plan(w, hop, fb, 0)
+        plan_mfcc, _, _ = zaf._mel_plan(w, hop, fb, 20)
+        od = zaf.empty((clips, nt, 128), np.float32)
+        ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_melspectrogram_f32(
+            plan_mel, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+        emit(line("melspectrogram-2048", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 128 * 4, nl))
+        ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_mfcc_f32(
+            plan_mfcc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
+        emit(line("mfcc-2048", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 20 * 4, nl))
+        xd.free(), od.free()
 
     # ---- cfg 5: cqtspectrogram, 512 clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8, 25 frames/s
     if "cqt" in only:

@@ -35,8 +35,8 @@ struct zafb_mel_plan {
     int grp_len[4] = {0, 0, 0, 0};  // longest band of each row group
     int grp_off[4] = {0, 0, 0, 0};  // offset of the group's [c][lane] weight block in d_wt
     float* d_wt = nullptr;          // zero-padded band weights, [g][c][lane]
-    float2* d_tw_4step = nullptr;   // W_512^{k1 n2}, [k1][n2]
-    float2* d_tw_n = nullptr;       // W_1024^t, t < 32
+    float2* d_tw_4step = nullptr;   // W_{n/2}^{k1 n2}, [k1][n2]
+    float2* d_tw_n = nullptr;       // W_n^t, t < 32
     int* d_lo = nullptr;            // first column of row lane + 32 g, at [g * 32 + lane]
     float* d_dh = nullptr;          // DCT-II half table, float4 at [(m / 4) * coef_pad + i] = D[i + 1][4 (m / 4) .. +3]
     int coef_pad = 0;               // n_coef rounded up to 32
@@ -149,8 +149,9 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
 //   ln ratio -> DCT-II through its even/odd symmetry  C[k] = sum_{m < n/2} D[k][m] (L[m] +- L[n-1-m])
 //   with lane l owning coefficients l and l + 32.
 // ------------------------------------------------------------------------------------------
-constexpr int kWarps = 8;
-constexpr int kMelWarpTile = 16 * kFft1024Pitch;  // float2 per warp: FFT transpose tile, then spectrum / log-mel scratch
+constexpr int kWarps = 8;        // N = 1024
+constexpr int kWarps2048 = 6;    // N = 2048: the tiles are twice as large; 6 warps keep two CTAs per SM
+constexpr int kMelWarpTile = 16 * kFft1024Pitch;  // float2 per warp at N = 1024: FFT transpose tile, then spectrum / log-mel scratch
 
 __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
     uint32_t h, l;
@@ -160,35 +161,49 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
-// SPLIT = true: the kernel stops after the spectrum and writes |X| (MODE 0) or |X|^2 (MODE 1) of bins 1..512 as TF32
-// hi/lo halves to out / out_lo ([frame][512]) -- the A operand of the tensor-core filterbank product.
-template <int MODE, bool SPLIT = false>  // 0 melspectrogram, 1 mfcc
-__global__ void __launch_bounds__(kWarps * 32, 2)
-mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
-                    const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
-                    const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
-                    int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
-                    int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames,
-                    float* __restrict__ out_lo = nullptr) {
+// N = 1024 (BASELINE cfg 3) or 2048 (the reference's own example, zaf.py:347-357: 44.1 kHz, 0.04 s window).
+// SPLIT = true (N = 1024): the kernel stops after the spectrum and writes |X| (MODE 0) or |X|^2 (MODE 1) of bins 1..512 as
+// TF32 hi/lo halves to out / out_lo ([frame][512]) -- the A operand of the tensor-core filterbank product.
+template <int N, int MODE, bool SPLIT = false>  // MODE 0 melspectrogram, 1 mfcc
+__global__ void __launch_bounds__((N == 1024 ? kWarps : kWarps2048) * 32, 2)
+mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
+                const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
+                const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
+                int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
+                int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames,
+                float* __restrict__ out_lo) {
+    constexpr int M = N / 2, REGS = M / 32, LOGR = clog2(REGS);
+    constexpr int WARPS = N == 1024 ? kWarps : kWarps2048;
+    constexpr int TILE = REGS * kFft1024Pitch;               // float2 per warp
+    constexpr bool WIN_REGS = N == 1024;                     // N = 2048: 32 more float2 registers do not fit, window from shared memory
+    static_assert(!SPLIT || N == 1024, "the tensor-core front end is written for N = 1024");
     extern __shared__ float2 smem2[];
-    float2* s_tw = smem2;                                    // 512: W_512^{k1 n2}
-    float* s_wt = reinterpret_cast<float*>(smem2 + 512);     // wt_total floats
+    float2* s_tw = smem2;                                    // M: W_M^{k1 n2}
+    float2* s_win = smem2 + M;                               // M (N = 2048 only): 0.5 * window pairs
+    float* s_wt = reinterpret_cast<float*>(smem2 + (WIN_REGS ? M : 2 * M));  // wt_total floats
     float4* s_dh = reinterpret_cast<float4*>(s_wt + ((wt_total + 3) & ~3));  // (half_mels/4 rounded up) * coef_pad float4
     const int dh_count = MODE == 1 ? ((half_mels + 3) / 4) * coef_pad : 0;
     float2* s_warp = reinterpret_cast<float2*>(s_dh + dh_count);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = s_warp + warp * kMelWarpTile;
-    float* s_spec = reinterpret_cast<float*>(s_buf);         // 512 floats (+ slack) once the FFT is done
-    for (int i = tid; i < 512; i += kWarps * 32) s_tw[i] = tw4[i];
-    for (int i = tid; i < wt_total; i += kWarps * 32) s_wt[i] = wt[i];
-    for (int i = tid; i < dh_count; i += kWarps * 32) s_dh[i] = dh[i];
-    float2 win[16];
+    float2* s_buf = s_warp + warp * TILE;
+    float* s_spec = reinterpret_cast<float*>(s_buf);         // M floats (+ slack) once the FFT is done
+    for (int i = tid; i < M; i += WARPS * 32) s_tw[i] = tw4[i];
+    if constexpr (!WIN_REGS)
+        for (int i = tid; i < M; i += WARPS * 32) {
+            const float2 w = win_pairs[i];
+            s_win[i] = make_float2(0.5f * w.x, 0.5f * w.y);
+        }
+    for (int i = tid; i < wt_total; i += WARPS * 32) s_wt[i] = wt[i];
+    for (int i = tid; i < dh_count; i += WARPS * 32) s_dh[i] = dh[i];
+    float2 win[WIN_REGS ? REGS : 1];
+    if constexpr (WIN_REGS) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const float2 w = win_pairs[lane + 32 * r];
-        win[r] = make_float2(0.5f * w.x, 0.5f * w.y);  // the 1/2 of the real-input split, exact in fp32
+        for (int r = 0; r < REGS; ++r) {
+            const float2 w = win_pairs[lane + 32 * r];
+            win[r] = make_float2(0.5f * w.x, 0.5f * w.y);  // the 1/2 of the real-input split, exact in fp32
+        }
     }
-    const float2 c_lane = tw_full[lane];  // W_1024^lane
+    const float2 c_lane = tw_full[lane];  // W_N^lane
     int lo[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) lo[g] = lo_tab[g * 32 + lane];
@@ -196,59 +211,63 @@ mel1024_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride
     const int goff[4] = {grp_off.x, grp_off.y, grp_off.z, grp_off.w};
     __syncthreads();
 
-    for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
+    for (int64_t f = int64_t(blockIdx.x) * WARPS + warp; f < total_frames; f += int64_t(gridDim.x) * WARPS) {
         const int64_t clip = f / nt, j = f - clip * nt;
-        const int64_t start = j * hop - 512;
+        const int64_t start = j * hop - M;
         const float* xc = x + clip * clip_stride;
-        float2 v[16];
-        if (start >= 0 && start + 1024 <= ns) {
+        float2 v[REGS];
+        if (start >= 0 && start + N <= ns) {
             const float2* fp = reinterpret_cast<const float2*>(xc + start) + lane;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = __ldg(fp + 32 * r);
+            for (int r = 0; r < REGS; ++r) v[r] = __ldg(fp + 32 * r);
         } else {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
+            for (int r = 0; r < REGS; ++r) {
                 const int64_t s0 = start + 2 * (lane + 32 * r);
                 v[r].x = (s0 >= 0 && s0 < ns) ? __ldg(xc + s0) : 0.f;
                 v[r].y = (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f;
             }
         }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            v[r].x *= win[r].x;
-            v[r].y *= win[r].y;
+        for (int r = 0; r < REGS; ++r) {
+            const float2 w = WIN_REGS ? win[WIN_REGS ? r : 0] : s_win[lane + 32 * r];
+            v[r].x *= w.x;
+            v[r].y *= w.y;
         }
-        warp_fft512(v, s_tw, s_buf, lane);  // Z[lane + 32 k] = v[bitrev(k, 4)]
+        // Z[lane + 32 k] = v[bitrev(k, LOGR)]
+        if constexpr (N == 1024) warp_fft512(v, s_tw, s_buf, lane);
+        else warp_fft1024<false>(v, s_tw, s_buf, lane);
 
-        // X[k] = E + W_1024^k O,  E = Z[k] + conj(Z[512-k]),  O = -i (Z[k] - conj(Z[512-k])),  k = lane + 32 kap;
+        // X[k] = E + W_N^k O,  E = Z[k] + conj(Z[M-k]),  O = -i (Z[k] - conj(Z[M-k])),  k = lane + 32 kap;
         // column c = k - 1 (zaf.py:370 drops DC, keeps Nyquist); lane 0 / kap 0 produces the Nyquist bin instead of DC.
         const int src = (32 - lane) & 31;
-        static_for<0, 16>([&](auto kc) {
+        static_for<0, REGS>([&](auto kc) {
             constexpr int kap = decltype(kc)::value;
-            const float2 z = v[bitrev(kap, 4)];
-            const float2 mine = v[bitrev(15 - kap, 4)];
+            const float2 z = v[bitrev(kap, LOGR)];
+            const float2 mine = v[bitrev(REGS - 1 - kap, LOGR)];
             float2 pz;
             pz.x = __shfl_sync(0xffffffffu, mine.x, src);
             pz.y = __shfl_sync(0xffffffffu, mine.y, src);
-            if (lane == 0) pz = v[bitrev((16 - kap) & 15, 4)];
+            if (lane == 0) pz = v[bitrev((REGS - kap) & (REGS - 1), LOGR)];
             const float2 e = make_float2(z.x + pz.x, z.y - pz.y);
             const float2 od = make_float2(z.y + pz.y, pz.x - z.x);
-            const float2 t = cmul(mul_tw<kap, 32>(c_lane), od);
+            const float2 t = cmul(mul_tw<kap, N / 32>(c_lane), od);
             float2 xk = cadd(e, t);
-            if (kap == 0 && lane == 0) xk = csub(e, t);  // X[512] = E[0] - O[0]
-            const float pw = xk.x * xk.x + xk.y * xk.y;
-            const int col = (kap == 0 && lane == 0) ? 511 : lane + 32 * kap - 1;
-            s_spec[col] = MODE == 0 ? sqrtf(pw) : pw;
+            if (kap == 0 && lane == 0) xk = csub(e, t);  // X[M] = E[0] - O[0]
+            const float p2 = xk.x * xk.x + xk.y * xk.y;
+            // (the spectrum overwrites the transpose tile: every lane finished reading it inside the FFT)
+            const int col = (kap == 0 && lane == 0) ? M - 1 : lane + 32 * kap - 1;
+            s_spec[col] = MODE == 0 ? sqrtf(p2) : p2;
         });
         __syncwarp();
 
         if constexpr (SPLIT) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < REGS; ++i) {
                 float hi, lo_part;
                 split_tf32_dev(s_spec[lane + 32 * i], hi, lo_part);
-                out[f * 512 + lane + 32 * i] = hi;
-                out_lo[f * 512 + lane + 32 * i] = lo_part;
+                out[f * M + lane + 32 * i] = hi;
+                out_lo[f * M + lane + 32 * i] = lo_part;
             }
             __syncwarp();
             continue;
@@ -338,10 +357,12 @@ bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(mel1024_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA((cudaFuncSetAttribute(mel1024_warp_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(mel1024_warp_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<2048, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -355,7 +376,7 @@ int upload_vec(T** dev, const std::vector<T>& v) {
 
 // ------------------------------------------------------------------------------------------
 // Tensor-core route (north star: "the mel filterbank matmul on tensor cores ... a dense contraction"):
-//   (1) mel1024_warp_kernel<MODE, true>  frames -> |X| or |X|^2 of bins 1..512, split into TF32 hi/lo halves
+//   (1) mel_warp_kernel<1024, MODE, true>  frames -> |X| or |X|^2 of bins 1..512, split into TF32 hi/lo halves
 //   (2) gemm3xtf32 (tcgen05 / TMEM / TMA): [frames x 512] . filterbank[n_mels x 512]^T -> mel [frames x n_mels]
 //   (3) MFCC only: log-ratio + split, then gemm3xtf32 with the DCT-II rows 1..n_coef
 // in chunks of 16 384 frames so that the 64 MB of split spectra stay in the 126 MB L2 between (1) and (2).
@@ -393,7 +414,7 @@ int launch_tensor(const zafb_mel_plan* p, int mode, const float* x, int64_t n_cl
         const int64_t frames = nc * nt;
         int64_t ctas = ceil_div(frames, kWarps);
         if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
-        auto kern = mode == 0 ? mel1024_warp_kernel<0, true> : mel1024_warp_kernel<1, true>;
+        auto kern = mode == 0 ? mel_warp_kernel<1024, 0, true> : mel_warp_kernel<1024, 1, true>;
         kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(x + c0 * clip_stride, ns, clip_stride, nt, int(p->hop),
                                                          reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                                                          p->d_wt, p->d_lo, zero4, zero4, 0, nullptr, int(n_mels), 0, 0, 0, spec_hi, frames,
@@ -440,7 +461,7 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         }
         const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
         if (p->force_kernel == 2 && !ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N=1024, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
+            return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N = 1024 or 2048, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
         if (p->route == ZAFB_MEL_ROUTE_TENSOR) {
             if (!ok || p->d_fb_hi == nullptr)
                 return fail(ZAFB_E_UNSUPPORTED, "mel tensor-core route needs N=1024, <=128 mels, frame-major layout, even hop/stride");
@@ -449,15 +470,19 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         if (ok && p->force_kernel != 1) {
             const int wt_total = p->grp_off[3] + 32 * p->grp_len[3];
             const int dh_count = mode == 1 ? ((p->half_mels + 3) / 4) * p->coef_pad : 0;
-            const size_t smem = 512 * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) + size_t(dh_count) * sizeof(float4) +
-                                size_t(kWarps) * kMelWarpTile * sizeof(float2);
-            if (smem <= size_t(kMaxDynSmem) / 2) {
-                int64_t ctas = ceil_div(total, kWarps);
+            const bool big = p->n == 2048;
+            const int warps = big ? kWarps2048 : kWarps;
+            const int64_t half = p->n / 2;
+            const size_t smem = size_t(big ? 2 * half : half) * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) +
+                                size_t(dh_count) * sizeof(float4) + size_t(warps) * (half / 32) * kFft1024Pitch * sizeof(float2);
+            if (smem <= size_t(kMaxDynSmem) / 2 + 8 * 1024) {  // two CTAs per SM fit (227 KB per SM)
+                int64_t ctas = ceil_div(total, warps);
                 if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
                 const int4 gl = make_int4(p->grp_len[0], p->grp_len[1], p->grp_len[2], p->grp_len[3]);
                 const int4 go = make_int4(p->grp_off[0], p->grp_off[1], p->grp_off[2], p->grp_off[3]);
-                auto kern = mode == 0 ? mel1024_warp_kernel<0> : mel1024_warp_kernel<1>;
-                kern<<<unsigned(ctas), kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+                auto kern = big ? (mode == 0 ? mel_warp_kernel<2048, 0> : mel_warp_kernel<2048, 1>)
+                                : (mode == 0 ? mel_warp_kernel<1024, 0> : mel_warp_kernel<1024, 1>);
+                kern<<<unsigned(ctas), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                     x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                     p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
                     int(p->n_coef), p->coef_pad, out, total, nullptr);
@@ -531,7 +556,7 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct, d);
-    if (rc == ZAFB_OK && n == 1024 && n_mels <= 128 && p->n_coef <= 64) {
+    if (rc == ZAFB_OK && (n == 1024 || n == 2048) && n_mels <= 128 && p->n_coef <= 64) {
         // row groups of 32 rows, zero-padded to the longest band of the group; the band start is clamped so that
         // lo + grp_len never leaves the 512-column spectrum (the padding weights are zero)
         std::vector<int> lo4(128, 0);
@@ -562,20 +587,21 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
             for (int64_t mm = 0; mm < p->half_mels; ++mm)
                 dh[((mm / 4) * p->coef_pad + i) * 4 + (mm % 4)] = static_cast<float>(
                     std::sqrt(2.0 / double(n_mels)) * std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels)));
-        std::vector<double> t4(2 * 512);
-        for (int k1 = 0; k1 < 16; ++k1)
-            for (int n2 = 0; n2 < 32; ++n2) {
-                const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+        const int64_t half = n / 2;  // four-step twiddles W_half^{k1 n2}, [k1][n2], half = (half / 32) x 32
+        std::vector<double> t4(2 * half);
+        for (int64_t k1 = 0; k1 < half / 32; ++k1)
+            for (int64_t n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % half) / double(half);
                 t4[2 * (k1 * 32 + n2)] = std::cos(a);
                 t4[2 * (k1 * 32 + n2) + 1] = std::sin(a);
             }
-        rc = upload_c32(&p->d_tw_4step, t4.data(), 512);
-        if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_n, 1024, 32);
+        rc = upload_c32(&p->d_tw_4step, t4.data(), half);
+        if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_n, n, 32);
         if (rc == ZAFB_OK) rc = upload_vec(&p->d_wt, wt);
         if (rc == ZAFB_OK) rc = upload_vec(&p->d_lo, lo4);
         if (rc == ZAFB_OK) rc = upload_vec(&p->d_dh, dh);
         p->warp_ok = rc == ZAFB_OK;
-        if (rc == ZAFB_OK) {  // dense TF32 hi/lo operands of the tensor-core route
+        if (rc == ZAFB_OK && n == 1024) {  // dense TF32 hi/lo operands of the tensor-core route
             p->ld_mel = (n_mels + 3) & ~int64_t(3);
             std::vector<float> hi(size_t(n_mels) * 512), lo(hi.size());
             split_tf32_host(fb, hi.size(), hi.data(), lo.data());
