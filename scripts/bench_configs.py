@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,mdct,imdct,mel,mfcc,meltc,mel2048,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mel,mfcc,meltc,mel2048,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -167,6 +167,26 @@ def main():
         ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_istft_f32(
             plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, s.ptr)), args.steps)
         emit(line("istft-1024", cfg, clips * nt, "frames", ms, clips * nt * n * 8 + clips * ylen * 4, nl))
+        xd.free(), spec.free(), yd.free()
+
+    # ---- speech shape (N = 512, hop = 128 at 16 kHz): the third window length with warp kernels
+    if "stft512" in only:
+        clips, ns, n, hop = max(1, int(4096 * args.scale)), 80000, 512, 128
+        w = hamming_periodic(n)
+        xd, _ = device_batch(clips, ns, 20261017 + 8)
+        nt = zaf.stft_geometry(ns, n, hop)[1]
+        spec = zaf.empty((clips, nt, n), np.complex64)
+        plan, _ = zaf._stft_plan(w, hop)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        cfg = f"{clips} clips x 5 s @ 16 kHz, N=512 hop=128"
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_stft_f32(
+            plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 0, s.ptr)), args.steps)
+        emit(line("stft-512", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * n * 8, nl))
+        ylen = zaf.istft_geometry(n, nt, hop)[2]
+        yd = zaf.empty((clips, ylen), np.float32)
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_istft_f32(
+            plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, s.ptr)), args.steps)
+        emit(line("istft-512", cfg, clips * nt, "frames", ms, clips * nt * n * 8 + clips * ylen * 4, nl))
         xd.free(), spec.free(), yd.free()
 
     # ---- cfg 4: mdct + imdct, 2048 clips x 30 s @ 44.1 kHz, KBD N = 2048

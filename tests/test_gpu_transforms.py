@@ -262,7 +262,7 @@ def test_mel_mfcc_tensor_core_route(zaf_gpu, n_mels, ncoef, fs):
         zaf_gpu.melspectrogram(x[0], w, 256, fb, route="nope")
 
 
-@pytest.mark.parametrize("n", [1024, 2048])
+@pytest.mark.parametrize("n", [1024, 2048, 512])
 @pytest.mark.parametrize("force", [1, 2])
 @pytest.mark.parametrize("n_mels,ncoef,fs", [(128, 40, 16000), (40, 13, 16000), (77, 60, 44100), (100, 99, 22050), (1, 1, 16000),
                                              (128, 20, 44100)])

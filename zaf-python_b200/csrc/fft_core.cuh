@@ -167,6 +167,53 @@ __device__ __forceinline__ void warp_fft512(float2 (&v)[16], const float2* __res
     fft_reg<16>(v);
 }
 
+// ---------------------------------------------------------------- one warp, 256 complex points
+// Four-step FFT 256 = 8 x 32 by ONE warp.  In: v[r] = x[lane + 32 r], r < 8.  Out: X[lane + 32 k] is v[bitrev(k, 3)].
+// tw[k1 * 32 + n2] = W_256^{k1 n2} (shared memory, 8 x 32); buf: 8 x kFft1024Pitch float2.
+// Step 1: FFT-8 over the register index.  Step 2: the 8 FFT-32 over n2 are shared by lane quads (k1 = lane & 7,
+// q = lane >> 3): with n2 = a + 8 b and k2 = q + 4 j,
+//     X[k1 + 8 k2] = sum_a W_8^{a j} W_32^{a q} ( (y[a] + (-1)^q y[a+16]) + (-i)^q (y[a+8] + (-1)^q y[a+24]) ),
+// i.e. each lane forms output q of the radix-4 butterflies of its row while reading it back from the transpose
+// tile, applies its own twiddles tq[a] = W_32^{a q} (8 per-lane constants, see warp_fft256_lane_twiddles) and
+// finishes with an FFT-8 in registers.  (Validated in float64 against numpy.fft.)
+__device__ __forceinline__ void warp_fft256_lane_twiddles(float2 (&tq)[8], int lane) {
+    const int q = lane >> 3;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        float sn, cs;
+        sincospif(-float(a * q) / 16.0f, &sn, &cs);  // W_32^{a q} = exp(-2 pi i a q / 32); exact for the multiples of pi/2
+        tq[a] = make_float2(cs, sn);
+    }
+}
+
+__device__ __forceinline__ void warp_fft256(float2 (&v)[8], const float2* __restrict__ tw, float2* buf, int lane,
+                                            const float2 (&tq)[8]) {
+    fft_reg<8>(v);
+    static_for<0, 8>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        float2 y = v[bitrev(k1, 3)];
+        if constexpr (k1 > 0) y = cmul(y, tw[k1 * 32 + lane]);
+        buf[k1 * kFft1024Pitch + lane] = y;
+    });
+    __syncwarp();
+    const float2* row = buf + (lane & 7) * kFft1024Pitch;
+    const int q = lane >> 3;
+    const float sgn = (q & 1) ? -1.f : 1.f;
+    const float cq = q == 0 ? 1.f : (q == 2 ? -1.f : 0.f);  // (-i)^q = cq - i sq
+    const float sq = q == 1 ? 1.f : (q == 3 ? -1.f : 0.f);
+    static_for<0, 8>([&](auto ac) {
+        constexpr int a = decltype(ac)::value;
+        const float2 y0 = row[a], y1 = row[a + 8], y2 = row[a + 16], y3 = row[a + 24];
+        const float2 e = make_float2(fmaf(sgn, y2.x, y0.x), fmaf(sgn, y2.y, y0.y));
+        const float2 o = make_float2(fmaf(sgn, y3.x, y1.x), fmaf(sgn, y3.y, y1.y));
+        const float2 t = make_float2(e.x + cq * o.x + sq * o.y, e.y + cq * o.y - sq * o.x);
+        if constexpr (a == 0) v[a] = t;
+        else v[a] = cmul(t, tq[a]);
+    });
+    __syncwarp();
+    fft_reg<8>(v);
+}
+
 // Whole-block M-point FFT in shared memory (ping-pong between a and b).  Every thread of the
 // group [0, nthreads) calls it with its tid; a leading __syncthreads() is the caller's job
 // (data in `a` must be visible).  Returns the buffer that holds the result; ends with a barrier.

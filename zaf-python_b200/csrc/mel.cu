@@ -165,7 +165,7 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
 // SPLIT = true (N = 1024): the kernel stops after the spectrum and writes |X| (MODE 0) or |X|^2 (MODE 1) of bins 1..512 as
 // TF32 hi/lo halves to out / out_lo ([frame][512]) -- the A operand of the tensor-core filterbank product.
 template <int N, int MODE, bool SPLIT = false>  // MODE 0 melspectrogram, 1 mfcc
-__global__ void __launch_bounds__((N == 1024 ? kWarps : kWarps2048) * 32, 2)
+__global__ void __launch_bounds__((N == 2048 ? kWarps2048 : kWarps) * 32, 2)
 mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                 const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
                 const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
@@ -173,9 +173,11 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames,
                 float* __restrict__ out_lo) {
     constexpr int M = N / 2, REGS = M / 32, LOGR = clog2(REGS);
-    constexpr int WARPS = N == 1024 ? kWarps : kWarps2048;
-    constexpr int TILE = REGS * kFft1024Pitch;               // float2 per warp
-    constexpr bool WIN_REGS = N == 1024;                     // N = 2048: 32 more float2 registers do not fit, window from shared memory
+    static_assert(N == 512 || N == 1024 || N == 2048, "warp kernels exist for window lengths 512, 1024 and 2048");
+    constexpr int WARPS = N == 2048 ? kWarps2048 : kWarps;
+    // float2 per warp: the FFT transpose tile, then the spectrum (M floats) / log-mel scratch (256 floats at least)
+    constexpr int TILE = (REGS < 16 ? 16 : REGS) * kFft1024Pitch;
+    constexpr bool WIN_REGS = N != 2048;                     // N = 2048: 32 more float2 registers do not fit, window from shared memory
     static_assert(!SPLIT || N == 1024, "the tensor-core front end is written for N = 1024");
     extern __shared__ float2 smem2[];
     float2* s_tw = smem2;                                    // M: W_M^{k1 n2}
@@ -204,6 +206,8 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
         }
     }
     const float2 c_lane = tw_full[lane];  // W_N^lane
+    float2 tq[N == 512 ? 8 : 1];          // per-lane twiddles of warp_fft256
+    if constexpr (N == 512) warp_fft256_lane_twiddles(tq, lane);
     int lo[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) lo[g] = lo_tab[g * 32 + lane];
@@ -235,7 +239,8 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
             v[r].y *= w.y;
         }
         // Z[lane + 32 k] = v[bitrev(k, LOGR)]
-        if constexpr (N == 1024) warp_fft512(v, s_tw, s_buf, lane);
+        if constexpr (N == 512) warp_fft256(v, s_tw, s_buf, lane, tq);
+        else if constexpr (N == 1024) warp_fft512(v, s_tw, s_buf, lane);
         else warp_fft1024<false>(v, s_tw, s_buf, lane);
 
         // X[k] = E + W_N^k O,  E = Z[k] + conj(Z[M-k]),  O = -i (Z[k] - conj(Z[M-k])),  k = lane + 32 kap;
@@ -363,6 +368,8 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<2048, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<512, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -461,7 +468,7 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         }
         const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
         if (p->force_kernel == 2 && !ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N = 1024 or 2048, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
+            return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N = 512, 1024 or 2048, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
         if (p->route == ZAFB_MEL_ROUTE_TENSOR) {
             if (!ok || p->d_fb_hi == nullptr)
                 return fail(ZAFB_E_UNSUPPORTED, "mel tensor-core route needs N=1024, <=128 mels, frame-major layout, even hop/stride");
@@ -473,15 +480,17 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
             const bool big = p->n == 2048;
             const int warps = big ? kWarps2048 : kWarps;
             const int64_t half = p->n / 2;
+            const int64_t tile_rows = half / 32 < 16 ? 16 : half / 32;  // the tile also holds the spectrum / log-mel scratch
             const size_t smem = size_t(big ? 2 * half : half) * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) +
-                                size_t(dh_count) * sizeof(float4) + size_t(warps) * (half / 32) * kFft1024Pitch * sizeof(float2);
+                                size_t(dh_count) * sizeof(float4) + size_t(warps) * tile_rows * kFft1024Pitch * sizeof(float2);
             if (smem <= size_t(kMaxDynSmem) / 2 + 8 * 1024) {  // two CTAs per SM fit (227 KB per SM)
                 int64_t ctas = ceil_div(total, warps);
                 if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
                 const int4 gl = make_int4(p->grp_len[0], p->grp_len[1], p->grp_len[2], p->grp_len[3]);
                 const int4 go = make_int4(p->grp_off[0], p->grp_off[1], p->grp_off[2], p->grp_off[3]);
                 auto kern = big ? (mode == 0 ? mel_warp_kernel<2048, 0> : mel_warp_kernel<2048, 1>)
-                                : (mode == 0 ? mel_warp_kernel<1024, 0> : mel_warp_kernel<1024, 1>);
+                            : p->n == 512 ? (mode == 0 ? mel_warp_kernel<512, 0> : mel_warp_kernel<512, 1>)
+                                          : (mode == 0 ? mel_warp_kernel<1024, 0> : mel_warp_kernel<1024, 1>);
                 kern<<<unsigned(ctas), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                     x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                     p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
@@ -556,7 +565,7 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct, d);
-    if (rc == ZAFB_OK && (n == 1024 || n == 2048) && n_mels <= 128 && p->n_coef <= 64) {
+    if (rc == ZAFB_OK && (n == 512 || n == 1024 || n == 2048) && n_mels <= 128 && p->n_coef <= 64) {
         // row groups of 32 rows, zero-padded to the longest band of the group; the band start is clamped so that
         // lo + grp_len never leaves the 512-column spectrum (the padding weights are zero)
         std::vector<int> lo4(128, 0);

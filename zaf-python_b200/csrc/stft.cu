@@ -66,24 +66,35 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // N = 1024 -> warp_fft512.  In: v[r] = z[lane + 32 r].  Out: Z[lane + 32 k2] = v[bitrev(k2, log2 REGS)].
 template <int N>
 struct WarpGeom {
-    static_assert(N == 1024 || N == 2048, "warp kernels exist for window lengths 1024 and 2048");
+    static_assert(N == 512 || N == 1024 || N == 2048, "warp kernels exist for window lengths 512, 1024 and 2048");
     static constexpr int M = N / 2;
     static constexpr int REGS = M / 32;
     static constexpr int LOGR = clog2(REGS);
     static constexpr int TILE = REGS * kFft1024Pitch;  // float2 per warp: the transpose tile of the four-step FFT
 };
 
+// per-lane constants of the N = 512 transform (warp_fft256); empty for the other sizes
 template <int N>
-__device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2* __restrict__ tw4, float2* buf, int lane) {
+struct LaneTw {
+    float2 tq[N == 512 ? 8 : 1];
+    __device__ __forceinline__ void init(int lane) {
+        if constexpr (N == 512) warp_fft256_lane_twiddles(tq, lane);
+    }
+};
+
+template <int N>
+__device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2* __restrict__ tw4, float2* buf, int lane,
+                                              const LaneTw<N>& lt) {
     if constexpr (N == 2048) warp_fft1024<false>(v, tw4, buf, lane);
-    else warp_fft512(v, tw4, buf, lane);
+    else if constexpr (N == 1024) warp_fft512(v, tw4, buf, lane);
+    else warp_fft256(v, tw4, buf, lane, lt.tq);
 }
 
 // N = 2048 or 1024, one warp per frame.
 // BULK = true (N = 2048 only): the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame
 // (issued by one lane, executed by the TMA engine) instead of 64 st.global per lane.
 template <int N, bool BULK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, N == 1024 ? 3 : 2)
+__global__ void __launch_bounds__(WARPS * 32, N == 2048 ? 2 : 3)
 stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                  const float2* __restrict__ win_half, const float2* __restrict__ tw4,
                  const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames) {
@@ -103,6 +114,8 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
         s_tw[i] = tw4[i];
     }
     const float2 c_lane = tw_full[lane];  // W_N^lane
+    LaneTw<N> lt;
+    lt.init(lane);
     __syncthreads();
 
     for (int64_t f = int64_t(blockIdx.x) * WARPS + warp; f < total_frames; f += int64_t(gridDim.x) * WARPS) {
@@ -131,7 +144,7 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
             v[r].y *= w.y;
         }
 
-        warp_fft_half<N>(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2)]
+        warp_fft_half<N>(v, s_tw, s_buf, lane, lt);  // Z[lane + 32 k2] = v[bitrev(k2)]
 
         // real-input unpack: X[k] = E + w_k O, X[k+M] = E - w_k O with
         //   E = Z[k] + conj(Z[M-k]),  O = -i (Z[k] - conj(Z[M-k])),  w_k = W_N^k   (the 1/2 is in the window)
@@ -260,7 +273,7 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
     constexpr int RING = SLOTS * (HOP / 2);  // float2 per warp
     // transpose tile per warp: N = 2048 uses the split (float) tile of warp_fft1024<true>, N = 1024 the float2 tile of
     // warp_fft512 -- REGS * pitch * 4 bytes * (N == 2048 ? 1 : 2) = the same 4224 bytes either way
-    constexpr int TILE_FLOATS = N == 2048 ? 32 * kFft1024Pitch : 2 * 16 * kFft1024Pitch;
+    constexpr int TILE_FLOATS = N == 2048 ? 32 * kFft1024Pitch : 2 * REGS * kFft1024Pitch;
     extern __shared__ float2 smem[];
     float2* s_tw = smem;  // M
     const int tid = threadIdx.x;
@@ -271,6 +284,8 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
 
     for (int i = tid; i < M; i += kWarpsPerCta * 32) s_tw[i] = tw4[i];
     const float2 c_lane = tw_full[lane];  // W_N^lane
+    LaneTw<N> lt;
+    lt.init(lane);
     __syncthreads();
 
     for (int64_t task = int64_t(blockIdx.x) * kWarpsPerCta + warp; task < total_runs;
@@ -289,7 +304,7 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
             const float2* X = spec + (clip * nt + j) * N;
             if (prefetch && j + 1 < h_end) {  // the next frame of this run towards L2: N * 8 / 128 lines, N / 512 per lane
 #pragma unroll
-                for (int i = 0; i < N / 512; ++i) prefetch_l2(X + N + (lane + 32 * i) * 16);
+                for (int i = 0; i < N / 512; ++i) prefetch_l2(X + N + (lane + 32 * i) * 16);  // (N = 512: one line per lane)
             }
             float2 v[REGS];
             // r and REGS - 1 - r back to back: the mirrored loads (c, d) of one hit the lines the direct
@@ -312,7 +327,8 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
 
             // conj(z[lane + 32 k2]) = v[bitrev(k2)]
             if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, s_buf, lane);
-            else warp_fft512(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
+            else if constexpr (N == 1024) warp_fft512(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
+            else warp_fft256(v, s_tw, reinterpret_cast<float2*>(s_buf), lane, lt.tq);
 
             static_for<0, REGS>([&](auto k2c) {
                 constexpr int k2 = decltype(k2c)::value;
@@ -499,12 +515,16 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -571,7 +591,7 @@ int zafb_stft_plan_create(zafb_stft_plan** out, const double* window, int64_t n,
         p->d_window_half = reinterpret_cast<float2*>(tmp);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
     }
-    if (rc == ZAFB_OK && (n == 2048 || n == 1024)) {
+    if (rc == ZAFB_OK && (n == 2048 || n == 1024 || n == 512)) {
         // four-step twiddles of the warp kernels: W_M^{k1*n2} laid out [k1][n2], M = n/2 = (M/32) x 32
         const int64_t m = n / 2;
         std::vector<double> t(2 * m);
@@ -632,9 +652,9 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     float2* o = reinterpret_cast<float2*>(out);
 
     const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
-    const bool warp_ok = (p->n == 2048 || p->n == 1024) && aligned;
+    const bool warp_ok = (p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
     if (p->force_kernel == 2 && !warp_ok)
-        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 1024 or 2048, even hop/stride, 8-byte aligned x");
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 512, 1024 or 2048, even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
         // measured on cfg 2 (B200), profiles/r01_stft_experiments.txt: direct streaming stores 3.04-3.11 ms, TMA bulk stores
         // 3.13-3.20 ms; 6 warps per CTA 3.04, 8 -> 3.11, 10 -> 3.36, 4 -> 3.40.  The defaults are the fastest combination.
@@ -645,9 +665,10 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             const int warps = (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
             const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(frames, warps);
-            const int64_t resident = int64_t(sms) * (n == 1024 ? 3 : 2);
+            const int64_t resident = int64_t(sms) * (n == 2048 ? 2 : 3);
             if (ctas > resident) ctas = resident;
-            auto kern = n == 1024 ? stft_warp_kernel<1024, false, 8>
+            auto kern = n == 512 ? stft_warp_kernel<512, false, 8>
+                        : n == 1024 ? stft_warp_kernel<1024, false, 8>
                         : warps == 6 ? stft_warp_kernel<2048, false, 6>
                         : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft_warp_kernel<2048, true, 8>
                                                                              : stft_warp_kernel<2048, false, 8>);
@@ -699,9 +720,9 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
                              (n_clips <= 1 || y_stride % 2 == 0);
         const int64_t ratio = (p->hop > 0 && n % p->hop == 0) ? n / p->hop : 0;
-        const bool warp_ok = (n == 2048 || n == 1024) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
+        const bool warp_ok = (n == 2048 || n == 1024 || n == 512) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 1024 or 2048, hop = N/2, N/4 or N/8, even y_stride");
+            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 512, 1024 or 2048, hop = N/2, N/4 or N/8, even y_stride");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
@@ -710,9 +731,14 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
                     if (ratio == 4) return launch_istft_warp<2048, 4>(p, s2, clips, nt, yy, y_stride, st);
                     return launch_istft_warp<2048, 8>(p, s2, clips, nt, yy, y_stride, st);
                 }
-                if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st);
-                if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st);
-                return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st);
+                if (n == 1024) {
+                    if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st);
+                    return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st);
+                }
+                if (ratio == 2) return launch_istft_warp<512, 2>(p, s2, clips, nt, yy, y_stride, st);
+                if (ratio == 4) return launch_istft_warp<512, 4>(p, s2, clips, nt, yy, y_stride, st);
+                return launch_istft_warp<512, 8>(p, s2, clips, nt, yy, y_stride, st);
             };
             const float2* s2 = reinterpret_cast<const float2*>(spec);
             if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y);
