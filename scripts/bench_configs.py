@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mel,mfcc,meltc,mel2048,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mdct1024,mel,mfcc,meltc,mel2048,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -219,6 +219,27 @@ def main():
             yd.free()
         xd.free()
         spec.free()
+
+    # ---- mdct + imdct at N = 1024 (the second window length with warp kernels)
+    if "mdct1024" in only:
+        clips, ns, n = max(1, int(2048 * args.scale)), 1323000, 1024
+        w = kbd(n)
+        xd, _ = device_batch(clips, ns, 20261017 + 9)
+        m, nt, _ = zaf.mdct_geometry(ns, n)
+        plan, _ = zaf._mdct_plan(w)
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        spec = zaf.empty((clips, nt, m), np.float32)
+        cfg = f"{clips} clips x 30 s @ 44.1 kHz, KBD N=1024"
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_mdct_f32(
+            plan, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(spec.ptr), 0, s.ptr)), args.steps)
+        emit(line("mdct-1024", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * m * 4, nl))
+        ylen = zaf.imdct_geometry(m, nt)[1]
+        pitch = (ylen + 1) & ~1
+        yd = zaf.empty((clips, pitch), np.float32)
+        ms, _, nl = timeit(lambda s: zaf._lib.check(lib.zafb_imdct_f32(
+            plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), pitch, s.ptr)), args.steps)
+        emit(line("imdct-1024", cfg, clips * nt, "frames", ms, clips * nt * m * 4 + clips * ylen * 4, nl))
+        xd.free(), spec.free(), yd.free()
 
     # ---- cfg 3: melspectrogram + mfcc, 4096 clips x 5 s @ 16 kHz, N = 1024, hop = 256, 128 mels, 40 coefficients
     if only & {"mel", "mfcc", "meltc"}:

@@ -30,7 +30,7 @@ struct zafb_mdct_plan {
     float2* d_pre = nullptr;      // e^{-i pi m / M}, m < M/2
     float2* d_post = nullptr;     // e^{-i pi (m + 1/4) / M}, m < M/2
     float* d_cos = nullptr;       // direct path: cos(2 pi t / (8M)), t < 8M
-    float2* d_tw_4step = nullptr; // n == 2048: W_512^{k1*n2} at [k1*32 + n2], k1 < 16
+    float2* d_tw_4step = nullptr; // n == 2048 / 1024: W_H^{k1*n2} at [k1*32 + n2], H = n/4 (warp kernels)
     int force_kernel = 0;         // 0 auto, 1 generic, 2 warp (tests)
 };
 
@@ -137,46 +137,71 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = 8;
 
-constexpr int kWarpSmemF2 = 1024 + 512;  // window pairs, W_512 four-step table
+// N = 2048 (M = 1024, 512-point FFT, warp_fft512) or N = 1024 (M = 512, 256-point FFT, warp_fft256)
+template <int N>
+struct MdctGeom {
+    static_assert(N == 1024 || N == 2048, "mdct warp kernels exist for window lengths 1024 and 2048");
+    static constexpr int M = N / 2;          // coefficients per frame
+    static constexpr int H = M / 2;          // complex FFT length
+    static constexpr int REGS = H / 32;      // float2 per lane
+    static constexpr int LOGR = clog2(REGS);
+    static constexpr int Q = M / 4;          // quarter of the frame, in sample pairs
+    static constexpr int TWDEN = M / 16;     // pre[lane + 32 r] = pre[lane] W_TWDEN^r (e^{-i pi 32 r / M})
+    static constexpr int TABLES = M + H;     // float2: window pairs, W_H four-step table
+    static constexpr int TILE = REGS * kFft1024Pitch;
+};
 
+template <int N>
 __device__ __forceinline__ void load_tables(float2* smem, const float2* __restrict__ win_pairs,
                                             const float2* __restrict__ tw4, int tid) {
-    for (int i = tid; i < 1024; i += kWarps * 32) smem[i] = win_pairs[i];
-    for (int i = tid; i < 512; i += kWarps * 32) smem[1024 + i] = tw4[i];
+    using G = MdctGeom<N>;
+    for (int i = tid; i < G::M; i += kWarps * 32) smem[i] = win_pairs[i];
+    for (int i = tid; i < G::H; i += kWarps * 32) smem[G::M + i] = tw4[i];
 }
 
-template <int OCC>
+template <int N>
+__device__ __forceinline__ void mdct_warp_fft(float2 (&v)[MdctGeom<N>::REGS], const float2* __restrict__ tw, float2* buf, int lane,
+                                              const float2 (&tq)[N == 1024 ? 8 : 1]) {
+    if constexpr (N == 2048) warp_fft512(v, tw, buf, lane);
+    else warp_fft256(v, tw, buf, lane, tq);
+}
+
+template <int N, int OCC>
 __global__ void __launch_bounds__(kWarps * 32, OCC)
-mdct2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
-                     const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
-                     const float2* __restrict__ pre, const float2* __restrict__ post, float* __restrict__ out,
-                     int64_t total_frames) {
+mdct_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt,
+                 const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
+                 const float2* __restrict__ pre, const float2* __restrict__ post, float* __restrict__ out,
+                 int64_t total_frames) {
+    using G = MdctGeom<N>;
+    constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR, Q = G::Q, QR = REGS / 2;
     extern __shared__ float2 smem2[];
-    const float2* s_win = smem2;          // 1024 pairs of the window
-    const float2* s_tw = smem2 + 1024;    // 512: W_512^{k1 n2}
+    const float2* s_win = smem2;          // M pairs of the window
+    const float2* s_tw = smem2 + M;       // H: W_H^{k1 n2}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = smem2 + kWarpSmemF2 + warp * (16 * kFft1024Pitch);
-    load_tables(smem2, win_pairs, tw4, tid);
-    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane; pre[lane + 32 r] = c_lane W_64^r
-    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M};       post[lane + 32 k] = p_lane W_64^k
+    float2* s_buf = smem2 + G::TABLES + warp * G::TILE;
+    load_tables<N>(smem2, win_pairs, tw4, tid);
+    const float2 c_lane = pre[lane];   // e^{-i pi lane / M}; pre[lane + 32 r] = c_lane W_TWDEN^r
+    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M}; post[lane + 32 k] = p_lane W_TWDEN^k
+    float2 tq[N == 1024 ? 8 : 1];
+    if constexpr (N == 1024) warp_fft256_lane_twiddles(tq, lane);
     __syncthreads();
 
     for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
         const int64_t clip = f / nt, j = f - clip * nt;
-        const int64_t start = (j - 1) * 1024;  // frame j covers original samples [(j-1)M, (j+1)M)
+        const int64_t start = (j - 1) * M;  // frame j covers original samples [(j-1)M, (j+1)M)
         const float* xc = x + clip * clip_stride;
 
-        // pairs 768+m, 767-m, 255-m, 256+m for m = lane + 32 r, r < 8
-        float2 pr[8][4];
-        if (start >= 0 && start + 2048 <= ns) {
+        // pairs 3Q+m, 3Q-1-m, Q-1-m, Q+m for m = lane + 32 r, r < QR
+        float2 pr[QR][4];
+        if (start >= 0 && start + N <= ns) {
             const float2* fp = reinterpret_cast<const float2*>(xc + start);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < QR; ++r) {
                 const int m = lane + 32 * r;
-                pr[r][0] = __ldg(fp + 768 + m);
-                pr[r][1] = __ldg(fp + 767 - m);
-                pr[r][2] = __ldg(fp + 255 - m);
-                pr[r][3] = __ldg(fp + 256 + m);
+                pr[r][0] = __ldg(fp + 3 * Q + m);
+                pr[r][1] = __ldg(fp + 3 * Q - 1 - m);
+                pr[r][2] = __ldg(fp + Q - 1 - m);
+                pr[r][3] = __ldg(fp + Q + m);
             }
         } else {
             auto ld = [&](int p) {
@@ -185,67 +210,71 @@ mdct2048_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
                                    (s0 + 1 >= 0 && s0 + 1 < ns) ? __ldg(xc + s0 + 1) : 0.f);
             };
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < QR; ++r) {
                 const int m = lane + 32 * r;
-                pr[r][0] = ld(768 + m);
-                pr[r][1] = ld(767 - m);
-                pr[r][2] = ld(255 - m);
-                pr[r][3] = ld(256 + m);
+                pr[r][0] = ld(3 * Q + m);
+                pr[r][1] = ld(3 * Q - 1 - m);
+                pr[r][2] = ld(Q - 1 - m);
+                pr[r][3] = ld(Q + m);
             }
         }
-        float2 v[16];
-        static_for<0, 8>([&](auto rc) {
+        float2 v[REGS];
+        static_for<0, QR>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const int m = lane + 32 * r;
-            const float2 w1 = s_win[768 + m], w2 = s_win[767 - m], w3 = s_win[255 - m], w4 = s_win[256 + m];
+            const float2 w1 = s_win[3 * Q + m], w2 = s_win[3 * Q - 1 - m], w3 = s_win[Q - 1 - m], w4 = s_win[Q + m];
             const float2 p1 = make_float2(pr[r][0].x * w1.x, pr[r][0].y * w1.y);
             const float2 p2 = make_float2(pr[r][1].x * w2.x, pr[r][1].y * w2.y);
             const float2 p3 = make_float2(pr[r][2].x * w3.x, pr[r][2].y * w3.y);
             const float2 p4 = make_float2(pr[r][3].x * w4.x, pr[r][3].y * w4.y);
             v[r] = make_float2(-p2.y - p1.x, p3.y - p4.x);               // raw t[m]
-            const float2 other = make_float2(p3.x - p4.y, -p2.x - p1.y);  // raw t[511 - m], belongs to lane 31 - lane
-            v[15 - r].x = __shfl_xor_sync(0xffffffffu, other.x, 31);
-            v[15 - r].y = __shfl_xor_sync(0xffffffffu, other.y, 31);
+            const float2 other = make_float2(p3.x - p4.y, -p2.x - p1.y);  // raw t[H - 1 - m], belongs to lane 31 - lane
+            v[REGS - 1 - r].x = __shfl_xor_sync(0xffffffffu, other.x, 31);
+            v[REGS - 1 - r].y = __shfl_xor_sync(0xffffffffu, other.y, 31);
         });
-        static_for<0, 16>([&](auto rc) {
+        static_for<0, REGS>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
-            v[r] = cmul(v[r], mul_tw<r, 64>(c_lane));
+            v[r] = cmul(v[r], mul_tw<r, G::TWDEN>(c_lane));
         });
 
-        warp_fft512(v, s_tw, s_buf, lane);  // Y[lane + 32 k] = v[bitrev(k, 4)]
+        mdct_warp_fft<N>(v, s_tw, s_buf, lane, tq);  // Y[lane + 32 k] = v[bitrev(k)]
 
-        static_for<0, 16>([&](auto kc) {
+        static_for<0, REGS>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            v[bitrev(k, 4)] = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(p_lane));
+            v[bitrev(k, LOGR)] = cmul(v[bitrev(k, LOGR)], mul_tw<k, G::TWDEN>(p_lane));
         });
-        float2* o = reinterpret_cast<float2*>(out + f * 1024) + lane;
-        static_for<0, 16>([&](auto kc) {
+        float2* o = reinterpret_cast<float2*>(out + f * M) + lane;
+        static_for<0, REGS>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(15 - k, 4)].y, 31);
-            __stcs(o + 32 * k, make_float2(v[bitrev(k, 4)].x, -im));
+            const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(REGS - 1 - k, LOGR)].y, 31);
+            __stcs(o + 32 * k, make_float2(v[bitrev(k, LOGR)].x, -im));
         });
     }
 }
 
-// IMDCT, N = 2048: one warp per run of consecutive hop-blocks of one clip; the second half of the
+// IMDCT, N = 2048 or 1024: one warp per run of consecutive hop-blocks of one clip; the second half of the
 // previous frame (already scaled and windowed) is carried in registers, so every output sample is
 // carry (frame h-1) + first half (frame h), written once.  A run re-reads the one frame before it.
-template <int OCC>
+template <int N, int OCC>
 __global__ void __launch_bounds__(kWarps * 32, OCC)
-imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __restrict__ win_pairs,
-                      const float2* __restrict__ tw4, const float2* __restrict__ pre,
-                      const float2* __restrict__ post, int64_t runs_per_clip, int run_len, int64_t total_runs,
-                      int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned, int prefetch) {
+imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __restrict__ win_pairs,
+                  const float2* __restrict__ tw4, const float2* __restrict__ pre,
+                  const float2* __restrict__ post, int64_t runs_per_clip, int run_len, int64_t total_runs,
+                  int64_t out_len, float* __restrict__ y, int64_t y_stride, int y_aligned, int prefetch) {
+    using G = MdctGeom<N>;
+    constexpr int M = G::M, H = G::H, REGS = G::REGS, LOGR = G::LOGR, HR = REGS / 2;
     extern __shared__ float2 smem2[];
     const float2* s_win = smem2;
-    const float2* s_tw = smem2 + 1024;
+    const float2* s_tw = smem2 + M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = smem2 + kWarpSmemF2 + warp * (16 * kFft1024Pitch);
-    load_tables(smem2, win_pairs, tw4, tid);
-    const float2 c_lane = pre[lane];   // e^{-i pi lane / M} = W_2048^lane; pre[lane + 32 r] = c_lane W_64^r
-    const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M};       post[lane + 32 k] = p_lane W_64^k
+    float2* s_buf = smem2 + G::TABLES + warp * G::TILE;
+    load_tables<N>(smem2, win_pairs, tw4, tid);
+    const float2 c_lane = pre[lane];
+    const float2 p_lane = post[lane];
+    float2 tq[N == 1024 ? 8 : 1];
+    if constexpr (N == 1024) warp_fft256_lane_twiddles(tq, lane);
     __syncthreads();
-    constexpr float kScale = 2.0f / 1024.0f;
+    constexpr float kScale = 2.0f / float(M);
 
     for (int64_t task = int64_t(blockIdx.x) * kWarps + warp; task < total_runs; task += int64_t(gridDim.x) * kWarps) {
         const int64_t clip = task / runs_per_clip;
@@ -254,50 +283,51 @@ imdct2048_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* 
         int64_t h1 = h0 + run_len;
         if (h1 > nt) h1 = nt;
         float* yc = y + clip * y_stride;
-        float2 carry[16];
+        float2 carry[REGS];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) carry[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < REGS; ++i) carry[i] = make_float2(0.f, 0.f);
 
         for (int64_t j = h0 - 1; j < h1; ++j) {
-            const float2* X = reinterpret_cast<const float2*>(spec + (clip * nt + j) * 1024) + lane;
-            if (prefetch && j + 1 < h1) prefetch_l2(reinterpret_cast<const char*>(X - lane + 512) + lane * 128);  // next frame: 32 lines
-            float2 xp[16], v[16];
+            const float2* X = reinterpret_cast<const float2*>(spec + (clip * nt + j) * M) + lane;
+            // next frame of the run towards L2: M * 4 / 128 lines (one per lane at M = 1024)
+            if (prefetch && j + 1 < h1 && lane < M / 32) prefetch_l2(reinterpret_cast<const char*>(X - lane + H) + lane * 128);
+            float2 xp[REGS], v[REGS];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) xp[r] = __ldg(X + 32 * r);
-            static_for<0, 16>([&](auto rc) {
+            for (int r = 0; r < REGS; ++r) xp[r] = __ldg(X + 32 * r);
+            static_for<0, REGS>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
-                const float im = __shfl_xor_sync(0xffffffffu, xp[15 - r].y, 31);  // X[1023 - 2m]
-                v[r] = cmul(make_float2(xp[r].x, im), mul_tw<r, 64>(c_lane));
+                const float im = __shfl_xor_sync(0xffffffffu, xp[REGS - 1 - r].y, 31);  // X[M - 1 - 2m]
+                v[r] = cmul(make_float2(xp[r].x, im), mul_tw<r, G::TWDEN>(c_lane));
             });
 
-            warp_fft512(v, s_tw, s_buf, lane);
+            mdct_warp_fft<N>(v, s_tw, s_buf, lane, tq);
 
-            // A[k] = res[2k] = Re(Y post), B[k] = res[1023 - 2k] = -Im(Y post), k = lane + 32 kap
-            static_for<0, 16>([&](auto kc) {
+            // A[k] = res[2k] = Re(Y post), B[k] = res[M - 1 - 2k] = -Im(Y post), k = lane + 32 kap
+            static_for<0, REGS>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                const float2 t = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(p_lane));
-                v[bitrev(k, 4)] = make_float2(t.x, -t.y);
+                const float2 t = cmul(v[bitrev(k, LOGR)], mul_tw<k, G::TWDEN>(p_lane));
+                v[bitrev(k, LOGR)] = make_float2(t.x, -t.y);
             });
             const bool emit = j >= h0;
-            const int64_t base = (j - 1) * 1024;  // output index of OLA sample j*M (trim = M)
-            static_for<0, 16>([&](auto rc) {
+            const int64_t base = (j - 1) * M;  // output index of OLA sample j*M (trim = M)
+            static_for<0, REGS>([&](auto rc) {
                 constexpr int rho = decltype(rc)::value;
-                constexpr int own = rho < 8 ? rho + 8 : rho - 8;   // register (kap) of this lane's value
-                constexpr int oth = rho < 8 ? 7 - rho : 23 - rho;  // register of lane 31 - lane's value
-                const float2 mine = v[bitrev(own, 4)];
+                constexpr int own = rho < HR ? rho + HR : rho - HR;                  // register (kap) of this lane's value
+                constexpr int oth = rho < HR ? HR - 1 - rho : 3 * HR - 1 - rho;      // register of lane 31 - lane's value
+                const float2 mine = v[bitrev(own, LOGR)];
                 float2 part;
-                part.x = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, 4)].x, 31);
-                part.y = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, 4)].y, 31);
+                part.x = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, LOGR)].x, 31);
+                part.y = __shfl_xor_sync(0xffffffffu, v[bitrev(oth, LOGR)].y, 31);
                 float2 first, second;
-                if constexpr (rho < 8) {
-                    first = make_float2(mine.x, part.y);     // ( A[P+256],  B[255-P])
-                    second = make_float2(-mine.y, -part.x);  // (-B[P+256], -A[255-P])
+                if constexpr (rho < HR) {
+                    first = make_float2(mine.x, part.y);     // ( A[P + M/4],  B[M/4 - 1 - P])
+                    second = make_float2(-mine.y, -part.x);  // (-B[P + M/4], -A[M/4 - 1 - P])
                 } else {
-                    first = make_float2(-mine.y, -part.x);   // (-B[P-256], -A[767-P])
-                    second = make_float2(-mine.x, -part.y);  // (-A[P-256], -B[767-P])
+                    first = make_float2(-mine.y, -part.x);   // (-B[P - M/4], -A[3M/4 - 1 - P])
+                    second = make_float2(-mine.x, -part.y);  // (-A[P - M/4], -B[3M/4 - 1 - P])
                 }
                 const int P = lane + 32 * rho;
-                const float2 w1 = s_win[P], w2 = s_win[512 + P];
+                const float2 w1 = s_win[P], w2 = s_win[H + P];
                 if (emit) {
                     const float2 o = make_float2(fmaf(kScale * w1.x, first.x, carry[rho].x),
                                                  fmaf(kScale * w1.y, first.y, carry[rho].y));
@@ -384,8 +414,10 @@ __global__ void imdct_tile_kernel(const float* __restrict__ spec, int64_t nt, in
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
-    ZAFB_CUDA(cudaFuncSetAttribute(mdct2048_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(imdct2048_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<2048, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<2048, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<1024, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(imdct_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -426,15 +458,16 @@ int zafb_mdct_plan_create(zafb_mdct_plan** out, const double* window, int64_t n)
         rc = upload_c32(&p->d_pre, pre.data(), h);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_post, post.data(), h);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_fft, h, h);
-        if (rc == ZAFB_OK && n == 2048) {  // W_512^{k1*n2} laid out [k1][n2] for the warp kernels
-            std::vector<double> t(2 * 512);
-            for (int k1 = 0; k1 < 16; ++k1)
-                for (int n2 = 0; n2 < 32; ++n2) {
-                    const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+        if (rc == ZAFB_OK && (n == 2048 || n == 1024)) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels, H = n/4
+            const int64_t hh = n / 4;
+            std::vector<double> t(2 * hh);
+            for (int64_t k1 = 0; k1 < hh / 32; ++k1)
+                for (int64_t n2 = 0; n2 < 32; ++n2) {
+                    const double a = -2.0 * pi * double((k1 * n2) % hh) / double(hh);
                     t[2 * (k1 * 32 + n2)] = std::cos(a);
                     t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
                 }
-            rc = upload_c32(&p->d_tw_4step, t.data(), 512);
+            rc = upload_c32(&p->d_tw_4step, t.data(), hh);
         }
     } else if (rc == ZAFB_OK) {
         std::vector<double> c(8 * p->m);
@@ -486,25 +519,28 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
                              reinterpret_cast<uintptr_t>(out) % 8 == 0;
-        const bool warp_ok = p->n == 2048 && aligned;
+        const bool warp_ok = (p->n == 2048 || p->n == 1024) && aligned;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N=2048, even clip_stride, 8-byte aligned x/out");
+            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 1024 or 2048, even clip_stride, 8-byte aligned x/out");
         if (warp_ok && p->force_kernel != 1) {
             auto run = [&](const float* xs, int64_t clips, float* dst) -> int {
                 const int64_t frames = clips * nt;
-                const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+                const bool big = p->n == 2048;
+                const size_t smem = big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                        : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
                 constexpr int occ = 3;
                 int64_t ctas = ceil_div(frames, kWarps);
                 if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-                mdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
+                auto kern = big ? mdct_warp_kernel<2048, occ> : mdct_warp_kernel<1024, occ>;
+                kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     xs, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
                     dst, frames);
                 ZAFB_LAUNCH_CHECK();
                 return ZAFB_OK;
             };
             if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, out);
-            return bin_major_from_frame_major(out, n_clips, nt, int64_t(1024), st, [&](int64_t c0, int64_t n, float* scratch) {
+            return bin_major_from_frame_major(out, n_clips, nt, p->m, st, [&](int64_t c0, int64_t n, float* scratch) {
                 return run(x + c0 * clip_stride, n, scratch);
             });
         }
@@ -538,9 +574,9 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
     {
-        const bool warp_ok = p->n == 2048 && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
+        const bool warp_ok = (p->n == 2048 || p->n == 1024) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N=2048, 8-byte aligned spectra");
+            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N = 1024 or 2048, 8-byte aligned spectra");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float* sp, int64_t clips, float* yy) -> int {
@@ -560,16 +596,19 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
                 const int64_t total = clips * runs_per_clip;
                 int64_t ctas = ceil_div(total, kWarps);
                 if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-                const size_t smem = (kWarpSmemF2 + kWarps * 16 * kFft1024Pitch) * sizeof(float2);
+                const bool big = p->n == 2048;
+                const size_t smem = big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                        : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 const int y_aligned = (reinterpret_cast<uintptr_t>(yy) % 8 == 0 && (clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
-                imdct2048_warp_kernel<occ><<<unsigned(ctas), kWarps * 32, smem, st>>>(
+                auto kern = big ? imdct_warp_kernel<2048, occ> : imdct_warp_kernel<1024, occ>;
+                kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     sp, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
                     int(best_len), total, len, yy, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));
                 ZAFB_LAUNCH_CHECK();
                 return ZAFB_OK;
             };
             if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(spec, n_clips, y);
-            return frame_major_from_bin_major(spec, n_clips, nt, int64_t(1024), st, [&](int64_t c0, int64_t nc, const float* scratch) {
+            return frame_major_from_bin_major(spec, n_clips, nt, p->m, st, [&](int64_t c0, int64_t nc, const float* scratch) {
                 return run(scratch, nc, y + c0 * y_stride);
             });
         }
