@@ -97,7 +97,7 @@ template <int N, bool BULK, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, N == 2048 ? 2 : 3)
 stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                  const float2* __restrict__ win_half, const float2* __restrict__ tw4,
-                 const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames) {
+                 const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int sequential) {
     using G = WarpGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
     static_assert(!BULK || N == 2048, "the bulk-store variant is written for N = 2048");
@@ -215,6 +215,44 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
         }
         float2* o = out + f * N + lane;
         float2* om = out + f * N + M - lane;
+        if (sequential) {
+            // the same unpack, but the results first replace the registers they were computed from (descending k2,
+            // see the bulk variant), then the frame is written in ascending address order, quarter by quarter
+            const float2 zmid = v[bitrev(REGS / 2, LOGR)];
+            static_for<0, REGS / 2>([&](auto ic) {
+                constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
+                const float2 z = v[bitrev(k2, LOGR)];
+                const float2 mine = v[bitrev(REGS - 1 - k2, LOGR)];
+                float2 p;
+                p.x = __shfl_sync(0xffffffffu, mine.x, src);
+                p.y = __shfl_sync(0xffffffffu, mine.y, src);
+                if (lane == 0) p = v[bitrev((REGS - k2) & (REGS - 1), LOGR)];
+                const float2 e = make_float2(z.x + p.x, z.y - p.y);
+                const float2 od = make_float2(z.y + p.y, p.x - z.x);
+                const float2 t = cmul(mul_tw<k2, N / 32>(c_lane), od);
+                v[bitrev(k2, LOGR)] = cadd(e, t);             // X[k]
+                v[bitrev(REGS - 1 - k2, LOGR)] = csub(e, t);  // X[k + M]
+            });
+            static_for<0, REGS / 2>([&](auto kc) {            // [0, M/2): X[k]
+                constexpr int k2 = decltype(kc)::value;
+                st_stream(o + 32 * k2, v[bitrev(k2, LOGR)]);
+            });
+            if (lane == 0) st_stream(out + f * N + M / 2, make_float2(2.f * zmid.x, -2.f * zmid.y));
+            static_for<0, REGS / 2>([&](auto ic) {            // (M/2, M): conj(X[k + M]) mirrored, ascending addresses
+                constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
+                if (k2 > 0 || lane != 0) st_stream(om - 32 * k2, cconj(v[bitrev(REGS - 1 - k2, LOGR)]));
+            });
+            static_for<0, REGS / 2>([&](auto kc) {            // [M, 3M/2): X[k + M]
+                constexpr int k2 = decltype(kc)::value;
+                st_stream(o + M + 32 * k2, v[bitrev(REGS - 1 - k2, LOGR)]);
+            });
+            if (lane == 0) st_stream(out + f * N + M + M / 2, make_float2(2.f * zmid.x, 2.f * zmid.y));
+            static_for<0, REGS / 2>([&](auto ic) {            // (3M/2, N): conj(X[k]) mirrored
+                constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
+                if (k2 > 0 || lane != 0) st_stream(om + M - 32 * k2, cconj(v[bitrev(k2, LOGR)]));
+            });
+            continue;
+        }
         static_for<0, REGS / 2>([&](auto k2c) {
             constexpr int k2 = decltype(k2c)::value;
             const float2 z = v[bitrev(k2, LOGR)];
@@ -673,7 +711,8 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
                         : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft_warp_kernel<2048, true, 8>
                                                                              : stft_warp_kernel<2048, false, 8>);
             kern<<<static_cast<unsigned>(ctas), warps * 32, smem, st>>>(
-                xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames);
+                xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
+                env_flag("ZAFB_STFT_SEQ", 1));
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         };
