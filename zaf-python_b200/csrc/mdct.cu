@@ -153,9 +153,12 @@ struct MdctGeom {
 
 template <int N>
 __device__ __forceinline__ void load_tables(float2* smem, const float2* __restrict__ win_pairs,
-                                            const float2* __restrict__ tw4, int tid) {
+                                            const float2* __restrict__ tw4, int tid, float win_scale = 1.0f) {
     using G = MdctGeom<N>;
-    for (int i = tid; i < G::M; i += kWarps * 32) smem[i] = win_pairs[i];
+    for (int i = tid; i < G::M; i += kWarps * 32) {
+        const float2 w = win_pairs[i];
+        smem[i] = make_float2(w.x * win_scale, w.y * win_scale);
+    }
     for (int i = tid; i < G::H; i += kWarps * 32) smem[G::M + i] = tw4[i];
 }
 
@@ -268,13 +271,14 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
     const float2* s_tw = smem2 + M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* s_buf = smem2 + G::TABLES + warp * G::TILE;
-    load_tables<N>(smem2, win_pairs, tw4, tid);
+    constexpr float kScale = 2.0f / float(M);  // a power of two: folding it into the window table changes no bit
+    load_tables<N>(smem2, win_pairs, tw4, tid, kScale);
+
     const float2 c_lane = pre[lane];
     const float2 p_lane = post[lane];
     float2 tq[N == 1024 ? 8 : 1];
     if constexpr (N == 1024) warp_fft256_lane_twiddles(tq, lane);
     __syncthreads();
-    constexpr float kScale = 2.0f / float(M);
 
     for (int64_t task = int64_t(blockIdx.x) * kWarps + warp; task < total_runs; task += int64_t(gridDim.x) * kWarps) {
         const int64_t clip = task / runs_per_clip;
@@ -329,8 +333,7 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
                 const int P = lane + 32 * rho;
                 const float2 w1 = s_win[P], w2 = s_win[H + P];
                 if (emit) {
-                    const float2 o = make_float2(fmaf(kScale * w1.x, first.x, carry[rho].x),
-                                                 fmaf(kScale * w1.y, first.y, carry[rho].y));
+                    const float2 o = make_float2(fmaf(w1.x, first.x, carry[rho].x), fmaf(w1.y, first.y, carry[rho].y));
                     const int64_t idx = base + 2 * P;
                     if (y_aligned && idx + 1 < out_len) {
                         __stcs(reinterpret_cast<float2*>(yc + idx), o);
@@ -339,7 +342,7 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
                         if (idx + 1 < out_len) yc[idx + 1] = o.y;
                     }
                 }
-                carry[rho] = make_float2(kScale * w2.x * second.x, kScale * w2.y * second.y);
+                carry[rho] = make_float2(w2.x * second.x, w2.y * second.y);
             });
         }
     }
