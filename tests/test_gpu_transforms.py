@@ -411,3 +411,23 @@ def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
     sd = zaf_gpu.stft(zaf_gpu.to_device(x2), w, 512, layout="bin_major")
     assert not sd.transposed and np.array_equal(sd.to_host(), a2)
     assert np.array_equal(zaf_gpu.istft(sd, w, 512).to_host(), zaf_gpu.istft(a2, w, 512))
+
+
+def test_sum_of_sinusoids_parity_and_the_fp32_floor_of_mfcc(zaf_gpu):
+    """A sum of sinusoids (SURVEY.md section 8d asks for one): the linear outputs keep the 1e-5 bar.  MFCC takes the
+    LOG of mel energies that sit 100+ dB below the spectral peak; an fp32 FFT resolves a bin only to about 1e-8 of the
+    peak amplitude, so those energies carry relative errors of 1e-4..1e-3 and the coefficients agree with the float64
+    reference to a few 1e-5 of their maximum, not 1e-5 (measured 2.3e-5; broadband clips: 3e-7).  The tolerance for this
+    one case is therefore 1e-4, stated here and in DESIGN.md."""
+    t = np.arange(80000) / 16000.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.1 * np.sin(2 * np.pi * 3000 * t)).astype(np.float32)
+    w = oracle.hamming_periodic(1024)
+    fb = zaf_gpu.melfilterbank(16000, 1024, 128)
+    dense = fb.toarray()
+    assert_parity(zaf_gpu.stft(x, w, 256), oracle.stft(x, w, 256))
+    assert_parity(zaf_gpu.melspectrogram(x, w, 256, fb), oracle.melspectrogram(x, w, 256, dense))
+    wk = oracle.kbd_window(2048)
+    assert_parity(zaf_gpu.mdct(x, wk), oracle.mdct(x, wk))
+    for t_ in (2, 4):
+        assert_parity(zaf_gpu.dct(x[:1024], t_), oracle.dct(x[:1024], t_))
+    assert_parity(zaf_gpu.mfcc(x, w, 256, fb, 40), oracle.mfcc(x, w, 256, dense, 40), tol=1e-4)

@@ -149,6 +149,10 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
 //   ln ratio -> DCT-II through its even/odd symmetry  C[k] = sum_{m < n/2} D[k][m] (L[m] +- L[n-1-m])
 //   with lane l owning coefficients l and l + 32.
 // ------------------------------------------------------------------------------------------
+#ifndef ZAFB_MEL_OCC1024
+#define ZAFB_MEL_OCC1024 3
+#endif
+constexpr int kMelOcc1024 = ZAFB_MEL_OCC1024;   // CTAs per SM at N = 1024 (3 needs the window in shared memory)
 constexpr int kWarps = 8;        // N = 1024
 constexpr int kWarps2048 = 6;    // N = 2048: the tiles are twice as large; 6 warps keep two CTAs per SM
 constexpr int kMelWarpTile = 16 * kFft1024Pitch;  // float2 per warp at N = 1024: FFT transpose tile, then spectrum / log-mel scratch
@@ -165,7 +169,7 @@ __device__ __forceinline__ void split_tf32_dev(float v, float& hi, float& lo) {
 // SPLIT = true (N = 1024): the kernel stops after the spectrum and writes |X| (MODE 0) or |X|^2 (MODE 1) of bins 1..512 as
 // TF32 hi/lo halves to out / out_lo ([frame][512]) -- the A operand of the tensor-core filterbank product.
 template <int N, int MODE, bool SPLIT = false>  // MODE 0 melspectrogram, 1 mfcc
-__global__ void __launch_bounds__((N == 2048 ? kWarps2048 : kWarps) * 32, 2)
+__global__ void __launch_bounds__((N == 2048 ? kWarps2048 : kWarps) * 32, N == 1024 ? kMelOcc1024 : 2)
 mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                 const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
                 const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
@@ -177,7 +181,8 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     constexpr int WARPS = N == 2048 ? kWarps2048 : kWarps;
     // float2 per warp: the FFT transpose tile, then the spectrum (M floats) / log-mel scratch (256 floats at least)
     constexpr int TILE = (REGS < 16 ? 16 : REGS) * kFft1024Pitch;
-    constexpr bool WIN_REGS = N != 2048;                     // N = 2048: 32 more float2 registers do not fit, window from shared memory
+    // window pairs in registers unless they do not fit (N = 2048: 32 more float2; N = 1024 at three CTAs per SM)
+    constexpr bool WIN_REGS = N == 512 || (N == 1024 && kMelOcc1024 == 2);
     static_assert(!SPLIT || N == 1024, "the tensor-core front end is written for N = 1024");
     extern __shared__ float2 smem2[];
     float2* s_tw = smem2;                                    // M: W_M^{k1 n2}
@@ -413,7 +418,7 @@ int launch_tensor(const zafb_mel_plan* p, int mode, const float* x, int64_t n_cl
     float* ws = nullptr;
     ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (2 * spec_f + mel_f + 2 * log_f) * sizeof(float), st));
     float *spec_hi = ws, *spec_lo = ws + spec_f, *mel_buf = ws + 2 * spec_f, *log_hi = mel_buf + mel_f, *log_lo = log_hi + log_f;
-    const size_t smem = 512 * sizeof(float2) + 16 + size_t(kWarps) * kMelWarpTile * sizeof(float2);
+    const size_t smem = (kMelOcc1024 == 2 ? 512 : 1024) * sizeof(float2) + 16 + size_t(kWarps) * kMelWarpTile * sizeof(float2);
     const int4 zero4 = make_int4(0, 0, 0, 0);
     int rc = ZAFB_OK;
     for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += clips_per_chunk) {
@@ -481,11 +486,13 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
             const int warps = big ? kWarps2048 : kWarps;
             const int64_t half = p->n / 2;
             const int64_t tile_rows = half / 32 < 16 ? 16 : half / 32;  // the tile also holds the spectrum / log-mel scratch
-            const size_t smem = size_t(big ? 2 * half : half) * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) +
+            const bool win_smem = big || (p->n == 1024 && kMelOcc1024 != 2);
+            const size_t smem = size_t(win_smem ? 2 * half : half) * sizeof(float2) + size_t((wt_total + 3) & ~3) * sizeof(float) +
                                 size_t(dh_count) * sizeof(float4) + size_t(warps) * tile_rows * kFft1024Pitch * sizeof(float2);
             if (smem <= size_t(kMaxDynSmem) / 2 + 8 * 1024) {  // two CTAs per SM fit (227 KB per SM)
                 int64_t ctas = ceil_div(total, warps);
-                if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+                const int occ = p->n == 1024 ? kMelOcc1024 : 2;
+                if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
                 const int4 gl = make_int4(p->grp_len[0], p->grp_len[1], p->grp_len[2], p->grp_len[3]);
                 const int4 go = make_int4(p->grp_off[0], p->grp_off[1], p->grp_off[2], p->grp_off[3]);
                 auto kern = big ? (mode == 0 ? mel_warp_kernel<2048, 0> : mel_warp_kernel<2048, 1>)
