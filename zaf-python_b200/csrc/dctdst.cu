@@ -211,7 +211,7 @@ __global__ void dct_fft_kernel(const float* __restrict__ x, int64_t batch, int64
 constexpr int kDctWarps = 8;
 
 template <int MODE, bool DST>
-__global__ void __launch_bounds__(kDctWarps * 32, 2)
+__global__ void __launch_bounds__(kDctWarps * 32, MODE == 3 ? 2 : 3)   // type III holds the 1024 inputs AND 512 products
 dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, const float2* __restrict__ tw4,
                     const float2* __restrict__ tw_a, const float2* __restrict__ tw_b, float* __restrict__ out,
                     int64_t out_stride) {
@@ -557,7 +557,8 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
         if (warp_ok && (p->force_direct == 0 || p->force_direct == 4)) {
             const size_t smem = (512 + kDctWarps * 16 * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(batch, kDctWarps);
-            if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+            const int occ = p->type == 3 ? 2 : 3;
+            if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
             const unsigned g = unsigned(ctas), b = kDctWarps * 32;
 #define ZAFB_DCT_WARP(MODE, DST)                                                                                  \
     dct1024_warp_kernel<MODE, DST><<<g, b, smem, st>>>(x, batch, stride, p->d_tw_4step, p->d_tw_a, p->d_tw_b, out, out_stride)
