@@ -38,8 +38,10 @@ struct zafb_mel_plan {
     float2* d_tw_4step = nullptr;   // W_{n/2}^{k1 n2}, [k1][n2]
     float2* d_tw_n = nullptr;       // W_n^t, t < 32
     int* d_lo = nullptr;            // first column of row lane + 32 g, at [g * 32 + lane]
-    float* d_dh = nullptr;          // DCT-II half table, float4 at [(m / 4) * coef_pad + i] = D[i + 1][4 (m / 4) .. +3]
-    int coef_pad = 0;               // n_coef rounded up to 32
+    float* d_dh = nullptr;          // DCT-II half table for lane (c8 = lane & 7, g = lane >> 3): float4 at [(t * qm4 + mq) * 32 + lane]
+                                    //   = D[c8 + 8 t + 1][g * 4 qm4 + 4 mq .. +3]  (zero beyond n_coef / half_mels)
+    int coef_pad = 0;               // t groups: ceil(n_coef / 8), at most 8
+    int qm4 = 0;                    // float4 per quarter of the folded mel axis: ceil(half_mels / 16)
     int half_mels = 0;              // ceil(n_mels / 2)
     int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
     // tensor-core route (ZAFB_MEL_ROUTE_TENSOR): the filterbank and the MFCC DCT rows as dense TF32 hi/lo operands
@@ -174,8 +176,9 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 const float2* __restrict__ win_pairs, const float2* __restrict__ tw4,
                 const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
                 int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
-                int n_coef, int coef_pad, float* __restrict__ out, int64_t total_frames,
+                int n_coef, int dct_shape, float* __restrict__ out, int64_t total_frames,
                 float* __restrict__ out_lo) {
+    const int tgroups = dct_shape >> 8, qm4 = dct_shape & 255;  // MFCC DCT: coefficient groups of 8, float4 per mel quarter
     constexpr int M = N / 2, REGS = M / 32, LOGR = clog2(REGS);
     static_assert(N == 512 || N == 1024 || N == 2048, "warp kernels exist for window lengths 512, 1024 and 2048");
     constexpr int WARPS = N == 2048 ? kWarps2048 : kWarps;
@@ -188,8 +191,8 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     float2* s_tw = smem2;                                    // M: W_M^{k1 n2}
     float2* s_win = smem2 + M;                               // M (N = 2048 only): 0.5 * window pairs
     float* s_wt = reinterpret_cast<float*>(smem2 + (WIN_REGS ? M : 2 * M));  // wt_total floats
-    float4* s_dh = reinterpret_cast<float4*>(s_wt + ((wt_total + 3) & ~3));  // (half_mels/4 rounded up) * coef_pad float4
-    const int dh_count = MODE == 1 ? ((half_mels + 3) / 4) * coef_pad : 0;
+    float4* s_dh = reinterpret_cast<float4*>(s_wt + ((wt_total + 3) & ~3));  // tgroups * qm4 * 32 float4
+    const int dh_count = MODE == 1 ? tgroups * qm4 * 32 : 0;
     float2* s_warp = reinterpret_cast<float2*>(s_dh + dh_count);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* s_buf = s_warp + warp * TILE;
@@ -324,22 +327,37 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 s_sym[64 + m] = av;
             }
             __syncwarp();
-            const int quads = (half_mels + 3) >> 2;
-            for (int i0 = 0; i0 < n_coef; i0 += 32) {
-                const int i = i0 + lane;                       // coefficient row k = i + 1
-                const float4* sa = reinterpret_cast<const float4*>(s_sym + ((i & 1) ? 0 : 64));  // k even -> S, k odd -> A
-                const float4* d = s_dh + i;
-                float acc0 = 0.f, acc1 = 0.f;
-                for (int q = 0; q < quads; ++q) {
-                    const float4 s4 = sa[q];
-                    const float4 d4 = d[q * coef_pad];
-                    acc0 = fmaf(d4.x, s4.x, acc0);
-                    acc1 = fmaf(d4.y, s4.y, acc1);
-                    acc0 = fmaf(d4.z, s4.z, acc0);
-                    acc1 = fmaf(d4.w, s4.w, acc1);
-                }
-                if (i < n_coef) out[f * n_coef + i] = acc0 + acc1;
+            // C[k] = sum_{m < half} D[k][m] (L[m] +- L[n-1-m]).  Lane (c8 = lane & 7, g = lane >> 3) accumulates the
+            // coefficients k = c8 + 8 t + 1 (t < tgroups) over quarter g of the folded mel axis -- every lane busy, every
+            // table entry read once -- then the four quarters are added with two xor shuffles and lane c8 + 8 g ends up
+            // holding coefficient index lane (t = g) and 32 + lane (t = 4 + g).
+            const int c8 = lane & 7, g = lane >> 3;
+            const float4* sa = reinterpret_cast<const float4*>(s_sym + ((c8 & 1) ? 0 : 64)) + g * qm4;  // k even -> S, k odd -> A
+            const float4* d = s_dh + lane;
+            float acc[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+            for (int mq = 0; mq < qm4; ++mq) {
+                const float4 s4 = sa[mq];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < tgroups) {
+                        const float4 d4 = d[(t * qm4 + mq) * 32];
+                        acc[t] = fmaf(d4.x, s4.x, fmaf(d4.y, s4.y, fmaf(d4.z, s4.z, fmaf(d4.w, s4.w, acc[t]))));
+                    }
             }
+            float lo_val = 0.f, hi_val = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (t < tgroups) {
+                    float a = acc[t];
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    if (t < 4) lo_val = (g == t) ? a : lo_val;
+                    else hi_val = (g == t - 4) ? a : hi_val;
+                }
+            if (lane < n_coef) out[f * n_coef + lane] = lo_val;
+            if (32 + lane < n_coef) out[f * n_coef + 32 + lane] = hi_val;
             __syncwarp();
         }
     }
@@ -481,7 +499,7 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         }
         if (ok && p->force_kernel != 1) {
             const int wt_total = p->grp_off[3] + 32 * p->grp_len[3];
-            const int dh_count = mode == 1 ? ((p->half_mels + 3) / 4) * p->coef_pad : 0;
+            const int dh_count = mode == 1 ? p->coef_pad * p->qm4 * 32 : 0;
             const bool big = p->n == 2048;
             const int warps = big ? kWarps2048 : kWarps;
             const int64_t half = p->n / 2;
@@ -501,7 +519,7 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
                 kern<<<unsigned(ctas), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                     x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                     p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
-                    int(p->n_coef), p->coef_pad, out, total, nullptr);
+                    int(p->n_coef), (p->coef_pad << 8) | p->qm4, out, total, nullptr);
                 ZAFB_LAUNCH_CHECK();
                 return ZAFB_OK;
             }
@@ -596,13 +614,20 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
             }
         }
         p->half_mels = int((n_mels + 1) / 2);
-        p->coef_pad = int((p->n_coef + 31) / 32 * 32);
-        const int quads = (p->half_mels + 3) / 4;
-        std::vector<float> dh(size_t(quads) * (p->coef_pad ? p->coef_pad : 32) * 4, 0.f);
-        for (int64_t i = 0; i < p->n_coef; ++i)
-            for (int64_t mm = 0; mm < p->half_mels; ++mm)
-                dh[((mm / 4) * p->coef_pad + i) * 4 + (mm % 4)] = static_cast<float>(
-                    std::sqrt(2.0 / double(n_mels)) * std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels)));
+        p->coef_pad = int((p->n_coef + 7) / 8);
+        p->qm4 = (p->half_mels + 15) / 16;
+        std::vector<float> dh(size_t(p->coef_pad ? p->coef_pad : 1) * (p->qm4 ? p->qm4 : 1) * 32 * 4, 0.f);
+        for (int t = 0; t < p->coef_pad; ++t)
+            for (int mq = 0; mq < p->qm4; ++mq)
+                for (int l = 0; l < 32; ++l) {
+                    const int64_t i = (l & 7) + 8 * t;  // coefficient index, row k = i + 1
+                    for (int e = 0; e < 4; ++e) {
+                        const int64_t mm = int64_t(l >> 3) * 4 * p->qm4 + 4 * mq + e;
+                        if (i < p->n_coef && mm < p->half_mels)
+                            dh[(size_t(t * p->qm4 + mq) * 32 + l) * 4 + e] = static_cast<float>(
+                                std::sqrt(2.0 / double(n_mels)) * std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels)));
+                    }
+                }
         const int64_t half = n / 2;  // four-step twiddles W_half^{k1 n2}, [k1][n2], half = (half / 32) x 32
         std::vector<double> t4(2 * half);
         for (int64_t k1 = 0; k1 < half / 32; ++k1)
