@@ -13,10 +13,10 @@ echo "== bench"; timeout 600 python bench.py 2>&1 | tail -3 | tee $OUT/bench.jso
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 0 > $OUT/ncu_launches_bench.log 2>&1
+    python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 0 --sustained-steps 0 > $OUT/ncu_launches_bench.log 2>&1
 tail -3 $OUT/launches.csv
 echo "== ncu full (stft kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-stft2048} -s 3 -c 1 -f -o $OUT/prof_stft \
-    python bench.py --steps 3 --warmup 3 --clips 128 --no-cpu --e2e-steps 0 > $OUT/ncu_full_bench.log 2>&1
+    python bench.py --steps 3 --warmup 3 --clips 128 --no-cpu --e2e-steps 0 --sustained-steps 0 > $OUT/ncu_full_bench.log 2>&1
 ls -la $OUT
 fi

@@ -8,7 +8,7 @@ mkdir -p $OUT
 echo "== link probe"; timeout 300 python scripts/pcie_probe.py --out $OUT/pcie_probe.jsonl 2>&1 | head -20
 echo "== ncu launch list (bench.py)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 0 > $OUT/ncu_launches_bench.log 2>&1
+    python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 0 --sustained-steps 0 > $OUT/ncu_launches_bench.log 2>&1
 tail -3 $OUT/launches.csv
 full() {  # name, kernel regex, skip, command...
     local name=$1 regex=$2 skip=$3; shift 3
@@ -23,7 +23,7 @@ full() {  # name, kernel regex, skip, command...
         tail -5 $OUT/ncu_$name.log
     fi
 }
-full stft2048 '^stft_warp_kernel' 3 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 0
+full stft2048 '^stft_warp_kernel' 3 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 0 --sustained-steps 0
 S="--scale 0.125 --steps 2"
 full istft2048 '^istft_warp_kernel' 3 python scripts/bench_configs.py --only istft $S
 full mdct2048 '^mdct2048' 3 python scripts/bench_configs.py --only mdct $S
