@@ -297,8 +297,8 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
 //   Z[k] = E[k] + i O[k],  E = H[k] + H[k+1024],  O = (H[k] - H[k+1024]) conj(W_2048^k),
 //   y[2n] + i y[2n+1] = conj(FFT_1024(conj(Z)))[n] / (2 N)        (validated in float64).
 // ------------------------------------------------------------------------------------------
-template <int N, int R>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+template <int N, int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
                   int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
@@ -318,16 +318,16 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
     const int lane = tid & 31;
     const int warp = tid >> 5;
     float2* s_ring = smem + M + warp * RING;
-    float* s_buf = reinterpret_cast<float*>(smem + M + kWarpsPerCta * RING) + warp * TILE_FLOATS;
+    float* s_buf = reinterpret_cast<float*>(smem + M + WARPS * RING) + warp * TILE_FLOATS;
 
-    for (int i = tid; i < M; i += kWarpsPerCta * 32) s_tw[i] = tw4[i];
+    for (int i = tid; i < M; i += WARPS * 32) s_tw[i] = tw4[i];
     const float2 c_lane = tw_full[lane];  // W_N^lane
     LaneTw<N> lt;
     lt.init(lane);
     __syncthreads();
 
-    for (int64_t task = int64_t(blockIdx.x) * kWarpsPerCta + warp; task < total_runs;
-         task += int64_t(gridDim.x) * kWarpsPerCta) {
+    for (int64_t task = int64_t(blockIdx.x) * WARPS + warp; task < total_runs;
+         task += int64_t(gridDim.x) * WARPS) {
         const int64_t clip = task / runs_per_clip;
         const int64_t run = task - clip * runs_per_clip;
         const int64_t h_begin = (R - 1) + run * run_len;  // first finished block of the run (OLA coordinates)
@@ -554,15 +554,6 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<2048, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -570,11 +561,16 @@ int set_kernel_attrs() {
     return ZAFB_OK;
 }
 
-template <int N, int R>
-int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                      int64_t y_stride, cudaStream_t st) {
+template <int N, int R, int WARPS>
+int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
+                        int64_t y_stride, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        attr = true;
+    }
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
-    const int64_t resident_warps = int64_t(sm_count()) * 2 * kWarpsPerCta;
+    const int64_t resident_warps = int64_t(sm_count()) * 2 * WARPS;
     // run length: minimise (runs per warp) x (frames per run, warm-up included)
     int64_t best_len = nblocks, best_cost = INT64_MAX;
     for (int64_t len = nblocks < 8 ? nblocks : 8; len <= nblocks && len <= 1024; ++len) {
@@ -587,17 +583,24 @@ int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_cli
     }
     const int64_t runs_per_clip = ceil_div(nblocks, best_len);
     const int64_t total = n_clips * runs_per_clip;
-    int64_t ctas = ceil_div(total, kWarpsPerCta);
+    int64_t ctas = ceil_div(total, WARPS);
     if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
     constexpr int HOP = N / R;
-    const size_t smem = (N / 2) * sizeof(float2) + size_t(kWarpsPerCta) * ((R - 1) * (HOP / 2) * sizeof(float2) +
+    const size_t smem = (N / 2) * sizeof(float2) + size_t(WARPS) * ((R - 1) * (HOP / 2) * sizeof(float2) +
                                                                            32 * kFft1024Pitch * sizeof(float));
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
-    istft_warp_kernel<N, R><<<static_cast<unsigned>(ctas), kWarpsPerCta * 32, smem, st>>>(
+    istft_warp_kernel<N, R, WARPS><<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
         env_flag("ZAFB_ISTFT_PREFETCH", 1));
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
+}
+
+template <int N, int R>
+int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
+                      int64_t y_stride, cudaStream_t st) {
+    if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
+    return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st);
 }
 
 int fft_threads(int points) {  // threads for a block FFT of `points` complex points
