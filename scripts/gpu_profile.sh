@@ -26,8 +26,8 @@ full() {  # name, kernel regex, skip, command...
 full stft2048 '^stft_warp_kernel' 3 python bench.py --steps 3 --warmup 3 --no-cpu --e2e-steps 0 --sustained-steps 0
 S="--scale 0.125 --steps 2"
 full istft2048 '^istft_warp_kernel' 3 python scripts/bench_configs.py --only istft $S
-full mdct2048 '^mdct2048' 3 python scripts/bench_configs.py --only mdct $S
-full imdct2048 imdct2048 3 python scripts/bench_configs.py --only imdct $S
+full mdct2048 '^mdct_warp_kernel' 3 python scripts/bench_configs.py --only mdct $S
+full imdct2048 '^imdct_warp_kernel' 3 python scripts/bench_configs.py --only imdct $S
 full dct1024 dct1024_warp 3 python scripts/bench_configs.py --only dct $S
 full transpose transpose_tile 1 python scripts/bench_configs.py --only stftbin $S
 for k in ${EXTRA_KERNELS:-}; do
