@@ -171,6 +171,10 @@ int zafb_mel_plan_destroy(zafb_mel_plan* plan);
 #define ZAFB_MEL_ROUTE_FUSED 0
 #define ZAFB_MEL_ROUTE_TENSOR 1
 int zafb_mel_plan_set_route(zafb_mel_plan* plan, int route);
+/* Arithmetic of the spectrum, filterbank sums and logarithm: 32 (default) or 64 bits.  The float64 route (any
+ * power-of-two window length) exists for purely tonal material, where the LOG in mfcc amplifies the fp32 floor of the
+ * FFT; pass the float64 window again.  Inputs and outputs stay fp32. */
+int zafb_mel_plan_set_precision(zafb_mel_plan* plan, int bits, const double* window);
 /* zaf.melspectrogram (zaf.py:369-375): out n_clips * n_mels * nt float32 in `layout`. */
 int zafb_melspectrogram_f32(const zafb_mel_plan* plan, const float* x, int64_t n_clips, int64_t ns,
                             int64_t clip_stride, float* out, int layout, void* stream);

@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mdct1024,mel,mfcc,meltc,mel2048,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mdct1024,mel,mfcc,meltc,melf64,mel2048,cqt,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -242,7 +242,7 @@ def main():
         xd.free(), spec.free(), yd.free()
 
     # ---- cfg 3: melspectrogram + mfcc, 4096 clips x 5 s @ 16 kHz, N = 1024, hop = 256, 128 mels, 40 coefficients
-    if only & {"mel", "mfcc", "meltc"}:
+    if only & {"mel", "mfcc", "meltc", "melf64"}:
         clips, ns, n, hop, fs = max(1, int(4096 * args.scale)), 80000, 1024, 256, 16000
         w = hamming_periodic(n)
         fb = zaf.melfilterbank(fs, n, 128)
@@ -263,6 +263,12 @@ def main():
                 plan_mfcc, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), args.steps)
             emit(line("mfcc", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
                       "FP32/shared-memory bound, not HBM (SURVEY 8d)"))
+        if "melf64" in only:  # the float64 route (accuracy option for purely tonal material)
+            plan64, _, _ = zaf._mel_plan(w, hop, fb, 40, "fused", "float64")
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_mfcc_f32(
+                plan64, C.c_void_p(xd.ptr), clips, ns, ns, C.c_void_p(od.ptr), 0, s.ptr)), max(2, args.steps // 5))
+            emit(line("mfcc-float64", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * 40 * 4, nl,
+                      "spectrum, filterbank sums and logarithm in FP64 (generic block kernel)"))
         if "meltc" in only:  # the dense tensor-core route of the same two transforms
             plan_mel_tc, _, _ = zaf._mel_plan(w, hop, fb, 0, "tensor")
             plan_mfcc_tc, _, _ = zaf._mel_plan(w, hop, fb, 40, "tensor")

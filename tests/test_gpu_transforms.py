@@ -431,3 +431,29 @@ def test_sum_of_sinusoids_parity_and_the_fp32_floor_of_mfcc(zaf_gpu):
     for t_ in (2, 4):
         assert_parity(zaf_gpu.dct(x[:1024], t_), oracle.dct(x[:1024], t_))
     assert_parity(zaf_gpu.mfcc(x, w, 256, fb, 40), oracle.mfcc(x, w, 256, dense, 40), tol=1e-4)
+    # the float64 route closes that gap: 1e-5 holds on the tonal signal as well
+    assert_parity(zaf_gpu.mfcc(x, w, 256, fb, 40, precision="float64"), oracle.mfcc(x, w, 256, dense, 40))
+    assert_parity(zaf_gpu.melspectrogram(x, w, 256, fb, precision="float64"), oracle.melspectrogram(x, w, 256, dense))
+
+
+@pytest.mark.parametrize("n,hop,n_mels,ncoef,fs", [(1024, 256, 128, 40, 16000), (2048, 1024, 128, 20, 44100), (256, 64, 40, 13, 8000),
+                                                  (4096, 1000, 77, 76, 44100)])
+def test_mel_mfcc_float64_route(zaf_gpu, n, hop, n_mels, ncoef, fs):
+    """precision="float64": any power-of-two window length, both layouts, batches, silent stretches; results within
+    2e-7 of the float64 oracle (the only fp32 roundings left are the input, the filterbank weights and the output)."""
+    rng = np.random.default_rng(n + n_mels)
+    x = rng.uniform(-1, 1, (3, 12001)).astype(np.float32)
+    x[1, 2000:6000] = 0.0
+    w = oracle.hamming_periodic(n)
+    fb = zaf_gpu.melfilterbank(fs, n, n_mels)
+    dense = fb.toarray()
+    mel = zaf_gpu.melspectrogram(x, w, hop, fb, precision="float64")
+    cep = zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64")
+    for c in range(3):
+        assert_parity(mel[c], oracle.melspectrogram(x[c], w, hop, dense), tol=2e-7)
+        ref = oracle.mfcc(x[c], w, hop, dense, ncoef)
+        assert cep[c].shape == ref.shape
+        assert_parity(cep[c], ref, tol=1e-6)
+    assert np.array_equal(zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64", layout="bin_major"), cep)
+    with pytest.raises(ValueError):
+        zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float16")

@@ -378,7 +378,7 @@ def dst(audio_signal, dst_type):
 _MEL_ROUTES = {"fused": 0, "tensor": 1}
 
 
-def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused"):
+def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused", precision="float32"):
     w = _window64(window_function)
     fb = mel_filterbank.toarray() if hasattr(mel_filterbank, "toarray") else np.asarray(mel_filterbank)  # zaf.py:373
     fb = np.ascontiguousarray(fb, dtype=np.float64)
@@ -386,17 +386,22 @@ def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients,
         raise ValueError(f"mel_filterbank must have shape (number_mels, window_length/2 = {len(w) // 2})")
     if route not in _MEL_ROUTES:
         raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
-    key = ("mel", len(w), int(step_length), int(number_coefficients), route, w.tobytes(), fb.tobytes())
+    if precision not in ("float32", "float64"):
+        raise ValueError("precision must be 'float32' or 'float64'")
+    key = ("mel", len(w), int(step_length), int(number_coefficients), route, precision, w.tobytes(), fb.tobytes())
     fresh = key not in _mel_plans._d
     plan = _mel_plans.get(key, w.ctypes.data, len(w), int(step_length), fb.ctypes.data, fb.shape[0],
                           int(number_coefficients))
     if fresh and route != "fused":
         _lib.check(_lib.lib().zafb_mel_plan_set_route(plan, _MEL_ROUTES[route]))
+    if fresh and precision == "float64":
+        _lib.check(_lib.lib().zafb_mel_plan_set_precision(plan, 64, w.ctypes.data))
     return plan, w, fb.shape[0]
 
 
-def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, ncoef, rows_of, layout, stream, route):
-    plan, w, n_mels = _mel_plan(window_function, step_length, mel_filterbank, ncoef, route)
+def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, ncoef, rows_of, layout, stream, route,
+              precision):
+    plan, w, n_mels = _mel_plan(window_function, step_length, mel_filterbank, ncoef, route, precision)
     lay = _layout_id(layout)
     rows = rows_of(n_mels)
     if isinstance(audio_signal, DeviceArray):
@@ -418,22 +423,25 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
 
 
 def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *, layout="frame_major", stream=None,
-                   route="fused"):
+                   route="fused", precision="float32"):
     """Mel spectrogram -- drop-in for ``zaf.melspectrogram`` (zaf.py:324-375): filterbank times the
     magnitude of STFT rows 1..N/2 (no DC, with Nyquist).  Returns (number_mels, number_times).
     ``route="tensor"`` applies the filterbank as the dense product of zaf.py:373 on the tcgen05 tensor
-    cores (3xTF32, window_length 1024); the default fuses the banded filterbank into the STFT kernel."""
+    cores (3xTF32, window_length 1024); the default fuses the banded filterbank into the STFT kernel.
+    ``precision="float64"`` computes the spectrum and the filterbank sums in double precision on the GPU."""
     return _mel_like("zafb_melspectrogram_f32", audio_signal, window_function, step_length, mel_filterbank, 0,
-                     lambda n_mels: n_mels, layout, stream, route)
+                     lambda n_mels: n_mels, layout, stream, route, precision)
 
 
 def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coefficients, *,
-         layout="frame_major", stream=None, route="fused"):
+         layout="frame_major", stream=None, route="fused", precision="float32"):
     """MFCCs -- drop-in for ``zaf.mfcc`` (zaf.py:378-454): orthonormal DCT-II over the mel axis of
-    ln(filterbank @ |STFT|^2 + eps), rows 1..number_coefficients.  Returns (number_coefficients, number_times)."""
+    ln(filterbank @ |STFT|^2 + eps), rows 1..number_coefficients.  Returns (number_coefficients, number_times).
+    ``precision="float64"``: spectrum, filterbank sums and logarithm in double precision on the GPU -- for purely tonal
+    signals, whose quietest mel bands sit at the fp32 floor of the FFT and get amplified by the logarithm."""
     ncoef = int(number_coefficients)
     return _mel_like("zafb_mfcc_f32", audio_signal, window_function, step_length, mel_filterbank, ncoef,
-                     lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream, route)
+                     lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream, route, precision)
 
 
 # ------------------------------------------------------------------ CQT

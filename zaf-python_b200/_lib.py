@@ -70,6 +70,7 @@ PROTOTYPES = {
     "zafb_mel_plan_create": (_int, [_pvp, _vp, _i64, _i64, _vp, _i64, _i64]),
     "zafb_mel_plan_destroy": (_int, [_vp]),
     "zafb_mel_plan_set_route": (_int, [_vp, _int]),
+    "zafb_mel_plan_set_precision": (_int, [_vp, _int, _vp]),
     "zafb_melspectrogram_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_mfcc_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_melspectrogram_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),

@@ -75,6 +75,13 @@ ZAFB_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s);
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
 
+// float64 twins (the optional float64 route of melspectrogram / mfcc)
+ZAFB_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+ZAFB_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+ZAFB_HD double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
 // ---------------------------------------------------------------- compile-time trigonometry
 // constexpr sin/cos in double (argument reduced to [0, pi/4], Taylor to < 1e-17) so that every
 // in-register twiddle is an immediate operand rounded once from float64.
@@ -154,6 +161,24 @@ ZAFB_HD float2 mul_tw(float2 a) {
     } else {
         constexpr float wr = Tw<NUM, DEN>::re, wi = Tw<NUM, DEN>::im;
         return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+}
+
+// the same rotation for a float64 value (constants in full double precision)
+template <int NUM_, int DEN>
+ZAFB_HD double2 mul_tw(double2 a) {
+    constexpr int NUM = ((NUM_ % DEN) + DEN) % DEN;
+    if constexpr (NUM == 0) {
+        return a;
+    } else if constexpr (4 * NUM == DEN) {
+        return make_double2(a.y, -a.x);
+    } else if constexpr (2 * NUM == DEN) {
+        return make_double2(-a.x, -a.y);
+    } else if constexpr (4 * NUM == 3 * DEN) {
+        return make_double2(-a.y, a.x);
+    } else {
+        constexpr double wr = ct::cos2pi(NUM, DEN), wi = -ct::sin2pi(NUM, DEN);
+        return make_double2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
     }
 }
 

@@ -19,10 +19,11 @@ namespace zafb {
 // ---------------------------------------------------------------- in-register FFT
 template <int N, int J, int STRIDE>
 struct DifButterflies {
-    static ZAFB_HD void run(float2* v) {
+    template <class C>  // C = float2 or double2
+    static ZAFB_HD void run(C* v) {
         // span N/2 butterflies of one radix-2 DIF stage on v[0], v[STRIDE], ...
-        float2 a = v[J * STRIDE];
-        float2 b = v[(J + N / 2) * STRIDE];
+        C a = v[J * STRIDE];
+        C b = v[(J + N / 2) * STRIDE];
         v[J * STRIDE] = cadd(a, b);
         v[(J + N / 2) * STRIDE] = mul_tw<J, N>(csub(a, b));
         if constexpr (J + 1 < N / 2) DifButterflies<N, J + 1, STRIDE>::run(v);
@@ -30,8 +31,8 @@ struct DifButterflies {
 };
 
 // In-place DIF FFT of v[0], v[STRIDE], ..., v[(N-1)*STRIDE]; output bit-reversed.
-template <int N, int STRIDE = 1>
-ZAFB_HD void fft_reg(float2* v) {
+template <int N, int STRIDE = 1, class C>
+ZAFB_HD void fft_reg(C* v) {
     if constexpr (N >= 2) {
         DifButterflies<N, 0, STRIDE>::run(v);
         fft_reg<N / 2, STRIDE>(v);
@@ -42,12 +43,12 @@ ZAFB_HD void fft_reg(float2* v) {
 // ---------------------------------------------------------------- Stockham pass (shared memory)
 // One radix-R butterfly j (0 <= j < M/R) of the pass with sub-transform length Ns (product of the
 // radices of the previous passes).  tw[t] = exp(-2 pi i t / M), t < M.  Natural order in and out.
-template <int R>
-ZAFB_HD void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out,
-                           const float2* __restrict__ tw, int M, int Ns, int j) {
+template <int R, class C>
+ZAFB_HD void stockham_pass(const C* __restrict__ in, C* __restrict__ out,
+                           const C* __restrict__ tw, int M, int Ns, int j) {
     const int k = j & (Ns - 1);
     const int tstride = M / (Ns * R);
-    float2 v[R];
+    C v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         v[r] = in[j + r * (M / R)];
@@ -217,8 +218,8 @@ __device__ __forceinline__ void warp_fft256(float2 (&v)[8], const float2* __rest
 // Whole-block M-point FFT in shared memory (ping-pong between a and b).  Every thread of the
 // group [0, nthreads) calls it with its tid; a leading __syncthreads() is the caller's job
 // (data in `a` must be visible).  Returns the buffer that holds the result; ends with a barrier.
-__device__ __forceinline__ float2* block_fft(float2* a, float2* b, const float2* __restrict__ tw,
-                                             int log2m, int tid, int nthreads) {
+template <class C>
+__device__ __forceinline__ C* block_fft(C* a, C* b, const C* __restrict__ tw, int log2m, int tid, int nthreads) {
     const int M = 1 << log2m;
     int radix[16];
     const int npass = stockham_schedule(log2m, radix);
@@ -231,7 +232,7 @@ __device__ __forceinline__ float2* block_fft(float2* a, float2* b, const float2*
             else stockham_pass<2>(a, b, tw, M, Ns, j);
         }
         __syncthreads();
-        float2* t = a;
+        C* t = a;
         a = b;
         b = t;
         Ns *= R;

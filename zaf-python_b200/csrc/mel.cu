@@ -44,6 +44,11 @@ struct zafb_mel_plan {
     int qm4 = 0;                    // float4 per quarter of the folded mel axis: ceil(half_mels / 16)
     int half_mels = 0;              // ceil(n_mels / 2)
     int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
+    // float64 route (ZAFB_MEL_PRECISION_F64): window and twiddles in double, any power-of-two window length
+    int precision = 32;
+    double* d_window64 = nullptr;
+    double2* d_tw_half64 = nullptr;  // W_{N/2}^t
+    double2* d_tw_full64 = nullptr;  // W_N^t, t < N/2
     // tensor-core route (ZAFB_MEL_ROUTE_TENSOR): the filterbank and the MFCC DCT rows as dense TF32 hi/lo operands
     int route = 0;
     float* d_fb_hi = nullptr;       // n_mels x (n/2)
@@ -135,6 +140,82 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
                 const float v = acc0 + acc1;
                 if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * rows + i] = v;
                 else out[(clip * rows + i) * nt + j] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// float64 route: the same pipeline as mel_frame_kernel with the window multiply, the FFT, |X|^2, the filterbank
+// sums and the logarithm in double precision (B200 runs FP64 at half the FP32 rate).  An fp32 FFT resolves a bin
+// only to ~1e-8 of the spectral peak, which the LOG in mfcc turns into 1e-4..1e-3 errors on the mel bands of
+// purely tonal signals that lie 100+ dB below the peak; this route keeps them at 1e-7.  Inputs and outputs stay fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void mel_frame_kernel_f64(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t hop,
+                                     int log2n, const double* __restrict__ window, const double2* __restrict__ tw_half,
+                                     const double2* __restrict__ tw_full, const int* __restrict__ band_lo,
+                                     const int* __restrict__ band_len, const int* __restrict__ band_off,
+                                     const float* __restrict__ weights, const float* __restrict__ dct, int n_mels, int n_coef,
+                                     int mode, float* __restrict__ out, int layout, int64_t total_frames) {
+    extern __shared__ double2 smem_d[];
+    const int n = 1 << log2n, m = n >> 1;
+    double2* a = smem_d;
+    double2* b = smem_d + m;
+    double* spec = reinterpret_cast<double*>(smem_d + 2 * m);  // m doubles: column c <-> FFT bin c + 1
+    double* mel = spec + m;                                    // n_mels doubles
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int rows = mode == 0 ? n_mels : n_coef;
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * hop - m;
+        const float* xc = x + clip * clip_stride;
+        for (int i = tid; i < m; i += nth) {
+            const int64_t s = start + 2 * i;
+            const double x0 = (s >= 0 && s < ns) ? double(xc[s]) : 0.0;
+            const double x1 = (s + 1 >= 0 && s + 1 < ns) ? double(xc[s + 1]) : 0.0;
+            a[i] = make_double2(x0 * window[2 * i], x1 * window[2 * i + 1]);
+        }
+        __syncthreads();
+        const double2* z = block_fft(a, b, tw_half, log2n - 1, tid, nth);
+        for (int k = 1 + tid; k <= m; k += nth) {  // bins 1 .. N/2 (zaf.py:370: no DC, with Nyquist)
+            double re, im;
+            if (k == m) {
+                re = z[0].x - z[0].y;
+                im = 0.0;
+            } else {
+                const double2 zk = z[k], zp = z[m - k];
+                const double2 e = make_double2(0.5 * (zk.x + zp.x), 0.5 * (zk.y - zp.y));
+                const double2 od = make_double2(0.5 * (zk.y + zp.y), 0.5 * (zp.x - zk.x));
+                const double2 t = cmul(tw_full[k], od);
+                re = e.x + t.x;
+                im = e.y + t.y;
+            }
+            const double p = re * re + im * im;
+            spec[k - 1] = mode == 0 ? sqrt(p) : p;
+        }
+        __syncthreads();
+        for (int r = tid; r < n_mels; r += nth) {
+            const int lo = band_lo[r], len = band_len[r];
+            const float* w = weights + band_off[r];
+            double acc = 0.0;
+            for (int c = 0; c < len; ++c) acc = fma(double(w[c]), spec[lo + c], acc);
+            if (mode == 0) {
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_mels + r] = float(acc);
+                else out[(clip * n_mels + r) * nt + j] = float(acc);
+            } else {
+                mel[r] = log(acc + 2.220446049250313e-16);  // np.finfo(float).eps, zaf.py:445
+            }
+        }
+        if (mode == 1) {
+            __syncthreads();
+            for (int i = tid; i < n_coef; i += nth) {
+                const float* d = dct + int64_t(i) * n_mels;
+                double acc = 0.0;
+                for (int r = 0; r < n_mels; ++r) acc = fma(double(d[r]), mel[r], acc);
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * rows + i] = float(acc);
+                else out[(clip * rows + i) * nt + j] = float(acc);
             }
         }
         __syncthreads();
@@ -385,6 +466,7 @@ bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
@@ -479,6 +561,20 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
     const int64_t rows = mode == 0 ? p->n_mels : p->n_coef;
     if (total == 0 || rows == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    if (p->precision == 64) {
+        const int mh = int(p->n / 2);
+        const size_t smem64 = size_t(p->n) * sizeof(double2) + size_t(mh + p->n_mels) * sizeof(double) + 16;
+        if (smem64 > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mel float64 route: window_length %lld too large", (long long)p->n);
+        int th = mh / 4;
+        if (th < 64) th = 64;
+        if (th > 256) th = 256;
+        const int64_t grid = total < int64_t(sm_count()) * 16 ? total : int64_t(sm_count()) * 16;
+        mel_frame_kernel_f64<<<unsigned(grid), th, smem64, static_cast<cudaStream_t>(stream)>>>(
+            x, ns, clip_stride, nt, p->hop, p->log2n, p->d_window64, p->d_tw_half64, p->d_tw_full64, p->d_band_lo, p->d_band_len,
+            p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, out, layout, total);
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    }
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
         if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->warp_ok && aligned && p->force_kernel != 1) {
@@ -676,6 +772,28 @@ int zafb_mel_plan_force_kernel(zafb_mel_plan* p, int which) {
     return ZAFB_OK;
 }
 
+int zafb_mel_plan_set_precision(zafb_mel_plan* p, int bits, const double* window) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(bits == 32 || bits == 64, "precision must be 32 or 64 (got %d)", bits);
+    if (bits == 64 && p->d_window64 == nullptr) {
+        ZAFB_REQUIRE(window != nullptr, "the float64 route needs the window again (float64)");
+        const double pi = 3.14159265358979323846264338327950288;
+        const int64_t n = p->n, h = n / 2;
+        std::vector<double2> th(h), tf(h);
+        for (int64_t t = 0; t < h; ++t) {
+            th[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(h)), std::sin(-2.0 * pi * double(t) / double(h)));
+            tf[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(n)), std::sin(-2.0 * pi * double(t) / double(n)));
+        }
+        std::vector<double> w(window, window + n);
+        int rc = upload_vec(&p->d_window64, w);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_half64, th);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_full64, tf);
+        if (rc != ZAFB_OK) return rc;
+    }
+    p->precision = bits;
+    return ZAFB_OK;
+}
+
 int zafb_mel_plan_set_route(zafb_mel_plan* p, int route) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
     ZAFB_REQUIRE(route == ZAFB_MEL_ROUTE_FUSED || route == ZAFB_MEL_ROUTE_TENSOR, "bad route %d", route);
@@ -687,6 +805,9 @@ int zafb_mel_plan_set_route(zafb_mel_plan* p, int route) {
 
 int zafb_mel_plan_destroy(zafb_mel_plan* p) {
     if (!p) return ZAFB_OK;
+    cudaFree(p->d_window64);
+    cudaFree(p->d_tw_half64);
+    cudaFree(p->d_tw_full64);
     cudaFree(p->d_fb_hi);
     cudaFree(p->d_fb_lo);
     cudaFree(p->d_dct_hi);
