@@ -314,6 +314,7 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
             });
             const bool emit = j >= h0;
             const int64_t base = (j - 1) * M;  // output index of OLA sample j*M (trim = M)
+            const bool whole = y_aligned && base + M <= out_len;
             static_for<0, REGS>([&](auto rc) {
                 constexpr int rho = decltype(rc)::value;
                 constexpr int own = rho < HR ? rho + HR : rho - HR;                  // register (kap) of this lane's value
@@ -334,12 +335,16 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
                 const float2 w1 = s_win[P], w2 = s_win[H + P];
                 if (emit) {
                     const float2 o = make_float2(fmaf(w1.x, first.x, carry[rho].x), fmaf(w1.y, first.y, carry[rho].y));
-                    const int64_t idx = base + 2 * P;
-                    if (y_aligned && idx + 1 < out_len) {
-                        __stcs(reinterpret_cast<float2*>(yc + idx), o);
+                    if (whole) {  // the hop-block lies inside the output and rows are 8-byte aligned: no per-store checks
+                        __stcs(reinterpret_cast<float2*>(yc + base) + P, o);
                     } else {
-                        if (idx < out_len) yc[idx] = o.x;
-                        if (idx + 1 < out_len) yc[idx + 1] = o.y;
+                        const int64_t idx = base + 2 * P;
+                        if (y_aligned && idx + 1 < out_len) {
+                            __stcs(reinterpret_cast<float2*>(yc + idx), o);
+                        } else {
+                            if (idx < out_len) yc[idx] = o.x;
+                            if (idx + 1 < out_len) yc[idx + 1] = o.y;
+                        }
                     }
                 }
                 carry[rho] = make_float2(w2.x * second.x, w2.y * second.y);
