@@ -195,6 +195,12 @@ int zafb_cqt_plan_create(zafb_cqt_plan** plan, int64_t n_freqs, int64_t fft_leng
                          const int32_t* indptr, const int32_t* indices, const double* data_ri,
                          int64_t step_length);
 int zafb_cqt_plan_destroy(zafb_cqt_plan* plan);
+/* How the kernel is applied.  FUSED (default): banded multiply-add inside the FFT kernel.  TENSOR: the spectrum's
+ * (Re, Im) rows against the dense real kernel block on the tcgen05 tensor cores in 3xTF32 (fft_length 32768, real
+ * kernels whose bands stay below fft_length/2 -- every kernel zaf.cqtkernel builds). */
+#define ZAFB_CQT_ROUTE_FUSED 0
+#define ZAFB_CQT_ROUTE_TENSOR 1
+int zafb_cqt_plan_set_route(zafb_cqt_plan* plan, int route);
 /* zaf.cqtspectrogram (zaf.py:603-635): out n_clips * n_freqs * nt float32 in `layout`.
  * octave_resolution > 0 additionally folds rows i::octave_resolution (zaf.cqtchromagram,
  * zaf.py:682-700) and the output has octave_resolution rows instead. */

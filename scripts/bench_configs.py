@@ -79,7 +79,7 @@ def line(name, cfg, frames, unit, ms, algo_bytes, launches, note=""):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mdct1024,mel,mfcc,meltc,melf64,mel2048,cqt,dct")
+    ap.add_argument("--only", default="cfg1,stft,stftbin,istft,stft1024,stft512,mdct,imdct,mdct1024,mel,mfcc,meltc,melf64,mel2048,cqt,cqttc,dct")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of each BASELINE batch")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
@@ -303,7 +303,7 @@ def main():
         xd.free(), od.free()
 
     # ---- cfg 5: cqtspectrogram, 512 clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8, 25 frames/s
-    if "cqt" in only:
+    if only & {"cqt", "cqttc"}:
         clips, ns, fs = max(1, int(512 * args.scale)), 882000, 44100
         kern = zaf.cqtkernel(fs, 12, 32.70319566257483, 4186.009044809578)
         xd, _ = device_batch(clips, ns, 20261017 + 5)
@@ -316,6 +316,12 @@ def main():
             plan_cqt, C.c_void_p(xd.ptr), clips, ns, ns, 0, C.c_void_p(od.ptr), 0, s.ptr)), max(3, args.steps // 3))
         emit(line("cqtspectrogram", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * kern.shape[0] * 4, nl,
                   "FP32/shared-memory bound: 32768-point FFT per frame (SURVEY 8d)"))
+        if "cqttc" in only:
+            plan_tc, _, _ = zaf._cqt_plan(kern, step, "tensor")
+            ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_cqt_f32(
+                plan_tc, C.c_void_p(xd.ptr), clips, ns, ns, 0, C.c_void_p(od.ptr), 0, s.ptr)), max(2, args.steps // 5))
+            emit(line("cqtspectrogram-tensor", cfg, clips * nt, "frames", ms, clips * ns * 4 + clips * nt * kern.shape[0] * 4, nl,
+                      "kernel applied as a dense 3xTF32 tcgen05 product, spectra staged through HBM"))
         xd.free()
 
     # ---- dct / dst: 2^20 vectors of 1024 samples (the reference's example length)

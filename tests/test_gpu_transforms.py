@@ -357,6 +357,33 @@ def test_cqt_32768_kernels_agree_with_oracle(zaf_gpu, force):
     assert_parity(got, oracle.cqtspectrogram(x[1], fs, 10, kk))
 
 
+def test_cqt_tensor_core_route(zaf_gpu):
+    """route="tensor": the CQT kernel as a dense 3xTF32 product on the tcgen05 tensor cores (BASELINE cfg 5: "sparse CQT
+    kernel as packed tensor-core GEMM").  The cfg 5 kernel (84 rows, one N tile) and the reference's example kernel (144
+    rows, two N tiles); spectrogram and chromagram; both layouts; same parity bar as the fused route."""
+    rng = np.random.default_rng(20261017 + 55)
+    fs = 44100
+    x = rng.uniform(-1, 1, (3, 40001)).astype(np.float32)
+    for res, fmin, fmax, rows in ((12, 32.70319566257483, 4186.009044809578, 84), (24, 55.0, 3520.0, 144)):
+        k = zaf_gpu.cqtkernel(fs, res, fmin, fmax)
+        assert k.shape == (rows, 32768)
+        spec = zaf_gpu.cqtspectrogram(x, fs, 25, k, route="tensor")
+        chroma = zaf_gpu.cqtchromagram(x, fs, 25, res, k, route="tensor")
+        fused = zaf_gpu.cqtspectrogram(x, fs, 25, k)
+        assert oracle.parity_metrics(spec, fused)[0] <= 2e-6
+        for c in range(3):
+            assert_parity(spec[c], oracle.cqtspectrogram(x[c], fs, 25, k), what=f"spec {rows} {c}")
+            assert_parity(chroma[c], oracle.cqtchromagram(x[c], fs, 25, res, k), what=f"chroma {rows} {c}")
+        spec_c = zaf_gpu.cqtspectrogram(x[1], fs, 25, k, layout="bin_major", route="tensor")
+        assert spec_c.flags.c_contiguous and np.array_equal(spec_c, spec[1])
+    # a complex kernel, or one with a band in the mirrored half, has no dense real operand: the route must refuse
+    dense = scipy.sparse.lil_matrix((2, 32768), dtype=complex)
+    dense[0, 100:200] = 1j * rng.standard_normal(100)
+    dense[1, 300:400] = rng.standard_normal(100)
+    with pytest.raises(NotImplementedError):
+        zaf_gpu.cqtspectrogram(x[0], fs, 10, scipy.sparse.csr_matrix(dense), route="tensor")
+
+
 def test_cqt_small_kernels_vs_oracle(zaf_gpu):
     """Smaller FFT lengths (odd and even log2), columns in the upper half of the spectrum, complex weights."""
     rng = np.random.default_rng(9)

@@ -445,7 +445,7 @@ def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coef
 
 
 # ------------------------------------------------------------------ CQT
-def _cqt_plan(cqt_kernel, step):
+def _cqt_plan(cqt_kernel, step, route="fused"):
     import scipy.sparse
 
     k = scipy.sparse.csr_matrix(cqt_kernel)
@@ -454,14 +454,19 @@ def _cqt_plan(cqt_kernel, step):
     indptr = np.ascontiguousarray(k.indptr, dtype=np.int32)
     indices = np.ascontiguousarray(k.indices, dtype=np.int32)
     nf, fft_length = k.shape
-    key = ("cqt", nf, fft_length, int(step), data.tobytes(), indices.tobytes(), indptr.tobytes())
+    if route not in _MEL_ROUTES:
+        raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
+    key = ("cqt", nf, fft_length, int(step), route, data.tobytes(), indices.tobytes(), indptr.tobytes())
+    fresh = key not in _cqt_plans._d
     plan = _cqt_plans.get(key, nf, fft_length, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, int(step))
+    if fresh and route != "fused":
+        _lib.check(_lib.lib().zafb_cqt_plan_set_route(plan, _MEL_ROUTES[route]))
     return plan, nf, fft_length
 
 
-def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resolution, cqt_kernel, layout, stream):
+def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resolution, cqt_kernel, layout, stream, route):
     step = round(sampling_frequency / time_resolution)  # zaf.py:603 (Python round-half-even)
-    plan, nf, fft_length = _cqt_plan(cqt_kernel, step)
+    plan, nf, fft_length = _cqt_plan(cqt_kernel, step, route)
     lay = _layout_id(layout)
     rows = octave_resolution if octave_resolution else nf
     if isinstance(audio_signal, DeviceArray):
@@ -484,15 +489,16 @@ def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resoluti
 
 
 def cqtspectrogram(audio_signal, sampling_frequency, time_resolution, cqt_kernel, *, layout="frame_major",
-                   stream=None):
+                   stream=None, route="fused"):
     """Constant-Q spectrogram -- drop-in for ``zaf.cqtspectrogram`` (zaf.py:562-635).
-    Returns (number_frequencies, number_times) float32."""
-    return _cqt_like(audio_signal, sampling_frequency, time_resolution, 0, cqt_kernel, layout, stream)
+    Returns (number_frequencies, number_times) float32.  ``route="tensor"`` applies the kernel as a dense 3xTF32
+    product on the tcgen05 tensor cores (fft_length 32768) instead of the banded multiply-add fused into the FFT kernel."""
+    return _cqt_like(audio_signal, sampling_frequency, time_resolution, 0, cqt_kernel, layout, stream, route)
 
 
 def cqtchromagram(audio_signal, sampling_frequency, time_resolution, octave_resolution, cqt_kernel, *,
-                  layout="frame_major", stream=None):
+                  layout="frame_major", stream=None, route="fused"):
     """CQT chromagram -- drop-in for ``zaf.cqtchromagram`` (zaf.py:638-700): rows i::octave_resolution
     of the CQT spectrogram summed.  Returns (octave_resolution, number_times) float32."""
     return _cqt_like(audio_signal, sampling_frequency, time_resolution, int(octave_resolution), cqt_kernel, layout,
-                     stream)
+                     stream, route)

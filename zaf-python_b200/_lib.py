@@ -77,6 +77,7 @@ PROTOTYPES = {
     "zafb_mfcc_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
     "zafb_cqt_plan_create": (_int, [_pvp, _i64, _i64, _vp, _vp, _vp, _i64]),
     "zafb_cqt_plan_destroy": (_int, [_vp]),
+    "zafb_cqt_plan_set_route": (_int, [_vp, _int]),
     "zafb_cqt_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_cqt_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int]),
     "zafb_dist_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),

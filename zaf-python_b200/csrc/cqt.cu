@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "gemm_tc.cuh"
 #include "host_pipe.cuh"
 
 using namespace zafb;
@@ -40,6 +41,13 @@ struct zafb_cqt_plan {
     int* d_sched_cnt = nullptr;    // rows per warp
     int sched_stride = 0;
     int force_kernel = 0;          // 0 auto, 1 generic, 2 register-FFT kernel (tests)
+    // tensor-core route: the kernel as a dense real (n_freqs x kp) operand over the columns [col_lo, col_hi] the bands
+    // touch, TF32 hi/lo halves; the spectrum's real and imaginary parts are two rows of the other operand
+    int route = 0;
+    int col_lo = 0, col_hi = -1;
+    int64_t kp = 0;                // col_hi - col_lo + 1 rounded up to 4
+    float* d_kern_hi = nullptr;
+    float* d_kern_lo = nullptr;
 };
 
 namespace {
@@ -193,6 +201,9 @@ constexpr int kRegM = 16384;
 
 __device__ __forceinline__ int swz(int a) { return a ^ (((a >> 4) ^ (a >> 9)) & 15); }
 
+// EXPORT = true (tensor-core route): the kernel stops after the real-input split and writes Re X[k] and Im X[k],
+// k in [col_lo, col_hi], as rows 2 f and 2 f + 1 of the TF32 hi / lo matrices a_hi / a_lo (row pitch kp).
+template <bool EXPORT>
 __global__ void __launch_bounds__(kRegThreads, 1)
 cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
                 const float2* __restrict__ t1, const float2* __restrict__ t2, const float2* __restrict__ tw_full,
@@ -200,7 +211,7 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 const float2* __restrict__ weights, const float* __restrict__ weights_re, int packed, int smem_weights,
                 int smem_split_tw, const int* __restrict__ sched, const int* __restrict__ sched_cnt, int sched_stride,
                 int n_freqs, int octave, int pair_lo, int pair_hi, float* __restrict__ out, int layout,
-                int64_t total_frames) {
+                int64_t total_frames, float* __restrict__ a_hi, float* __restrict__ a_lo, int col_lo, int col_hi, int64_t kp) {
     extern __shared__ float2 smem2[];
     constexpr int M = kRegM, L = 2 * kRegM;
     float2* z = smem2;
@@ -305,6 +316,28 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
             }
         }
         __syncthreads();
+        if constexpr (EXPORT) {
+            float* rh = a_hi + 2 * f * kp;
+            float* rl = a_lo + 2 * f * kp;
+            for (int c = tid; c < int(kp); c += kRegThreads) {
+                const int k = col_lo + c;
+                float2 X = make_float2(0.f, 0.f);  // padding columns beyond col_hi stay zero
+                if (k <= col_hi) X = (k == M) ? make_float2(s_nyq, 0.f) : z[swz(k)];
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(X.x));
+                float hv = __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(X.x - hv));
+                rh[c] = hv;
+                rl[c] = __uint_as_float(l);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(X.y));
+                hv = __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(X.y - hv));
+                rh[kp + c] = hv;
+                rl[kp + c] = __uint_as_float(l);
+            }
+            __syncthreads();  // z is rewritten by the next frame's pass 1
+            continue;
+        }
         // ---- banded kernel rows, one warp per row; rows are dealt to the warps longest-first at plan time
         for (int it = 0; it < my_rows; ++it) {
             const int r = sched[warp * sched_stride + it];
@@ -368,11 +401,33 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     }
 }
 
+// tensor-core route: magnitude (and optional chroma fold, zaf.py:693-698) of the product rows (Re, Im) per frame
+__global__ void cqt_magnitude_kernel(const float* __restrict__ c, int64_t frames, int n_freqs, int octave, int64_t nt,
+                                     int64_t frame0, float* __restrict__ out, int layout) {
+    const int rows = octave > 0 ? octave : n_freqs;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < frames * rows; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t f = i / rows;
+        const int r = int(i - f * rows);
+        const float* re = c + 2 * f * n_freqs;
+        const float* im = re + n_freqs;
+        float v = 0.f;
+        if (octave > 0) {
+            for (int k = r; k < n_freqs; k += octave) v += sqrtf(re[k] * re[k] + im[k] * im[k]);
+        } else {
+            v = sqrtf(re[r] * re[r] + im[r] * im[r]);
+        }
+        const int64_t fg = frame0 + f, clip = fg / nt, j = fg - clip * nt;
+        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[fg * rows + r] = v;
+        else out[(clip * rows + r) * nt + j] = v;
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(cqt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -474,6 +529,28 @@ int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_lengt
         for (size_t i = 0; i < w.size(); ++i) wre[i] = w[i].x;
         p->real_weights = real;
         if (rc == ZAFB_OK && real) rc = upload_vec(&p->d_weights_re, wre);
+        {   // dense operand of the tensor-core route (real kernels whose bands stay in the half spectrum)
+            int clo = int(fft_length), chi = -1;
+            bool half = true;
+            for (int64_t r = 0; r < n_freqs; ++r) {
+                if (len[r] == 0) continue;
+                clo = lo[r] < clo ? lo[r] : clo;
+                chi = lo[r] + len[r] - 1 > chi ? lo[r] + len[r] - 1 : chi;
+                if (lo[r] + len[r] - 1 > m) half = false;
+            }
+            if (rc == ZAFB_OK && real && half && chi >= clo) {
+                p->col_lo = clo;
+                p->col_hi = chi;
+                p->kp = (int64_t(chi - clo + 1) + 3) & ~int64_t(3);
+                std::vector<double> dense(size_t(n_freqs) * p->kp, 0.0);
+                for (int64_t r = 0; r < n_freqs; ++r)
+                    for (int c = 0; c < len[r]; ++c) dense[r * p->kp + (lo[r] - clo + c)] = double(w[off[r] + c].x);
+                std::vector<float> hi(dense.size()), lo_(dense.size());
+                split_tf32_host(dense.data(), dense.size(), hi.data(), lo_.data());
+                rc = upload_vec(&p->d_kern_hi, hi);
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_kern_lo, lo_);
+            }
+        }
         // longest-processing-time-first deal of the rows to the 16 warps
         constexpr int kW = kRegThreads / 32;
         std::vector<int> order(n_freqs);
@@ -525,7 +602,18 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
     cudaFree(p->d_weights_re);
     cudaFree(p->d_sched);
     cudaFree(p->d_sched_cnt);
+    cudaFree(p->d_kern_hi);
+    cudaFree(p->d_kern_lo);
     delete p;
+    return ZAFB_OK;
+}
+
+int zafb_cqt_plan_set_route(zafb_cqt_plan* p, int route) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(route == ZAFB_CQT_ROUTE_FUSED || route == ZAFB_CQT_ROUTE_TENSOR, "bad route %d", route);
+    if (route == ZAFB_CQT_ROUTE_TENSOR && p->d_kern_hi == nullptr)
+        return fail(ZAFB_E_UNSUPPORTED, "cqt tensor-core route needs fft_length 32768 and a real kernel whose bands stay below fft_length/2");
+    p->route = route;
     return ZAFB_OK;
 }
 
@@ -566,13 +654,65 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
             smem_reg += size_t(p->packed) * sizeof(float);
         }
         if (p->force_kernel == 2 && !ok) return fail(ZAFB_E_UNSUPPORTED, "cqt register-FFT kernel needs fft_length 32768");
+        if (p->route == ZAFB_CQT_ROUTE_TENSOR) {
+            // The kernel application as a dense contraction on the tensor cores (BASELINE cfg 5: "sparse CQT kernel as packed
+            // tensor-core GEMM"): per chunk of clips (1) cqt32768_kernel<true>: FFT + real-input split, Re / Im of the bins
+            // [col_lo, col_hi] written as two TF32 hi/lo rows per frame, (2) gemm3xtf32: (2 frames x kp) . (n_freqs x kp)^T,
+            // (3) magnitude (+ chroma fold).  The fused banded form above does 7x fewer multiply-adds and never writes the
+            // spectrum; this route is the dense-operand form and the measured evidence.
+            if (!ok || p->d_kern_hi == nullptr)
+                return fail(ZAFB_E_UNSUPPORTED, "cqt tensor-core route needs fft_length 32768 and a real half-spectrum kernel");
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            static bool pool_ready = false;
+            if (!pool_ready) {
+                int dev = 0;
+                cudaMemPool_t pool;
+                uint64_t keep = UINT64_MAX;
+                if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                pool_ready = true;
+            }
+            const int64_t kp = p->kp, nf = p->n_freqs;
+            // chunk: one wave of 128-row GEMM tiles over all SMs (2 rows per frame), at most 512 MB of split spectra
+            const int64_t frames_cap = std::max<int64_t>(1, std::min<int64_t>(int64_t(sm_count()) * 64, (int64_t(512) << 20) / (2 * kp * 4 * 2)));
+            const int64_t clips_per = std::max<int64_t>(1, std::min<int64_t>(n_clips, frames_cap / nt));
+            auto round64 = [](size_t v) { return (v + 63) & ~size_t(63); };
+            const size_t a_f = round64(size_t(clips_per) * nt * 2 * kp), c_f = round64(size_t(clips_per) * nt * 2 * nf);
+            float* ws = nullptr;
+            ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (2 * a_f + c_f) * sizeof(float), st));
+            float *a_hi = ws, *a_lo = ws + a_f, *cbuf = ws + 2 * a_f;
+            const size_t smem_x = size_t(kRegM + 1536) * sizeof(float2) + size_t((nf + 1) & ~int64_t(1)) * sizeof(float) + 64 +
+                                  (smem_split ? split_bytes : 0);
+            for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += clips_per) {
+                const int64_t nc = std::min(clips_per, n_clips - c0), frames = nc * nt;
+                const int64_t grid = frames < int64_t(sm_count()) ? frames : int64_t(sm_count());
+                cqt32768_kernel<true><<<unsigned(grid), kRegThreads, smem_x, st>>>(
+                    x + c0 * clip_stride, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo,
+                    p->d_band_len, p->d_band_off, p->d_weights, p->d_weights_re, int(p->packed), 0, smem_split, p->d_sched,
+                    p->d_sched_cnt, p->sched_stride, int(nf), 0, p->pair_lo, p->pair_hi, nullptr, layout, frames, a_hi, a_lo,
+                    p->col_lo, p->col_hi, kp);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                rc = gemm3xtf32(a_hi, a_lo, kp, p->d_kern_hi, p->d_kern_lo, kp, cbuf, nf, 2 * frames, nf, kp, st);
+                if (rc == ZAFB_OK) {
+                    const int rows = octave_resolution > 0 ? int(octave_resolution) : int(nf);
+                    int64_t blocks = ceil_div(frames * rows, 256);
+                    if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+                    cqt_magnitude_kernel<<<unsigned(blocks), 256, 0, st>>>(cbuf, frames, int(nf), int(octave_resolution), nt, c0 * nt,
+                                                                           out, layout);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
+            }
+            cudaFreeAsync(ws, st);
+            if (rc == ZAFB_OK) ZAFB_CUDA(cudaGetLastError());
+            return rc;
+        }
         if (ok && p->force_kernel != 1) {
             const int64_t grid = total < int64_t(sm_count()) ? total : int64_t(sm_count());
-            cqt32768_kernel<<<unsigned(grid), kRegThreads, smem_reg, static_cast<cudaStream_t>(stream)>>>(
+            cqt32768_kernel<false><<<unsigned(grid), kRegThreads, smem_reg, static_cast<cudaStream_t>(stream)>>>(
                 x, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo, p->d_band_len,
                 p->d_band_off, p->d_weights, p->d_weights_re, int(p->packed), smem_weights, smem_split, p->d_sched,
                 p->d_sched_cnt, p->sched_stride, int(p->n_freqs), int(octave_resolution), p->pair_lo, p->pair_hi, out, layout,
-                total);
+                total, nullptr, nullptr, 0, -1, 0);
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         }
