@@ -313,3 +313,45 @@ def test_device_batches_with_odd_length_rows(zaf_gpu):
     assert np.array_equal(md.to_host(), zaf_gpu.mdct(x, wk))
     back = zaf_gpu.imdct(md, wk)            # odd output length M(nt-1)-1: padded pitch again
     assert np.array_equal(back.to_host(), zaf_gpu.imdct(zaf_gpu.mdct(x, wk), wk))
+
+
+@pytest.mark.parametrize("n", [2048, 1024, 512])
+def test_stft_bin_major_direct_kernel(zaf_gpu, monkeypatch, n):
+    """layout="bin_major" on the warp-kernel window lengths is written directly by stft_warp_binmajor_kernel (a CTA walks
+    a clip in tiles of 16 frames kept in a shared-memory ring; every row is stored through its own sector-aligned
+    window).  It must equal the frame-major result bit for bit (same arithmetic) for frame counts of every residue
+    mod 4 and mod 16, single-frame clips, few and many clips (whole-clip runs and split runs), and for result buffers at
+    every sector phase; ZAFB_STFT_BM_DIRECT=0 (scratch + transpose route) and streaming stores must give the same bits."""
+    rng = np.random.default_rng(20261017 + n)
+    w = oracle.hamming_periodic(n)
+    cases = [((5, 30010), n // 4), ((2, 9000), n // 2), ((3, 40), n // 8), ((1, 12346), 300), ((7, 2 * n), n // 4),
+             ((700, 9 * n // 4), n // 4)]
+    cases += [((3, 33 * n // 4 + r * n // 4), n // 4) for r in range(4)]   # nt mod 4 = every residue
+    for shape, hop in cases:
+        x = rng.uniform(-1, 1, shape).astype(np.float32)
+        ref = zaf_gpu.stft(x, w, hop)
+        for env in ({}, {"ZAFB_STFT_BM_CS": "1"}, {"ZAFB_STFT_BM_DIRECT": "0"}, {"ZAFB_STFT_BM_RUNS_PER_CLIP": "1"},
+                    {"ZAFB_STFT_BM_RUNS_PER_CLIP": "2"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = zaf_gpu.stft(x, w, hop, layout="bin_major")
+            for k in env:
+                monkeypatch.delenv(k)
+            assert got.flags.c_contiguous and got.shape == ref.shape
+            assert np.array_equal(got, ref), (shape, hop, env)
+        assert_parity(ref[-1], oracle.stft(x[-1], w, hop))
+    # device-resident input and output (even clip pitch): the result stays in C order on the device; result pointers
+    # at every 8-byte phase of a 32-byte sector
+    x = rng.uniform(-1, 1, (4, 20000)).astype(np.float32)
+    ref = zaf_gpu.stft(x, w, n // 4)
+    xd = zaf_gpu.to_device(x)
+    sd = zaf_gpu.stft(xd, w, n // 4, layout="bin_major")
+    assert not sd.transposed and np.array_equal(sd.to_host(), ref)
+    plan, _ = zaf_gpu._stft_plan(w, n // 4)
+    lib = zaf_gpu._lib.lib()
+    count = int(np.prod(ref.shape))
+    for off in (1, 2, 3):
+        buf = zaf_gpu.empty((count + 4,), np.complex64)
+        zaf_gpu._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), 4, 20000, xd.pitch, C.c_void_p(buf.ptr + 8 * off), 1, None))
+        zaf_gpu.synchronize()
+        assert np.array_equal(buf.to_host()[off:off + count].reshape(ref.shape), ref), off

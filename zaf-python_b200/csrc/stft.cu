@@ -13,6 +13,7 @@
 //                         transforms every frame that touches it in increasing frame order (the
 //                         reference's summation order, zaf.py:227-233) and writes each sample once:
 //                         no atomics, bit-reproducible.
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -277,6 +278,201 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
             const float2 z = v[bitrev(REGS / 2, LOGR)];
             st_stream(out + f * N + M / 2, make_float2(2.f * z.x, -2.f * z.y));
             st_stream(out + f * N + M + M / 2, make_float2(2.f * z.x, 2.f * z.y));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same transform writing BIN_MAJOR memory [clip][bin][frame] -- the reference's C order (zaf.py:128) -- directly.
+//
+// A CTA of 16 warps walks along one clip in tiles of F = 16 consecutive frames.  Each warp transforms one frame exactly
+// like stft_warp_kernel (same arithmetic, bit-identical values) and parks its M + 1 distinct results
+//     R[k] = X[k],  R[M/2 + k] = X[M + k]  (k < M/2),  R[M] = X[M/2]
+// in the frame's slot of a ring of F + 3 shared-memory regions (the slot doubles as the FFT's transpose tile).  After a
+// barrier the CTA stores the tile bin by bin: thread (u, w) writes frame w of row b1(u) and of the mirror row b2(u)
+// (conjugated), so 16 frames of a row leave as one 128-byte run.
+//
+// Why the ring: rows are nt * 8 bytes long, and for odd nt (939 at cfg 2) a run that starts at a tile boundary starts
+// in the middle of a 32-byte sector of most rows.  Partial-sector writes are what makes a transposed store slow on
+// this memory system (measured on cfg 2: 16.0 ms with 64-byte runs, 9.1 ms with 128-byte runs; 6.6 / 4.5 ms for the
+// same kernels when nt is a multiple of 4, i.e. every run sector-aligned; profiles/r01n_bm_probe.log).  So every row
+// gets its own window: row b writes frames [j0 - s, j0 + 16 - s) with s = (address of element (b, j0) / 8) mod 4, which
+// makes every run start on a sector boundary; the up to 3 frames before j0 are still in the ring from the previous
+// tile.  s depends only on b mod 4 (N, M and M/2 are multiples of 4), i.e. it is one constant per thread for the
+// rows it stores directly and one for their mirrors.  A run of tiles ends with a flush step for the last s frames.
+// ------------------------------------------------------------------------------------------
+template <int N>
+struct BinMajorGeom {
+    static constexpr int F = 16;          // frames per tile == warps per CTA
+    static constexpr int SLOTS = F + 3;   // ring of frame regions: the tile plus the three frames before it
+    static constexpr int M = N / 2;
+    static constexpr int NEED = WarpGeom<N>::TILE > M + 1 ? WarpGeom<N>::TILE : M + 1;
+    // region pitch (float2): >= NEED, == 1 mod 16 -> the 16 frames of one bin (consecutive slots) land in 16 distinct
+    // bank pairs (except for the slots on either side of the ring's wrap-around)
+    static constexpr int PITCH = ((NEED + 14) / 16) * 16 + 1;
+    static_assert(PITCH >= NEED && PITCH % 16 == 1, "bad region pitch");
+    static constexpr size_t SMEM = (size_t(N) + size_t(SLOTS) * PITCH) * sizeof(float2);
+};
+
+template <int N, bool STREAMING>
+__global__ void __launch_bounds__(512, 1)
+stft_warp_binmajor_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int nt, int hop,
+                          const float2* __restrict__ win_half, const float2* __restrict__ tw4,
+                          const float2* __restrict__ tw_full, float2* __restrict__ out, int phase0, int runs_per_clip,
+                          int tiles_per_run, int64_t total_runs) {
+    using G = WarpGeom<N>;
+    using B = BinMajorGeom<N>;
+    constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
+    constexpr int F = B::F, SLOTS = B::SLOTS, PITCH = B::PITCH;
+    extern __shared__ __align__(128) float2 smem[];
+    float2* s_win = smem;       // M: (0.5 w[2n], 0.5 w[2n+1])
+    float2* s_tw = smem + M;    // M: W_M^{k1*n2} at [k1*32+n2]
+    float2* s_reg = smem + 2 * M;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    for (int i = tid; i < M; i += F * 32) {
+        s_win[i] = win_half[i];
+        s_tw[i] = tw4[i];
+    }
+    const float2 c_lane = tw_full[lane];  // W_N^lane
+    LaneTw<N> lt;
+    lt.init(lane);
+    __syncthreads();
+
+    auto store = [](float2* p, float2 v) {
+        if constexpr (STREAMING) __stcs(p, v);
+        else *p = v;
+    };
+    const int sw = tid & (F - 1);  // store phase: frame within the row's window
+    const int su = tid / F;        // store phase: bin index mod 32
+    // sector phase of element (b, j0): (phase0 + b * nt + j0) mod 4 with j0 = 0 mod 4; b = su mod 4 for the direct rows
+    // (u, M + k), -su mod 4 for the mirrors (N - u, M - k), 0 for the rows M/2 and 3M/2 (handled by su == 0: same as sa)
+    const int sa = (phase0 + (su & 3) * (nt & 3)) & 3;
+    const int sb = (phase0 + ((4 - su) & 3) * (nt & 3)) & 3;
+    const int tiles_per_clip = (nt + F - 1) / F;
+
+    for (int64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
+        const int64_t clip = run / runs_per_clip;
+        const int t0 = int(run - clip * runs_per_clip) * tiles_per_run;
+        const int t1 = min(t0 + tiles_per_run, tiles_per_clip);
+        const int jlo = t0 * F, jhi = min(nt, t1 * F);  // the frames this run owns
+        const float* xc = x + clip * clip_stride;
+        float2* oc = out + clip * int64_t(N) * nt;
+
+        for (int t = t0; t <= t1; ++t) {  // t == t1: flush of the frames still waiting for their row's window
+            const int j0 = t * F;
+            const int j = j0 + warp;
+            if (t < t1 && j < nt) {  // warp-uniform
+                // the frame's N samples as N/2 complex points, straight into registers (zeros outside [0, ns): zaf.py:99-125)
+                const int64_t start = int64_t(j) * hop - M;
+                float2 v[REGS];
+                if (start >= 0 && start + N <= ns) {
+                    const float2* p = reinterpret_cast<const float2*>(xc + start) + lane;
+#pragma unroll
+                    for (int r = 0; r < REGS; ++r) v[r] = __ldg(p + 32 * r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < REGS; ++r) {
+                        const int64_t s = start + 2 * (lane + 32 * r);
+                        v[r].x = (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f;
+                        v[r].y = (s + 1 >= 0 && s + 1 < ns) ? __ldg(xc + s + 1) : 0.f;
+                    }
+                }
+                // the samples the NEXT tile adds (F hops further on) towards L2 while this tile is transformed and stored
+                if (t + 1 < t1) {
+                    const int64_t nx = start + int64_t(F) * hop + N - hop;  // first sample frame j + F has and frame j + F - 1 has not
+                    for (int64_t s = nx + 32 * lane; s < nx + hop && s < ns; s += 32 * 32)
+                        if (s >= 0) prefetch_l2(xc + s);
+                }
+                float2* s_buf = s_reg + (j % SLOTS) * PITCH;
+#pragma unroll
+                for (int r = 0; r < REGS; ++r) {
+                    const float2 w = s_win[lane + 32 * r];
+                    v[r].x *= w.x;
+                    v[r].y *= w.y;
+                }
+                warp_fft_half<N>(v, s_tw, s_buf, lane, lt);  // Z[lane + 32 k2] = v[bitrev(k2)]
+
+                // the real-input unpack of stft_warp_kernel (see there), results parked in the frame's region
+                const int src = (32 - lane) & 31;
+                const float2 zmid = v[bitrev(REGS / 2, LOGR)];
+                static_for<0, REGS / 2>([&](auto ic) {
+                    constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
+                    const float2 z = v[bitrev(k2, LOGR)];
+                    const float2 mine = v[bitrev(REGS - 1 - k2, LOGR)];
+                    float2 p;
+                    p.x = __shfl_sync(0xffffffffu, mine.x, src);
+                    p.y = __shfl_sync(0xffffffffu, mine.y, src);
+                    if (lane == 0) p = v[bitrev((REGS - k2) & (REGS - 1), LOGR)];
+                    const float2 e = make_float2(z.x + p.x, z.y - p.y);
+                    const float2 od = make_float2(z.y + p.y, p.x - z.x);
+                    const float2 tt = cmul(mul_tw<k2, N / 32>(c_lane), od);
+                    v[bitrev(k2, LOGR)] = cadd(e, tt);             // X[k]
+                    v[bitrev(REGS - 1 - k2, LOGR)] = csub(e, tt);  // X[k + M]
+                });
+                __syncwarp();  // every lane is done with the transpose tile
+                static_for<0, REGS / 2>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    s_buf[lane + 32 * k2] = v[bitrev(k2, LOGR)];
+                    s_buf[M / 2 + lane + 32 * k2] = v[bitrev(REGS - 1 - k2, LOGR)];
+                });
+                if (lane == 0) s_buf[M] = make_float2(2.f * zmid.x, -2.f * zmid.y);  // X[M/2]: Z[M/2] pairs with itself, w = -i
+            }
+            __syncthreads();
+            // Rows leave in batches of 8 (4 values of u x the two families): all shared-memory reads of a batch are issued
+            // before its stores and every store has its own address registers, so nothing serialises on a register.
+            constexpr int kBatch = 4;
+            static_assert((M / 64) % kBatch == 0, "batches of four bins");
+            const int64_t step = int64_t(32) * nt;   // 32 rows
+            const int64_t half = int64_t(M) * nt;    // M rows
+            const int ja = j0 - sa + sw;  // the frame this thread stores for its direct rows
+            if (ja >= jlo && ja < jhi) {
+                const float2* r = s_reg + (ja % SLOTS) * PITCH + su;
+                float2* o = oc + ja + int64_t(su) * nt;
+#pragma unroll 1
+                for (int i = 0; i < M / 64; i += kBatch, o += kBatch * step) {  // rows u = su + 32 i and M + u
+                    float2 va[kBatch], vb[kBatch];
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        va[b] = r[32 * (i + b)];
+                        vb[b] = r[M / 2 + 32 * (i + b)];
+                    }
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        store(o + b * step, va[b]);
+                        store(o + b * step + half, vb[b]);
+                    }
+                }
+                if (su == 0) {  // rows M/2 and 3M/2
+                    const float2 val = r[M];
+                    store(oc + ja + int64_t(M / 2) * nt, val);
+                    store(oc + ja + int64_t(M + M / 2) * nt, cconj(val));
+                }
+            }
+            const int jb = j0 - sb + sw;  // ... and for their conjugate mirrors, rows N - u and M - u
+            if (jb >= jlo && jb < jhi) {
+                const float2* r = s_reg + (jb % SLOTS) * PITCH + su;
+                float2* o = oc + jb + int64_t(N - su) * nt;
+#pragma unroll 1
+                for (int i = 0; i < M / 64; i += kBatch, o -= kBatch * step) {
+                    float2 va[kBatch], vb[kBatch];
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        va[b] = cconj(r[32 * (i + b)]);
+                        vb[b] = cconj(r[M / 2 + 32 * (i + b)]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < kBatch; ++b) {
+                        if (b > 0 || i > 0 || su > 0) {  // rows 0 and M have no mirror
+                            store(o - b * step, va[b]);
+                            store(o - b * step - half, vb[b]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // the ring slots of the next tile become transpose tiles again
         }
     }
 }
@@ -561,6 +757,48 @@ int set_kernel_attrs() {
     return ZAFB_OK;
 }
 
+template <int N, bool STREAMING>
+int launch_stft_binmajor_t(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                           int64_t nt, float2* out, cudaStream_t st) {
+    using B = BinMajorGeom<N>;
+    static_assert(B::SMEM <= size_t(kMaxDynSmem), "ring of frame regions does not fit");
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_binmajor_kernel<N, STREAMING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kMaxDynSmem)));
+        attr = true;
+    }
+    // runs of consecutive tiles of one clip: whole clips when there are enough of them, else about four runs per SM
+    const int64_t sms = sm_count();
+    const int64_t tiles_per_clip = ceil_div(nt, B::F);
+    int64_t runs_per_clip = n_clips >= 4 * sms ? 1 : std::min<int64_t>(tiles_per_clip, ceil_div(4 * sms, n_clips));
+    if (const int forced = env_flag("ZAFB_STFT_BM_RUNS_PER_CLIP", 0); forced > 0)  // tests
+        runs_per_clip = std::min<int64_t>(tiles_per_clip, forced);
+    const int64_t tiles_per_run = ceil_div(tiles_per_clip, runs_per_clip);
+    runs_per_clip = ceil_div(tiles_per_clip, tiles_per_run);
+    const int64_t runs = n_clips * runs_per_clip;
+    const int64_t ctas = std::min<int64_t>(sms, runs);
+    const int phase0 = int((reinterpret_cast<uintptr_t>(out) >> 3) & 3);
+    stft_warp_binmajor_kernel<N, STREAMING><<<static_cast<unsigned>(ctas), B::F * 32, B::SMEM, st>>>(
+        x, ns, clip_stride, int(nt), static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, out, phase0,
+        int(runs_per_clip), int(tiles_per_run), runs);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+int launch_stft_binmajor(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                         int64_t nt, float2* out, cudaStream_t st) {
+    const bool cs = env_flag("ZAFB_STFT_BM_CS", 0) != 0;  // 1: streaming (evict-first) stores
+    if (p->n == 2048)
+        return cs ? launch_stft_binmajor_t<2048, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
+                  : launch_stft_binmajor_t<2048, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
+    if (p->n == 1024)
+        return cs ? launch_stft_binmajor_t<1024, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
+                  : launch_stft_binmajor_t<1024, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
+    return cs ? launch_stft_binmajor_t<512, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
+              : launch_stft_binmajor_t<512, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
+}
+
 template <int N, int R, int WARPS>
 int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
                         int64_t y_stride, cudaStream_t st) {
@@ -720,7 +958,10 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             return ZAFB_OK;
         };
         if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
-        // the reference's C-order memory: frame-major into scratch, then a tiled transpose (transpose.cuh)
+        // the reference's C-order memory, written directly by stft_warp_binmajor_kernel (ZAFB_STFT_BM_DIRECT=0: the
+        // older route, frame-major into scratch + tiled transpose)
+        if (env_flag("ZAFB_STFT_BM_DIRECT", 1) && nt < (int64_t(1) << 27) && reinterpret_cast<uintptr_t>(out) % 8 == 0)
+            return launch_stft_binmajor(p, x, n_clips, ns, clip_stride, nt, o, st);
         return bin_major_from_frame_major(o, n_clips, nt, p->n, st, [&](int64_t c0, int64_t nc, float2* scratch) {
             return run(x + c0 * clip_stride, nc, scratch);
         });
