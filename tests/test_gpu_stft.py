@@ -48,10 +48,10 @@ def test_istft_golden(zaf_gpu, golden):
         assert_parity(got_f, ref)
 
 
-@pytest.mark.parametrize("n", [2048, 1024, 512])
+@pytest.mark.parametrize("n", [4096, 2048, 1024, 512])
 @pytest.mark.parametrize("force", [1, 2])
 def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force, n):
-    """The warp-per-frame kernel (2; window lengths 2048 and 1024) and the generic Stockham kernel (1) on the same input."""
+    """The warp-per-frame kernel (2; window lengths 512 ... 4096) and the generic Stockham kernel (1) on the same input."""
     rng = np.random.default_rng(20261017 + 2)
     x = rng.uniform(-1, 1, (3, 20000)).astype(np.float32)
     w = oracle.hamming_periodic(n)
@@ -66,7 +66,7 @@ def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force, n):
             assert_parity(got[c], oracle.stft(x[c], w, hop))
 
 
-@pytest.mark.parametrize("n", [2048, 1024, 512])
+@pytest.mark.parametrize("n", [4096, 2048, 1024, 512])
 @pytest.mark.parametrize("force", [1, 2])
 @pytest.mark.parametrize("ratio", [8, 4, 2])
 def test_istft_2048_kernels_agree_with_oracle(zaf_gpu, force, ratio, n):

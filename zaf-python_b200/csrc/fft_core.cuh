@@ -133,6 +133,31 @@ __device__ __forceinline__ void warp_fft1024(float2 (&v)[32], const float2* __re
     fft_reg<32>(v);  // over n2; thread = k1
 }
 
+// ---------------------------------------------------------------- one warp, 2048 complex points
+// Four-step FFT 2048 = 64 x 32 by ONE warp (window length 4096).  In: v[r] = x[lane + 32 r], r < 64.  Out: X[lane + 32 k]
+// is v[bitrev(k, 6)], the convention of the smaller transforms.  Step 1: FFT-64 over the register index (n1), twiddle
+// W_2048^{k1 n2} from tw4[k1 * 32 + n2] (64 x 32 table).  Step 2: 64 FFT-32 over n2, two per lane: rows k1 = lane and
+// lane + 32 of the 64 x kFft1024Pitch transpose tile, held in v[0..31] and v[32..63]; their outputs k2 are
+// X[k1 + 64 k2] = X[lane + 32 (h + 2 k2)] with h the row half, and bitrev(h + 2 k2, 6) = 32 h + bitrev(k2, 5).
+__device__ __forceinline__ void warp_fft2048(float2 (&v)[64], const float2* __restrict__ tw4, float2* buf, int lane) {
+    fft_reg<64>(v);
+    static_for<0, 64>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        float2 y = v[bitrev(k1, 6)];
+        if constexpr (k1 > 0) y = cmul(y, tw4[k1 * 32 + lane]);
+        buf[k1 * kFft1024Pitch + lane] = y;
+    });
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+        v[n2] = buf[lane * kFft1024Pitch + n2];
+        v[32 + n2] = buf[(lane + 32) * kFft1024Pitch + n2];
+    }
+    __syncwarp();
+    fft_reg<32>(&v[0]);
+    fft_reg<32>(&v[32]);
+}
+
 // ---------------------------------------------------------------- one warp, 512 complex points
 // Four-step FFT 512 = 16 x 32 by ONE warp.  In: v[r] = x[lane + 32 r], r < 16.  Out: X[lane + 32 k]
 // is v[bitrev(k, 4)].  tw[k1 * 32 + n2] = W_512^{k1 n2} (shared memory, 16 x 32); buf: 16 x

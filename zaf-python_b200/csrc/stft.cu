@@ -41,7 +41,7 @@ struct zafb_stft_plan {
 
 namespace {
 
-constexpr int kMaxDynSmem = 200 * 1024;
+constexpr int kMaxDynSmem = 227 * 1024;  // the sm_100 opt-in maximum per CTA
 
 // ------------------------------------------------------------------------------------------
 // N = 2048: one warp per frame
@@ -67,7 +67,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // N = 1024 -> warp_fft512.  In: v[r] = z[lane + 32 r].  Out: Z[lane + 32 k2] = v[bitrev(k2, log2 REGS)].
 template <int N>
 struct WarpGeom {
-    static_assert(N == 512 || N == 1024 || N == 2048, "warp kernels exist for window lengths 512, 1024 and 2048");
+    static_assert(N == 512 || N == 1024 || N == 2048 || N == 4096, "warp kernels exist for window lengths 512 ... 4096");
+    static constexpr int CTAS_PER_SM = N == 4096 ? 1 : N == 2048 ? 2 : 3;  // registers: 2 * REGS of frame state per lane
     static constexpr int M = N / 2;
     static constexpr int REGS = M / 32;
     static constexpr int LOGR = clog2(REGS);
@@ -86,7 +87,8 @@ struct LaneTw {
 template <int N>
 __device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2* __restrict__ tw4, float2* buf, int lane,
                                               const LaneTw<N>& lt) {
-    if constexpr (N == 2048) warp_fft1024<false>(v, tw4, buf, lane);
+    if constexpr (N == 4096) warp_fft2048(v, tw4, buf, lane);
+    else if constexpr (N == 2048) warp_fft1024<false>(v, tw4, buf, lane);
     else if constexpr (N == 1024) warp_fft512(v, tw4, buf, lane);
     else warp_fft256(v, tw4, buf, lane, lt.tq);
 }
@@ -95,7 +97,7 @@ __device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2*
 // BULK = true (N = 2048 only): the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame
 // (issued by one lane, executed by the TMA engine) instead of 64 st.global per lane.
 template <int N, bool BULK, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, N == 2048 ? 2 : 3)
+__global__ void __launch_bounds__(WARPS * 32, WarpGeom<N>::CTAS_PER_SM)
 stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                  const float2* __restrict__ win_half, const float2* __restrict__ tw4,
                  const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int sequential) {
@@ -493,8 +495,11 @@ stft_warp_binmajor_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_
 //   Z[k] = E[k] + i O[k],  E = H[k] + H[k+1024],  O = (H[k] - H[k+1024]) conj(W_2048^k),
 //   y[2n] + i y[2n+1] = conj(FFT_1024(conj(Z)))[n] / (2 N)        (validated in float64).
 // ------------------------------------------------------------------------------------------
+// floats of transpose tile per warp
+__host__ __device__ constexpr int istft_tile_floats(int n) { return n == 2048 ? 32 * kFft1024Pitch : 2 * (n / 64) * kFft1024Pitch; }
+
 template <int N, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, N == 4096 ? 1 : 2)
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
                   int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
@@ -507,7 +512,7 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
     constexpr int RING = SLOTS * (HOP / 2);  // float2 per warp
     // transpose tile per warp: N = 2048 uses the split (float) tile of warp_fft1024<true>, N = 1024 the float2 tile of
     // warp_fft512 -- REGS * pitch * 4 bytes * (N == 2048 ? 1 : 2) = the same 4224 bytes either way
-    constexpr int TILE_FLOATS = N == 2048 ? 32 * kFft1024Pitch : 2 * REGS * kFft1024Pitch;
+    constexpr int TILE_FLOATS = istft_tile_floats(N);
     extern __shared__ float2 smem[];
     float2* s_tw = smem;  // M
     const int tid = threadIdx.x;
@@ -560,7 +565,8 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
             });
 
             // conj(z[lane + 32 k2]) = v[bitrev(k2)]
-            if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, s_buf, lane);
+            if constexpr (N == 4096) warp_fft2048(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
+            else if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, s_buf, lane);
             else if constexpr (N == 1024) warp_fft512(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
             else warp_fft256(v, s_tw, reinterpret_cast<float2*>(s_buf), lane, lt.tq);
 
@@ -750,6 +756,7 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -808,7 +815,8 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
         attr = true;
     }
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
-    const int64_t resident_warps = int64_t(sm_count()) * 2 * WARPS;
+    constexpr int kCtasPerSm = N == 4096 ? 1 : 2;
+    const int64_t resident_warps = int64_t(sm_count()) * kCtasPerSm * WARPS;
     // run length: minimise (runs per warp) x (frames per run, warm-up included)
     int64_t best_len = nblocks, best_cost = INT64_MAX;
     for (int64_t len = nblocks < 8 ? nblocks : 8; len <= nblocks && len <= 1024; ++len) {
@@ -822,10 +830,11 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
     const int64_t runs_per_clip = ceil_div(nblocks, best_len);
     const int64_t total = n_clips * runs_per_clip;
     int64_t ctas = ceil_div(total, WARPS);
-    if (ctas > int64_t(sm_count()) * 2) ctas = int64_t(sm_count()) * 2;
+    if (ctas > int64_t(sm_count()) * kCtasPerSm) ctas = int64_t(sm_count()) * kCtasPerSm;
     constexpr int HOP = N / R;
-    const size_t smem = (N / 2) * sizeof(float2) + size_t(WARPS) * ((R - 1) * (HOP / 2) * sizeof(float2) +
-                                                                           32 * kFft1024Pitch * sizeof(float));
+    constexpr size_t smem = (N / 2) * sizeof(float2) + size_t(WARPS) * ((R - 1) * (HOP / 2) * sizeof(float2) +
+                                                                               istft_tile_floats(N) * sizeof(float));
+    static_assert(smem <= size_t(kMaxDynSmem), "istft warp kernel: shared memory");
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
     istft_warp_kernel<N, R, WARPS><<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
@@ -837,8 +846,12 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
 template <int N, int R>
 int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
                       int64_t y_stride, cudaStream_t st) {
-    if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
-    return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st);
+    // N = 4096: 6 warps (a 17 KB transpose tile plus up to 14 KB of overlap-add ring per warp)
+    if constexpr (N == 4096) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
+    else {
+        if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
+        return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st);
+    }
 }
 
 int fft_threads(int points) {  // threads for a block FFT of `points` complex points
@@ -870,7 +883,7 @@ int zafb_stft_plan_create(zafb_stft_plan** out, const double* window, int64_t n,
         p->d_window_half = reinterpret_cast<float2*>(tmp);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
     }
-    if (rc == ZAFB_OK && (n == 2048 || n == 1024 || n == 512)) {
+    if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024 || n == 512)) {
         // four-step twiddles of the warp kernels: W_M^{k1*n2} laid out [k1][n2], M = n/2 = (M/32) x 32
         const int64_t m = n / 2;
         std::vector<double> t(2 * m);
@@ -931,9 +944,9 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     float2* o = reinterpret_cast<float2*>(out);
 
     const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
-    const bool warp_ok = (p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
+    const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
     if (p->force_kernel == 2 && !warp_ok)
-        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 512, 1024 or 2048, even hop/stride, 8-byte aligned x");
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 512, 1024, 2048 or 4096, even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
         // measured on cfg 2 (B200), profiles/r01_stft_experiments.txt: direct streaming stores 3.04-3.11 ms, TMA bulk stores
         // 3.13-3.20 ms; 6 warps per CTA 3.04, 8 -> 3.11, 10 -> 3.36, 4 -> 3.40.  The defaults are the fastest combination.
@@ -944,9 +957,10 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             const int warps = (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
             const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(frames, warps);
-            const int64_t resident = int64_t(sms) * (n == 2048 ? 2 : 3);
+            const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : 3);
             if (ctas > resident) ctas = resident;
-            auto kern = n == 512 ? stft_warp_kernel<512, false, 8>
+            auto kern = n == 4096 ? stft_warp_kernel<4096, false, 8>
+                        : n == 512 ? stft_warp_kernel<512, false, 8>
                         : n == 1024 ? stft_warp_kernel<1024, false, 8>
                         : warps == 6 ? stft_warp_kernel<2048, false, 6>
                         : (bulk && reinterpret_cast<uintptr_t>(dst) % 16 == 0 ? stft_warp_kernel<2048, true, 8>
@@ -960,7 +974,7 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
         if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
         // the reference's C-order memory, written directly by stft_warp_binmajor_kernel (ZAFB_STFT_BM_DIRECT=0: the
         // older route, frame-major into scratch + tiled transpose)
-        if (env_flag("ZAFB_STFT_BM_DIRECT", 1) && nt < (int64_t(1) << 27) && reinterpret_cast<uintptr_t>(out) % 8 == 0)
+        if (n <= 2048 && env_flag("ZAFB_STFT_BM_DIRECT", 1) && nt < (int64_t(1) << 27) && reinterpret_cast<uintptr_t>(out) % 8 == 0)
             return launch_stft_binmajor(p, x, n_clips, ns, clip_stride, nt, o, st);
         return bin_major_from_frame_major(o, n_clips, nt, p->n, st, [&](int64_t c0, int64_t nc, float2* scratch) {
             return run(x + c0 * clip_stride, nc, scratch);
@@ -1003,12 +1017,17 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
                              (n_clips <= 1 || y_stride % 2 == 0);
         const int64_t ratio = (p->hop > 0 && n % p->hop == 0) ? n / p->hop : 0;
-        const bool warp_ok = (n == 2048 || n == 1024 || n == 512) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
+        const bool warp_ok = (n == 4096 || n == 2048 || n == 1024 || n == 512) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 512, 1024 or 2048, hop = N/2, N/4 or N/8, even y_stride");
+            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 512 ... 4096, hop = N/2, N/4 or N/8, even y_stride");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
+                if (n == 4096) {
+                    if (ratio == 2) return launch_istft_warp<4096, 2>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 4) return launch_istft_warp<4096, 4>(p, s2, clips, nt, yy, y_stride, st);
+                    return launch_istft_warp<4096, 8>(p, s2, clips, nt, yy, y_stride, st);
+                }
                 if (n == 2048) {
                     if (ratio == 2) return launch_istft_warp<2048, 2>(p, s2, clips, nt, yy, y_stride, st);
                     if (ratio == 4) return launch_istft_warp<2048, 4>(p, s2, clips, nt, yy, y_stride, st);
