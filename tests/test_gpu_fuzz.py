@@ -45,7 +45,7 @@ def test_stft_istft_random_shapes(zaf_gpu, n):
             _check(yd[batch - 1], oracle.stft(x[batch - 1], w, hop), ("stft device", n, hop, ns))
 
 
-@pytest.mark.parametrize("n", [1024, 2048])
+@pytest.mark.parametrize("n", [1024, 2048, 4096])
 def test_mdct_imdct_random_shapes(zaf_gpu, n):
     rng = np.random.default_rng(9100 + n)
     w = oracle.kbd_window(n)

@@ -137,10 +137,11 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = 8;
 
-// N = 2048 (M = 1024, 512-point FFT, warp_fft512) or N = 1024 (M = 512, 256-point FFT, warp_fft256)
+// N = 4096 (M = 2048, 1024-point FFT, warp_fft1024), N = 2048 (M = 1024, 512-point FFT, warp_fft512) or
+// N = 1024 (M = 512, 256-point FFT, warp_fft256)
 template <int N>
 struct MdctGeom {
-    static_assert(N == 1024 || N == 2048, "mdct warp kernels exist for window lengths 1024 and 2048");
+    static_assert(N == 1024 || N == 2048 || N == 4096, "mdct warp kernels exist for window lengths 1024, 2048 and 4096");
     static constexpr int M = N / 2;          // coefficients per frame
     static constexpr int H = M / 2;          // complex FFT length
     static constexpr int REGS = H / 32;      // float2 per lane
@@ -165,7 +166,8 @@ __device__ __forceinline__ void load_tables(float2* smem, const float2* __restri
 template <int N>
 __device__ __forceinline__ void mdct_warp_fft(float2 (&v)[MdctGeom<N>::REGS], const float2* __restrict__ tw, float2* buf, int lane,
                                               const float2 (&tq)[N == 1024 ? 8 : 1]) {
-    if constexpr (N == 2048) warp_fft512(v, tw, buf, lane);
+    if constexpr (N == 4096) warp_fft1024<false>(v, tw, buf, lane);
+    else if constexpr (N == 2048) warp_fft512(v, tw, buf, lane);
     else warp_fft256(v, tw, buf, lane, tq);
 }
 
@@ -294,7 +296,10 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
         for (int64_t j = h0 - 1; j < h1; ++j) {
             const float2* X = reinterpret_cast<const float2*>(spec + (clip * nt + j) * M) + lane;
             // next frame of the run towards L2: M * 4 / 128 lines (one per lane at M = 1024)
-            if (prefetch && j + 1 < h1 && lane < M / 32) prefetch_l2(reinterpret_cast<const char*>(X - lane + H) + lane * 128);
+            if (prefetch && j + 1 < h1) {
+#pragma unroll
+                for (int i = lane; i < M / 32; i += 32) prefetch_l2(reinterpret_cast<const char*>(X - lane + H) + i * 128);
+            }
             float2 xp[REGS], v[REGS];
 #pragma unroll
             for (int r = 0; r < REGS; ++r) xp[r] = __ldg(X + 32 * r);
@@ -424,6 +429,8 @@ int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<2048, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<2048, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<4096, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<4096, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<1024, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -466,7 +473,7 @@ int zafb_mdct_plan_create(zafb_mdct_plan** out, const double* window, int64_t n)
         rc = upload_c32(&p->d_pre, pre.data(), h);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_post, post.data(), h);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_fft, h, h);
-        if (rc == ZAFB_OK && (n == 2048 || n == 1024)) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels, H = n/4
+        if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024)) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels, H = n/4
             const int64_t hh = n / 4;
             std::vector<double> t(2 * hh);
             for (int64_t k1 = 0; k1 < hh / 32; ++k1)
@@ -527,20 +534,23 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
                              reinterpret_cast<uintptr_t>(out) % 8 == 0;
-        const bool warp_ok = (p->n == 2048 || p->n == 1024) && aligned;
+        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024) && aligned;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 1024 or 2048, even clip_stride, 8-byte aligned x/out");
+            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 1024, 2048 or 4096, even clip_stride, 8-byte aligned x/out");
         if (warp_ok && p->force_kernel != 1) {
             auto run = [&](const float* xs, int64_t clips, float* dst) -> int {
                 const int64_t frames = clips * nt;
-                const bool big = p->n == 2048;
-                const size_t smem = big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
-                                        : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
+                const bool big = p->n == 2048, huge = p->n == 4096;
+                const size_t smem = huge  ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
+                                    : big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                          : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
+                // (N = 4096: 64 points and 4 x 16 sample pairs per lane -- one CTA per SM)
                 constexpr int occ = 3;
+                const int occ_n = huge ? 1 : occ;
                 int64_t ctas = ceil_div(frames, kWarps);
-                if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-                auto kern = big ? mdct_warp_kernel<2048, occ> : mdct_warp_kernel<1024, occ>;
+                if (ctas > int64_t(sm_count()) * occ_n) ctas = int64_t(sm_count()) * occ_n;
+                auto kern = huge ? mdct_warp_kernel<4096, 1> : big ? mdct_warp_kernel<2048, occ> : mdct_warp_kernel<1024, occ>;
                 kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     xs, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
                     dst, frames);
@@ -582,15 +592,17 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
     {
-        const bool warp_ok = (p->n == 2048 || p->n == 1024) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
+        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N = 1024 or 2048, 8-byte aligned spectra");
+            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N = 1024, 2048 or 4096, 8-byte aligned spectra");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float* sp, int64_t clips, float* yy) -> int {
                 const int64_t nblocks = nt - 1;
                 constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
-                const int64_t resident_warps = int64_t(sm_count()) * occ * kWarps;
+                const bool big = p->n == 2048, huge = p->n == 4096;
+                const int occ_n = huge ? 1 : occ;
+                const int64_t resident_warps = int64_t(sm_count()) * occ_n * kWarps;
                 int64_t best_len = nblocks, best_cost = INT64_MAX;
                 for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
                     const int64_t runs = clips * ceil_div(nblocks, l);
@@ -603,12 +615,12 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
                 const int64_t runs_per_clip = ceil_div(nblocks, best_len);
                 const int64_t total = clips * runs_per_clip;
                 int64_t ctas = ceil_div(total, kWarps);
-                if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
-                const bool big = p->n == 2048;
-                const size_t smem = big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
-                                        : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
+                if (ctas > int64_t(sm_count()) * occ_n) ctas = int64_t(sm_count()) * occ_n;
+                const size_t smem = huge  ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
+                                    : big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                          : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 const int y_aligned = (reinterpret_cast<uintptr_t>(yy) % 8 == 0 && (clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
-                auto kern = big ? imdct_warp_kernel<2048, occ> : imdct_warp_kernel<1024, occ>;
+                auto kern = huge ? imdct_warp_kernel<4096, 1> : big ? imdct_warp_kernel<2048, occ> : imdct_warp_kernel<1024, occ>;
                 kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     sp, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
                     int(best_len), total, len, yy, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));
