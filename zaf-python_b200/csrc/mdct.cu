@@ -563,19 +563,31 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
             });
         }
     }
-    if (p->log2m >= 1) {
-        const size_t smem = size_t(m) * sizeof(float2) + 2 * size_t(m) * sizeof(float);
-        if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
-        mdct_generic_kernel<<<unsigned(grid), threads_for(m / 2), smem, st>>>(x, ns, clip_stride, nt, p->log2m, p->d_window,
-                                                                              p->d_tw_fft, p->d_pre, p->d_post, out, layout, total);
-    } else {
-        const size_t smem = size_t(2 * m) * sizeof(float) + 16;
-        if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
-        int th = m < 256 ? ((m + 31) / 32) * 32 : 256;
-        mdct_direct_kernel<<<unsigned(grid), th, smem, st>>>(x, ns, clip_stride, nt, m, p->d_window, p->d_cos, out, layout, total);
-    }
-    ZAFB_LAUNCH_CHECK();
-    return ZAFB_OK;
+    // generic kernels (one CTA per frame) can store either layout, but BIN_MAJOR means one 4-byte element per row: that
+    // layout goes through frame-major scratch and the tiled transpose (ZAFB_GENERIC_BM_DIRECT=1 keeps the strided stores)
+    auto run_generic = [&](const float* xs, int64_t clips, float* dst, int lay) -> int {
+        const int64_t frames = clips * nt;
+        const int64_t g = frames < int64_t(sm_count()) * 32 ? frames : int64_t(sm_count()) * 32;
+        if (p->log2m >= 1) {
+            const size_t smem = size_t(m) * sizeof(float2) + 2 * size_t(m) * sizeof(float);
+            if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
+            mdct_generic_kernel<<<unsigned(g), threads_for(m / 2), smem, st>>>(xs, ns, clip_stride, nt, p->log2m, p->d_window,
+                                                                               p->d_tw_fft, p->d_pre, p->d_post, dst, lay, frames);
+        } else {
+            const size_t smem = size_t(2 * m) * sizeof(float) + 16;
+            if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mdct: window too large for shared memory");
+            int th = m < 256 ? ((m + 31) / 32) * 32 : 256;
+            mdct_direct_kernel<<<unsigned(g), th, smem, st>>>(xs, ns, clip_stride, nt, m, p->d_window, p->d_cos, dst, lay, frames);
+        }
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    };
+    (void)grid;
+    if (layout == ZAFB_LAYOUT_FRAME_MAJOR || nt == 1 || m == 1 || env_flag("ZAFB_GENERIC_BM_DIRECT", 0))
+        return run_generic(x, n_clips, out, layout);
+    return bin_major_from_frame_major(out, n_clips, nt, p->m, st, [&](int64_t c0, int64_t nc, float* scratch) {
+        return run_generic(x + c0 * clip_stride, nc, scratch, ZAFB_LAYOUT_FRAME_MAJOR);
+    });
 }
 
 int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
@@ -640,13 +652,22 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     const int h = m / 2 > 0 ? m / 2 : 1;
     const size_t smem = size_t(2 * h) * sizeof(float2) + 4 * size_t(m) * sizeof(float) + 16;
     if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "imdct: window too large for shared memory");
-    const int64_t blocks = n_clips * tiles;
-    if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "imdct: too many tiles");
-    imdct_tile_kernel<<<unsigned(blocks), threads_for(m / 2), smem, static_cast<cudaStream_t>(stream)>>>(
-        spec, nt, m, p->log2m, layout, p->d_window, p->d_tw_fft, p->d_pre, p->d_post, p->d_cos, per_tile, tiles, len, y,
-        y_stride);
-    ZAFB_LAUNCH_CHECK();
-    return ZAFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto run_generic = [&](const float* sp, int64_t clips, float* yy, int lay) -> int {
+        const int64_t blocks = clips * tiles;
+        if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "imdct: too many tiles");
+        imdct_tile_kernel<<<unsigned(blocks), threads_for(m / 2), smem, st>>>(
+            sp, nt, m, p->log2m, lay, p->d_window, p->d_tw_fft, p->d_pre, p->d_post, p->d_cos, per_tile, tiles, len, yy,
+            y_stride);
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    };
+    // BIN_MAJOR input would be read one 4-byte element per row: transpose it into frame-major scratch first
+    if (layout == ZAFB_LAYOUT_FRAME_MAJOR || nt == 1 || m == 1 || env_flag("ZAFB_GENERIC_BM_DIRECT", 0))
+        return run_generic(spec, n_clips, y, layout);
+    return frame_major_from_bin_major(spec, n_clips, nt, p->m, st, [&](int64_t c0, int64_t nc, const float* scratch) {
+        return run_generic(scratch, nc, y + c0 * y_stride, ZAFB_LAYOUT_FRAME_MAJOR);
+    });
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines

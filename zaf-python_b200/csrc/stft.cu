@@ -980,24 +980,35 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             return run(x + c0 * clip_stride, nc, scratch);
         });
     }
-    const int64_t grid = total < int64_t(sms) * 32 ? total : int64_t(sms) * 32;
-    if (p->log2n >= 1) {
-        const int m = int(p->n / 2);
-        const size_t smem = size_t(p->n) * sizeof(float2);
-        if (smem > size_t(kMaxDynSmem))
-            return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
-        stft_generic_kernel<<<static_cast<unsigned>(grid), fft_threads(m), smem, st>>>(
-            x, ns, clip_stride, nt, p->hop, p->log2n, p->d_window, p->d_tw_half, p->d_tw_full, o, layout, total);
-    } else {
-        const size_t smem = size_t(p->n) * sizeof(float) + 16;
-        if (smem > size_t(kMaxDynSmem))
-            return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
-        int th = int(p->n) < 256 ? ((int(p->n) + 31) / 32) * 32 : 256;
-        stft_dft_kernel<<<static_cast<unsigned>(grid), th, smem, st>>>(x, ns, clip_stride, nt, p->hop, int(p->n),
-                                                                        p->d_window, p->d_tw_full, o, layout, total);
-    }
-    ZAFB_LAUNCH_CHECK();
-    return ZAFB_OK;
+    // generic kernels: one CTA per frame.  They can store either layout, but a BIN_MAJOR store is one 8-byte element per
+    // row (measured 0.035 of the HBM peak at N = 256), so that layout goes through frame-major scratch and the tiled
+    // transpose as well (ZAFB_GENERIC_BM_DIRECT=1 keeps the strided stores).
+    auto run_generic = [&](const float* xs, int64_t clips, float2* dst, int lay) -> int {
+        const int64_t frames = clips * nt;
+        const int64_t grid = frames < int64_t(sms) * 32 ? frames : int64_t(sms) * 32;
+        if (p->log2n >= 1) {
+            const int m = int(p->n / 2);
+            const size_t smem = size_t(p->n) * sizeof(float2);
+            if (smem > size_t(kMaxDynSmem))
+                return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
+            stft_generic_kernel<<<static_cast<unsigned>(grid), fft_threads(m), smem, st>>>(
+                xs, ns, clip_stride, nt, p->hop, p->log2n, p->d_window, p->d_tw_half, p->d_tw_full, dst, lay, frames);
+        } else {
+            const size_t smem = size_t(p->n) * sizeof(float) + 16;
+            if (smem > size_t(kMaxDynSmem))
+                return fail(ZAFB_E_UNSUPPORTED, "window_length %lld needs %zu B of shared memory", (long long)p->n, smem);
+            int th = int(p->n) < 256 ? ((int(p->n) + 31) / 32) * 32 : 256;
+            stft_dft_kernel<<<static_cast<unsigned>(grid), th, smem, st>>>(xs, ns, clip_stride, nt, p->hop, int(p->n),
+                                                                            p->d_window, p->d_tw_full, dst, lay, frames);
+        }
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    };
+    if (layout == ZAFB_LAYOUT_FRAME_MAJOR || nt == 1 || p->n == 1 || env_flag("ZAFB_GENERIC_BM_DIRECT", 0))
+        return run_generic(x, n_clips, o, layout);
+    return bin_major_from_frame_major(o, n_clips, nt, p->n, st, [&](int64_t c0, int64_t nc, float2* scratch) {
+        return run_generic(x + c0 * clip_stride, nc, scratch, ZAFB_LAYOUT_FRAME_MAJOR);
+    });
 }
 
 int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
@@ -1060,13 +1071,23 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     const int64_t tiles = ceil_div(len, tile);
     const size_t smem = fft_bytes + size_t(tile) * sizeof(float);
     const float scale = static_cast<float>(1.0 / (double(n) * p->gain));
-    const int64_t blocks = n_clips * tiles;
-    if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "istft: too many tiles (%lld)", (long long)blocks);
-    istft_tile_kernel<<<static_cast<unsigned>(blocks), fft_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float2*>(spec), nt, p->hop, n, p->log2n >= 1 ? p->log2n : (n == 1 ? 0 : -1), layout,
-        p->d_tw_full, scale, tile, tiles, ola, start, len, y, y_stride);
-    ZAFB_LAUNCH_CHECK();
-    return ZAFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto run_generic = [&](const float2* s2, int64_t clips, float* yy, int lay) -> int {
+        const int64_t blocks = clips * tiles;
+        if (blocks > 0x7fffffffLL) return fail(ZAFB_E_UNSUPPORTED, "istft: too many tiles (%lld)", (long long)blocks);
+        istft_tile_kernel<<<static_cast<unsigned>(blocks), fft_threads(n), smem, st>>>(
+            s2, nt, p->hop, n, p->log2n >= 1 ? p->log2n : (n == 1 ? 0 : -1), lay, p->d_tw_full, scale, tile, tiles, ola, start,
+            len, yy, y_stride);
+        ZAFB_LAUNCH_CHECK();
+        return ZAFB_OK;
+    };
+    const float2* s2 = reinterpret_cast<const float2*>(spec);
+    // BIN_MAJOR input would be read one 8-byte element per row: transpose it into frame-major scratch first
+    if (layout == ZAFB_LAYOUT_FRAME_MAJOR || nt == 1 || n == 1 || env_flag("ZAFB_GENERIC_BM_DIRECT", 0))
+        return run_generic(s2, n_clips, y, layout);
+    return frame_major_from_bin_major(s2, n_clips, nt, int64_t(n), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
+        return run_generic(scratch, nc, y + c0 * y_stride, ZAFB_LAYOUT_FRAME_MAJOR);
+    });
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
