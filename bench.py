@@ -445,15 +445,41 @@ def run_ours(args):
         x_host = pin_x.array[:e2e_clips]
         zaf.stft(x_host, w, HOP, out=pin_out.array)
         dist.barrier()
+        b0 = zaf.host_copy_bytes()
         t0 = time.perf_counter()
         ksteps = max(1, args.e2e_steps)
         for _ in range(ksteps):
             zaf.stft(x_host, w, HOP, out=pin_out.array)
         e2e_s = dist.max((time.perf_counter() - t0) / ksteps)
+        b1 = zaf.host_copy_bytes()
+        # bytes that crossed PCIe, counted by the library where it enqueues the copies.  The result in host memory is the
+        # full two-sided spectrum (result_bytes); for large frame-major results only bins 0..N/2 are copied and host
+        # threads write the Hermitian mirror (include/zafb200.h, zafb_stft_host_f32).
         e2e = {"value": e2e_clips * nt * dist.world / e2e_s, "unit": "frames/s",
-               "h2d_bytes_per_step": int(x_host.nbytes), "d2h_bytes_per_step": int(pin_out.nbytes),
+               "h2d_bytes_per_step": (b1[0] - b0[0]) // ksteps, "d2h_bytes_per_step": (b1[1] - b0[1]) // ksteps,
+               "result_bytes_per_step": int(pin_out.nbytes),
                "clips_per_step": e2e_clips, "ms_per_step": 1e3 * e2e_s,
                "api": "zaf.stft(x_host, w, hop, out=pinned) -> zafb_stft_host_f32"}
+        if dist.rank == 0:  # what the timed calls left in host memory, against the oracle (checker only)
+            import oracle
+
+            worst = 0.0
+            for c in (0, e2e_clips - 1):
+                worst = max(worst, *oracle.parity_metrics(pin_out.array[c].T, oracle.stft(x_host[c], w, HOP)))
+            e2e["parity_max_rel_err"] = worst
+            assert worst <= 1e-5, f"e2e parity broken: {worst}"
+        # the same call returning the reference's own memory order (C-order (N, nt) per clip), reported beside it
+        out_c = pin_out.array.reshape(e2e_clips, N_WIN, nt)
+        zaf.stft(x_host, w, HOP, out=out_c, layout="bin_major")
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            zaf.stft(x_host, w, HOP, out=out_c, layout="bin_major")
+        c_s = dist.max((time.perf_counter() - t0) / 2)
+        e2e["c_order"] = {"value": e2e_clips * nt * dist.world / c_s, "ms_per_step": 1e3 * c_s, "layout": "bin_major"}
+        if dist.rank == 0:
+            e2e["c_order"]["parity_max_rel_err"] = max(oracle.parity_metrics(out_c[0], oracle.stft(x_host[0], w, HOP)))
+            assert e2e["c_order"]["parity_max_rel_err"] <= 1e-5
         pin_out.free()
     except (MemoryError, RuntimeError) as exc:  # e.g. not enough pinnable host memory
         e2e = {"value": None, "unit": "frames/s", "error": str(exc)[:200]}

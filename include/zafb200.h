@@ -85,6 +85,8 @@ int zafb_pcm16_to_f32(const int16_t* pcm_dev, int64_t frames, int channels, int 
                       int64_t out_stride, void* stream);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t zafb_launch_count(void);
+/* Bytes the *_host_f32 pipelines have copied host->device and device->host since the library was loaded. */
+int zafb_host_copy_bytes(int64_t* h2d, int64_t* d2h);
 
 /* ------------------------------------------------------- integer bookkeeping
  * Bit-exact restatements of the reference's frame arithmetic (no device needed). */
@@ -121,11 +123,20 @@ int zafb_stft_f32(const zafb_stft_plan* plan, const float* x, int64_t n_clips, i
  * y: n_clips rows of nt*hop-(N-hop) samples, row c at y + c*y_stride. */
 int zafb_istft_f32(const zafb_stft_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
                    int layout, float* y, int64_t y_stride, void* stream);
-/* Host-buffer versions (pinned or pageable host memory; chunked and pipelined). */
+/* Host-buffer versions (pinned or pageable host memory; chunked and pipelined).
+ * zafb_stft_host_f32, results of 256 MB and more (either layout): the spectrum of a real signal is Hermitian, so only bins
+ * 0 .. N/2 of each frame cross PCIe and host threads write the mirrored half, X[N-k] = conj(X[k]) -- exact, the same bits
+ * the device kernel stores (ZAFB_HOST_MIRROR=0 copies the full spectrum instead; ZAFB_HOST_MIRROR_THREADS sets the
+ * thread count; default min(16, host cores / LOCAL_WORLD_SIZE), and the path stays off below 6 threads). */
 int zafb_stft_host_f32(const zafb_stft_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
                        int64_t clip_stride, float* out_host, int layout);
 int zafb_istft_host_f32(const zafb_stft_plan* plan, const float* spec_host, int64_t n_clips,
                         int64_t nt, int layout, float* y_host, int64_t y_stride);
+
+/* The host-side half of that path, usable on its own: given `frames` frame-major frames of `window_length` complex64
+ * bins (window_length a multiple of 4) whose bins 0 .. N/2 are valid, writes bins N/2+1 .. N-1 as conj of bins
+ * N/2-1 .. 1 -- the two-sided spectrum zaf.stft returns (zaf.py:139) from a one-sided one.  No device involved. */
+int zafb_host_mirror_fill(float* spectrum_host, int64_t frames, int64_t window_length);
 
 /* ------------------------------------------------------------- MDCT / IMDCT */
 typedef struct zafb_mdct_plan zafb_mdct_plan;

@@ -109,6 +109,24 @@ def test_no_cpu_fallback(zaf):
         zaf.mdct(np.zeros(1000, np.float32), np.ones(64))
 
 
+def test_host_mirror_fill_is_the_hermitian_half(zaf):
+    """zafb_host_mirror_fill (the host half of the half-spectrum D2H path, no device involved): bins N/2+1 .. N-1 become
+    conj of bins N/2-1 .. 1, bit for bit, for aligned and unaligned buffers; bins 0 .. N/2 are left alone."""
+    import ctypes as C
+    lib = zaf._lib.lib()
+    rng = np.random.default_rng(3)
+    for n, frames, off in ((4, 3, 0), (8, 5, 0), (64, 7, 0), (2048, 3, 0), (1024, 4, 1), (12, 2, 1)):
+        buf = np.zeros(frames * n + 1, np.complex64)
+        a = buf[off:off + frames * n].reshape(frames, n)
+        a[:] = (rng.standard_normal((frames, n)) + 1j * rng.standard_normal((frames, n))).astype(np.complex64)
+        want = a.copy()
+        want[:, n // 2 + 1:] = np.conj(want[:, 1:n // 2][:, ::-1])
+        zaf._lib.check(lib.zafb_host_mirror_fill(C.c_void_p(a.ctypes.data), frames, n))
+        assert np.array_equal(a.view(np.uint32), want.view(np.uint32)), (n, frames, off)
+    with pytest.raises(ValueError):
+        zaf._lib.check(lib.zafb_host_mirror_fill(C.c_void_p(buf.ctypes.data), 1, 6))
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "zaf-python_b200")
     for dirpath, _, files in os.walk(pkg):

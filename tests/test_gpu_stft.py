@@ -355,3 +355,34 @@ def test_stft_bin_major_direct_kernel(zaf_gpu, monkeypatch, n):
         zaf_gpu._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), 4, 20000, xd.pitch, C.c_void_p(buf.ptr + 8 * off), 1, None))
         zaf_gpu.synchronize()
         assert np.array_equal(buf.to_host()[off:off + count].reshape(ref.shape), ref), off
+
+
+def test_stft_host_half_spectrum_path(zaf_gpu, monkeypatch):
+    """Large frame-major host results cross PCIe as bins 0 .. N/2 only; host threads write the Hermitian mirror
+    (stft_host_mirrored).  Forced on small inputs here: the result must equal the full-copy pipeline bit for bit, for
+    several chunks, ragged last chunks, odd signal lengths, pinned and pageable result memory, 1 .. 5 fill threads."""
+    rng = np.random.default_rng(77)
+    for n, hop, shape in ((2048, 512, (9, 30011)), (1024, 256, (5, 8000)), (512, 128, (3, 999)), (4096, 1024, (4, 20000)),
+                          (64, 16, (7, 1000)), (100, 25, (6, 3000))):
+        w = oracle.hamming_periodic(n) if n != 100 else np.hanning(102)[1:-1]
+        x = rng.uniform(-1, 1, shape).astype(np.float32)
+        monkeypatch.setenv("ZAFB_HOST_MIRROR", "0")
+        ref = zaf_gpu.stft(x, w, hop)
+        monkeypatch.setenv("ZAFB_HOST_MIRROR", "1")
+        monkeypatch.setenv("ZAFB_HOST_MIRROR_MIN_MB", "0")
+        monkeypatch.setenv("ZAFB_PIPE_CHUNK_MB", "1")
+        for threads in (2, 3, 5):
+            monkeypatch.setenv("ZAFB_HOST_MIRROR_THREADS", str(threads))
+            for layout in ("frame_major", "bin_major"):
+                got = zaf_gpu.stft(x, w, hop, layout=layout)
+                assert np.array_equal(np.ascontiguousarray(got).view(np.uint32),
+                                      np.ascontiguousarray(ref).view(np.uint32)), (n, hop, shape, threads, layout)
+        nt = ref.shape[-1]
+        pin = zaf_gpu.PinnedArray((shape[0], nt, n), np.complex64)
+        pin.array[:] = 0
+        got = zaf_gpu.stft(x, w, hop, out=pin.array)
+        assert np.array_equal(np.ascontiguousarray(got), np.ascontiguousarray(ref))
+        pin.free()
+        for k in ("ZAFB_HOST_MIRROR", "ZAFB_HOST_MIRROR_MIN_MB", "ZAFB_PIPE_CHUNK_MB", "ZAFB_HOST_MIRROR_THREADS"):
+            monkeypatch.delenv(k)
+        assert_parity(ref[-1], oracle.stft(x[-1], w, hop))

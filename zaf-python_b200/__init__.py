@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _lib, _pinned
 from ._device import (DeviceArray, Event, PinnedArray, Stream, device_count, empty, ensure_init, init,  # noqa: F401
-                      launch_count, synchronize, to_device)
+                      host_copy_bytes, launch_count, synchronize, to_device)
 from ._lib import LAYOUT_BIN_MAJOR, LAYOUT_FRAME_MAJOR, ZafbError  # noqa: F401
 from ._operators import cqtkernel, melfilterbank  # noqa: F401
 from . import _dist as dist  # noqa: F401
@@ -35,7 +35,7 @@ from ._dist import shard_range  # noqa: F401
 __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
     "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
-    "to_device", "empty", "from_pcm16", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count",
+    "to_device", "empty", "from_pcm16", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count", "host_copy_bytes",
     "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry", "dist", "shard_range",
 ]
 

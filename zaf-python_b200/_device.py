@@ -34,6 +34,14 @@ def synchronize() -> None:
     _lib.check(_lib.lib().zafb_device_sync())
 
 
+def host_copy_bytes():
+    """(h2d, d2h) bytes the host-buffer pipelines have moved over the link so far."""
+    import ctypes as C
+    a, b = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.lib().zafb_host_copy_bytes(C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
 def launch_count() -> int:
     return int(_lib.lib().zafb_launch_count())
 

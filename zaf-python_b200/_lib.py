@@ -46,6 +46,7 @@ PROTOTYPES = {
     "zafb_event_elapsed_ms": (_int, [_vp, _vp, C.POINTER(C.c_float)]),
     "zafb_pcm16_to_f32": (_int, [_vp, _i64, _int, _int, _vp, _i64, _vp]),
     "zafb_launch_count": (_i64, []),
+    "zafb_host_copy_bytes": (_int, [_vp, _vp]),
     "zafb_stft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
     "zafb_istft_geometry": (_int, [_i64, _i64, _i64, _pi64, _pi64, _pi64]),
     "zafb_mdct_geometry": (_int, [_i64, _i64, _pi64, _pi64, _pi64]),
@@ -56,6 +57,7 @@ PROTOTYPES = {
     "zafb_stft_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_istft_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp]),
     "zafb_stft_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
+    "zafb_host_mirror_fill": (_int, [_vp, _i64, _i64]),
     "zafb_istft_host_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64]),
     "zafb_mdct_plan_create": (_int, [_pvp, _vp, _i64]),
     "zafb_mdct_plan_destroy": (_int, [_vp]),

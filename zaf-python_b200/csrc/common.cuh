@@ -17,6 +17,7 @@ namespace zafb {
 std::string& last_error_ref();
 int fail(int code, const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_h2d_bytes, g_d2h_bytes;  // bytes the host pipelines have moved over the link
 
 #define ZAFB_CUDA(expr)                                                                   \
     do {                                                                                  \

@@ -62,6 +62,8 @@ int run_host_pipeline(const void* in_host, size_t in_host_pitch, size_t in_width
                 ZAFB_CUDA(cudaMemcpy2DAsync(hp.d_in[s], in_dev_pitch, src, in_host_pitch, in_width, size_t(nr),
                                             cudaMemcpyHostToDevice, hp.st[s]));
         }
+        g_h2d_bytes.fetch_add(int64_t(nr) * int64_t(in_width), std::memory_order_relaxed);
+        g_d2h_bytes.fetch_add(int64_t(nr) * int64_t(out_width), std::memory_order_relaxed);
         rc = launch(hp.d_in[s], hp.d_out[s], r0, nr, hp.st[s]);
         if (rc != ZAFB_OK) break;
         if (out_width > 0) {

@@ -26,6 +26,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 
 int upload_f32(float** dev, const double* host, size_t n) {
     std::vector<float> tmp(n ? n : 1);
@@ -303,6 +304,11 @@ int zafb_event_elapsed_ms(void* a, void* b, float* ms) {
     return ZAFB_OK;
 }
 int64_t zafb_launch_count(void) { return g_launches.load(); }
+int zafb_host_copy_bytes(int64_t* h2d, int64_t* d2h) {
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    return ZAFB_OK;
+}
 
 // ------------------------------------------------------------------ integer bookkeeping
 // The reference computes these with Python floats (true division + ceil/floor); IEEE double

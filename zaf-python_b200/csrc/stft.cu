@@ -17,8 +17,12 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <atomic>
+#include <thread>
 #include <type_traits>
 #include <vector>
+
+#include <emmintrin.h>
 
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
@@ -1091,6 +1095,172 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
+}  // extern "C"
+
+namespace {
+
+// out[N - k] = conj(out[k]), k = 1 .. N/2 - 1, for `frames` consecutive frame-major frames (N a multiple of 4).
+// Streaming 16-byte stores when the frames are 16-byte aligned: the mirrored half is written once and not read again here.
+void mirror_fill(float2* out, int64_t frames, int64_t n) {
+    const bool aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));  // negate the imaginary parts
+    for (int64_t f = 0; f < frames; ++f) {
+        float2* o = out + f * n;
+        const int64_t h = n / 2;
+        o[h + 1] = make_float2(o[h - 1].x, -o[h - 1].y);
+        // destinations (n - k, n - k + 1) <- sources (k, k - 1), k = h - 2, h - 4, ..., 2 (k even: destination 16-byte aligned)
+        for (int64_t k = h - 2; k >= 2; k -= 2) {
+            const __m128 v = _mm_loadu_ps(reinterpret_cast<const float*>(o + k - 1));  // (o[k-1], o[k])
+            const __m128 r = _mm_xor_ps(_mm_shuffle_ps(v, v, _MM_SHUFFLE(1, 0, 3, 2)), sign);  // (conj o[k], conj o[k-1])
+            if (aligned) _mm_stream_ps(reinterpret_cast<float*>(o + n - k), r);
+            else _mm_storeu_ps(reinterpret_cast<float*>(o + n - k), r);
+        }
+    }
+    _mm_sfence();
+}
+
+// BIN_MAJOR twin: rows [r_lo, r_hi) of the flattened (clip, k) index, k = 1 .. N/2 - 1: row N - k of the clip = conj(row k).
+void mirror_fill_rows(float2* out, int64_t nt, int64_t n, int64_t r_lo, int64_t r_hi) {
+    const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));
+    const int64_t per_clip = n / 2 - 1;
+    for (int64_t r = r_lo; r < r_hi; ++r) {
+        const int64_t clip = r / per_clip, k = 1 + (r - clip * per_clip);
+        const float2* src = out + (clip * n + k) * nt;
+        float2* dst = out + (clip * n + (n - k)) * nt;
+        int64_t j = 0;
+        if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 && nt > 0) {  // peel one element: the rest of the row is 16-byte aligned
+            dst[0] = make_float2(src[0].x, -src[0].y);
+            j = 1;
+        }
+        const bool aligned = reinterpret_cast<uintptr_t>(dst + j) % 16 == 0;
+        for (; j + 2 <= nt; j += 2) {
+            const __m128 v = _mm_xor_ps(_mm_loadu_ps(reinterpret_cast<const float*>(src + j)), sign);
+            if (aligned) _mm_stream_ps(reinterpret_cast<float*>(dst + j), v);
+            else _mm_storeu_ps(reinterpret_cast<float*>(dst + j), v);
+        }
+        for (; j < nt; ++j) dst[j] = make_float2(src[j].x, -src[j].y);
+    }
+    _mm_sfence();
+}
+
+// Fill threads: ZAFB_HOST_MIRROR_THREADS, else min(16, host cores / processes sharing the host), where the process count
+// is LOCAL_WORLD_SIZE (set by torchrun: one rank per GPU) or 1.  Measured on a 16-core B200 host (cfg 2, 15.75 GB
+// result): 4 threads 276 ms (no better than the full copy, 282 ms), 8 -> 193 ms, 12-16 -> 172-177 ms; fewer than 6
+// threads leave the path off.
+int host_mirror_threads() {
+    int t = env_flag("ZAFB_HOST_MIRROR_THREADS", -1);
+    if (t >= 0) return t;
+    int procs = env_flag("LOCAL_WORLD_SIZE", 1);
+    if (procs < 1) procs = 1;
+    t = int(std::thread::hardware_concurrency()) / procs;
+    if (t > 16) t = 16;
+    return t >= 6 ? t : 0;
+}
+
+// STFT into HOST memory with half the PCIe traffic: the spectrum of a real signal is Hermitian, so only bins 0 .. N/2
+// (of every frame, or -- C order -- the first N/2 + 1 rows of every clip) cross the link, one strided D2H copy per chunk,
+// and host threads write the mirrored half, X[N - k] = conj(X[k]) -- an exact copy with a sign flip, bit-identical to
+// what the kernel stores on the device.
+// Chunk c's fill overlaps the copies of the chunks after it.
+int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, float* out,
+                       int64_t nt, int layout, int threads) {
+    const bool frame_major = layout == ZAFB_LAYOUT_FRAME_MAJOR;
+    HostPipe& hp = host_pipe();
+    std::lock_guard<std::mutex> lock(hp.mu);
+    const int64_t n = p->n;
+    const size_t out_clip = size_t(nt) * n * sizeof(float2);
+    const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    const size_t in_dev = size_t(dpitch) * sizeof(float);
+    int64_t per = int64_t(host_pipe_chunk_bytes() / out_clip);
+    if (per < 1) per = 1;
+    if (per * HostPipe::kStages > n_clips) per = (n_clips + HostPipe::kStages - 1) / HostPipe::kStages;
+    if (per < 1) per = 1;
+    int rc = hp.ensure(size_t(per) * in_dev, size_t(per) * out_clip);
+    if (rc != ZAFB_OK) return rc;
+    const int64_t n_chunks = ceil_div(n_clips, per);
+    static std::vector<cudaEvent_t> events;  // guarded by hp.mu
+    while (int64_t(events.size()) < n_chunks) {
+        cudaEvent_t e;
+        ZAFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        events.push_back(e);
+    }
+    int dev = 0;
+    ZAFB_CUDA(cudaGetDevice(&dev));
+    std::atomic<int64_t> recorded{0};
+    std::atomic<int> stop{0};
+    float2* o2 = reinterpret_cast<float2*>(out);
+    std::vector<std::thread> pool;
+    pool.reserve(threads);
+    for (int w = 0; w < threads; ++w)
+        pool.emplace_back([&, w]() {
+            cudaSetDevice(dev);
+            for (int64_t c = 0; c < n_chunks; ++c) {
+                while (recorded.load(std::memory_order_acquire) <= c) {
+                    if (stop.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                if (cudaEventSynchronize(events[c]) != cudaSuccess) return;
+                const int64_t c0 = c * per;
+                const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
+                if (frame_major) {
+                    const int64_t frames = nc * nt;
+                    const int64_t f_lo = frames * w / threads, f_hi = frames * (w + 1) / threads;
+                    mirror_fill(o2 + (c0 * nt + f_lo) * n, f_hi - f_lo, n);
+                } else {  // C order: whole rows, N - k <- conj(k)
+                    const int64_t rows = nc * (n / 2 - 1);
+                    mirror_fill_rows(o2 + c0 * nt * n, nt, n, rows * w / threads, rows * (w + 1) / threads);
+                }
+            }
+        });
+    int s = 0;
+    for (int64_t c = 0; c < n_chunks && rc == ZAFB_OK; ++c, s = (s + 1) % HostPipe::kStages) {
+        const int64_t c0 = c * per;
+        const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
+        cudaError_t e = cudaSuccess;
+        if (ns > 0)
+            e = cudaMemcpy2DAsync(hp.d_in[s], in_dev, x + c0 * clip_stride, size_t(clip_stride) * sizeof(float),
+                                  size_t(ns) * sizeof(float), size_t(nc), cudaMemcpyHostToDevice, hp.st[s]);
+        if (e == cudaSuccess) {
+            rc = zafb_stft_f32(p, static_cast<const float*>(hp.d_in[s]), nc, ns, dpitch, static_cast<float*>(hp.d_out[s]),
+                               layout, hp.st[s]);
+            if (rc != ZAFB_OK) break;
+            if (frame_major)  // bins 0 .. N/2 of every frame
+                e = cudaMemcpy2DAsync(o2 + c0 * nt * n, size_t(n) * sizeof(float2), hp.d_out[s], size_t(n) * sizeof(float2),
+                                      size_t(n / 2 + 1) * sizeof(float2), size_t(nc * nt), cudaMemcpyDeviceToHost, hp.st[s]);
+            else              // rows 0 .. N/2 of every clip
+                e = cudaMemcpy2DAsync(o2 + c0 * nt * n, out_clip, hp.d_out[s], out_clip, size_t(n / 2 + 1) * nt * sizeof(float2),
+                                      size_t(nc), cudaMemcpyDeviceToHost, hp.st[s]);
+        }
+        g_h2d_bytes.fetch_add(nc * ns * int64_t(sizeof(float)), std::memory_order_relaxed);
+        g_d2h_bytes.fetch_add(nc * nt * (n / 2 + 1) * int64_t(sizeof(float2)), std::memory_order_relaxed);
+        if (e == cudaSuccess) e = cudaEventRecord(events[c], hp.st[s]);
+        if (e != cudaSuccess) {
+            rc = fail(ZAFB_E_CUDA, "host pipeline (mirrored): %s", cudaGetErrorString(e));
+            break;
+        }
+        recorded.store(c + 1, std::memory_order_release);
+    }
+    if (rc != ZAFB_OK) stop.store(1);
+    for (auto& t : pool) t.join();
+    for (int i = 0; i < HostPipe::kStages; ++i) {
+        cudaError_t e = cudaStreamSynchronize(hp.st[i]);
+        if (e != cudaSuccess && rc == ZAFB_OK) rc = fail(ZAFB_E_CUDA, "host pipeline: %s", cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zafb_host_mirror_fill(float* spectrum, int64_t frames, int64_t n) {
+    ZAFB_REQUIRE(frames >= 0 && n >= 4 && n % 4 == 0, "window_length must be a positive multiple of 4");
+    if (frames == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spectrum != nullptr, "spectrum is NULL");
+    mirror_fill(reinterpret_cast<float2*>(spectrum), frames, n);
+    return ZAFB_OK;
+}
+
 int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
                        float* out, int layout) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
@@ -1102,6 +1272,12 @@ int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     const size_t out_clip = size_t(nt) * p->n * sizeof(float2);
     // device-side clip pitch: even number of samples so the float2 fast path stays aligned
     const int64_t dpitch = (ns + 1) & ~int64_t(1);
+    // large results: half-spectrum copy + mirror fill on host threads (ZAFB_HOST_MIRROR=0 turns it off)
+    if (p->n % 4 == 0 && p->n >= 64 &&
+        size_t(n_clips) * out_clip >= (size_t(env_flag("ZAFB_HOST_MIRROR_MIN_MB", 256)) << 20) && env_flag("ZAFB_HOST_MIRROR", 1)) {
+        const int threads = host_mirror_threads();
+        if (threads >= 2) return stft_host_mirrored(p, x, n_clips, ns, clip_stride, out, nt, layout, threads);
+    }
     return run_host_pipeline(x, size_t(clip_stride) * sizeof(float), size_t(ns) * sizeof(float), size_t(dpitch) * sizeof(float),
                              out, out_clip, out_clip, out_clip, n_clips,
                              [&](void* d_in, void* d_out, int64_t, int64_t nc, cudaStream_t st) {
