@@ -48,7 +48,7 @@ def test_istft_golden(zaf_gpu, golden):
         assert_parity(got_f, ref)
 
 
-@pytest.mark.parametrize("n", [4096, 2048, 1024, 512])
+@pytest.mark.parametrize("n", [4096, 2048, 1024, 512, 256])
 @pytest.mark.parametrize("force", [1, 2])
 def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force, n):
     """The warp-per-frame kernel (2; window lengths 512 ... 4096) and the generic Stockham kernel (1) on the same input."""
@@ -66,13 +66,15 @@ def test_stft_2048_kernels_agree_with_oracle(zaf_gpu, force, n):
             assert_parity(got[c], oracle.stft(x[c], w, hop))
 
 
-@pytest.mark.parametrize("n", [4096, 2048, 1024, 512])
+@pytest.mark.parametrize("n", [4096, 2048, 1024, 512, 256])
 @pytest.mark.parametrize("force", [1, 2])
 @pytest.mark.parametrize("ratio", [8, 4, 2])
 def test_istft_2048_kernels_agree_with_oracle(zaf_gpu, force, ratio, n):
     """The warp-per-run overlap-add kernel (2) and the generic tile kernel (1) on the same
     NON-Hermitian spectra (the reference keeps Re(ifft) of whatever it is given, zaf.py:223);
     97 frames per clip so that a clip is split into several runs."""
+    if n == 256 and ratio == 8 and force == 2:
+        pytest.skip("N = 256 has 4 points per lane: the warp kernel serves hop = N/2 and N/4 only")
     hop = n // ratio
     rng = np.random.default_rng(20261017 + hop)
     nt, clips = 97, 3
@@ -315,7 +317,7 @@ def test_device_batches_with_odd_length_rows(zaf_gpu):
     assert np.array_equal(back.to_host(), zaf_gpu.imdct(zaf_gpu.mdct(x, wk), wk))
 
 
-@pytest.mark.parametrize("n", [2048, 1024, 512])
+@pytest.mark.parametrize("n", [2048, 1024, 512, 256])
 def test_stft_bin_major_direct_kernel(zaf_gpu, monkeypatch, n):
     """layout="bin_major" on the warp-kernel window lengths is written directly by stft_warp_binmajor_kernel (a CTA walks
     a clip in tiles of 16 frames kept in a shared-memory ring; every row is stored through its own sector-aligned

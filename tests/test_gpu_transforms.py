@@ -50,7 +50,7 @@ def test_mdct_imdct_vs_oracle(zaf_gpu, n, ns):
         assert np.max(np.abs(y[:m] - x[:m])) <= 2e-5
 
 
-@pytest.mark.parametrize("n", [4096, 2048, 1024])
+@pytest.mark.parametrize("n", [4096, 2048, 1024, 512])
 @pytest.mark.parametrize("force", [1, 2])
 def test_mdct_imdct_2048_kernels_agree_with_oracle(zaf_gpu, force, n):
     """The warp-per-frame MDCT / warp-per-run IMDCT kernels (2; window lengths 2048 and 1024) and the generic kernels

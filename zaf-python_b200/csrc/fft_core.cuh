@@ -240,6 +240,57 @@ __device__ __forceinline__ void warp_fft256(float2 (&v)[8], const float2* __rest
     fft_reg<8>(v);
 }
 
+// ---------------------------------------------------------------- one warp, 128 complex points
+// Four-step FFT 128 = 4 x 32 by ONE warp (window length 256; MDCT window 512).  In: v[r] = x[lane + 32 r], r < 4.  Out:
+// X[lane + 32 k] is v[bitrev(k, 2)].  tw[k1 * 32 + n2] = W_128^{k1 n2} (shared memory, 4 x 32); buf: 4 x kFft1024Pitch
+// float2.  Step 1: FFT-4 over the register index.  Step 2: the 4 FFT-32 over n2 are shared by lane octets (k1 = lane & 3,
+// o = lane >> 2): with n2 = a + 4 b and k2 = o + 8 j,
+//     X[k1 + 4 k2] = sum_a W_4^{a j} W_32^{a o} ( sum_b W_8^{b o} y[a + 4 b] ),
+// i.e. each lane forms output o of the four radix-8 butterflies of its row while reading it back from the transpose
+// tile (per-lane constants tq[b] = W_8^{b o}, b < 8), applies tq[8 + a] = W_32^{a o} and finishes with an FFT-4 in registers.
+__device__ __forceinline__ void warp_fft128_lane_twiddles(float2 (&tq)[12], int lane) {
+    const int o = lane >> 2;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        float sn, cs;
+        sincospif(-float(b * o) / 4.0f, &sn, &cs);  // W_8^{b o}
+        tq[b] = make_float2(cs, sn);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float sn, cs;
+        sincospif(-float(a * o) / 16.0f, &sn, &cs);  // W_32^{a o}
+        tq[8 + a] = make_float2(cs, sn);
+    }
+}
+
+__device__ __forceinline__ void warp_fft128(float2 (&v)[4], const float2* __restrict__ tw, float2* buf, int lane,
+                                            const float2 (&tq)[12]) {
+    fft_reg<4>(v);
+    static_for<0, 4>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        float2 y = v[bitrev(k1, 2)];
+        if constexpr (k1 > 0) y = cmul(y, tw[k1 * 32 + lane]);
+        buf[k1 * kFft1024Pitch + lane] = y;
+    });
+    __syncwarp();
+    const float2* row = buf + (lane & 3) * kFft1024Pitch;
+    static_for<0, 4>([&](auto ac) {
+        constexpr int a = decltype(ac)::value;
+        float2 u = row[a];
+#pragma unroll
+        for (int b = 1; b < 8; ++b) {
+            const float2 y = row[a + 4 * b];
+            u.x = fmaf(y.x, tq[b].x, fmaf(-y.y, tq[b].y, u.x));
+            u.y = fmaf(y.x, tq[b].y, fmaf(y.y, tq[b].x, u.y));
+        }
+        if constexpr (a == 0) v[a] = u;
+        else v[a] = cmul(u, tq[8 + a]);
+    });
+    __syncwarp();
+    fft_reg<4>(v);
+}
+
 // Whole-block M-point FFT in shared memory (ping-pong between a and b).  Every thread of the
 // group [0, nthreads) calls it with its tid; a leading __syncthreads() is the caller's job
 // (data in `a` must be visible).  Returns the buffer that holds the result; ends with a barrier.

@@ -137,11 +137,12 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = 8;
 
-// N = 4096 (M = 2048, 1024-point FFT, warp_fft1024), N = 2048 (M = 1024, 512-point FFT, warp_fft512) or
-// N = 1024 (M = 512, 256-point FFT, warp_fft256)
+// N = 4096 (M = 2048, 1024-point FFT, warp_fft1024), N = 2048 (M = 1024, 512-point FFT, warp_fft512),
+// N = 1024 (M = 512, 256-point FFT, warp_fft256) or N = 512 (M = 256, 128-point FFT, warp_fft128)
 template <int N>
 struct MdctGeom {
-    static_assert(N == 1024 || N == 2048 || N == 4096, "mdct warp kernels exist for window lengths 1024, 2048 and 4096");
+    static_assert(N == 512 || N == 1024 || N == 2048 || N == 4096, "mdct warp kernels exist for window lengths 512 ... 4096");
+    static constexpr int NTQ = N == 1024 ? 8 : N == 512 ? 12 : 1;  // per-lane twiddles of the warp FFT
     static constexpr int M = N / 2;          // coefficients per frame
     static constexpr int H = M / 2;          // complex FFT length
     static constexpr int REGS = H / 32;      // float2 per lane
@@ -165,10 +166,11 @@ __device__ __forceinline__ void load_tables(float2* smem, const float2* __restri
 
 template <int N>
 __device__ __forceinline__ void mdct_warp_fft(float2 (&v)[MdctGeom<N>::REGS], const float2* __restrict__ tw, float2* buf, int lane,
-                                              const float2 (&tq)[N == 1024 ? 8 : 1]) {
+                                              const float2 (&tq)[MdctGeom<N>::NTQ]) {
     if constexpr (N == 4096) warp_fft1024<false>(v, tw, buf, lane);
     else if constexpr (N == 2048) warp_fft512(v, tw, buf, lane);
-    else warp_fft256(v, tw, buf, lane, tq);
+    else if constexpr (N == 1024) warp_fft256(v, tw, buf, lane, tq);
+    else warp_fft128(v, tw, buf, lane, tq);
 }
 
 template <int N, int OCC>
@@ -187,8 +189,9 @@ mdct_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
     load_tables<N>(smem2, win_pairs, tw4, tid);
     const float2 c_lane = pre[lane];   // e^{-i pi lane / M}; pre[lane + 32 r] = c_lane W_TWDEN^r
     const float2 p_lane = post[lane];  // e^{-i pi (lane + 1/4) / M}; post[lane + 32 k] = p_lane W_TWDEN^k
-    float2 tq[N == 1024 ? 8 : 1];
+    float2 tq[G::NTQ];
     if constexpr (N == 1024) warp_fft256_lane_twiddles(tq, lane);
+    if constexpr (N == 512) warp_fft128_lane_twiddles(tq, lane);
     __syncthreads();
 
     for (int64_t f = int64_t(blockIdx.x) * kWarps + warp; f < total_frames; f += int64_t(gridDim.x) * kWarps) {
@@ -278,8 +281,9 @@ imdct_warp_kernel(const float* __restrict__ spec, int64_t nt, const float2* __re
 
     const float2 c_lane = pre[lane];
     const float2 p_lane = post[lane];
-    float2 tq[N == 1024 ? 8 : 1];
+    float2 tq[G::NTQ];
     if constexpr (N == 1024) warp_fft256_lane_twiddles(tq, lane);
+    if constexpr (N == 512) warp_fft128_lane_twiddles(tq, lane);
     __syncthreads();
 
     for (int64_t task = int64_t(blockIdx.x) * kWarps + warp; task < total_runs; task += int64_t(gridDim.x) * kWarps) {
@@ -473,7 +477,7 @@ int zafb_mdct_plan_create(zafb_mdct_plan** out, const double* window, int64_t n)
         rc = upload_c32(&p->d_pre, pre.data(), h);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_post, post.data(), h);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_fft, h, h);
-        if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024)) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels, H = n/4
+        if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024 || n == 512)) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels, H = n/4
             const int64_t hh = n / 4;
             std::vector<double> t(2 * hh);
             for (int64_t k1 = 0; k1 < hh / 32; ++k1)
@@ -534,23 +538,25 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
                              reinterpret_cast<uintptr_t>(out) % 8 == 0;
-        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024) && aligned;
+        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 1024, 2048 or 4096, even clip_stride, 8-byte aligned x/out");
+            return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 512, 1024, 2048 or 4096, even clip_stride, 8-byte aligned x/out");
         if (warp_ok && p->force_kernel != 1) {
             auto run = [&](const float* xs, int64_t clips, float* dst) -> int {
                 const int64_t frames = clips * nt;
-                const bool big = p->n == 2048, huge = p->n == 4096;
-                const size_t smem = huge  ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
-                                    : big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
-                                          : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
+                const bool big = p->n == 2048, huge = p->n == 4096, small = p->n == 512;
+                const size_t smem = huge    ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
+                                    : big   ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                    : small ? (MdctGeom<512>::TABLES + kWarps * MdctGeom<512>::TILE) * sizeof(float2)
+                                            : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 // 80 registers, no spills: 3 CTAs (24 warps) per SM measured 4.5 % faster than 2 on cfg 4
                 // (N = 4096: 64 points and 4 x 16 sample pairs per lane -- one CTA per SM)
                 constexpr int occ = 3;
                 const int occ_n = huge ? 1 : occ;
                 int64_t ctas = ceil_div(frames, kWarps);
                 if (ctas > int64_t(sm_count()) * occ_n) ctas = int64_t(sm_count()) * occ_n;
-                auto kern = huge ? mdct_warp_kernel<4096, 1> : big ? mdct_warp_kernel<2048, occ> : mdct_warp_kernel<1024, occ>;
+                auto kern = huge ? mdct_warp_kernel<4096, 1> : big ? mdct_warp_kernel<2048, occ>
+                            : small ? mdct_warp_kernel<512, occ> : mdct_warp_kernel<1024, occ>;
                 kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     xs, ns, clip_stride, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post,
                     dst, frames);
@@ -604,15 +610,15 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
     {
-        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
+        const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N = 1024, 2048 or 4096, 8-byte aligned spectra");
+            return fail(ZAFB_E_UNSUPPORTED, "imdct warp kernel needs N = 512, 1024, 2048 or 4096, 8-byte aligned spectra");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float* sp, int64_t clips, float* yy) -> int {
                 const int64_t nblocks = nt - 1;
                 constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
-                const bool big = p->n == 2048, huge = p->n == 4096;
+                const bool big = p->n == 2048, huge = p->n == 4096, small = p->n == 512;
                 const int occ_n = huge ? 1 : occ;
                 const int64_t resident_warps = int64_t(sm_count()) * occ_n * kWarps;
                 int64_t best_len = nblocks, best_cost = INT64_MAX;
@@ -628,11 +634,13 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
                 const int64_t total = clips * runs_per_clip;
                 int64_t ctas = ceil_div(total, kWarps);
                 if (ctas > int64_t(sm_count()) * occ_n) ctas = int64_t(sm_count()) * occ_n;
-                const size_t smem = huge  ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
-                                    : big ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
-                                          : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
+                const size_t smem = huge    ? (MdctGeom<4096>::TABLES + kWarps * MdctGeom<4096>::TILE) * sizeof(float2)
+                                    : big   ? (MdctGeom<2048>::TABLES + kWarps * MdctGeom<2048>::TILE) * sizeof(float2)
+                                    : small ? (MdctGeom<512>::TABLES + kWarps * MdctGeom<512>::TILE) * sizeof(float2)
+                                            : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 const int y_aligned = (reinterpret_cast<uintptr_t>(yy) % 8 == 0 && (clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
-                auto kern = huge ? imdct_warp_kernel<4096, 1> : big ? imdct_warp_kernel<2048, occ> : imdct_warp_kernel<1024, occ>;
+                auto kern = huge ? imdct_warp_kernel<4096, 1> : big ? imdct_warp_kernel<2048, occ>
+                            : small ? imdct_warp_kernel<512, occ> : imdct_warp_kernel<1024, occ>;
                 kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     sp, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
                     int(best_len), total, len, yy, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include <emmintrin.h>
+#include <sched.h>
 
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
@@ -71,7 +72,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // N = 1024 -> warp_fft512.  In: v[r] = z[lane + 32 r].  Out: Z[lane + 32 k2] = v[bitrev(k2, log2 REGS)].
 template <int N>
 struct WarpGeom {
-    static_assert(N == 512 || N == 1024 || N == 2048 || N == 4096, "warp kernels exist for window lengths 512 ... 4096");
+    static_assert(N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096, "warp kernels exist for window lengths 256 ... 4096");
     static constexpr int CTAS_PER_SM = N == 4096 ? 1 : N == 2048 ? 2 : 3;  // registers: 2 * REGS of frame state per lane
     static constexpr int M = N / 2;
     static constexpr int REGS = M / 32;
@@ -82,9 +83,10 @@ struct WarpGeom {
 // per-lane constants of the N = 512 transform (warp_fft256); empty for the other sizes
 template <int N>
 struct LaneTw {
-    float2 tq[N == 512 ? 8 : 1];
+    float2 tq[N == 512 ? 8 : N == 256 ? 12 : 1];
     __device__ __forceinline__ void init(int lane) {
         if constexpr (N == 512) warp_fft256_lane_twiddles(tq, lane);
+        if constexpr (N == 256) warp_fft128_lane_twiddles(tq, lane);
     }
 };
 
@@ -94,7 +96,8 @@ __device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2*
     if constexpr (N == 4096) warp_fft2048(v, tw4, buf, lane);
     else if constexpr (N == 2048) warp_fft1024<false>(v, tw4, buf, lane);
     else if constexpr (N == 1024) warp_fft512(v, tw4, buf, lane);
-    else warp_fft256(v, tw4, buf, lane, lt.tq);
+    else if constexpr (N == 512) warp_fft256(v, tw4, buf, lane, lt.tq);
+    else warp_fft128(v, tw4, buf, lane, lt.tq);
 }
 
 // N = 2048 or 1024, one warp per frame.
@@ -429,7 +432,7 @@ stft_warp_binmajor_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_
             __syncthreads();
             // Rows leave in batches of 8 (4 values of u x the two families): all shared-memory reads of a batch are issued
             // before its stores and every store has its own address registers, so nothing serialises on a register.
-            constexpr int kBatch = 4;
+            constexpr int kBatch = M / 64 < 4 ? M / 64 : 4;
             static_assert((M / 64) % kBatch == 0, "batches of four bins");
             const int64_t step = int64_t(32) * nt;   // 32 rows
             const int64_t half = int64_t(M) * nt;    // M rows
@@ -572,7 +575,8 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
             if constexpr (N == 4096) warp_fft2048(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
             else if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, s_buf, lane);
             else if constexpr (N == 1024) warp_fft512(v, s_tw, reinterpret_cast<float2*>(s_buf), lane);
-            else warp_fft256(v, s_tw, reinterpret_cast<float2*>(s_buf), lane, lt.tq);
+            else if constexpr (N == 512) warp_fft256(v, s_tw, reinterpret_cast<float2*>(s_buf), lane, lt.tq);
+            else warp_fft128(v, s_tw, reinterpret_cast<float2*>(s_buf), lane, lt.tq);
 
             static_for<0, REGS>([&](auto k2c) {
                 constexpr int k2 = decltype(k2c)::value;
@@ -761,6 +765,7 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<256, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -806,8 +811,11 @@ int launch_stft_binmajor(const zafb_stft_plan* p, const float* x, int64_t n_clip
     if (p->n == 1024)
         return cs ? launch_stft_binmajor_t<1024, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
                   : launch_stft_binmajor_t<1024, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
-    return cs ? launch_stft_binmajor_t<512, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
-              : launch_stft_binmajor_t<512, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
+    if (p->n == 512)
+        return cs ? launch_stft_binmajor_t<512, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
+                  : launch_stft_binmajor_t<512, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
+    return cs ? launch_stft_binmajor_t<256, true>(p, x, n_clips, ns, clip_stride, nt, out, st)
+              : launch_stft_binmajor_t<256, false>(p, x, n_clips, ns, clip_stride, nt, out, st);
 }
 
 template <int N, int R, int WARPS>
@@ -887,7 +895,7 @@ int zafb_stft_plan_create(zafb_stft_plan** out, const double* window, int64_t n,
         p->d_window_half = reinterpret_cast<float2*>(tmp);
         if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
     }
-    if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024 || n == 512)) {
+    if (rc == ZAFB_OK && (n == 4096 || n == 2048 || n == 1024 || n == 512 || n == 256)) {
         // four-step twiddles of the warp kernels: W_M^{k1*n2} laid out [k1][n2], M = n/2 = (M/32) x 32
         const int64_t m = n / 2;
         std::vector<double> t(2 * m);
@@ -948,9 +956,9 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     float2* o = reinterpret_cast<float2*>(out);
 
     const bool aligned = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (n_clips <= 1 || clip_stride % 2 == 0) && (p->hop % 2 == 0);
-    const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
+    const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512 || p->n == 256) && aligned;
     if (p->force_kernel == 2 && !warp_ok)
-        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 512, 1024, 2048 or 4096, even hop/stride, 8-byte aligned x");
+        return fail(ZAFB_E_UNSUPPORTED, "warp kernel needs N = 256 ... 4096 (a power of two), even hop/stride, 8-byte aligned x");
     if (warp_ok && p->force_kernel != 1) {
         // measured on cfg 2 (B200), profiles/r01_stft_experiments.txt: direct streaming stores 3.04-3.11 ms, TMA bulk stores
         // 3.13-3.20 ms; 6 warps per CTA 3.04, 8 -> 3.11, 10 -> 3.36, 4 -> 3.40.  The defaults are the fastest combination.
@@ -964,6 +972,7 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : 3);
             if (ctas > resident) ctas = resident;
             auto kern = n == 4096 ? stft_warp_kernel<4096, false, 8>
+                        : n == 256 ? stft_warp_kernel<256, false, 8>
                         : n == 512 ? stft_warp_kernel<512, false, 8>
                         : n == 1024 ? stft_warp_kernel<1024, false, 8>
                         : warps == 6 ? stft_warp_kernel<2048, false, 6>
@@ -1032,9 +1041,10 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
         const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
                              (n_clips <= 1 || y_stride % 2 == 0);
         const int64_t ratio = (p->hop > 0 && n % p->hop == 0) ? n / p->hop : 0;
-        const bool warp_ok = (n == 4096 || n == 2048 || n == 1024 || n == 512) && aligned && (ratio == 2 || ratio == 4 || ratio == 8);
+        const bool warp_ok = (n == 4096 || n == 2048 || n == 1024 || n == 512 || n == 256) && aligned &&
+                             (ratio == 2 || ratio == 4 || (ratio == 8 && n != 256));  // N = 256: 4 points per lane, at most 4 parts
         if (p->force_kernel == 2 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 512 ... 4096, hop = N/2, N/4 or N/8, even y_stride");
+            return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 256 ... 4096, hop = N/2, N/4 or N/8 (N/8: N >= 512), even y_stride");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
             auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
@@ -1052,6 +1062,10 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
                     if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st);
                     if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st);
                     return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st);
+                }
+                if (n == 256) {
+                    if (ratio == 2) return launch_istft_warp<256, 2>(p, s2, clips, nt, yy, y_stride, st);
+                    return launch_istft_warp<256, 4>(p, s2, clips, nt, yy, y_stride, st);
                 }
                 if (ratio == 2) return launch_istft_warp<512, 2>(p, s2, clips, nt, yy, y_stride, st);
                 if (ratio == 4) return launch_istft_warp<512, 4>(p, s2, clips, nt, yy, y_stride, st);
@@ -1152,7 +1166,11 @@ int host_mirror_threads() {
     if (t >= 0) return t;
     int procs = env_flag("LOCAL_WORLD_SIZE", 1);
     if (procs < 1) procs = 1;
-    t = int(std::thread::hardware_concurrency()) / procs;
+    int cores = int(std::thread::hardware_concurrency());
+    cpu_set_t set;  // the cores this process may run on (a container's affinity mask can be smaller than the machine)
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+    t = cores / procs;
     if (t > 16) t = 16;
     return t >= 6 ? t : 0;
 }
