@@ -29,7 +29,12 @@ full istft2048 '^istft_warp_kernel' 3 python scripts/bench_configs.py --only ist
 full mdct2048 '^mdct_warp_kernel' 3 python scripts/bench_configs.py --only mdct $S
 full imdct2048 '^imdct_warp_kernel' 3 python scripts/bench_configs.py --only imdct $S
 full dct1024 dct1024_warp 3 python scripts/bench_configs.py --only dct $S
-full transpose transpose_tile 1 python scripts/bench_configs.py --only stftbin $S
+full stft_binmajor '^stft_warp_binmajor' 1 python scripts/bench_configs.py --only stftbin $S
+full stft4096 '^stft_warp_kernel' 3 python scripts/stft_probe.py 4096:1024:480000:128
+full istft4096 '^istft_warp_kernel' 3 python scripts/stft_probe.py 4096:1024:480000:128
+full stft256 '^stft_warp_kernel' 3 python scripts/stft_probe.py 256:64:80000:512
+full mdct512 '^mdct_warp_kernel' 3 python scripts/mdct_probe.py 512:1323000:256
+full transpose transpose_tile 1 python scripts/mdct_probe.py 2048:1323000:64
 for k in ${EXTRA_KERNELS:-}; do
     full $k $k 2 python scripts/bench_configs.py --only ${EXTRA_ONLY:-mel,mfcc,cqt,dct} $S
 done
