@@ -1291,7 +1291,10 @@ int zafb_stft_host_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     // device-side clip pitch: even number of samples so the float2 fast path stays aligned
     const int64_t dpitch = (ns + 1) & ~int64_t(1);
     // large results: half-spectrum copy + mirror fill on host threads (ZAFB_HOST_MIRROR=0 turns it off)
-    if (p->n % 4 == 0 && p->n >= 64 &&
+    // (cudaMemcpy2D pitches are limited to 2 GB: a C-order clip longer than that takes the full-copy pipeline)
+    const bool pitch_ok = (layout == ZAFB_LAYOUT_FRAME_MAJOR || out_clip < (size_t(1) << 31)) &&
+                          size_t(clip_stride) * sizeof(float) < (size_t(1) << 31);
+    if (pitch_ok && p->n % 4 == 0 && p->n >= 64 &&
         size_t(n_clips) * out_clip >= (size_t(env_flag("ZAFB_HOST_MIRROR_MIN_MB", 256)) << 20) && env_flag("ZAFB_HOST_MIRROR", 1)) {
         const int threads = host_mirror_threads();
         if (threads >= 2) return stft_host_mirrored(p, x, n_clips, ns, clip_stride, out, nt, layout, threads);
