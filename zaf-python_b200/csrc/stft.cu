@@ -46,6 +46,9 @@ struct zafb_stft_plan {
 
 namespace {
 
+#ifndef ZAFB_STFT256_CTAS
+#define ZAFB_STFT256_CTAS 4  // CTAs per SM of stft_warp_kernel<256>: 3 -> 2.56 ms, 4 -> 2.44, 5 -> 2.50, 6 -> 2.78 (profiles/r01t_stft256_occupancy.txt)
+#endif
 constexpr int kMaxDynSmem = 227 * 1024;  // the sm_100 opt-in maximum per CTA
 
 // ------------------------------------------------------------------------------------------
@@ -73,7 +76,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int N>
 struct WarpGeom {
     static_assert(N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096, "warp kernels exist for window lengths 256 ... 4096");
-    static constexpr int CTAS_PER_SM = N == 4096 ? 1 : N == 2048 ? 2 : 3;  // registers: 2 * REGS of frame state per lane
+    static constexpr int CTAS_PER_SM = N == 4096 ? 1 : N == 2048 ? 2 : N == 256 ? ZAFB_STFT256_CTAS : 3;  // registers: 2 * REGS of frame state per lane
     static constexpr int M = N / 2;
     static constexpr int REGS = M / 32;
     static constexpr int LOGR = clog2(REGS);
@@ -969,7 +972,7 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             const int warps = (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
             const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(frames, warps);
-            const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : 3);
+            const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : n == 256 ? ZAFB_STFT256_CTAS : 3);
             if (ctas > resident) ctas = resident;
             auto kern = n == 4096 ? stft_warp_kernel<4096, false, 8>
                         : n == 256 ? stft_warp_kernel<256, false, 8>
