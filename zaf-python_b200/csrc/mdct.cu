@@ -136,6 +136,9 @@ __global__ void mdct_direct_kernel(const float* __restrict__ x, int64_t ns, int6
 // (Index maps validated in float64 against the closed form of zaf.py:1047-1073.)
 // ------------------------------------------------------------------------------------------
 constexpr int kWarps = 8;
+#ifndef ZAFB_IMDCT_SMALL_OCC
+#define ZAFB_IMDCT_SMALL_OCC 3  // CTAs per SM of imdct_warp_kernel<512> (2 -> 5.39 ms, 3 -> 5.21; N = 1024 spills with 3: 4.54 -> 4.88)
+#endif
 
 // N = 4096 (M = 2048, 1024-point FFT, warp_fft1024), N = 2048 (M = 1024, 512-point FFT, warp_fft512),
 // N = 1024 (M = 512, 256-point FFT, warp_fft256) or N = 512 (M = 256, 128-point FFT, warp_fft128)
@@ -437,6 +440,7 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<4096, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mdct_warp_kernel<1024, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(imdct_warp_kernel<512, ZAFB_IMDCT_SMALL_OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mdct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(imdct_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -619,7 +623,7 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
                 const int64_t nblocks = nt - 1;
                 constexpr int occ = 2;  // the carried half-frame needs 32 more registers; 3 CTAs/SM would spill
                 const bool big = p->n == 2048, huge = p->n == 4096, small = p->n == 512;
-                const int occ_n = huge ? 1 : occ;
+                const int occ_n = huge ? 1 : (small ? ZAFB_IMDCT_SMALL_OCC : occ);
                 const int64_t resident_warps = int64_t(sm_count()) * occ_n * kWarps;
                 int64_t best_len = nblocks, best_cost = INT64_MAX;
                 for (int64_t l = nblocks < 8 ? nblocks : 8; l <= nblocks && l <= 2048; ++l) {
@@ -640,7 +644,7 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
                                             : (MdctGeom<1024>::TABLES + kWarps * MdctGeom<1024>::TILE) * sizeof(float2);
                 const int y_aligned = (reinterpret_cast<uintptr_t>(yy) % 8 == 0 && (clips <= 1 || y_stride % 2 == 0)) ? 1 : 0;
                 auto kern = huge ? imdct_warp_kernel<4096, 1> : big ? imdct_warp_kernel<2048, occ>
-                            : small ? imdct_warp_kernel<512, occ> : imdct_warp_kernel<1024, occ>;
+                            : small ? imdct_warp_kernel<512, ZAFB_IMDCT_SMALL_OCC> : imdct_warp_kernel<1024, occ>;
                 kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(
                     sp, nt, reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_pre, p->d_post, runs_per_clip,
                     int(best_len), total, len, yy, y_stride, y_aligned, env_flag("ZAFB_IMDCT_PREFETCH", 1));

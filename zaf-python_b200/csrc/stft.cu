@@ -49,6 +49,12 @@ namespace {
 #ifndef ZAFB_STFT256_CTAS
 #define ZAFB_STFT256_CTAS 4  // CTAs per SM of stft_warp_kernel<256>: 3 -> 2.56 ms, 4 -> 2.44, 5 -> 2.50, 6 -> 2.78 (profiles/r01t_stft256_occupancy.txt)
 #endif
+#ifndef ZAFB_ISTFT_SMALL_CTAS
+#define ZAFB_ISTFT_SMALL_CTAS 3  // CTAs per SM of istft_warp_kernel<256> (2 -> 2.94 ms, 3 -> 2.86; N = 512 is slower with 3)
+#endif
+#ifndef ZAFB_STFT4096_WARPS
+#define ZAFB_STFT4096_WARPS 8    // warps per CTA of stft_warp_kernel<4096> (one CTA per SM; 10 warps spill: 4.50 -> 5.31 ms)
+#endif
 constexpr int kMaxDynSmem = 227 * 1024;  // the sm_100 opt-in maximum per CTA
 
 // ------------------------------------------------------------------------------------------
@@ -505,11 +511,12 @@ stft_warp_binmajor_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_
 //   Z[k] = E[k] + i O[k],  E = H[k] + H[k+1024],  O = (H[k] - H[k+1024]) conj(W_2048^k),
 //   y[2n] + i y[2n+1] = conj(FFT_1024(conj(Z)))[n] / (2 N)        (validated in float64).
 // ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int istft_ctas_per_sm(int n) { return n == 4096 ? 1 : n <= 256 ? ZAFB_ISTFT_SMALL_CTAS : 2; }
 // floats of transpose tile per warp
 __host__ __device__ constexpr int istft_tile_floats(int n) { return n == 2048 ? 32 * kFft1024Pitch : 2 * (n / 64) * kFft1024Pitch; }
 
 template <int N, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, N == 4096 ? 1 : 2)
+__global__ void __launch_bounds__(WARPS * 32, istft_ctas_per_sm(N))
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
                   int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
@@ -767,7 +774,7 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
-    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<256, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -830,7 +837,7 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
         attr = true;
     }
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
-    constexpr int kCtasPerSm = N == 4096 ? 1 : 2;
+    constexpr int kCtasPerSm = istft_ctas_per_sm(N);
     const int64_t resident_warps = int64_t(sm_count()) * kCtasPerSm * WARPS;
     // run length: minimise (runs per warp) x (frames per run, warm-up included)
     int64_t best_len = nblocks, best_cost = INT64_MAX;
@@ -969,12 +976,12 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
         const int n = int(p->n);
         auto run = [&](const float* xs, int64_t clips, float2* dst) -> int {
             const int64_t frames = clips * nt;
-            const int warps = (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
+            const int warps = n == 4096 ? ZAFB_STFT4096_WARPS : (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
             const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(frames, warps);
             const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : n == 256 ? ZAFB_STFT256_CTAS : 3);
             if (ctas > resident) ctas = resident;
-            auto kern = n == 4096 ? stft_warp_kernel<4096, false, 8>
+            auto kern = n == 4096 ? stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS>
                         : n == 256 ? stft_warp_kernel<256, false, 8>
                         : n == 512 ? stft_warp_kernel<512, false, 8>
                         : n == 1024 ? stft_warp_kernel<1024, false, 8>
