@@ -1,18 +1,24 @@
 // STFT / ISTFT kernels (zaf.py:45-141, 144-243).
 //
-//   stft2048_warp_kernel  the north-star path: N = 2048, one warp per frame.  The frame's 2048 real
-//                         samples are read as 1024 complex points straight into registers
-//                         (coalesced 8-byte loads), windowed, transformed by two in-register
-//                         radix-32 FFTs with one shared-memory transpose between them (four-step
-//                         1024 = 32 x 32), unpacked to the real-input spectrum with warp shuffles
-//                         and stored as the full two-sided spectrum with coalesced streaming stores.
-//   stft_generic_kernel   any power-of-two N >= 2: one CTA per frame, Stockham FFT of N/2 complex
-//                         points in shared memory, either output layout.
-//   stft_dft_kernel       any other N (the reference accepts every N): direct O(N^2) DFT.
-//   istft_tile_kernel     overlap-add in gather form: a CTA owns a tile of output samples, inverse
-//                         transforms every frame that touches it in increasing frame order (the
-//                         reference's summation order, zaf.py:227-233) and writes each sample once:
-//                         no atomics, bit-reproducible.
+//   stft_warp_kernel<N>          the north-star path (N = 2048; also 256, 512, 1024, 4096): one warp per frame.  The
+//                                frame's N real samples are read as N/2 complex points straight into registers
+//                                (coalesced 8-byte loads), windowed, transformed by a four-step FFT (in-register
+//                                radix-2 FFTs around one shared-memory transpose), unpacked to the real-input spectrum
+//                                with warp shuffles and stored as the full two-sided spectrum, frame-major, with
+//                                coalesced streaming stores.
+//   stft_warp_binmajor_kernel<N> the same transform written directly into the reference's C-order memory
+//                                [clip][bin][frame]: 16-frame tiles in a shared-memory ring, per-row sector-aligned
+//                                store windows.
+//   istft_warp_kernel<N, R>      hop = N / R: one warp per run of consecutive output hop-blocks, overlap-add in a
+//                                private shared-memory ring, every sample written once in the reference's order.
+//   stft_generic_kernel          any power-of-two N >= 2: one CTA per frame, Stockham FFT of N/2 complex points in
+//                                shared memory.
+//   stft_dft_kernel              any other N (the reference accepts every N): direct O(N^2) DFT.
+//   istft_tile_kernel            overlap-add in gather form: a CTA owns a tile of output samples, inverse transforms
+//                                every frame that touches it in increasing frame order (the reference's summation
+//                                order, zaf.py:227-233) and writes each sample once: no atomics, bit-reproducible.
+//   stft_host_mirrored           host-buffer pipeline that copies bins 0 .. N/2 only and lets host threads write the
+//                                Hermitian mirror.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -58,9 +64,8 @@ namespace {
 constexpr int kMaxDynSmem = 227 * 1024;  // the sm_100 opt-in maximum per CTA
 
 // ------------------------------------------------------------------------------------------
-// N = 2048: one warp per frame
+// N = 256 ... 4096: one warp per frame
 // ------------------------------------------------------------------------------------------
-constexpr int kWarpsPerCta = 8;
 
 __device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
 
