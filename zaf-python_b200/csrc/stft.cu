@@ -1211,14 +1211,20 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     int rc = hp.ensure(size_t(per) * in_dev, size_t(per) * out_clip);
     if (rc != ZAFB_OK) return rc;
     const int64_t n_chunks = ceil_div(n_clips, per);
-    static std::vector<cudaEvent_t> events;  // guarded by hp.mu
+    int dev = 0;
+    ZAFB_CUDA(cudaGetDevice(&dev));
+    static std::vector<cudaEvent_t> events;  // guarded by hp.mu; they belong to events_dev
+    static int events_dev = -1;
+    if (events_dev != dev) {  // the process switched devices: events cannot be recorded on another device's stream
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
+        events_dev = dev;
+    }
     while (int64_t(events.size()) < n_chunks) {
         cudaEvent_t e;
         ZAFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         events.push_back(e);
     }
-    int dev = 0;
-    ZAFB_CUDA(cudaGetDevice(&dev));
     std::atomic<int64_t> recorded{0};
     std::atomic<int> stop{0};
     float2* o2 = reinterpret_cast<float2*>(out);
