@@ -19,17 +19,20 @@ class Golden:
     """Access to tests/golden/golden_<name>.npz as nested 'case/field' keys."""
 
     def __init__(self, name):
-        self._z = np.load(os.path.join(GOLDEN_DIR, f"golden_{name}.npz"))
+        self._z = dict(np.load(os.path.join(GOLDEN_DIR, f"golden_{name}.npz")))
+        extra = os.path.join(GOLDEN_DIR, f"golden_{name}_sizes.npz")  # later window lengths (make_golden_sizes.py)
+        if os.path.exists(extra):
+            self._z.update(np.load(extra))
 
     def cases(self):
-        return sorted({k.split("/")[0] for k in self._z.files if "/" in k})
+        return sorted({k.split("/")[0] for k in self._z if "/" in k})
 
     def get(self, case, field):
         v = self._z[f"{case}/{field}"]
         return v.item() if v.ndim == 0 else v
 
     def has(self, case, field):
-        return f"{case}/{field}" in self._z.files
+        return f"{case}/{field}" in self._z
 
     def raw(self, key):
         return self._z[key]
