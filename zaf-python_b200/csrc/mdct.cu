@@ -536,7 +536,6 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     const int64_t total = n_clips * nt;
     if (total == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
-    const int64_t grid = total < int64_t(sm_count()) * 32 ? total : int64_t(sm_count()) * 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int m = int(p->m);
     {
@@ -592,7 +591,6 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
         ZAFB_LAUNCH_CHECK();
         return ZAFB_OK;
     };
-    (void)grid;
     if (layout == ZAFB_LAYOUT_FRAME_MAJOR || nt == 1 || m == 1 || env_flag("ZAFB_GENERIC_BM_DIRECT", 0))
         return run_generic(x, n_clips, out, layout);
     return bin_major_from_frame_major(out, n_clips, nt, p->m, st, [&](int64_t c0, int64_t nc, float* scratch) {
