@@ -1230,7 +1230,7 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     float2* o2 = reinterpret_cast<float2*>(out);
     std::vector<std::thread> pool;
     pool.reserve(threads);
-    for (int w = 0; w < threads; ++w)
+    auto spawn = [&](int w) {
         pool.emplace_back([&, w]() {
             cudaSetDevice(dev);
             for (int64_t c = 0; c < n_chunks; ++c) {
@@ -1251,6 +1251,14 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
                 }
             }
         });
+    };
+    try {
+        for (int w = 0; w < threads; ++w) spawn(w);
+    } catch (...) {  // no exception crosses the C ABI: the threads that did start are told to stop, the call fails
+        stop.store(1);  // nothing has been recorded yet: every started worker is in its wait loop and sees this
+        for (auto& t : pool) t.join();
+        return fail(ZAFB_E_NOMEM, "host pipeline (mirrored): could not start %d fill threads", threads);
+    }
     int s = 0;
     for (int64_t c = 0; c < n_chunks && rc == ZAFB_OK; ++c, s = (s + 1) % HostPipe::kStages) {
         const int64_t c0 = c * per;
