@@ -23,6 +23,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <atomic>
 #include <thread>
 #include <type_traits>
@@ -1204,7 +1205,10 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     const size_t out_clip = size_t(nt) * n * sizeof(float2);
     const int64_t dpitch = (ns + 1) & ~int64_t(1);
     const size_t in_dev = size_t(dpitch) * sizeof(float);
-    int64_t per = int64_t(host_pipe_chunk_bytes() / out_clip);
+    // 16 MB stages unless ZAFB_PIPE_CHUNK_MB says otherwise: the fill threads start sooner and read a chunk soon after
+    // the DMA wrote it (cfg 2: 207 ms against 214 ms with 64 MB stages, profiles/r01q_e2e_mirror.log)
+    const size_t stage = getenv("ZAFB_PIPE_CHUNK_MB") ? host_pipe_chunk_bytes() : (size_t(16) << 20);
+    int64_t per = int64_t(stage / out_clip);
     if (per < 1) per = 1;
     if (per * HostPipe::kStages > n_clips) per = (n_clips + HostPipe::kStages - 1) / HostPipe::kStages;
     if (per < 1) per = 1;
