@@ -7,12 +7,20 @@ full two-sided complex64 spectrum as the reference returns it.  Inputs are resid
 when the timed region starts (`value`); `e2e` repeats the measurement through the public
 drop-in call with pinned HOST buffers (H2D and D2H inside the timed region).
 
+The same JSON line carries, under `extra.configs`, EVERY other BASELINE config on its own shape
+(cfg 2 istft, cfg 3 melspectrogram + mfcc, cfg 4 mdct + imdct, cfg 5 cqtspectrogram on both routes):
+device-timed ms, units/s, roofline (HBM fraction and, for the compute-bound ones, FP32 fraction), a
+CPU baseline of that function and a post-timing parity check of two clips against the oracle (1e-5).
+At N > 1 `extra.split_merge` holds one strong-scaling leg per transform -- scatter (NCCL) ->
+transform -> gather (NCCL) of ONE batch held by rank 0 -- each with a BITWISE comparison of the merged
+result against rank 0's unsharded result.
+
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [...]                         # the reference's CPU algorithm
+    python bench.py --impl reference [...]                         # the reference's own CPU implementation
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Multi-GPU: one process per GPU, clips are sharded by rank with no data-path collective (weak
-scaling: every rank transforms its own 1024-clip batch); torch.distributed is used only for the
+scaling: every rank transforms its own full batch); torch.distributed is used only for the
 barrier and the max-over-ranks of the device-timed duration.
 """
 import argparse
@@ -34,46 +42,131 @@ N_WIN, HOP, FS, SECONDS, CLIPS = 2048, 512, 48000, 10, 1024
 NS = FS * SECONDS
 SEED = 20261017 + 2
 METRIC = "stft_frames_per_sec_win2048_hop512_fp32"
+TOL = 1e-5
 
 
 def hamming_periodic(n):
     return 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(n) / n)
 
 
-# ----------------------------------------------------------------------------- CPU baseline
-CPU_CLIPS_PER_CORE = 12  # ~0.9 core-seconds each: 16 cores -> ~14 core-seconds of CPU work per sample
+def kbd(n, alpha=5.0):
+    k = np.kaiser(n // 2 + 1, np.pi * alpha)
+    half = np.sqrt(np.cumsum(k[: n // 2]) / np.sum(k))
+    return np.concatenate([half, half[::-1]])
+
+
+# ----------------------------------------------------------------------------- the BASELINE configs
+# name -> shape of one per-GPU batch.  `cpu_clips` = clips per host core of the bounded CPU sample.
+WORK = {
+    "stft":  dict(cfg=2, clips=1024, ns=480000, n=2048, hop=512, cpu_clips=12),
+    "istft": dict(cfg=2, clips=1024, ns=480000, n=2048, hop=512, cpu_clips=6),
+    "melspectrogram": dict(cfg=3, clips=4096, ns=80000, n=1024, hop=256, fs=16000, mels=128, cpu_clips=24),
+    "mfcc":  dict(cfg=3, clips=4096, ns=80000, n=1024, hop=256, fs=16000, mels=128, ncoef=40, cpu_clips=24),
+    "mdct":  dict(cfg=4, clips=2048, ns=1323000, n=2048, cpu_clips=3),
+    "imdct": dict(cfg=4, clips=2048, ns=1323000, n=2048, cpu_clips=2),
+    "cqtspectrogram": dict(cfg=5, clips=512, ns=882000, fs=44100, tr=25, res=12, fmin=32.70319566257483,
+                           fmax=4186.009044809578, cpu_clips=1),
+}
+
+
+def config_text(name):
+    c = WORK[name]
+    if c["cfg"] == 2:
+        return f"cfg2: {c['clips']} clips x 10 s @ 48 kHz, Hamming N=2048 hop=512"
+    if c["cfg"] == 3:
+        return f"cfg3: {c['clips']} clips x 5 s @ 16 kHz, Hamming N=1024 hop=256, 128 mels" + (", 40 coeffs" if name == "mfcc" else "")
+    if c["cfg"] == 4:
+        return f"cfg4: {c['clips']} clips x 30 s @ 44.1 kHz, KBD N=2048"
+    return f"cfg5: {c['clips']} clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8 (84 rows, L=32768), 25 frames/s"
+
+
+# ----------------------------------------------------------------------------- CPU baseline (the reference itself)
+def cpu_module():
+    """(module, kind): the UNMODIFIED reference (oracle/_ref/zaf.py, vendored by oracle/make_ref.py) when present, else
+    the oracle's port of it.  Checker / baseline only -- never on the product path."""
+    try:
+        from oracle import ref_loader
+
+        mod = ref_loader.load()
+        if mod is not None:
+            return mod, "reference"
+    except Exception:  # noqa: BLE001 -- fall back to the port
+        pass
+    import oracle
+
+    return oracle, "port"
+
+
+def _cpu_inputs(name, seed, clips, mod):
+    """Untimed set-up of one worker: float64 clips (what the reference computes in) and the operators."""
+    c = WORK[name]
+    rng = np.random.default_rng(seed)
+    xs = [rng.uniform(-1, 1, c["ns"]).astype(np.float32).astype(np.float64) for _ in range(clips)]
+    if name in ("stft", "istft"):
+        w = hamming_periodic(c["n"])
+        if name == "stft":
+            return [(x, w, c["hop"]) for x in xs], mod.stft
+        return [(mod.stft(x, w, c["hop"]), w, c["hop"]) for x in xs], mod.istft
+    if name in ("melspectrogram", "mfcc"):
+        w = hamming_periodic(c["n"])
+        fb = mod.melfilterbank(c["fs"], c["n"], c["mels"])
+        if name == "mfcc":
+            return [(x, w, c["hop"], fb, c["ncoef"]) for x in xs], mod.mfcc
+        return [(x, w, c["hop"], fb) for x in xs], mod.melspectrogram
+    if name in ("mdct", "imdct"):
+        w = kbd(c["n"])
+        if name == "mdct":
+            return [(x, w) for x in xs], mod.mdct
+        return [(mod.mdct(x, w), w) for x in xs], mod.imdct
+    kern = mod.cqtkernel(c["fs"], c["res"], c["fmin"], c["fmax"])
+    if not hasattr(kern, "tocsr"):  # the port builds the dense kernel; the reference applies it as CSR (zaf.py:554, 631)
+        import scipy.sparse
+
+        kern = scipy.sparse.csr_matrix(kern)
+    return [(x, c["fs"], c["tr"], kern) for x in xs], mod.cqtspectrogram
 
 
 def _cpu_worker(args):
-    seed, clips = args
-    import oracle  # the CPU port of the reference algorithm: checker / baseline only
-
-    rng = np.random.default_rng(seed)
-    w = hamming_periodic(N_WIN)
-    xs = [rng.uniform(-1, 1, NS).astype(np.float32) for _ in range(clips)]  # inputs resident before timing
-    frames = 0
+    name, seed, clips = args
+    mod, _ = cpu_module()
+    calls, fn = _cpu_inputs(name, seed, clips, mod)  # inputs resident before timing
+    units = 0
     t0 = time.perf_counter()
-    for x in xs:
-        frames += oracle.stft(x, w, HOP).shape[1]
-    return frames, time.perf_counter() - t0
+    for a in calls:
+        out = fn(*a)
+        units += out.shape[-1] if name not in ("istft", "imdct") else a[0].shape[-1]  # frames
+    return units, time.perf_counter() - t0
 
 
-def cpu_baseline(clips_per_core=CPU_CLIPS_PER_CORE, cores=None):
-    """Time the oracle's port of zaf.stft (same operation sequence as zaf.py:95-141: Python framing
-    loop + float64 pocketfft c2c) on all host cores over a bounded sample of the cfg-2 workload.
-    Every process transforms its own clips; the duration is the slowest process's compute time."""
+def cpu_baseline(name="stft", clips_per_core=None, cores=None, pool=None, total_clips=None):
+    """Time the reference's own implementation of `name` on all host cores over a bounded sample of the config's
+    workload (`total_clips` clips dealt as evenly as possible, or `clips_per_core` each).  Every process transforms its
+    own clips; the duration is the slowest process's compute time."""
     cores = cores or len(os.sched_getaffinity(0))
-    jobs = [(SEED + 1000 + i, clips_per_core) for i in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1)] * cores)  # start the workers, import numpy, warm pocketfft
-        res = pool.map(_cpu_worker, jobs)
-    frames = sum(r[0] for r in res)
+    if total_clips:
+        counts = [total_clips // cores + (1 if i < total_clips % cores else 0) for i in range(cores)]
+    else:
+        counts = [clips_per_core or WORK[name]["cpu_clips"]] * cores
+    _, kind = cpu_module()
+    jobs = [(name, SEED + 1000 + i, n) for i, n in enumerate(counts) if n > 0]
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores)
+    try:
+        pool.map(_cpu_worker, [(name, 0, 1)] * cores)  # start the workers, import numpy/scipy, warm pocketfft
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    finally:
+        if own:
+            pool.close()
+            pool.join()
+    units = sum(r[0] for r in res)
     dt = max(r[1] for r in res)
+    c = WORK[name]
     return {
-        "value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-        "sample": f"{cores * clips_per_core} clips x {SECONDS} s @ {FS} Hz of the {CLIPS}-clip batch "
-                  f"({frames} frames, {dt:.2f} s wall = {sum(r[1] for r in res):.1f} core-seconds, {cores} processes, "
-                  f"float64 NumPy pocketfft)",
+        "value": units / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+        "sample": f"{sum(counts)} clips of the {c['clips']}-clip batch ({config_text(name)}; {units} frames, {dt:.2f} s wall = "
+                  f"{sum(r[1] for r in res):.1f} core-seconds, {len(jobs)} processes, "
+                  + ("unmodified zaf.py, float64 NumPy/SciPy)" if kind == "reference" else "oracle port of zaf.py, float64 NumPy/SciPy)"),
     }, dt
 
 
@@ -221,13 +314,14 @@ class Dist:
             self.td.destroy_process_group()
 
 
-def measured_peak():
+def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
 def ncu_traffic():
@@ -239,101 +333,477 @@ def ncu_traffic():
         return None
 
 
-# ----------------------------------------------------------------------------- arms
+def headline_config(clips, nt, world):
+    """The `config` object of BOTH arms (the reference arm times the same workload, so the two lines compare)."""
+    return {"workload": f"BASELINE cfg 2 forward STFT: {clips} clips x {SECONDS} s @ {FS} Hz fp32 per GPU, "
+                        f"Hamming window {N_WIN}, hop {HOP}, full two-sided complex64 spectrum ({nt} frames/clip)",
+            "window_length": N_WIN, "step_length": HOP, "clips_per_gpu": clips, "global_clips": clips * world,
+            "parallelism": f"clip-sharded x{world}, no data-path collective",
+            "layout": "frame_major", "l2": "inputs+outputs per step (17.7 GB) exceed L2 (126 MB); no flush needed"}
+
+
+# ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     cores = len(os.sched_getaffinity(0))
-    per_core = max(1, args.cpu_clips_per_core)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_baseline(1, cores)
-    vals, times = [], []
-    for _ in range(args.steps):
-        cb, dt = cpu_baseline(per_core, cores)
-        vals.append(cb["value"])
-        times.append(dt)
+    # every step = the reference's zaf.stft over the WHOLE 1024-clip batch (the GPU arm's per-GPU workload) on all host
+    # cores; --cpu-clips-per-core N bounds it to a sample instead (then cpu_baseline.sample says so)
+    total = args.cpu_clips_per_core * cores if args.cpu_clips_per_core > 0 else args.clips
+    import oracle
+
+    nt = oracle.stft_geometry(NS, N_WIN, HOP)[1]
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(1 if args.warmup > 0 else 0):
+            cpu_baseline("stft", 1, cores, pool)
+        vals, times = [], []
+        for _ in range(args.steps):
+            cb, dt = cpu_baseline("stft", None, cores, pool, total_clips=total)
+            vals.append(cb["value"])
+            times.append(dt)
     value = float(np.mean(vals))
     cb["value"] = value
+    cfg = headline_config(args.clips, nt, max(1, args.gpus))  # the GPU arm's config object, field for field
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE cfg 2: zaf.stft per clip, 10 s @ 48 kHz, Hamming 2048, hop 512 "
-                               "(each step = a bounded sample of the 1024-clip batch)",
-                   "window_length": N_WIN, "step_length": HOP, "clips_per_step": per_core * cores},
-        "cpu_baseline": cb, "gpu_launches": 0,
+        "config": cfg, "cpu_baseline": cb, "gpu_launches": 0,
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def split_merge_leg(zaf, dist, xd, w, nt, clips, stream, reps=3):
-    """scatter (NCCL) -> local STFT -> gather (NCCL) of ONE cfg-2 batch held by rank 0; device-timed, max over ranks."""
-    ids = [zaf.dist.make_unique_id() if dist.rank == 0 else None]
-    dist.td.broadcast_object_list(ids, src=0)
-    comm = zaf.dist.Communicator(dist.rank, dist.world, ids[0])
+# ----------------------------------------------------------------------------- device-side work items
+def device_batch(zaf, clips, ns, seed, distinct=32):
+    """(clips, ns) float32 on the device, built from `distinct` seeded clips tiled over the batch (the kernels have no
+    data-dependent behaviour, and every clip has its own addresses, so timing does not depend on the values)."""
+    rng = np.random.default_rng(seed)
+    distinct = min(distinct, clips)
+    host = rng.uniform(-1, 1, (distinct, ns)).astype(np.float32)
+    d = zaf.empty((clips, ns), np.float32)
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    for c0 in range(0, clips, distinct):
+        n = min(distinct, clips - c0)
+        zaf._lib.check(lib.zafb_memcpy_h2d(C.c_void_p(d.ptr + c0 * ns * 4), host.ctypes.data, n * ns * 4, None))
+    zaf.synchronize()
+    return d, host
+
+
+class Item:
+    """One transform on its BASELINE shape, driven through the C ABI with preallocated device buffers."""
+
+    def __init__(self, zaf, name, clips=None):
+        import oracle
+
+        self.zaf, self.name, self.oracle = zaf, name, oracle
+        c = dict(WORK[name])
+        if clips:
+            c["clips"] = clips
+        self.c = c
+        self.clips, self.ns = c["clips"], c["ns"]
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        self.lib, self.C = lib, C
+        self.route = None
+        if name in ("stft", "istft"):
+            self.w = hamming_periodic(c["n"])
+            self.plan, _ = zaf._stft_plan(self.w, c["hop"])
+            self.nt = zaf.stft_geometry(self.ns, c["n"], c["hop"])[1]
+            self.ylen = zaf.istft_geometry(c["n"], self.nt, c["hop"])[2]
+            spec_row = self.nt * c["n"] * 2  # floats
+            if name == "stft":
+                self.in_row, self.out_row, self.kernel = self.ns, spec_row, "stft_warp_kernel<2048,false,6>"
+            else:
+                self.in_row, self.out_row, self.kernel = spec_row, self.ylen, "istft_warp_kernel<2048,4,8>"
+            self.algo_bytes_per_clip = self.ns * 4 + self.nt * c["n"] * 8 if name == "stft" else self.nt * c["n"] * 8 + self.ylen * 4
+            self.flops_per_unit, self.bound = 2.5 * c["n"] * np.log2(c["n"]), "hbm"
+        elif name in ("melspectrogram", "mfcc"):
+            self.w = hamming_periodic(c["n"])
+            self.fb = zaf.melfilterbank(c["fs"], c["n"], c["mels"])
+            self.ncoef = c.get("ncoef", 0)
+            self.plan, _, _ = zaf._mel_plan(self.w, c["hop"], self.fb, self.ncoef)
+            self.nt = zaf.stft_geometry(self.ns, c["n"], c["hop"])[1]
+            rows = self.ncoef if name == "mfcc" else c["mels"]
+            self.rows = rows
+            self.in_row, self.out_row = self.ns, self.nt * rows
+            self.algo_bytes_per_clip = self.ns * 4 + self.nt * rows * 4
+            # real N-point FFT + banded filterbank (2 flops per nonzero) (+ log + 40 x 128 DCT-II)
+            nnz = int(self.fb.nnz)
+            self.flops_per_unit = 2.5 * c["n"] * np.log2(c["n"]) + 2 * nnz + (2 * self.ncoef * c["mels"] if name == "mfcc" else 0)
+            self.bound, self.kernel = "fp32", f"mel_warp_kernel<1024,{1 if name == 'mfcc' else 0}>"
+        elif name in ("mdct", "imdct"):
+            self.w = kbd(c["n"])
+            self.plan, _ = zaf._mdct_plan(self.w)
+            self.m, self.nt, _ = zaf.mdct_geometry(self.ns, c["n"])
+            self.ylen = zaf.imdct_geometry(self.m, self.nt)[1]
+            self.ypitch = (self.ylen + 1) & ~1
+            if name == "mdct":
+                self.in_row, self.out_row, self.kernel = self.ns, self.nt * self.m, "mdct_warp_kernel<2048>"
+            else:
+                self.in_row, self.out_row, self.kernel = self.nt * self.m, self.ypitch, "imdct_warp_kernel<2048>"
+            self.algo_bytes_per_clip = (self.ns if name == "mdct" else self.ylen) * 4 + self.nt * self.m * 4
+            self.flops_per_unit, self.bound = 5 * 512 * 9 + 10 * 1024, "hbm"
+        else:
+            self.kern = zaf.cqtkernel(c["fs"], c["res"], c["fmin"], c["fmax"])
+            self.step, self.nt, _, _ = zaf.cqt_geometry(self.ns, c["fs"], c["tr"], self.kern.shape[1])
+            self.nf = self.kern.shape[0]
+            self.plan, _, _ = zaf._cqt_plan(self.kern, self.step)
+            self.in_row, self.out_row = self.ns, self.nt * self.nf
+            self.algo_bytes_per_clip = self.ns * 4 + self.nt * self.nf * 4
+            L = self.kern.shape[1]
+            self.flops_per_unit = 2.5 * L * np.log2(L) + 8 * int(self.kern.nnz)
+            self.bound, self.kernel = "fp32", "cqt32768_kernel"
+        self.units_per_clip = self.nt
+
+    def set_route(self, route):
+        """cqtspectrogram only: 'fused' | 'tensor' (a second plan)."""
+        self.route = route
+        self.plan, _, _ = self.zaf._cqt_plan(self.kern, self.step, route)
+        self.kernel = "cqt32768_kernel" + ("<export> + gemm3xtf32_kernel + cqt_magnitude_kernel" if route == "tensor" else "")
+
+    def launch(self, in_ptr, clips, out_ptr, stream):
+        lib, C, c, p = self.lib, self.C, self.c, self.plan
+        sp = stream.ptr if stream is not None else None
+        i, o = C.c_void_p(in_ptr), C.c_void_p(out_ptr)
+        if self.name == "stft":
+            rc = lib.zafb_stft_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+        elif self.name == "istft":
+            rc = lib.zafb_istft_f32(p, i, clips, self.nt, 0, o, self.ylen, sp)
+        elif self.name == "melspectrogram":
+            rc = lib.zafb_melspectrogram_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+        elif self.name == "mfcc":
+            rc = lib.zafb_mfcc_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+        elif self.name == "mdct":
+            rc = lib.zafb_mdct_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+        elif self.name == "imdct":
+            rc = lib.zafb_imdct_f32(p, i, clips, self.nt, 0, o, self.ypitch, sp)
+        else:
+            rc = lib.zafb_cqt_f32(p, i, clips, self.ns, self.ns, 0, o, 0, sp)
+        self.zaf._lib.check(rc)
+
+    def forward_item(self):
+        """The transform whose output is this (inverse) transform's input."""
+        return {"istft": "stft", "imdct": "mdct"}.get(self.name)
+
+    def d2h_row(self, dev_ptr, row, n_floats):
+        got = np.empty(n_floats, np.float32)
+        self.zaf._lib.check(self.lib.zafb_memcpy_d2h(got.ctypes.data, self.C.c_void_p(dev_ptr + row * n_floats * 4), got.nbytes, None))
+        self.zaf.synchronize()
+        return got
+
+    def parity(self, in_ptr, out_ptr, clip, host_clips=None):
+        """max(normalised max-abs, relative L2) of clip `clip` of the device result against the oracle applied to the same
+        input (read back from the device, so inverse transforms are checked on exactly the spectrum they were given)."""
+        o, c = self.oracle, self.c
+        xin = self.d2h_row(in_ptr, clip, self.in_row)
+        got = self.d2h_row(out_ptr, clip, self.out_row)
+        if self.name == "stft":
+            ref = o.stft(xin, self.w, c["hop"])
+            got = got.view(np.complex64).reshape(self.nt, c["n"]).T
+        elif self.name == "istft":
+            ref = o.istft(xin.view(np.complex64).reshape(self.nt, c["n"]).T, self.w, c["hop"])
+        elif self.name == "melspectrogram":
+            ref = o.melspectrogram(xin, self.w, c["hop"], self.fb)
+            got = got.reshape(self.nt, self.rows).T
+        elif self.name == "mfcc":
+            ref = o.mfcc(xin, self.w, c["hop"], self.fb, self.ncoef)
+            got = got.reshape(self.nt, self.rows).T
+        elif self.name == "mdct":
+            ref = o.mdct(xin, self.w)
+            got = got.reshape(self.nt, self.m).T
+        elif self.name == "imdct":
+            ref = o.imdct(xin.reshape(self.nt, self.m).T, self.w)
+            got = got[: self.ylen]
+        else:
+            ref = o.cqtspectrogram(xin, c["fs"], c["tr"], self.kern)
+            got = got.reshape(self.nt, self.nf).T
+        return max(o.parity_metrics(got, ref))
+
+
+def time_item(zaf, item, in_ptr, out_ptr, stream, steps, warmup=3):
+    for _ in range(warmup):
+        item.launch(in_ptr, item.clips, out_ptr, stream)
+    stream.synchronize()
+    e0, e1 = zaf.Event(), zaf.Event()
+    l0 = zaf.launch_count()
+    e0.record(stream)
+    for _ in range(steps):
+        item.launch(in_ptr, item.clips, out_ptr, stream)
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_ms(e1) / steps, (zaf.launch_count() - l0) // steps
+
+
+def config_line(item, ms, launches, world, peak, sm_max_mhz, parity, cpu):
+    units = item.clips * item.units_per_clip
+    algo = item.clips * item.algo_bytes_per_clip
+    gbs = algo / (ms * 1e-3) / 1e9
+    fp32_peak = 148 * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    tflops = units * item.flops_per_unit / (ms * 1e-3) / 1e12
+    roof = {"bound": item.bound, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "algorithmic_bytes_per_launch": int(algo), "kernel": item.kernel,
+            "fp32": {"achieved_tflops": tflops, "peak_tflops": fp32_peak, "frac": tflops / fp32_peak,
+                     "flops_per_frame": float(item.flops_per_unit)}}
+    return {"transform": item.name + (f"[{item.route}]" if item.route else ""), "config": config_text(item.name),
+            "clips_per_gpu": item.clips, "frames_per_gpu": units, "ms_per_step": ms,
+            "frames_per_sec": units * world / (ms * 1e-3), "launches_per_step": int(launches), "roofline": roof,
+            "parity_max_rel_err": parity, "parity_tolerance": TOL, "parity_clips_checked": 2, "cpu_baseline": cpu}
+
+
+def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
+    """Every other BASELINE config on its own shape, one group at a time (a group shares its input; buffers are freed
+    in between)."""
+    out = []
+    groups = (("istft",), ("melspectrogram", "mfcc"), ("mdct",), ("imdct",), ("cqtspectrogram", "cqtspectrogram:tensor"))
+    for group in groups:
+        group = [g for g in group if not args.only_configs or g.split(":")[0] in args.only_configs]
+        if not group:
+            continue
+        ind = None
+        try:
+            first = Item(zaf, group[0].split(":")[0], clips=args.config_clips or None)
+            fwd = first.forward_item()
+            if fwd:  # an inverse transform is fed the forward transform's own device output
+                f_item = Item(zaf, fwd, clips=first.clips)
+                xd, _ = device_batch(zaf, f_item.clips, f_item.ns, 20261017 + first.c["cfg"])
+                ind = zaf.empty((f_item.clips, f_item.out_row), np.float32)
+                f_item.launch(xd.ptr, f_item.clips, ind.ptr, stream)
+                stream.synchronize()
+                xd.free()
+            else:
+                ind, _ = device_batch(zaf, first.clips, first.ns, 20261017 + first.c["cfg"])
+        except Exception as exc:  # noqa: BLE001 -- one config must not take the headline down
+            out.extend({"transform": g, "error": f"{type(exc).__name__}: {exc}"[:300]} for g in group)
+            continue
+        for full in group:
+            name, _, route = full.partition(":")
+            outd = None
+            try:
+                item = Item(zaf, name, clips=args.config_clips or None)
+                if route:
+                    item.set_route(route)
+                outd = zaf.empty((item.clips, item.out_row), np.float32)
+                ms, nl = time_item(zaf, item, ind.ptr, outd.ptr, stream, args.config_steps)
+                ms = dist.max(ms)
+                parity = None
+                if dist.rank == 0:
+                    parity = max(item.parity(ind.ptr, outd.ptr, c) for c in (0, item.clips - 1))
+                    assert parity <= TOL, f"{full}: parity broken: {parity}"
+                out.append(config_line(item, ms, nl, dist.world, peak, sm_max_mhz, parity, cpu_lines.get(name)))
+            except AssertionError:
+                raise
+            except Exception as exc:  # noqa: BLE001
+                out.append({"transform": full, "error": f"{type(exc).__name__}: {exc}"[:300]})
+            if outd is not None:
+                outd.free()
+        ind.free()
+    return out
+
+
+def chain_leg(zaf, stream, xd, clips, nt, w, spec):
+    """stft -> |X| -> mask -> X*mask -> istft with every stage on the device: the reference's
+    centre-extraction demo (zaf.py:166-191) on the cfg-2 batch, clip pairs (2i, 2i+1) as left/right."""
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    n, k = N_WIN, N_WIN // 2 + 1
+    plan, _ = zaf._stft_plan(w, HOP)
+    mag = zaf.empty((clips, nt, k), np.float32)
+    swp = zaf.empty((clips, nt, k), np.float32)
+    ylen = zaf.istft_geometry(n, nt, HOP)[2]
+    yd = zaf.empty((clips, ylen), np.float32)
+    pair = nt * k * 4
+
+    def run():
+        zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(spec.ptr), 0, stream.ptr))
+        zaf._lib.check(lib.zafb_spec_abs_f32(C.c_void_p(spec.ptr), clips, n, nt, 0, k, C.c_void_p(mag.ptr), stream.ptr))
+        # the other channel's magnitudes: swap the rows of each (left, right) pair
+        zaf._lib.check(lib.zafb_memcpy2d(C.c_void_p(swp.ptr), 2 * pair, C.c_void_p(mag.ptr + pair), 2 * pair, pair, clips // 2, 2, stream.ptr))
+        zaf._lib.check(lib.zafb_memcpy2d(C.c_void_p(swp.ptr + pair), 2 * pair, C.c_void_p(mag.ptr), 2 * pair, pair, clips // 2, 2, stream.ptr))
+        zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr), C.c_void_p(swp.ptr), clips * nt * k, C.c_void_p(mag.ptr), stream.ptr))
+        zaf._lib.check(lib.zafb_spec_mask_f32(C.c_void_p(spec.ptr), clips, n, nt, 0, C.c_void_p(mag.ptr), k, C.c_void_p(spec.ptr), stream.ptr))
+        zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, stream.ptr))
+
+    for _ in range(2):
+        run()
+    stream.synchronize()
+    e0, e1 = zaf.Event(), zaf.Event()
+    e0.record(stream)
+    for _ in range(3):
+        run()
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_ms(e1) / 3
+    import oracle
+
+    got = np.empty((2, ylen), np.float32)
+    x2 = np.empty((2, NS), np.float32)
+    zaf._lib.check(lib.zafb_memcpy_d2h(got.ctypes.data, C.c_void_p(yd.ptr), got.nbytes, None))
+    zaf._lib.check(lib.zafb_memcpy_d2h(x2.ctypes.data, C.c_void_p(xd.ptr), x2.nbytes, None))
+    zaf.synchronize()
+    s1, s2 = oracle.stft(x2[0], w, HOP), oracle.stft(x2[1], w, HOP)
+    a1, a2 = np.abs(s1[:k]), np.abs(s2[:k])
+    worst = 0.0
+    for s, a, g in ((s1, a1, got[0]), (s2, a2, got[1])):
+        m = np.minimum(a1, a2) / a
+        worst = max(worst, *oracle.parity_metrics(g, oracle.istft(np.concatenate((m, m[-2:0:-1])) * s, w, HOP)))
+    assert worst <= TOL, f"device chain parity broken: {worst}"
+    for d in (mag, swp, yd):
+        d.free()
+    return {"chain": "stft -> abs -> min-ratio mask -> mask multiply (mirrored) -> istft, device-resident (zaf.py:166-191)",
+            "ms_per_batch": ms, "frames_per_sec": clips * nt / (ms * 1e-3), "parity_max_rel_err": worst,
+            "pcie_bytes": 0}
+
+
+# ----------------------------------------------------------------------------- N > 1: split -> transform -> merge
+def split_merge_item(zaf, dist, comm, item, stream, reps=2):
+    """Strong scaling of ONE batch held by rank 0: scatter (NCCL) -> every rank transforms its shard -> gather (NCCL),
+    device-timed, max over ranks -- then the merged result is compared BITWISE with rank 0's unsharded result."""
+    clips = item.clips
     lo, hi = comm.shard_range(clips)
-    shard = zaf.empty((hi - lo, NS), np.float32)
-    full = zaf.empty((clips, nt, N_WIN), np.complex64) if dist.rank == 0 else None
-    spec_buf = zaf.empty((hi - lo, nt, N_WIN), np.complex64)
-    e0, e1, e2, e3 = zaf.Event(), zaf.Event(), zaf.Event(), zaf.Event()
+    fwd = item.forward_item()
+    xd = None
+    if dist.rank == 0:
+        if fwd:
+            f_item = Item(zaf, fwd, clips=clips)
+            src, _ = device_batch(zaf, clips, f_item.ns, 20261017 + item.c["cfg"])
+            xd = zaf.empty((clips, f_item.out_row), np.float32)
+            f_item.launch(src.ptr, clips, xd.ptr, stream)
+            stream.synchronize()
+            src.free()
+        else:
+            xd, _ = device_batch(zaf, clips, item.ns, 20261017 + item.c["cfg"])
+    shard = zaf.empty((hi - lo, item.in_row), np.float32)
+    part = zaf.empty((hi - lo, item.out_row), np.float32)
+    full = zaf.empty((clips, item.out_row), np.float32) if dist.rank == 0 else None
+    e = [zaf.Event() for _ in range(4)]
     best = None
     for _ in range(reps + 1):  # first pass = warm-up (NCCL channel set-up)
         dist.barrier()
-        e0.record(stream)
-        comm.scatter(xd if dist.rank == 0 else None, clips, (NS,), np.float32, stream=stream, out=shard)
-        e1.record(stream)
-        spec = zaf.stft(shard, w, HOP, stream=stream, out=spec_buf)
-        e2.record(stream)
-        comm.gather(spec, clips, stream=stream, out=full)
-        e3.record(stream)
-        e3.synchronize()
-        t = [dist.max(e0.elapsed_ms(e1)), dist.max(e1.elapsed_ms(e2)), dist.max(e2.elapsed_ms(e3)), dist.max(e0.elapsed_ms(e3))]
+        e[0].record(stream)
+        comm.scatter(xd, clips, (item.in_row,), np.float32, stream=stream, out=shard)
+        e[1].record(stream)
+        item.launch(shard.ptr, hi - lo, part.ptr, stream)
+        e[2].record(stream)
+        comm.gather(part, clips, stream=stream, out=full)
+        e[3].record(stream)
+        e[3].synchronize()
+        t = [dist.max(e[0].elapsed_ms(e[1])), dist.max(e[1].elapsed_ms(e[2])), dist.max(e[2].elapsed_ms(e[3])),
+             dist.max(e[0].elapsed_ms(e[3]))]
         if best is None or t[3] < best[3]:
             best = t
-    # the same merge without a collective: every rank's STFT kernel stores straight into rank 0's buffer
-    # (CUDA IPC mapping, the stores cross NVLink), one barrier at the end
-    direct = None
+    mismatch = None
+    single_ms = None
+    if dist.rank == 0:  # the unsharded result on rank 0 alone, into a second buffer
+        ref = zaf.empty((clips, item.out_row), np.float32)
+        item.launch(xd.ptr, clips, ref.ptr, stream)
+        stream.synchronize()
+        e[0].record(stream)
+        item.launch(xd.ptr, clips, ref.ptr, stream)
+        e[1].record(stream)
+        e[1].synchronize()
+        single_ms = e[0].elapsed_ms(e[1])
+        mismatch = zaf.count_mismatch(full, ref, stream=stream)
+        ref.free()
+        assert mismatch == 0, f"{item.name}: sharded result differs from the unsharded one in {mismatch} words"
+    for d in (shard, part, full, xd):
+        if d is not None:
+            d.free()
+    frames = clips * item.units_per_clip
+    return {"transform": item.name + (f"[{item.route}]" if item.route else ""), "config": config_text(item.name),
+            "scaling": "strong", "global_clips": clips, "scatter_ms": best[0], "transform_ms": best[1], "gather_ms": best[2],
+            "total_ms": best[3], "frames_per_sec": frames / (best[3] * 1e-3), "single_gpu_transform_ms": single_ms,
+            "scatter_bytes": int(clips * item.in_row * 4 * (dist.world - 1) / dist.world),
+            "gather_bytes": int(clips * item.out_row * 4 * (dist.world - 1) / dist.world),
+            "bitwise_mismatch_words_vs_unsharded": mismatch, "bitwise_equal": (mismatch == 0) if mismatch is not None else None}
+
+
+def split_merge_legs(zaf, dist, args, stream):
+    ids = [zaf.dist.make_unique_id() if dist.rank == 0 else None]
+    dist.td.broadcast_object_list(ids, src=0)
+    comm = zaf.dist.Communicator(dist.rank, dist.world, ids[0])
+    legs = []
+    for name in ("stft", "istft", "melspectrogram", "mfcc", "mdct", "imdct", "cqtspectrogram"):
+        if args.only_configs and name not in args.only_configs:
+            continue
+        try:
+            legs.append(split_merge_item(zaf, dist, comm, Item(zaf, name, clips=args.config_clips or None), stream))
+        except AssertionError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            legs.append({"transform": name, "error": f"{type(exc).__name__}: {exc}"[:300]})
+    extra = {}
     try:
-        view = comm.map_from_root(full, (clips, nt, N_WIN), np.complex64)
-        mine = comm.rows(view, lo, hi)
-        for _ in range(reps + 1):
-            dist.barrier()
-            e0.record(stream)
-            comm.scatter(xd if dist.rank == 0 else None, clips, (NS,), np.float32, stream=stream, out=shard)
-            e1.record(stream)
-            zaf.stft(shard, w, HOP, stream=stream, out=mine)
-            comm.barrier(stream)
-            e3.record(stream)
-            e3.synchronize()
-            t = [dist.max(e0.elapsed_ms(e1)), dist.max(e1.elapsed_ms(e3)), dist.max(e0.elapsed_ms(e3))]
-            if direct is None or t[2] < direct[2]:
-                direct = t
-        dist.barrier()
-        comm.unmap(view)
+        extra = stft_merge_variants(zaf, dist, comm, args, stream)
+    except AssertionError:
+        raise
     except Exception as exc:  # noqa: BLE001
-        direct = f"{type(exc).__name__}: {exc}"[:200]
+        extra = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     comm.close()
-    shard.free()
-    spec_buf.free()
-    if full is not None:
-        full.free()
-    return {"scaling": "strong", "global_clips": clips, "scatter_ms": best[0], "stft_ms": best[1], "gather_ms": best[2],
-            "total_ms": best[3], "frames_per_sec": clips * nt / (best[3] * 1e-3),
-            "scatter_bytes": int(clips * NS * 4 * (dist.world - 1) / dist.world),
-            "gather_bytes": int(clips * nt * N_WIN * 8 * (dist.world - 1) / dist.world),
-            "note": "rank 0 holds the batch; grouped ncclSend/ncclRecv over NVLink; best of %d" % reps,
-            "direct_store_merge": ({"scatter_ms": direct[0], "stft_into_root_ms": direct[1], "total_ms": direct[2],
-                                    "frames_per_sec": clips * nt / (direct[2] * 1e-3),
-                                    "note": "no gather: each rank's STFT kernel writes into rank 0's HBM through a CUDA-IPC mapping"}
-                                   if isinstance(direct, list) else {"error": direct})}
+    return legs, extra
 
 
+def stft_merge_variants(zaf, dist, comm, args, stream, reps=2):
+    """cfg-2 STFT merge without a full-spectrum gather.  (1) direct_store: every rank's STFT kernel stores straight into
+    rank 0's buffer through a CUDA-IPC mapping (the stores cross NVLink while the kernel computes).  Both are checked
+    bitwise against the unsharded result."""
+    clips = args.config_clips or CLIPS
+    item = Item(zaf, "stft", clips=clips)
+    nt = item.nt
+    lo, hi = comm.shard_range(clips)
+    xd = device_batch(zaf, clips, NS, 20261017 + 2)[0] if dist.rank == 0 else None
+    shard = zaf.empty((hi - lo, NS), np.float32)
+    full = zaf.empty((clips, nt, N_WIN), np.complex64) if dist.rank == 0 else None
+    e0, e1, e3 = zaf.Event(), zaf.Event(), zaf.Event()
+    out = {}
+    view = comm.map_from_root(full, (clips, nt, N_WIN), np.complex64)
+    mine = comm.rows(view, lo, hi)
+    direct = None
+    for _ in range(reps + 1):
+        dist.barrier()
+        e0.record(stream)
+        comm.scatter(xd, clips, (NS,), np.float32, stream=stream, out=shard)
+        e1.record(stream)
+        item.launch(shard.ptr, hi - lo, mine.ptr, stream)
+        comm.barrier(stream)
+        e3.record(stream)
+        e3.synchronize()
+        t = [dist.max(e0.elapsed_ms(e1)), dist.max(e1.elapsed_ms(e3)), dist.max(e0.elapsed_ms(e3))]
+        if direct is None or t[2] < direct[2]:
+            direct = t
+    mismatch = None
+    if dist.rank == 0:
+        ref = zaf.empty((clips, nt, N_WIN), np.complex64)
+        item.launch(xd.ptr, clips, ref.ptr, stream)
+        mismatch = zaf.count_mismatch(full, ref, stream=stream)
+        ref.free()
+        assert mismatch == 0, f"direct-store merge differs from the unsharded result in {mismatch} words"
+    dist.barrier()
+    comm.unmap(view)
+    out["direct_store_merge"] = {"scatter_ms": direct[0], "stft_into_root_ms": direct[1], "total_ms": direct[2],
+                                 "frames_per_sec": clips * nt / (direct[2] * 1e-3), "bitwise_equal": (mismatch == 0) if mismatch is not None else None,
+                                 "note": "no gather: each rank's STFT kernel writes into rank 0's HBM through a CUDA-IPC mapping"}
+    for d in (shard, full, xd):
+        if d is not None:
+            d.free()
+    return out
+
+
+# ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     dist = Dist(args.gpus)
     cb = None
-    if dist.rank == 0 and dist.world == 1 and not args.no_cpu:
-        cb, _ = cpu_baseline(max(1, args.cpu_clips_per_core))  # before any CUDA call (fork-safe)
+    cpu_lines = {}
+    if dist.rank == 0 and dist.world == 1 and not args.no_cpu:  # before any CUDA call (fork-safe)
+        cores = len(os.sched_getaffinity(0))
+        with mp.get_context("fork").Pool(cores) as pool:
+            cb, _ = cpu_baseline("stft", max(1, args.cpu_clips_per_core) if args.cpu_clips_per_core > 0 else None, cores, pool)
+            if not args.no_configs:
+                for name in ("istft", "melspectrogram", "mfcc", "mdct", "imdct", "cqtspectrogram"):
+                    if args.only_configs and name not in args.only_configs:
+                        continue
+                    try:
+                        cpu_lines[name], _ = cpu_baseline(name, None, cores, pool)
+                    except Exception as exc:  # noqa: BLE001
+                        cpu_lines[name] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     import zaf_python_b200 as zaf
 
@@ -396,7 +866,7 @@ def run_ours(args):
             zaf.synchronize()
             worst = max(worst, *oracle.parity_metrics(got.T, oracle.stft(pin_x.array[c], w, HOP)))
         parity = worst
-        assert worst <= 1e-5, f"parity broken: {worst}"
+        assert worst <= TOL, f"parity broken: {worst}"
 
     # the same launch held for ~1 s: the board reaches its power cap and the SM clock drops; reported next to the headline
     extra = {}
@@ -414,26 +884,16 @@ def run_ours(args):
         extra["sustained"] = {"steps": args.sustained_steps, "ms_per_step": sus_ms, "frames_per_sec": frames * dist.world / (sus_ms * 1e-3),
                               "clocks": sampler2.stop(tb, te)}
 
-    # the other direction (istft) and the round trip, for the record
-    yd = zaf.empty((clips, zaf.istft_geometry(N_WIN, nt, HOP)[2]), np.float32)
-
-    def istep():
-        zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(out.ptr), clips, nt, zaf.LAYOUT_FRAME_MAJOR,
-                                          C.c_void_p(yd.ptr), yd.shape[1], stream.ptr))
-
-    for _ in range(2):
-        istep()
-    stream.synchronize()
-    k2 = max(3, args.steps // 4)
-    e0.record(stream)
-    for _ in range(k2):
-        istep()
-    e1.record(stream)
-    e1.synchronize()
-    extra["istft_ms_per_step"] = e0.elapsed_ms(e1) / k2
-    extra["istft_frames_per_sec"] = frames / (extra["istft_ms_per_step"] * 1e-3)
-    extra["round_trip_frames_per_sec"] = frames / ((ms_per_step + extra["istft_ms_per_step"]) * 1e-3)
-    yd.free()
+    # the device-resident chain of the reference's centre-extraction demo (f3)
+    if not args.no_configs and clips % 2 == 0:
+        try:
+            extra["device_chain"] = chain_leg(zaf, stream, xd, clips, nt, w, out) if dist.rank == 0 else None
+            step()  # the chain masked `out` in place: restore the spectrum for the legs below
+            stream.synchronize()
+        except AssertionError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            extra["device_chain"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # end to end through the public drop-in call, host buffers, H2D + D2H inside the timed region
     e2e = None
@@ -467,7 +927,29 @@ def run_ours(args):
             for c in (0, e2e_clips - 1):
                 worst = max(worst, *oracle.parity_metrics(pin_out.array[c].T, oracle.stft(x_host[c], w, HOP)))
             e2e["parity_max_rel_err"] = worst
-            assert worst <= 1e-5, f"e2e parity broken: {worst}"
+            assert worst <= TOL, f"e2e parity broken: {worst}"
+        # the ceiling of this host for that call: plain pinned copies of the same bytes, all ranks at once (no kernels,
+        # no mirror fill) -- the aggregate link + host-memory rate the box gives N processes
+        try:
+            sub = e2e_clips * nt * N_WIN * 8
+            dist.barrier()
+            t0 = time.perf_counter()
+            zaf._lib.check(lib.zafb_memcpy_d2h(pin_out.array.ctypes.data, C.c_void_p(out.ptr), sub, stream.ptr))
+            stream.synchronize()
+            full_s = dist.max(time.perf_counter() - t0)
+            dist.barrier()
+            t0 = time.perf_counter()
+            zaf._lib.check(lib.zafb_memcpy_d2h(pin_out.array.ctypes.data, C.c_void_p(out.ptr), sub // 2, stream.ptr))
+            stream.synchronize()
+            half_s = dist.max(time.perf_counter() - t0)
+            e2e["host_link_probe"] = {
+                "full_copy_ms": 1e3 * full_s, "full_copy_aggregate_gbs": sub * dist.world / full_s / 1e9,
+                "full_copy_frames_per_sec_ceiling": e2e_clips * nt * dist.world / full_s,
+                "half_d2h_ms": 1e3 * half_s, "half_d2h_aggregate_gbs": (sub // 2) * dist.world / half_s / 1e9,
+                "note": "one pinned cudaMemcpyAsync D2H of the call's result (and of half of it), all ranks concurrently, wall clock, max over ranks"}
+            e2e["fraction_of_full_copy_ceiling"] = e2e["value"] / e2e["host_link_probe"]["full_copy_frames_per_sec_ceiling"]
+        except Exception as exc:  # noqa: BLE001
+            e2e["host_link_probe"] = {"error": str(exc)[:200]}
         # the same call returning the reference's own memory order (C-order (N, nt) per clip), reported beside it
         out_c = pin_out.array.reshape(e2e_clips, N_WIN, nt)
         zaf.stft(x_host, w, HOP, out=out_c, layout="bin_major")
@@ -479,33 +961,43 @@ def run_ours(args):
         e2e["c_order"] = {"value": e2e_clips * nt * dist.world / c_s, "ms_per_step": 1e3 * c_s, "layout": "bin_major"}
         if dist.rank == 0:
             e2e["c_order"]["parity_max_rel_err"] = max(oracle.parity_metrics(out_c[0], oracle.stft(x_host[0], w, HOP)))
-            assert e2e["c_order"]["parity_max_rel_err"] <= 1e-5
+            assert e2e["c_order"]["parity_max_rel_err"] <= TOL
         pin_out.free()
     except (MemoryError, RuntimeError) as exc:  # e.g. not enough pinnable host memory
         e2e = {"value": None, "unit": "frames/s", "error": str(exc)[:200]}
 
-    # N > 1: the batch split / merge leg (strong scaling): rank 0 holds the whole cfg-2 batch in HBM, scatters the
-    # clips over NCCL, every rank transforms its shard, the spectra are gathered back on rank 0
+    # the headline buffers are done: free them before the other configs allocate theirs
+    xd.free()
+    out.free()
+    peak, peak_src, sm_max_mhz = measured_peaks()
+    if clocks.get("sm_max_mhz"):
+        sm_max_mhz = clocks["sm_max_mhz"]
+
+    # every other BASELINE config on its own shape, with parity and its own CPU baseline
+    if not args.no_configs:
+        extra["configs"] = run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines)
+
+    # N > 1: the batch split / merge legs (strong scaling): rank 0 holds one whole batch in HBM, scatters the clips over
+    # NCCL, every rank transforms its shard, the results are gathered back on rank 0 and compared bitwise with the
+    # unsharded result
     if dist.world > 1 and not args.no_split_merge:
         try:
-            extra["split_merge"] = split_merge_leg(zaf, dist, xd, w, nt, clips, stream)
+            legs, variants = split_merge_legs(zaf, dist, args, stream)
+            extra["split_merge"] = {"legs": legs, "stft_variants": variants,
+                                    "note": "rank 0 holds the batch; grouped ncclSend/ncclRecv over NVLink; best of 2 after a warm-up"}
+        except AssertionError:
+            raise
         except Exception as exc:  # noqa: BLE001 -- the headline number does not depend on this leg
             extra["split_merge"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if dist.rank == 0:
         algo_bytes = clips * NS * 4 + frames * N_WIN * 8
-        peak, peak_src = measured_peak()
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": dist.world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE cfg 2 forward STFT: {clips} clips x {SECONDS} s @ {FS} Hz fp32 per GPU, "
-                                   f"Hamming window {N_WIN}, hop {HOP}, full two-sided complex64 spectrum "
-                                   f"({nt} frames/clip)",
-                       "window_length": N_WIN, "step_length": HOP, "clips_per_gpu": clips, "global_clips": clips * dist.world,
-                       "parallelism": f"clip-sharded x{dist.world}, no data-path collective",
-                       "layout": "frame_major", "l2": "inputs+outputs per step (17.7 GB) exceed L2 (126 MB); no flush needed"},
+            "config": headline_config(clips, nt, dist.world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel": "stft_warp_kernel<2048, false, 6>"},
@@ -527,11 +1019,17 @@ def main():
     ap.add_argument("--clips", type=int, default=CLIPS, help="clips per GPU (BASELINE cfg 2: 1024)")
     ap.add_argument("--e2e-clips", type=int, default=CLIPS)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--no-split-merge", action="store_true", help="N > 1: skip the NCCL split/merge leg")
-    ap.add_argument("--cpu-clips-per-core", type=int, default=CPU_CLIPS_PER_CORE,
-                    help="size of the bounded CPU sample (clips per host core)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip extra.configs (the other BASELINE configs) and the device chain")
+    ap.add_argument("--only-configs", default="", help="comma-separated subset of extra.configs / split-merge legs")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed launches per extra config")
+    ap.add_argument("--config-clips", type=int, default=0, help="override the clips per GPU of every extra config (tests)")
+    ap.add_argument("--no-split-merge", action="store_true", help="N > 1: skip the NCCL split/merge legs")
+    ap.add_argument("--cpu-clips-per-core", type=int, default=0,
+                    help="bound the CPU sample of the headline to this many clips per host core "
+                         "(default: 12 for cpu_baseline; the whole batch per step for --impl reference)")
     args = ap.parse_args()
+    args.only_configs = [s for s in args.only_configs.split(",") if s]
     if args.steps is None:
         args.steps = 5 if args.impl == "reference" else 50
     if args.impl == "reference":

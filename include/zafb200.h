@@ -222,6 +222,24 @@ int zafb_cqt_f32(const zafb_cqt_plan* plan, const float* x, int64_t n_clips, int
 int zafb_cqt_host_f32(const zafb_cqt_plan* plan, const float* x_host, int64_t n_clips, int64_t ns,
                       int64_t clip_stride, int64_t octave_resolution, float* out_host, int layout);
 
+/* ------------------------------------------------- device-resident stages between transforms
+ * SURVEY.md section 8f-3.  The reference's own demos are chains -- stft -> time-frequency mask -> istft (zaf.py:162-198),
+ * mdct -> coefficients processed -> imdct (zaf.py:1098-1105) -- whose middle step is NumPy elementwise arithmetic.  These
+ * entry points are that arithmetic on DEVICE pointers, so a chain never crosses PCIe.  `layout` as above; spectra are
+ * n_clips * bins * frames complex64, masks / magnitudes float32 in the same layout. */
+/* |X[k]| of bins 0 .. keep_bins-1 (zaf.py:176: abs(audio_stft[0:number_frequencies, :])) */
+int zafb_spec_abs_f32(const float* spec, int64_t n_clips, int64_t bins, int64_t frames, int layout,
+                      int64_t keep_bins, float* out, void* stream);
+/* out = spec * mask; mask_bins == bins, or bins/2 + 1 with the mask mirrored onto bins N-k like
+ * np.concatenate((mask, mask[-2:0:-1, :])) (zaf.py:185).  out may alias spec. */
+int zafb_spec_mask_f32(const float* spec, int64_t n_clips, int64_t bins, int64_t frames, int layout,
+                       const float* mask, int64_t mask_bins, float* out, void* stream);
+int zafb_ratio_min_f32(const float* a, const float* b, int64_t n, float* out, void* stream); /* min(a,b)/a, zaf.py:181 */
+int zafb_mul_f32(const float* a, const float* b, int64_t n, float* out, void* stream);       /* a*b */
+int zafb_quantize_f32(const float* x, int64_t n, float step, float* out, void* stream);      /* step*rint(x/step) */
+/* number of differing 32-bit words (bitwise check of a sharded result against the unsharded one); synchronises */
+int zafb_count_mismatch_u32(const void* a, const void* b, int64_t n_words, int64_t* count, void* stream);
+
 /* ------------------------------------------------- multi-GPU batch split / merge
  * One process per GPU.  The reference has no distributed code; clips are
  * independent, so the only collectives on the path move a batch: rows (a clip, or one clip's

@@ -65,5 +65,8 @@ def zaf_gpu():
     library is missing -- there is no fallback."""
     import zaf_python_b200 as zaf
 
+    zaf._lib.lib()  # a missing libzafb200.so is an error, never a skip
+    if not _gpu_available():
+        pytest.skip("libzafb200.so is built but this machine has no CUDA device (run with -m 'not gpu')")
     zaf.init(0)
     return zaf

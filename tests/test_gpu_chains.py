@@ -1,0 +1,145 @@
+"""Device-resident chains: the reference's own demos are stft -> mask -> istft (zaf.py:162-198)
+and mdct -> ... -> imdct (zaf.py:1098-1105).  Here the whole chain runs on DeviceArrays -- nothing crosses PCIe between
+the transforms -- and is compared with the oracle doing the same chain in float64 NumPy."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def assert_parity(got, ref, tol=TOL):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    mx, l2 = oracle.parity_metrics(got, ref)
+    assert mx <= tol and l2 <= tol, (mx, l2)
+
+
+def _stereo(seed, ns):
+    rng = np.random.default_rng(seed)
+    centre = rng.uniform(-0.5, 0.5, ns)
+    left = centre + 0.3 * rng.uniform(-1, 1, ns)
+    right = centre + 0.3 * rng.uniform(-1, 1, ns)
+    return left.astype(np.float32), right.astype(np.float32)
+
+
+@pytest.mark.parametrize("layout", ["frame_major", "bin_major"])
+@pytest.mark.parametrize("n", [2048, 1024])
+def test_centre_extraction_chain_on_device(zaf_gpu, layout, n):
+    """zaf.py:166-191 with both channels as a batch of two clips: STFT, magnitudes of rows 0..N/2, the two centre masks
+    min(|X1|, |X2|) / |Xc|, mask mirrored onto the upper rows, ISTFT."""
+    zaf = zaf_gpu
+    hop = n // 2
+    w = oracle.hamming_periodic(n)
+    left, right = _stereo(5, 30000)
+    x = np.stack([left, right])
+    launches = zaf.launch_count()
+    h2d0 = zaf.host_copy_bytes()
+    xd = zaf.to_device(x)
+    spec = zaf.stft(xd, w, hop, layout=layout)
+    mag = zaf.spec_abs(spec, n // 2 + 1)
+    assert mag.shape == (2, n // 2 + 1, spec.shape[-1]) and mag.transposed == spec.transposed
+    swapped = zaf.DeviceArray(mag.mem_shape, np.float32, transposed=mag.transposed)  # (|X2|, |X1|)
+    row = mag.nbytes // 2
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    zaf._lib.check(lib.zafb_memcpy_d2d(C.c_void_p(swapped.ptr), C.c_void_p(mag.ptr + row), row, None))
+    zaf._lib.check(lib.zafb_memcpy_d2d(C.c_void_p(swapped.ptr + row), C.c_void_p(mag.ptr), row, None))
+    mask = zaf.ratio_min(mag, swapped)  # clip 0: min(|X1|,|X2|)/|X1|, clip 1: min(|X2|,|X1|)/|X2|
+    centre = zaf.spec_mask(spec, mask)
+    y = zaf.istft(centre, w, hop).to_host()
+    assert zaf.launch_count() - launches >= 5
+    assert zaf.host_copy_bytes() == h2d0  # no host-pipeline traffic: the chain stayed on the device
+
+    s1 = oracle.stft(left, w, hop)
+    s2 = oracle.stft(right, w, hop)
+    a1, a2 = np.abs(s1[: n // 2 + 1]), np.abs(s2[: n // 2 + 1])
+    m1, m2 = np.minimum(a1, a2) / a1, np.minimum(a1, a2) / a2
+    c1 = np.concatenate((m1, m1[-2:0:-1])) * s1
+    c2 = np.concatenate((m2, m2[-2:0:-1])) * s2
+    assert_parity(y[0], oracle.istft(c1, w, hop))
+    assert_parity(y[1], oracle.istft(c2, w, hop))
+    # intermediate stages too
+    assert_parity(mag.to_host()[0], a1)
+    assert_parity(centre.to_host()[1], c2)
+
+
+def test_full_mask_and_in_place(zaf_gpu):
+    zaf = zaf_gpu
+    n, hop = 512, 128
+    w = oracle.hamming_periodic(n)
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, 9000).astype(np.float32)
+    spec = zaf.stft(zaf.to_device(x), w, hop)
+    nt = spec.shape[-1]
+    full = rng.uniform(0, 1, (n, nt)).astype(np.float32)
+    md = zaf.to_device(np.ascontiguousarray(full.T))
+    md = zaf.DeviceArray((nt, n), np.float32, ptr=md.ptr, owner=md, transposed=True)  # frame-major view
+    before = spec.to_host().copy()
+    out = zaf.spec_mask(spec, md, out=spec)
+    assert out is spec
+    got = spec.to_host()
+    assert np.array_equal(got, before * full)  # one fp32 multiply per component: bit-exact
+    with pytest.raises(ValueError):
+        zaf.spec_mask(spec, zaf.DeviceArray((nt, 7), np.float32, transposed=True))
+
+
+def test_mdct_quantise_imdct_chain_on_device(zaf_gpu):
+    """mdct -> uniform quantiser -> imdct on the device; the quantiser is bit-exact against NumPy float32 on the same
+    coefficients, the synthesis matches the oracle's imdct of those quantised coefficients."""
+    zaf = zaf_gpu
+    n = 2048
+    w = oracle.kbd_window(n)
+    rng = np.random.default_rng(23)
+    x = rng.uniform(-1, 1, (3, 50000)).astype(np.float32)
+    step = np.float32(0.37)
+    coef = zaf.mdct(zaf.to_device(x), w)
+    q = zaf.quantize(coef, step)
+    y = zaf.imdct(q, w).to_host()
+    c_host = coef.to_host()
+    q_host = q.to_host()
+    assert np.array_equal(q_host, step * np.round(c_host / step))
+    assert len(np.unique(q_host)) > 50
+    for c in range(3):
+        assert_parity(c_host[c], oracle.mdct(x[c], w))
+        assert_parity(y[c], oracle.imdct(q_host[c].astype(np.float64), w))
+    # a real mask on the coefficients (e.g. band-limiting), in place
+    keep = np.zeros(c_host.shape, np.float32)
+    keep[:, : n // 8, :] = 1.0
+    kd = zaf.to_device(np.ascontiguousarray(np.swapaxes(keep, 1, 2)))
+    kd = zaf.DeviceArray(kd.mem_shape, np.float32, ptr=kd.ptr, owner=kd, transposed=True)
+    zaf.multiply(coef, kd, out=coef)
+    assert np.array_equal(coef.to_host(), c_host * keep)
+
+
+def test_count_mismatch(zaf_gpu):
+    zaf = zaf_gpu
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(100003).astype(np.float32)
+    b = a.copy()
+    b[[5, 77, 100002]] += 1.0
+    ad, bd = zaf.to_device(a), zaf.to_device(b)
+    assert zaf.count_mismatch(ad, ad) == 0
+    assert zaf.count_mismatch(ad, bd) == 3
+
+
+def test_to_host_out_respects_row_padding(zaf_gpu):
+    """DeviceArray.to_host(out=...) with padded rows (every batched imdct result has an odd length and an even pitch):
+    `out` of the LOGICAL shape receives exactly the logical columns; wrong sizes and dtypes are refused."""
+    zaf = zaf_gpu
+    w = oracle.kbd_window(512)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (4, 6000)).astype(np.float32)
+    y = zaf.imdct(zaf.mdct(zaf.to_device(x), w), w)
+    assert y.cols is not None and y.pitch == y.cols + 1
+    want = y.to_host()
+    guard = np.full(4 * y.cols + 8, 7.0, np.float32)
+    out = guard[: 4 * y.cols].reshape(4, y.cols)
+    got = y.to_host(out=out)
+    assert np.array_equal(got, want) and np.all(guard[4 * y.cols:] == 7.0)
+    with pytest.raises(ValueError):
+        y.to_host(out=np.empty((4, y.cols), np.float64))
+    with pytest.raises(ValueError):
+        y.to_host(out=np.empty((3, y.cols), np.float32))
+    with pytest.raises(ValueError):
+        zaf.mdct(zaf.to_device(x.astype(np.float64)), w)  # float64 device input is refused, not reinterpreted

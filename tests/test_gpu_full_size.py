@@ -115,3 +115,44 @@ def test_dct_dst_million_vectors_inverse_pairs(zaf_gpu):
             zaf.synchronize()
             assert np.max(np.abs(back - host)) <= 1e-5
         yd.free(), zd.free()
+
+
+def test_cfg5_cqt_full_batch(zaf_gpu):
+    """512 clips x 20 s @ 44.1 kHz, 12 bins/octave C1-C8 (84 x 32768 kernel), 25 frames/s: 256 000 frames of a
+    32 768-point transform.  Size-independent properties: every clip equals the result of its 32-clip tile bitwise
+    (no cross-clip arithmetic, batch-invariant results on BOTH routes), linearity in the signal amplitude (|K X| is
+    homogeneous: an exact power-of-two gain scales the result exactly), the chromagram is the octave fold of the
+    spectrogram, and two clips match the oracle."""
+    import scipy.sparse
+
+    zaf = zaf_gpu
+    clips, ns, fs, tr = 512, 882000, 44100, 25
+    kern = zaf.cqtkernel(fs, 12, 32.70319566257483, 4186.009044809578)
+    assert kern.shape == (84, 32768)
+    xd, host = tiled_batch(zaf, clips, ns, 20261017 + 5)
+    spec = zaf.cqtspectrogram(xd, fs, tr, kern).to_host()
+    assert spec.shape == (clips, 84, 500)
+    for c0 in range(DISTINCT, clips, DISTINCT):
+        assert np.array_equal(spec[c0:c0 + DISTINCT], spec[:DISTINCT])
+    ksp = scipy.sparse.csr_matrix(kern)
+    for c in (0, 31):
+        mx, l2 = oracle.parity_metrics(spec[c], oracle.cqtspectrogram(host[c], fs, tr, ksp))
+        assert mx <= 1e-5 and l2 <= 1e-5, (c, mx, l2)
+    # the other route: same batch invariance, same parity, and agreement with the default route
+    other = zaf.cqtspectrogram(xd, fs, tr, kern, route="tensor").to_host()
+    for c0 in range(DISTINCT, clips, DISTINCT):
+        assert np.array_equal(other[c0:c0 + DISTINCT], other[:DISTINCT])
+    mx, l2 = oracle.parity_metrics(other[:DISTINCT], spec[:DISTINCT].astype(np.float64))
+    assert mx <= 1e-5 and l2 <= 1e-5, (mx, l2)
+    # homogeneity: 4 x (exact in fp32) scales every magnitude by exactly 4
+    x4 = zaf.to_device(host[:4] * np.float32(4.0))
+    s4 = zaf.cqtspectrogram(x4, fs, tr, kern).to_host()
+    assert np.array_equal(s4, spec[:4] * np.float32(4.0))
+    # chromagram == fold of the spectrogram rows i::12 (zaf.py:693-698), summed in the same order
+    chroma = zaf.cqtchromagram(x4, fs, tr, 12, kern).to_host()
+    fold = np.zeros((4, 12, 500), np.float32)
+    for i in range(12):
+        for r in range(i, 84, 12):
+            fold[:, i] += s4[:, r]
+    assert np.array_equal(chroma, fold)
+    xd.free(), x4.free()

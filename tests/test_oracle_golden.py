@@ -181,3 +181,32 @@ def test_stft_istft_round_trip_and_shift_quirk():
 def test_stft_rejects_2d():
     with pytest.raises(ValueError):
         oracle.stft(np.zeros((4, 100)), np.ones(16), 4)
+
+
+def test_vendored_reference_matches_port():
+    """oracle/_ref/zaf.py (the unmodified reference, vendored by oracle/make_ref.py; git-ignored, so absent in a fresh
+    clone until build() has run where /root/reference exists) against the port, on fresh inputs: the CPU baseline of
+    bench.py times the former, the parity tests use the latter."""
+    from oracle import ref_loader
+
+    ref = ref_loader.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/zaf.py has not been built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, 9000)
+    w = oracle.hamming_periodic(512)
+    for hop in (128, 256):
+        a, b = ref.stft(x, w, hop), oracle.stft(x, w, hop)
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-11
+        assert np.max(np.abs(ref.istft(a, w, hop) - oracle.istft(b, w, hop))) <= 1e-11
+    wk = oracle.kbd_window(256)
+    a, b = ref.mdct(x, wk), oracle.mdct(x, wk)
+    assert np.max(np.abs(a - b)) <= 1e-10
+    assert np.max(np.abs(ref.imdct(a, wk) - oracle.imdct(b, wk))) <= 1e-11
+    fb = ref.melfilterbank(16000, 512, 40)
+    assert np.max(np.abs(ref.melspectrogram(x, w, 128, fb) - oracle.melspectrogram(x, w, 128, fb))) <= 1e-10
+    assert np.max(np.abs(ref.mfcc(x, w, 128, fb, 13) - oracle.mfcc(x, w, 128, fb, 13))) <= 1e-10
+    for t in (1, 2, 3, 4):
+        v = x[:256]
+        assert np.max(np.abs(ref.dct(v, t) - oracle.dct(v, t))) <= 1e-12
+        assert np.max(np.abs(ref.dst(v, t) - oracle.dst(v, t))) <= 1e-12

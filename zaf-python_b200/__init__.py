@@ -36,6 +36,7 @@ __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
     "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
     "to_device", "empty", "from_pcm16", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count", "host_copy_bytes",
+    "spec_abs", "spec_mask", "ratio_min", "multiply", "quantize", "count_mismatch",
     "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry", "dist", "shard_range",
 ]
 
@@ -183,6 +184,23 @@ def _stream_ptr(stream):
     return stream.ptr if stream is not None else None
 
 
+def _device_signal(x):
+    """Validate a device-resident signal batch: float32, (ns,) or (B, ns), not a transposed view."""
+    if x.dtype != np.float32 or len(x.shape) not in (1, 2) or x.transposed:
+        raise ValueError("device input must be a float32 (number_samples,) or (batch, number_samples) DeviceArray")
+    one = len(x.shape) == 1
+    batch, ns = (1, x.shape[0]) if one else x.shape
+    return one, batch, ns
+
+
+def _device_matrix(s, dtype, what):
+    """Validate a device-resident (bins, frames) / (B, bins, frames) spectrum of the given dtype."""
+    if s.dtype != np.dtype(dtype) or len(s.shape) not in (2, 3) or s.cols is not None:
+        raise ValueError(f"device input must be a {np.dtype(dtype)} {what} DeviceArray")
+    one = len(s.shape) == 2
+    return one, (1 if one else s.shape[0])
+
+
 # ------------------------------------------------------------------ STFT / ISTFT
 def stft(audio_signal, window_function, step_length, *, layout="frame_major", stream=None, out=None):
     """Short-time Fourier transform -- drop-in for ``zaf.stft`` (zaf.py:45-141).
@@ -197,10 +215,7 @@ def stft(audio_signal, window_function, step_length, *, layout="frame_major", st
     n = len(w)
     if isinstance(audio_signal, DeviceArray):
         x = audio_signal
-        if x.dtype != np.float32 or len(x.shape) not in (1, 2) or x.transposed:
-            raise ValueError("device input must be a float32 (ns,) or (B, ns) DeviceArray")
-        one = len(x.shape) == 1
-        batch, ns = (1, x.shape[0]) if one else x.shape
+        one, batch, ns = _device_signal(x)
         nt = stft_geometry(ns, n, step_length)[1]
         mem_shape = (batch, nt, n) if lay == LAYOUT_FRAME_MAJOR else (batch, n, nt)
         if out is None:
@@ -256,11 +271,8 @@ def istft(audio_stft, window_function, step_length, *, stream=None):
     n = len(w)
     if isinstance(audio_stft, DeviceArray):
         s = audio_stft
-        if s.dtype != np.complex64 or len(s.shape) not in (2, 3):
-            raise ValueError("device input must be a complex64 (N, nt) or (B, N, nt) DeviceArray")
-        one = len(s.shape) == 2
+        one, batch = _device_matrix(s, np.complex64, "(N, nt) or (B, N, nt)")
         shape = s.shape
-        batch = 1 if one else shape[0]
         if shape[-2] != n:
             raise ValueError(f"audio_stft has {shape[-2]} bins but the window has {n} samples")
         nt = shape[-1]
@@ -280,6 +292,105 @@ def istft(audio_stft, window_function, step_length, *, stream=None):
     return y[0] if one else y
 
 
+# ------------------------------------------------------------------ device-resident stages between transforms
+def _spec_geometry(spec):
+    """(n_clips, bins, frames, layout id) of a complex64 / float32 (bins, frames) or (B, bins, frames) DeviceArray."""
+    if not isinstance(spec, DeviceArray) or len(spec.shape) not in (2, 3) or spec.cols is not None:
+        raise ValueError("expected a (bins, frames) or (batch, bins, frames) DeviceArray")
+    shape = spec.shape
+    clips = 1 if len(shape) == 2 else shape[0]
+    return clips, shape[-2], shape[-1], (LAYOUT_FRAME_MAJOR if spec.transposed else LAYOUT_BIN_MAJOR)
+
+
+def _like(spec, bins, dtype):
+    """A new DeviceArray with `bins` rows in the layout (and batch shape) of ``spec``."""
+    lead = spec.mem_shape[:-2]
+    frames = spec.shape[-1]
+    mem = lead + ((frames, bins) if spec.transposed else (bins, frames))
+    return DeviceArray(mem, dtype, transposed=spec.transposed)
+
+
+def spec_abs(audio_stft, number_frequencies=None, *, stream=None):
+    """|X| of rows 0 .. number_frequencies-1 of a device-resident spectrum, ON the device -- the
+    ``abs(audio_stft[0:number_frequencies, :])`` of the reference's examples (zaf.py:176-177).  Same layout as the input."""
+    clips, bins, frames, lay = _spec_geometry(audio_stft)
+    if audio_stft.dtype != np.complex64:
+        raise ValueError("spec_abs needs a complex64 spectrum")
+    keep = bins if number_frequencies is None else int(number_frequencies)
+    out = _like(audio_stft, keep, np.float32)
+    _lib.check(_lib.lib().zafb_spec_abs_f32(C.c_void_p(audio_stft.ptr), clips, bins, frames, lay, keep, C.c_void_p(out.ptr),
+                                            _stream_ptr(stream)))
+    return out
+
+
+def spec_mask(audio_stft, mask, *, out=None, stream=None):
+    """``audio_stft * mask`` ON the device.  ``mask`` (float32 DeviceArray, same layout) has either every row of the
+    spectrum or rows 0 .. N/2, in which case it is mirrored onto the upper half exactly like the reference's
+    ``np.concatenate((mask, mask[-2:0:-1, :]))`` (zaf.py:185-186).  ``out=audio_stft`` works in place."""
+    clips, bins, frames, lay = _spec_geometry(audio_stft)
+    mclips, mbins, mframes, mlay = _spec_geometry(mask)
+    if audio_stft.dtype != np.complex64 or mask.dtype != np.float32:
+        raise ValueError("spec_mask needs a complex64 spectrum and a float32 mask")
+    if (mclips, mframes, mlay) != (clips, frames, lay):
+        raise ValueError("mask and spectrum must agree in batch size, number of frames and layout")
+    if out is None:
+        out = _like(audio_stft, bins, np.complex64)
+    elif out.dtype != np.complex64 or out.mem_shape != audio_stft.mem_shape or out.transposed != audio_stft.transposed:
+        raise ValueError("out must match the spectrum")
+    _lib.check(_lib.lib().zafb_spec_mask_f32(C.c_void_p(audio_stft.ptr), clips, bins, frames, lay, C.c_void_p(mask.ptr), mbins,
+                                             C.c_void_p(out.ptr), _stream_ptr(stream)))
+    return out
+
+
+def _same_real(a, b):
+    if not (isinstance(a, DeviceArray) and isinstance(b, DeviceArray)) or a.dtype != np.float32 or b.dtype != np.float32 \
+            or a.mem_shape != b.mem_shape or a.transposed != b.transposed:
+        raise ValueError("operands must be float32 DeviceArrays of the same shape and layout")
+
+
+def _real_like(a):
+    return DeviceArray(a.mem_shape, np.float32, transposed=a.transposed, cols=a.cols)
+
+
+def ratio_min(a, b, *, stream=None):
+    """``np.minimum(a, b) / a`` ON the device -- the centre-mask estimate of zaf.py:181-182."""
+    _same_real(a, b)
+    out = _real_like(a)
+    _lib.check(_lib.lib().zafb_ratio_min_f32(C.c_void_p(a.ptr), C.c_void_p(b.ptr), a.nbytes // 4, C.c_void_p(out.ptr),
+                                             _stream_ptr(stream)))
+    return out
+
+
+def multiply(a, b, *, out=None, stream=None):
+    """``a * b`` for float32 DeviceArrays (e.g. a mask on MDCT coefficients), ON the device."""
+    _same_real(a, b)
+    out = _real_like(a) if out is None else out
+    _lib.check(_lib.lib().zafb_mul_f32(C.c_void_p(a.ptr), C.c_void_p(b.ptr), a.nbytes // 4, C.c_void_p(out.ptr),
+                                       _stream_ptr(stream)))
+    return out
+
+
+def quantize(x, step, *, out=None, stream=None):
+    """Uniform scalar quantise-dequantise ``step * np.round(x / step)`` (float32, round half to even) ON the device: the
+    coefficient-domain stage of an ``mdct -> ... -> imdct`` codec chain (zaf.py:1098-1105 is the chain without it)."""
+    if not isinstance(x, DeviceArray) or x.dtype != np.float32:
+        raise ValueError("quantize needs a float32 DeviceArray")
+    out = _real_like(x) if out is None else out
+    _lib.check(_lib.lib().zafb_quantize_f32(C.c_void_p(x.ptr), x.nbytes // 4, float(step), C.c_void_p(out.ptr),
+                                            _stream_ptr(stream)))
+    return out
+
+
+def count_mismatch(a, b, *, stream=None):
+    """Number of differing 32-bit words between two device buffers of equal size (bitwise comparison on the device)."""
+    if a.nbytes != b.nbytes:
+        raise ValueError("buffers differ in size")
+    n = C.c_int64(0)
+    _lib.check(_lib.lib().zafb_count_mismatch_u32(C.c_void_p(a.ptr), C.c_void_p(b.ptr), a.nbytes // 4, C.byref(n),
+                                                  _stream_ptr(stream)))
+    return int(n.value)
+
+
 # ------------------------------------------------------------------ MDCT / IMDCT
 def _mdct_plan(window_function):
     w = _window64(window_function)
@@ -296,8 +407,7 @@ def mdct(audio_signal, window_function, *, layout="frame_major", stream=None):
     n = len(w)
     if isinstance(audio_signal, DeviceArray):
         x = audio_signal
-        one = len(x.shape) == 1
-        batch, ns = (1, x.shape[0]) if one else x.shape
+        one, batch, ns = _device_signal(x)
         m, nt, _ = mdct_geometry(ns, n)
         mem_shape = (batch, nt, m) if lay == LAYOUT_FRAME_MAJOR else (batch, m, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
@@ -320,9 +430,8 @@ def imdct(audio_mdct, window_function, *, stream=None):
     n = len(w)
     if isinstance(audio_mdct, DeviceArray):
         s = audio_mdct
-        one = len(s.shape) == 2
+        one, batch = _device_matrix(s, np.float32, "(M, nt) or (B, M, nt)")
         shape = s.shape
-        batch = 1 if one else shape[0]
         if shape[-2] * 2 != n:
             raise ValueError("audio_mdct rows must equal window_length/2")
         nt = shape[-1]
@@ -349,8 +458,7 @@ def _dct_like(audio_signal, kind, dtype_code):
         return None  # the reference falls through its if/elif chain and returns None (zaf.py:759-839)
     if isinstance(audio_signal, DeviceArray):
         x = audio_signal
-        one = len(x.shape) == 1
-        batch, n = (1, x.shape[0]) if one else x.shape
+        one, batch, n = _device_signal(x)
         plan = _dct_plans.get((kind, dtype_code, n), kind, dtype_code, n)
         out = DeviceArray(x.shape, np.float32)
         _lib.check(_lib.lib().zafb_dct_f32(plan, C.c_void_p(x.ptr), batch, x.pitch, C.c_void_p(out.ptr), n, None))
@@ -406,8 +514,7 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
     rows = rows_of(n_mels)
     if isinstance(audio_signal, DeviceArray):
         x = audio_signal
-        one = len(x.shape) == 1
-        batch, ns = (1, x.shape[0]) if one else x.shape
+        one, batch, ns = _device_signal(x)
         nt = stft_geometry(ns, len(w), step_length)[1]
         mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)
@@ -471,8 +578,7 @@ def _cqt_like(audio_signal, sampling_frequency, time_resolution, octave_resoluti
     rows = octave_resolution if octave_resolution else nf
     if isinstance(audio_signal, DeviceArray):
         x = audio_signal
-        one = len(x.shape) == 1
-        batch, ns = (1, x.shape[0]) if one else x.shape
+        one, batch, ns = _device_signal(x)
         nt = cqt_geometry(ns, sampling_frequency, time_resolution, fft_length)[1]
         mem_shape = (batch, nt, rows) if lay == LAYOUT_FRAME_MAJOR else (batch, rows, nt)
         out = DeviceArray(mem_shape[1:] if one else mem_shape, np.float32, transposed=lay == LAYOUT_FRAME_MAJOR)

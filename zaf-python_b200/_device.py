@@ -94,18 +94,26 @@ class DeviceArray:
 
     def to_host(self, out=None, stream=None):
         """Copy to a NumPy array of the logical shape (a transposed *view* of the copied memory
-        for frame-major results -- no data movement on the host)."""
+        for frame-major results -- no data movement on the host).  ``out=``: a C-contiguous array of
+        this dtype holding either the logical rows (padding columns are skipped) or the whole padded memory."""
         sp = stream.ptr if stream else None
-        if self.cols is not None and out is None:  # padded rows: copy only the logical columns
-            host = np.empty(self.mem_shape[:-1] + (self.cols,), dtype=self.dtype)
+        item = self.dtype.itemsize
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.dtype != self.dtype or not out.flags.c_contiguous:
+                raise ValueError(f"out must be a C-contiguous NumPy array of dtype {self.dtype}")
+            logical = int(np.prod(self.mem_shape[:-1], dtype=np.int64)) * (self.cols or self.mem_shape[-1]) * item
+            if out.nbytes not in (logical, self.nbytes):
+                raise ValueError(f"out holds {out.nbytes} bytes; the array has {logical} (memory: {self.nbytes})")
+        packed = self.cols is not None and (out is None or out.nbytes != self.nbytes)
+        if packed:  # padded rows: copy only the logical columns
+            host = np.empty(self.mem_shape[:-1] + (self.cols,), dtype=self.dtype) if out is None else out
             rows = int(np.prod(self.mem_shape[:-1], dtype=np.int64))
-            item = self.dtype.itemsize
             _lib.check(_lib.lib().zafb_memcpy2d(host.ctypes.data, self.cols * item, C.c_void_p(self.ptr),
                                                 self.mem_shape[-1] * item, self.cols * item, rows, 1, sp))
             if stream is None:
                 synchronize()
-            return host
-        host = np.empty(self.mem_shape, dtype=self.dtype) if out is None else out
+            return host.reshape(self.mem_shape[:-1] + (self.cols,))
+        host = np.empty(self.mem_shape, dtype=self.dtype) if out is None else out.reshape(self.mem_shape)
         _lib.check(_lib.lib().zafb_memcpy_d2h(host.ctypes.data, C.c_void_p(self.ptr), self.nbytes, sp))
         if stream is None:
             synchronize()

@@ -82,6 +82,12 @@ PROTOTYPES = {
     "zafb_cqt_plan_set_route": (_int, [_vp, _int]),
     "zafb_cqt_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp]),
     "zafb_cqt_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _int]),
+    "zafb_spec_abs_f32": (_int, [_vp, _i64, _i64, _i64, _int, _i64, _vp, _vp]),
+    "zafb_spec_mask_f32": (_int, [_vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _vp]),
+    "zafb_ratio_min_f32": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "zafb_mul_f32": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "zafb_quantize_f32": (_int, [_vp, _i64, C.c_float, _vp, _vp]),
+    "zafb_count_mismatch_u32": (_int, [_vp, _vp, _i64, _pi64, _vp]),
     "zafb_dist_shard_range": (_int, [_i64, _int, _int, _pi64, _pi64]),
     "zafb_dist_nccl_version": (_int, [C.POINTER(_int)]),
     "zafb_dist_unique_id": (_int, [_vp]),

@@ -60,7 +60,8 @@ NcclApi& api() {
         for (const char* n : names)
             if (n && *n && !a.handle) a.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (!a.handle) {
-            a.error = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown error");
+            const char* why = dlerror();  // one call: dlerror() clears the error state it returns
+            a.error = std::string("cannot load libnccl.so.2: ") + (why ? why : "unknown error");
             return;
         }
         bool ok = true;
@@ -100,6 +101,30 @@ NcclApi& api() {
         ncclResult_t _r = (expr);                                                 \
         if (_r != ncclSuccess)                                                    \
             return fail(ZAFB_E_NCCL, "%s failed: %s (%s:%d)", #expr, nc.GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+// Inside ncclGroupStart / ncclGroupEnd an early return would leave the group open: the first failure is remembered,
+// the remaining calls are skipped and the group is always closed before the error is reported.
+#define ZAFB_NCCL_IN_GROUP(expr)                                                  \
+    do {                                                                          \
+        if (_grp == ncclSuccess) {                                                \
+            _grp = (expr);                                                        \
+            if (_grp != ncclSuccess) _grp_what = #expr;                           \
+        }                                                                         \
+    } while (0)
+
+#define ZAFB_NCCL_GROUP_BEGIN()                                                   \
+    ncclResult_t _grp = ncclSuccess;                                              \
+    const char* _grp_what = "";                                                   \
+    ZAFB_NCCL(nc.GroupStart())
+
+#define ZAFB_NCCL_GROUP_END()                                                     \
+    do {                                                                          \
+        ncclResult_t _e = nc.GroupEnd();                                          \
+        if (_grp != ncclSuccess)                                                  \
+            return fail(ZAFB_E_NCCL, "%s failed: %s (%s:%d)", _grp_what, nc.GetErrorString(_grp), __FILE__, __LINE__); \
+        if (_e != ncclSuccess)                                                    \
+            return fail(ZAFB_E_NCCL, "ncclGroupEnd failed: %s (%s:%d)", nc.GetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
 inline int64_t shard_begin(int64_t n, int r, int world) { return (int64_t(r) * n) / world; }
@@ -180,14 +205,14 @@ int zafb_dist_scatter_rows(zafb_comm* c, const void* src_root, void* dst, int64_
     if (c->rank == root) {
         ZAFB_REQUIRE(n_rows * row_bytes == 0 || src_root != nullptr, "src is NULL on root");
         const char* s = static_cast<const char*>(src_root);
-        ZAFB_NCCL(nc.GroupStart());
+        ZAFB_NCCL_GROUP_BEGIN();
         for (int r = 0; r < c->world; ++r) {
             if (r == root) continue;
             const int64_t rb = shard_begin(n_rows, r, c->world), re = shard_begin(n_rows, r + 1, c->world);
             const size_t bytes = size_t(re - rb) * size_t(row_bytes);
-            if (bytes) ZAFB_NCCL(nc.Send(s + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
+            if (bytes) ZAFB_NCCL_IN_GROUP(nc.Send(s + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
         }
-        ZAFB_NCCL(nc.GroupEnd());
+        ZAFB_NCCL_GROUP_END();
         if (mine && dst != s + size_t(b) * row_bytes)
             ZAFB_CUDA(cudaMemcpyAsync(dst, s + size_t(b) * row_bytes, mine, cudaMemcpyDeviceToDevice, st));
     } else if (mine) {
@@ -208,14 +233,14 @@ int zafb_dist_gather_rows(zafb_comm* c, const void* src, void* dst_root, int64_t
     if (c->rank == root) {
         ZAFB_REQUIRE(n_rows * row_bytes == 0 || dst_root != nullptr, "dst is NULL on root");
         char* d = static_cast<char*>(dst_root);
-        ZAFB_NCCL(nc.GroupStart());
+        ZAFB_NCCL_GROUP_BEGIN();
         for (int r = 0; r < c->world; ++r) {
             if (r == root) continue;
             const int64_t rb = shard_begin(n_rows, r, c->world), re = shard_begin(n_rows, r + 1, c->world);
             const size_t bytes = size_t(re - rb) * size_t(row_bytes);
-            if (bytes) ZAFB_NCCL(nc.Recv(d + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
+            if (bytes) ZAFB_NCCL_IN_GROUP(nc.Recv(d + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
         }
-        ZAFB_NCCL(nc.GroupEnd());
+        ZAFB_NCCL_GROUP_END();
         if (mine && src != d + size_t(b) * row_bytes)
             ZAFB_CUDA(cudaMemcpyAsync(d + size_t(b) * row_bytes, src, mine, cudaMemcpyDeviceToDevice, st));
     } else if (mine) {
@@ -241,13 +266,13 @@ int zafb_dist_allgather_rows(zafb_comm* c, const void* src, void* dst, int64_t n
     const int64_t b = shard_begin(n_rows, c->rank, c->world), e = shard_begin(n_rows, c->rank + 1, c->world);
     if (e > b && src != d + size_t(b) * row_bytes)
         ZAFB_CUDA(cudaMemcpyAsync(d + size_t(b) * row_bytes, src, size_t(e - b) * row_bytes, cudaMemcpyDeviceToDevice, st));
-    ZAFB_NCCL(nc.GroupStart());
+    ZAFB_NCCL_GROUP_BEGIN();
     for (int r = 0; r < c->world; ++r) {
         const int64_t rb = shard_begin(n_rows, r, c->world), re = shard_begin(n_rows, r + 1, c->world);
         const size_t bytes = size_t(re - rb) * size_t(row_bytes);
-        if (bytes) ZAFB_NCCL(nc.Broadcast(d + size_t(rb) * row_bytes, d + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
+        if (bytes) ZAFB_NCCL_IN_GROUP(nc.Broadcast(d + size_t(rb) * row_bytes, d + size_t(rb) * row_bytes, bytes, ncclChar, r, c->comm, st));
     }
-    ZAFB_NCCL(nc.GroupEnd());
+    ZAFB_NCCL_GROUP_END();
     return ZAFB_OK;
 }
 

@@ -56,11 +56,17 @@ int run_host_pipeline(const void* in_host, size_t in_host_pitch, size_t in_width
         const int64_t nr = (r0 + per <= n_rows) ? per : n_rows - r0;
         if (in_width > 0) {
             const char* src = static_cast<const char*>(in_host) + size_t(r0) * in_host_pitch;
-            if (in_host_pitch == in_width && in_dev_pitch == in_width)
-                ZAFB_CUDA(cudaMemcpyAsync(hp.d_in[s], src, size_t(nr) * in_width, cudaMemcpyHostToDevice, hp.st[s]));
-            else
-                ZAFB_CUDA(cudaMemcpy2DAsync(hp.d_in[s], in_dev_pitch, src, in_host_pitch, in_width, size_t(nr),
-                                            cudaMemcpyHostToDevice, hp.st[s]));
+            // a failed enqueue must not return before the streams are drained: earlier chunks' D2H copies may still be
+            // writing into the caller's result buffer
+            const cudaError_t e =
+                (in_host_pitch == in_width && in_dev_pitch == in_width)
+                    ? cudaMemcpyAsync(hp.d_in[s], src, size_t(nr) * in_width, cudaMemcpyHostToDevice, hp.st[s])
+                    : cudaMemcpy2DAsync(hp.d_in[s], in_dev_pitch, src, in_host_pitch, in_width, size_t(nr),
+                                        cudaMemcpyHostToDevice, hp.st[s]);
+            if (e != cudaSuccess) {
+                rc = fail(ZAFB_E_CUDA, "host pipeline: H2D copy failed: %s", cudaGetErrorString(e));
+                break;
+            }
         }
         g_h2d_bytes.fetch_add(int64_t(nr) * int64_t(in_width), std::memory_order_relaxed);
         g_d2h_bytes.fetch_add(int64_t(nr) * int64_t(out_width), std::memory_order_relaxed);
@@ -68,11 +74,15 @@ int run_host_pipeline(const void* in_host, size_t in_host_pitch, size_t in_width
         if (rc != ZAFB_OK) break;
         if (out_width > 0) {
             char* dst = static_cast<char*>(out_host) + size_t(r0) * out_host_pitch;
-            if (out_host_pitch == out_width && out_dev_pitch == out_width)
-                ZAFB_CUDA(cudaMemcpyAsync(dst, hp.d_out[s], size_t(nr) * out_width, cudaMemcpyDeviceToHost, hp.st[s]));
-            else
-                ZAFB_CUDA(cudaMemcpy2DAsync(dst, out_host_pitch, hp.d_out[s], out_dev_pitch, out_width, size_t(nr),
-                                            cudaMemcpyDeviceToHost, hp.st[s]));
+            const cudaError_t e =
+                (out_host_pitch == out_width && out_dev_pitch == out_width)
+                    ? cudaMemcpyAsync(dst, hp.d_out[s], size_t(nr) * out_width, cudaMemcpyDeviceToHost, hp.st[s])
+                    : cudaMemcpy2DAsync(dst, out_host_pitch, hp.d_out[s], out_dev_pitch, out_width, size_t(nr),
+                                        cudaMemcpyDeviceToHost, hp.st[s]);
+            if (e != cudaSuccess) {
+                rc = fail(ZAFB_E_CUDA, "host pipeline: D2H copy failed: %s", cudaGetErrorString(e));
+                break;
+            }
         }
     }
     const auto t2 = std::chrono::steady_clock::now();

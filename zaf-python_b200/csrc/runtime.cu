@@ -170,6 +170,14 @@ int zafb_device_count(int* count) {
 }
 
 int zafb_init(int device) {
+    // One process drives one GPU (one process per GPU is the multi-GPU model): plans, the host pipeline, the
+    // per-kernel shared-memory attributes and the SM count are per-device state cached for the life of the process,
+    // so a second zafb_init on ANOTHER device is refused instead of silently reusing device-0 tables.
+    static std::atomic<int> bound{-1};
+    int expected = -1;
+    if (!bound.compare_exchange_strong(expected, device) && expected != device)
+        return fail(ZAFB_E_UNSUPPORTED, "this process is bound to device %d; zafb_init(%d) refused (one process per GPU)",
+                    expected, device);
     ZAFB_CUDA(cudaSetDevice(device));
     ZAFB_CUDA(cudaFree(nullptr));
     int major = 0;

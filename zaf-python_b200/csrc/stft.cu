@@ -29,7 +29,12 @@
 #include <type_traits>
 #include <vector>
 
+#if defined(__x86_64__) || defined(__i386__)
 #include <emmintrin.h>
+#define ZAFB_HOST_SSE 1
+#else
+#define ZAFB_HOST_SSE 0  // aarch64 (Grace) and other hosts: the plain loops below, vectorised by the host compiler
+#endif
 #include <sched.h>
 
 #include "fft_core.cuh"
@@ -1132,6 +1137,7 @@ namespace {
 // out[N - k] = conj(out[k]), k = 1 .. N/2 - 1, for `frames` consecutive frame-major frames (N a multiple of 4).
 // Streaming 16-byte stores when the frames are 16-byte aligned: the mirrored half is written once and not read again here.
 void mirror_fill(float2* out, int64_t frames, int64_t n) {
+#if ZAFB_HOST_SSE
     const bool aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
     const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));  // negate the imaginary parts
     for (int64_t f = 0; f < frames; ++f) {
@@ -1147,17 +1153,26 @@ void mirror_fill(float2* out, int64_t frames, int64_t n) {
         }
     }
     _mm_sfence();
+#else
+    for (int64_t f = 0; f < frames; ++f) {
+        float2* o = out + f * n;
+        for (int64_t k = 1; k < n / 2; ++k) o[n - k] = make_float2(o[k].x, -o[k].y);
+    }
+#endif
 }
 
 // BIN_MAJOR twin: rows [r_lo, r_hi) of the flattened (clip, k) index, k = 1 .. N/2 - 1: row N - k of the clip = conj(row k).
 void mirror_fill_rows(float2* out, int64_t nt, int64_t n, int64_t r_lo, int64_t r_hi) {
+#if ZAFB_HOST_SSE
     const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));
+#endif
     const int64_t per_clip = n / 2 - 1;
     for (int64_t r = r_lo; r < r_hi; ++r) {
         const int64_t clip = r / per_clip, k = 1 + (r - clip * per_clip);
         const float2* src = out + (clip * n + k) * nt;
         float2* dst = out + (clip * n + (n - k)) * nt;
         int64_t j = 0;
+#if ZAFB_HOST_SSE
         if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 && nt > 0) {  // peel one element: the rest of the row is 16-byte aligned
             dst[0] = make_float2(src[0].x, -src[0].y);
             j = 1;
@@ -1168,9 +1183,12 @@ void mirror_fill_rows(float2* out, int64_t nt, int64_t n, int64_t r_lo, int64_t 
             if (aligned) _mm_stream_ps(reinterpret_cast<float*>(dst + j), v);
             else _mm_storeu_ps(reinterpret_cast<float*>(dst + j), v);
         }
+#endif
         for (; j < nt; ++j) dst[j] = make_float2(src[j].x, -src[j].y);
     }
+#if ZAFB_HOST_SSE
     _mm_sfence();
+#endif
 }
 
 // Fill threads: ZAFB_HOST_MIRROR_THREADS, else min(16, host cores / processes sharing the host), where the process count
@@ -1186,6 +1204,10 @@ int host_mirror_threads() {
     cpu_set_t set;  // the cores this process may run on (a container's affinity mask can be smaller than the machine)
     CPU_ZERO(&set);
     if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+    // More than two ranks sharing one host: the aggregate D2H rate is bounded by the host's memory system, not by a
+    // rank's own PCIe link (SCALE_r01: 88-99 GB/s over 4-8 ranks), and the fill's extra read + write of the mirrored half
+    // makes that bound worse (N = 4 with the fill 4.84e6 frames/s < N = 8 without it 5.36e6): the full copy is used.
+    if (procs > 2) return 0;
     t = cores / procs;
     if (t > 16) t = 16;
     return t >= 6 ? t : 0;
