@@ -131,11 +131,21 @@ def _cpu_worker(args):
     mod, _ = cpu_module()
     calls, fn = _cpu_inputs(name, seed, clips, mod)  # inputs resident before timing
     units = 0
+    # one process per host core already uses every core: the BLAS behind np.matmul (zaf.py:373, 445) is held to one
+    # thread per process, otherwise cores x cores threads fight each other and the reference looks slower than it is
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        limit = None
     t0 = time.perf_counter()
     for a in calls:
         out = fn(*a)
         units += out.shape[-1] if name not in ("istft", "imdct") else a[0].shape[-1]  # frames
-    return units, time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    if limit is not None:
+        limit.restore_original_limits()
+    return units, dt
 
 
 def cpu_baseline(name="stft", clips_per_core=None, cores=None, pool=None, total_clips=None):
