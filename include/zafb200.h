@@ -133,6 +133,18 @@ int zafb_stft_host_f32(const zafb_stft_plan* plan, const float* x_host, int64_t 
 int zafb_istft_host_f32(const zafb_stft_plan* plan, const float* spec_host, int64_t n_clips,
                         int64_t nt, int layout, float* y_host, int64_t y_stride);
 
+/* One-sided spectra -- an explicit NON-reference extension (zaf.stft always returns the two-sided
+ * spectrum, zaf.py:139): bins 0 .. floor(N/2) of every frame, FRAME_MAJOR, `pitch` complex64 elements between consecutive
+ * frames (pitch >= N/2 + 1; pitch == N lets a peer write the lower half of a two-sided buffer in place).  The warp kernels
+ * store / load the half directly -- half the HBM traffic of the spectrum; zafb_spec_mirror_f32 rebuilds the two-sided form
+ * (dst[k] = src[k], dst[N-k] = conj(src[k]); src == dst with src_pitch == N fills the upper half in place). */
+int zafb_stft_onesided_f32(const zafb_stft_plan* plan, const float* x, int64_t n_clips, int64_t ns,
+                           int64_t clip_stride, float* out, int64_t out_pitch, void* stream);
+int zafb_istft_onesided_f32(const zafb_stft_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
+                            int64_t spec_pitch, float* y, int64_t y_stride, void* stream);
+int zafb_spec_mirror_f32(const float* src, int64_t src_pitch, int64_t frames, int64_t window_length,
+                         float* dst, void* stream);
+
 /* The host-side half of that path, usable on its own: given `frames` frame-major frames of `window_length` complex64
  * bins (window_length a multiple of 4) whose bins 0 .. N/2 are valid, writes bins N/2+1 .. N-1 as conj of bins
  * N/2-1 .. 1 -- the two-sided spectrum zaf.stft returns (zaf.py:139) from a one-sided one.  No device involved. */

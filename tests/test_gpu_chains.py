@@ -143,3 +143,46 @@ def test_to_host_out_respects_row_padding(zaf_gpu):
         y.to_host(out=np.empty((3, y.cols), np.float32))
     with pytest.raises(ValueError):
         zaf.mdct(zaf.to_device(x.astype(np.float64)), w)  # float64 device input is refused, not reinterpreted
+
+
+@pytest.mark.parametrize("n,hop", [(2048, 512), (1024, 512), (4096, 1024), (512, 64), (256, 64), (2048, 300), (100, 25), (63, 10)])
+def test_onesided_stft_istft(zaf_gpu, n, hop):
+    """onesided=True (explicit non-reference mode): rows 0 .. N/2 of the reference's spectrum,
+    bit-identical to the two-sided result's lower rows on the warp kernels; spec_mirror rebuilds the two-sided spectrum
+    bit for bit; the one-sided inverse equals the reference's inverse of the Hermitian-completed spectrum."""
+    zaf = zaf_gpu
+    rng = np.random.default_rng(n + hop)
+    x = rng.uniform(-1, 1, (3, 20000)).astype(np.float32)
+    w = oracle.hamming_periodic(n) if n % 2 == 0 else np.hanning(n + 2)[1:-1]
+    bins = n // 2 + 1
+    full = zaf.stft(x, w, hop)
+    half = zaf.stft(x, w, hop, onesided=True)
+    assert half.shape == (3, bins, full.shape[-1]) and half.dtype == np.complex64
+    assert np.array_equal(half, full[:, :bins])
+    for c in range(3):
+        assert_parity(half[c], oracle.stft(x[c], w, hop)[:bins])
+    xd = zaf.to_device(x)
+    hd = zaf.stft(xd, w, hop, onesided=True)
+    assert np.array_equal(hd.to_host(), half)
+    mirrored = zaf.spec_mirror(hd, n).to_host()
+    if n in (256, 512, 1024, 2048, 4096):  # the warp kernels store the upper rows as exact conjugates of the lower ones
+        assert np.array_equal(mirrored, full)
+    else:                                  # the generic kernels compute every bin on its own
+        assert np.array_equal(mirrored[:, :bins], full[:, :bins])
+        for c in range(3):
+            assert_parity(mirrored[c], oracle.stft(x[c], w, hop))
+    # inverse: device and host inputs
+    y_full = zaf.istft(full, w, hop)
+    y_dev = zaf.istft(hd, w, hop, onesided=True).to_host()
+    y_host = zaf.istft(half, w, hop, onesided=True)
+    assert y_dev.shape == y_full.shape and np.array_equal(y_dev, y_host)
+    for c in range(3):
+        ref = oracle.istft(oracle.stft(x[c], w, hop), w, hop)
+        assert_parity(y_dev[c], ref)
+    # a one-sided spectrum with non-zero imaginary parts in the DC and Nyquist rows: Re(ifft) drops them (zaf.py:223)
+    spec = (rng.standard_normal((bins, 40)) + 1j * rng.standard_normal((bins, 40))).astype(np.complex64)
+    two = np.concatenate((spec, np.conj(spec[(n - 1) // 2:0:-1])))
+    assert two.shape[0] == n
+    assert_parity(zaf.istft(spec, w, hop, onesided=True), oracle.istft(two.astype(np.complex128), w, hop))
+    with pytest.raises(ValueError):
+        zaf.istft(spec[:-1], w, hop, onesided=True)

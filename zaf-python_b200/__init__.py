@@ -36,7 +36,7 @@ __all__ = [
     "stft", "istft", "melfilterbank", "melspectrogram", "mfcc", "cqtkernel", "cqtspectrogram",
     "cqtchromagram", "dct", "dst", "mdct", "imdct", "init", "device_count", "synchronize",
     "to_device", "empty", "from_pcm16", "DeviceArray", "PinnedArray", "Stream", "Event", "launch_count", "host_copy_bytes",
-    "spec_abs", "spec_mask", "ratio_min", "multiply", "quantize", "count_mismatch",
+    "spec_abs", "spec_mask", "spec_mirror", "ratio_min", "multiply", "quantize", "count_mismatch",
     "stft_geometry", "istft_geometry", "mdct_geometry", "imdct_geometry", "cqt_geometry", "dist", "shard_range",
 ]
 
@@ -202,15 +202,49 @@ def _device_matrix(s, dtype, what):
 
 
 # ------------------------------------------------------------------ STFT / ISTFT
-def stft(audio_signal, window_function, step_length, *, layout="frame_major", stream=None, out=None):
+def _stft_onesided(plan, w, audio_signal, step_length, layout, stream):
+    """Bins 0 .. N/2 only (non-reference extension), frame-major memory [clip][frame][N/2+1]."""
+    if layout != "frame_major":
+        raise ValueError("onesided=True returns frame-major memory (layout='frame_major')")
+    n = len(w)
+    bins = n // 2 + 1
+    on_device = isinstance(audio_signal, DeviceArray)
+    if on_device:
+        x = audio_signal
+        one, batch, ns = _device_signal(x)
+    else:
+        host, one = _signal_batch(audio_signal)
+        batch, ns = host.shape
+        x = to_device(host, stream=stream)
+    nt = stft_geometry(ns, n, step_length)[1]
+    out = DeviceArray((nt, bins) if one else (batch, nt, bins), np.complex64, transposed=True)
+    _lib.check(_lib.lib().zafb_stft_onesided_f32(plan, C.c_void_p(x.ptr), batch, ns, x.pitch, C.c_void_p(out.ptr), bins,
+                                                 _stream_ptr(stream)))
+    if on_device:
+        return out
+    res = out.to_host(stream=stream)
+    if stream is not None:
+        stream.synchronize()
+    x.free()
+    out.free()
+    return res
+
+
+def stft(audio_signal, window_function, step_length, *, layout="frame_major", stream=None, out=None, onesided=False):
     """Short-time Fourier transform -- drop-in for ``zaf.stft`` (zaf.py:45-141).
 
     Returns the full two-sided spectrum of shape (window_length, number_times) [complex64];
     centre padding floor(N/2), number of frames and tail padding follow zaf.py:99-121 exactly.
     ``out=`` supplies the result memory: a NumPy array (e.g. pinned) on the host path, a DeviceArray
-    on the device path.
+    on the device path.  ``onesided=True`` is an explicit NON-reference mode: only rows 0 .. N/2 are
+    computed and returned, shape (window_length/2 + 1, number_times) -- the other rows of the reference's
+    result are their conjugate mirror (``spec_mirror`` rebuilds them) -- at half the spectrum's memory traffic.
     """
     plan, w = _stft_plan(window_function, step_length)
+    if onesided:
+        if out is not None:
+            raise ValueError("out= is not supported with onesided=True")
+        return _stft_onesided(plan, w, audio_signal, step_length, layout, stream)
     lay = _layout_id(layout)
     n = len(w)
     if isinstance(audio_signal, DeviceArray):
@@ -260,14 +294,68 @@ def _spec_memory(audio_stft, dtype):
     return np.ascontiguousarray(a), LAYOUT_BIN_MAJOR, one, a.shape
 
 
-def istft(audio_stft, window_function, step_length, *, stream=None):
+def _istft_onesided(plan, w, audio_stft, step_length, stream):
+    n = len(w)
+    bins = n // 2 + 1
+    on_device = isinstance(audio_stft, DeviceArray)
+    if on_device:
+        s = audio_stft
+        one, batch = _device_matrix(s, np.complex64, "(N/2+1, nt) or (B, N/2+1, nt)")
+        if not s.transposed:
+            raise ValueError("a one-sided device spectrum must be frame-major (as stft(..., onesided=True) returns it)")
+        shape = s.shape
+    else:
+        a = np.asarray(audio_stft)
+        if a.ndim not in (2, 3):
+            raise ValueError("expected shape (N/2+1, nt) or (batch, N/2+1, nt)")
+        one = a.ndim == 2
+        a = a[None] if one else a
+        batch, shape = a.shape[0], a.shape
+        mem = np.ascontiguousarray(np.swapaxes(a, 1, 2), dtype=np.complex64)  # frame-major memory
+        d = to_device(mem, stream=stream)
+        s = DeviceArray(d.mem_shape, np.complex64, ptr=d.ptr, owner=d, transposed=True)
+    if shape[-2] != bins:
+        raise ValueError(f"a one-sided spectrum has {bins} rows for a window of {n} samples, not {shape[-2]}")
+    nt = shape[-1]
+    length = istft_geometry(n, nt, step_length)[2]
+    pitch = _even(length)
+    out = DeviceArray((pitch,) if one else (batch, pitch), np.float32, cols=length)
+    _lib.check(_lib.lib().zafb_istft_onesided_f32(plan, C.c_void_p(s.ptr), batch, nt, bins, C.c_void_p(out.ptr), pitch,
+                                                  _stream_ptr(stream)))
+    if on_device:
+        return out
+    y = out.to_host(stream=stream)
+    if stream is not None:
+        stream.synchronize()
+    out.free()
+    return y
+
+
+def spec_mirror(audio_stft_onesided, window_length, *, stream=None):
+    """The reference's two-sided spectrum (window_length rows) from a one-sided, frame-major device spectrum:
+    rows N-k = conj(rows k), ON the device."""
+    s = audio_stft_onesided
+    n = int(window_length)
+    one, batch = _device_matrix(s, np.complex64, "(N/2+1, nt) or (B, N/2+1, nt)")
+    if not s.transposed or s.shape[-2] != n // 2 + 1:
+        raise ValueError("expected the frame-major (N/2+1, nt) result of stft(..., onesided=True)")
+    nt = s.shape[-1]
+    out = DeviceArray((nt, n) if one else (batch, nt, n), np.complex64, transposed=True)
+    _lib.check(_lib.lib().zafb_spec_mirror_f32(C.c_void_p(s.ptr), n // 2 + 1, batch * nt, n, C.c_void_p(out.ptr), _stream_ptr(stream)))
+    return out
+
+
+def istft(audio_stft, window_function, step_length, *, stream=None, onesided=False):
     """Inverse STFT by constant overlap-add -- drop-in for ``zaf.istft`` (zaf.py:144-243).
 
     Output length nt*hop - (N - hop); only the real part of the inverse transform is kept, no
     synthesis window, division by sum(w[0:N:hop]) -- all as in the reference (including its
-    N-hop trim, which makes the round trip an identity only for hop = N/2).
+    N-hop trim, which makes the round trip an identity only for hop = N/2).  ``onesided=True``
+    (non-reference mode) takes rows 0 .. N/2 only and treats the rest as their conjugate mirror.
     """
     plan, w = _stft_plan(window_function, step_length)
+    if onesided:
+        return _istft_onesided(plan, w, audio_stft, step_length, stream)
     n = len(w)
     if isinstance(audio_stft, DeviceArray):
         s = audio_stft
@@ -486,7 +574,10 @@ def dst(audio_signal, dst_type):
 _MEL_ROUTES = {"fused": 0, "tensor": 1}
 
 
-def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused", precision="float32"):
+_MEL_PRECISIONS = {"auto": 0, "float32": 32, "float64": 64}
+
+
+def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused", precision="auto"):
     w = _window64(window_function)
     fb = mel_filterbank.toarray() if hasattr(mel_filterbank, "toarray") else np.asarray(mel_filterbank)  # zaf.py:373
     fb = np.ascontiguousarray(fb, dtype=np.float64)
@@ -494,16 +585,16 @@ def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients,
         raise ValueError(f"mel_filterbank must have shape (number_mels, window_length/2 = {len(w) // 2})")
     if route not in _MEL_ROUTES:
         raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
-    if precision not in ("float32", "float64"):
-        raise ValueError("precision must be 'float32' or 'float64'")
+    if precision not in _MEL_PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_MEL_PRECISIONS)}")
     key = ("mel", len(w), int(step_length), int(number_coefficients), route, precision, w.tobytes(), fb.tobytes())
     fresh = key not in _mel_plans._d
     plan = _mel_plans.get(key, w.ctypes.data, len(w), int(step_length), fb.ctypes.data, fb.shape[0],
                           int(number_coefficients))
     if fresh and route != "fused":
         _lib.check(_lib.lib().zafb_mel_plan_set_route(plan, _MEL_ROUTES[route]))
-    if fresh and precision == "float64":
-        _lib.check(_lib.lib().zafb_mel_plan_set_precision(plan, 64, w.ctypes.data))
+    if fresh:
+        _lib.check(_lib.lib().zafb_mel_plan_set_precision(plan, _MEL_PRECISIONS[precision], w.ctypes.data))
     return plan, w, fb.shape[0]
 
 
@@ -530,7 +621,7 @@ def _mel_like(fn, audio_signal, window_function, step_length, mel_filterbank, nc
 
 
 def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *, layout="frame_major", stream=None,
-                   route="fused", precision="float32"):
+                   route="fused", precision="auto"):
     """Mel spectrogram -- drop-in for ``zaf.melspectrogram`` (zaf.py:324-375): filterbank times the
     magnitude of STFT rows 1..N/2 (no DC, with Nyquist).  Returns (number_mels, number_times).
     ``route="tensor"`` applies the filterbank as the dense product of zaf.py:373 on the tcgen05 tensor
@@ -541,11 +632,13 @@ def melspectrogram(audio_signal, window_function, step_length, mel_filterbank, *
 
 
 def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coefficients, *,
-         layout="frame_major", stream=None, route="fused", precision="float32"):
+         layout="frame_major", stream=None, route="fused", precision="auto"):
     """MFCCs -- drop-in for ``zaf.mfcc`` (zaf.py:378-454): orthonormal DCT-II over the mel axis of
     ln(filterbank @ |STFT|^2 + eps), rows 1..number_coefficients.  Returns (number_coefficients, number_times).
-    ``precision="float64"``: spectrum, filterbank sums and logarithm in double precision on the GPU -- for purely tonal
-    signals, whose quietest mel bands sit at the fp32 floor of the FFT and get amplified by the logarithm."""
+    ``precision="auto"`` (default): fp32 kernels, and every frame whose quietest mel band lies more than 80 dB below its
+    strongest bin -- the fp32 floor of the FFT, which the logarithm would amplify (purely tonal material) -- is recomputed
+    in double precision by a second kernel on the same stream, so the 1e-5 bar holds for any signal.  ``"float64"``
+    computes every frame in double precision, ``"float32"`` none (the dense tensor-core route is always fp32)."""
     ncoef = int(number_coefficients)
     return _mel_like("zafb_mfcc_f32", audio_signal, window_function, step_length, mel_filterbank, ncoef,
                      lambda n_mels: max(0, min(ncoef, n_mels - 1)), layout, stream, route, precision)

@@ -40,7 +40,15 @@ struct zafb_cqt_plan {
     int* d_sched = nullptr;        // rows sorted by decreasing band length, dealt to the 16 warps longest-first
     int* d_sched_cnt = nullptr;    // rows per warp
     int sched_stride = 0;
-    int force_kernel = 0;          // 0 auto, 1 generic, 2 register-FFT kernel (tests)
+    int force_kernel = 0;          // 0 auto, 1 generic, 2 register-FFT kernel, 3 even/odd kernel (tests)
+    // even/odd kernel (L = 32768): W_8192^{tl k1} at [k1 * 32 + tl], W_256^{th k1} at [k1 * 8 + th], W_256^{t0 k2} at [k2 * 16 + t0]
+    float2* d_eo_t1 = nullptr;
+    float2* d_eo_t2 = nullptr;
+    float2* d_eo_t3 = nullptr;
+    int* d_eo_seg_xoff = nullptr;  // per thread (256): offset of its band segment in the unpacked-bin array
+    float* d_eo_seg_w = nullptr;   // segment weights transposed, [i][thread], i < eo_seg rounded up to 8, zero-padded
+    int2* d_eo_row_seg = nullptr;  // per row: (first segment, number of segments)
+    int eo_seg = 0;                // segment length (odd), 0 = the kernel cannot serve this operator
     // tensor-core route: the kernel as a dense real (n_freqs x kp) operand over the columns [col_lo, col_hi] the bands
     // touch, TF32 hi/lo halves; the spectrum's real and imaginary parts are two rows of the other operand
     int route = 0;
@@ -401,6 +409,271 @@ cqt32768_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// L = 32768, real kernels whose bands stay below L/2 (every kernel zaf.cqtkernel builds): the even/odd kernel.
+//
+// Only the bins the bands touch are needed (22 ... 3235 of 32768 at BASELINE cfg 5), and they are all even or odd bins of
+// the frame's spectrum X.  One decimation-in-frequency step on the REAL frame x[0 .. L) with H = L/2, Q = L/4 splits it
+// into two complex transforms of Q = 8192 points -- half the shared memory of the 16384-point form, so TWO CTAs of 256
+// threads fit on an SM and their barrier phases overlap:
+//   even bins  X[2k'] = RFFT_H(s)[k'],  s[n] = x[n] + x[n+H]: the usual packed form z[m] = s[2m] + i s[2m+1],
+//              Z = FFT_Q(z), X[2k'] = E + W_H^{k'} O with E, O from Z[k'] and conj(Z[Q-k']);
+//   odd bins   X[2k'+1] = Y[k'] = sum_n d[n] W_L^{n(2k'+1)},  d[n] = x[n] - x[n+H]: an odd-frequency DFT of a real
+//              sequence, which is ONE complex FFT_Q with no unpacking: v[n] = (d[n] - i d[n+Q]) W_L^n, V = FFT_Q(v),
+//              Y[2q] = V[q], Y[2q+1] = conj(V[Q-1-q])          (validated in float64 against numpy.fft).
+// FFT_Q, 8192 = 32 x 16 x 16, 32 points per thread and pass, butterflies in registers (fft_reg):
+//   n = t + 256 c, t = t0 + 16 t1,  k = k1 + 32 k2 + 512 k3
+//   pass 1  thread t: FFT-32 over c -> k1, times W_8192^{t k1}                         -> buf[k1][t]
+//   pass 2  item (k1, t0): FFT-16 over t1 -> k2, times W_256^{t0 k2}                   -> buf[k1][t0 + 16 k2]   (in place)
+//   pass 3  item (k1, k2): FFT-16 over t0 -> k3                                        -> buf[k1][16 k2 + k3]   (in place)
+// Rows of buf have a pitch of 257 complex values: every access of every pass is base + constant and conflict-free (half
+// warps run along t, t0 or k1).  The needed bins are unpacked into a small natural-order staging array that the band
+// phase (one warp per kernel row) reads with unit stride; the band weights come from global memory (L1 / L2).
+// ------------------------------------------------------------------------------------------
+constexpr int kEoThreads = 256;
+constexpr int kEoQ = 8192;
+constexpr int kEoPitch = 257;
+constexpr int kEoBuf = 32 * kEoPitch;  // float2
+constexpr int kEoPad = 512;            // zeroed entries behind the unpacked bins (>= the longest segment, rounded up to 8)
+
+__device__ __forceinline__ int eo_addr(int k) { return (k & 31) * kEoPitch + ((k >> 5) & 15) * 16 + (k >> 9); }
+
+// passes 1 (store side), 2 and 3 of FFT_Q on v[c] = point t + 256 c
+__device__ __forceinline__ void eo_fft8192(float2 (&v)[32], float2* __restrict__ buf, const float2* __restrict__ s_t1,
+                                           const float2* __restrict__ s_t2, const float2* __restrict__ s_t3, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    fft_reg<32>(v);
+    {
+        float2* b = buf + tid;
+        static_for<0, 32>([&](auto kc) {
+            constexpr int k1 = decltype(kc)::value;
+            float2 y = v[bitrev(k1, 5)];
+            if constexpr (k1 > 0) y = cmul(cmul(y, s_t1[k1 * 32 + lane]), s_t2[k1 * 8 + warp]);
+            b[k1 * kEoPitch] = y;
+        });
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // pass 2: item (k1, t0); both items unrolled so that the second one's loads overlap the first FFT
+        const int i = tid + kEoThreads * h;
+        const int k1 = i >> 4, t0 = i & 15;
+        float2* b = buf + k1 * kEoPitch + t0;
+        float2 u[16];
+#pragma unroll
+        for (int t1 = 0; t1 < 16; ++t1) u[t1] = b[16 * t1];
+        fft_reg<16>(u);
+        const float2* tw = s_t3 + t0;
+        static_for<0, 16>([&](auto kc) {
+            constexpr int k2 = decltype(kc)::value;
+            float2 y = u[bitrev(k2, 4)];
+            if constexpr (k2 > 0) y = cmul(y, tw[k2 * 16]);
+            b[16 * k2] = y;
+        });
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // pass 3: item (k1, k2)
+        const int j = tid + kEoThreads * h;
+        float2* b = buf + (j & 31) * kEoPitch + 16 * (j >> 5);
+        float2 u[16];
+#pragma unroll
+        for (int t0 = 0; t0 < 16; ++t0) u[t0] = b[t0];
+        fft_reg<16>(u);
+        static_for<0, 16>([&](auto kc) {
+            constexpr int k3 = decltype(kc)::value;
+            b[k3] = u[bitrev(k3, 4)];
+        });
+    }
+    __syncthreads();
+}
+
+// EXPORT = true (tensor-core route): stops after the unpack and writes Re X[k] and Im X[k], k in [col_lo, col_hi], as rows
+// 2 f and 2 f + 1 of the TF32 hi / lo matrices a_hi / a_lo (row pitch kp), like cqt32768_kernel<true>.
+template <bool EXPORT>
+__global__ void __launch_bounds__(kEoThreads, 2)
+cqt_eo_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int64_t step, int64_t front,
+              const float2* __restrict__ t1, const float2* __restrict__ t2, const float2* __restrict__ t3,
+              const float2* __restrict__ tw_full, const int* __restrict__ band_lo, const int* __restrict__ band_len,
+              const int* __restrict__ band_off, const float* __restrict__ weights_re, const int* __restrict__ seg_xoff,
+              const float* __restrict__ seg_w, const int2* __restrict__ row_seg, int seg, int n_freqs, int octave,
+              int col_lo, int col_hi,
+              float* __restrict__ out, int layout, int64_t total_frames, float* __restrict__ a_hi, float* __restrict__ a_lo,
+              int64_t kp) {
+    extern __shared__ float2 smem2[];
+    constexpr int L = 32768, H = L / 2, Q = kEoQ;
+    float2* buf = smem2;                    // kEoBuf
+    float2* s_t1 = buf + kEoBuf;            // 1024
+    float2* s_t2 = s_t1 + 1024;             // 256
+    float2* s_t3 = s_t2 + 256;              // 256
+    float2* xs = s_t3 + 256;                // col_hi - col_lo + 1 unpacked bins, natural order
+    // (kEoPad more entries behind the last bin: the zero-weight tail of a row's last segment reads them; they stay zero)
+    float2* part = xs + (col_hi - col_lo + 1) + kEoPad;                // one partial sum per thread
+    float* q = reinterpret_cast<float*>(part + kEoThreads);            // n_freqs magnitudes (chromagram fold)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kEoPad; i += kEoThreads) xs[(col_hi - col_lo + 1) + i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < 1024; i += kEoThreads) s_t1[i] = t1[i];
+    if (tid < 256) {
+        s_t2[tid] = t2[tid];
+        s_t3[tid] = t3[tid];
+    }
+    const float2 w_t = tw_full[tid];  // W_L^t
+    // bins k = 2 k' (even) and 2 k' + 1 (odd) inside [col_lo, col_hi]
+    const int e_lo = (col_lo + 1) >> 1, e_hi = col_hi >> 1;
+    const int o_lo = col_lo >> 1, o_hi = (col_hi - 1) >> 1;
+    __syncthreads();
+
+    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * step - front;
+        const float* xc = x + clip * clip_stride;
+        const bool inside = start >= 0 && start + L <= ns;
+        float2 v[32];
+        // ---- even bins: z[m] = s[2m] + i s[2m+1], s[n] = x[n] + x[n + H]
+        if (inside && ((reinterpret_cast<uintptr_t>(xc + start) & 7) == 0)) {
+            const float2* p = reinterpret_cast<const float2*>(xc + start) + tid;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float2 a = __ldg(p + 256 * c), b = __ldg(p + 256 * c + H / 2);
+                v[c] = make_float2(a.x + b.x, a.y + b.y);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int64_t s0 = start + 2 * (tid + 256 * c);
+                auto ld = [&](int64_t s) { return (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f; };
+                v[c] = make_float2(ld(s0) + ld(s0 + H), ld(s0 + 1) + ld(s0 + 1 + H));
+            }
+        }
+        eo_fft8192(v, buf, s_t1, s_t2, s_t3, tid);
+        for (int k = e_lo + tid; k <= e_hi; k += kEoThreads) {  // X[2k] = E + W_H^k O
+            float2 r;
+            if (k == 0) {
+                const float2 z0 = buf[0];
+                r = make_float2(z0.x + z0.y, 0.f);
+            } else {
+                const float2 zk = buf[eo_addr(k)], zp = buf[eo_addr(Q - k)];
+                const float2 e = make_float2(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+                const float2 od = make_float2(0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+                r = cadd(e, cmul(__ldg(tw_full + 2 * k), od));
+            }
+            xs[2 * k - col_lo] = r;
+        }
+        // ---- odd bins: v[n] = (d[n] - i d[n + Q]) W_L^n, d[n] = x[n] - x[n + H]; W_L^n = W_L^t W_128^c
+        if (inside) {
+            const float* p = xc + start + tid;
+            static_for<0, 32>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const float d1 = __ldg(p + 256 * c) - __ldg(p + 256 * c + H);
+                const float d2 = __ldg(p + 256 * c + Q) - __ldg(p + 256 * c + Q + H);
+                const float2 u = make_float2(fmaf(d2, w_t.y, d1 * w_t.x), fmaf(-d2, w_t.x, d1 * w_t.y));
+                v[c] = mul_tw<c, 128>(u);
+            });
+        } else {
+            static_for<0, 32>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const int64_t s0 = start + tid + 256 * c;
+                auto ld = [&](int64_t s) { return (s >= 0 && s < ns) ? __ldg(xc + s) : 0.f; };
+                const float d1 = ld(s0) - ld(s0 + H);
+                const float d2 = ld(s0 + Q) - ld(s0 + Q + H);
+                const float2 u = make_float2(fmaf(d2, w_t.y, d1 * w_t.x), fmaf(-d2, w_t.x, d1 * w_t.y));
+                v[c] = mul_tw<c, 128>(u);
+            });
+        }
+        __syncthreads();  // the even unpack has read buf
+        eo_fft8192(v, buf, s_t1, s_t2, s_t3, tid);
+        for (int k = o_lo + tid; k <= o_hi; k += kEoThreads) {  // X[2k+1] = Y[k]: V[k/2] or conj(V[Q-1-(k-1)/2])
+            float2 r;
+            if (k & 1) {
+                r = buf[eo_addr(Q - 1 - (k >> 1))];
+                r.y = -r.y;
+            } else {
+                r = buf[eo_addr(k >> 1)];
+            }
+            xs[2 * k + 1 - col_lo] = r;
+        }
+        __syncthreads();
+        if constexpr (EXPORT) {
+            float* rh = a_hi + 2 * f * kp;
+            float* rl = a_lo + 2 * f * kp;
+            for (int c = tid; c < int(kp); c += kEoThreads) {
+                float2 X = make_float2(0.f, 0.f);  // padding columns beyond col_hi stay zero
+                if (col_lo + c <= col_hi) X = xs[c];
+                uint32_t h, l;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(X.x));
+                float hv = __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(X.x - hv));
+                rh[c] = hv;
+                rl[c] = __uint_as_float(l);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(X.y));
+                hv = __uint_as_float(h);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(X.y - hv));
+                rh[kp + c] = hv;
+                rl[kp + c] = __uint_as_float(l);
+            }
+            __syncthreads();  // xs is rewritten by the next frame's even unpack
+            continue;
+        }
+        // ---- banded kernel rows, one SEGMENT per thread: a row is cut into segments of `seg` consecutive columns (seg odd:
+        // the lanes of a warp then read xs from distinct banks), at most one segment per thread, so the whole contraction is
+        // `seg` multiply-adds per thread with no cross-lane traffic.  The weights are stored transposed, wT[i][thread]
+        // (zero-padded to a multiple of 8 rows): coalesced loads from L1 / L2, eight in flight per thread.
+        {
+            const float2* X = xs + seg_xoff[tid];
+            const float* wp = seg_w + tid;
+            float ar = 0.f, ai = 0.f;
+            for (int i0 = 0; i0 < seg; i0 += 8) {
+                float wv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) wv[i] = __ldg(wp + (i0 + i) * kEoThreads);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 xv = X[i0 + i];
+                    ar = fmaf(wv[i], xv.x, ar);
+                    ai = fmaf(wv[i], xv.y, ai);
+                }
+            }
+            part[tid] = make_float2(ar, ai);
+        }
+        __syncthreads();
+        if (tid < n_freqs) {  // row sums over the row's segments, in segment order
+            const int2 rs = __ldg(row_seg + tid);  // (first segment, number of segments)
+            float ar = 0.f, ai = 0.f;
+            for (int i = 0; i < rs.y; ++i) {
+                const float2 pv = part[rs.x + i];
+                ar += pv.x;
+                ai += pv.y;
+            }
+            const float mag = sqrtf(ar * ar + ai * ai);
+            if (octave > 0) q[tid] = mag;
+            else if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_freqs + tid] = mag;
+            else out[(clip * int64_t(n_freqs) + tid) * nt + j] = mag;
+        }
+        for (int r = kEoThreads + tid; r < n_freqs; r += kEoThreads) {  // more rows than threads (not the case for zaf.cqtkernel's grids)
+            const int2 rs = __ldg(row_seg + r);
+            float ar = 0.f, ai = 0.f;
+            for (int i = 0; i < rs.y; ++i) {
+                const float2 pv = part[rs.x + i];
+                ar += pv.x;
+                ai += pv.y;
+            }
+            const float mag = sqrtf(ar * ar + ai * ai);
+            if (octave > 0) q[r] = mag;
+            else if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_freqs + r] = mag;
+            else out[(clip * int64_t(n_freqs) + r) * nt + j] = mag;
+        }
+        if (octave > 0) {
+            __syncthreads();
+            for (int i = tid; i < octave; i += kEoThreads) {
+                float acc = 0.f;
+                for (int r = i; r < n_freqs; r += octave) acc += q[r];  // zaf.py:693-698
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * octave + i] = acc;
+                else out[(clip * octave + i) * nt + j] = acc;
+            }
+        }
+        // q[] and xs are rewritten only after the next frame's barriers
+    }
+}
+
 // tensor-core route: magnitude (and optional chroma fold, zaf.py:693-698) of the product rows (Re, Im) per frame
 __global__ void cqt_magnitude_kernel(const float* __restrict__ c, int64_t frames, int n_freqs, int octave, int64_t nt,
                                      int64_t frame0, float* __restrict__ out, int layout) {
@@ -428,6 +701,8 @@ int set_kernel_attrs() {
     ZAFB_CUDA(cudaFuncSetAttribute(cqt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(cqt32768_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt_eo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(cqt_eo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -551,30 +826,91 @@ int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_lengt
                 if (rc == ZAFB_OK) rc = upload_vec(&p->d_kern_lo, lo_);
             }
         }
-        // longest-processing-time-first deal of the rows to the 16 warps
-        constexpr int kW = kRegThreads / 32;
-        std::vector<int> order(n_freqs);
-        for (int64_t r = 0; r < n_freqs; ++r) order[r] = int(r);
-        std::stable_sort(order.begin(), order.end(), [&](int x1, int x2) { return len[x1] > len[x2]; });
-        std::vector<std::vector<int>> lists(kW);
-        std::vector<int64_t> load(kW, 0);
-        for (int r : order) {
-            int best = 0;
-            for (int wv = 1; wv < kW; ++wv)
-                if (load[wv] < load[best]) best = wv;
-            lists[best].push_back(r);
-            load[best] += (len[r] + 31) / 32 + 1;  // iterations + the reduction
+        // longest-processing-time-first deal of the rows to the warps of a CTA (16 for the register-FFT kernel, 8 for the
+        // even/odd kernel)
+        auto deal = [&](int n_warps, int** d_sched, int** d_cnt, int* stride) -> int {
+            std::vector<int> order(n_freqs);
+            for (int64_t r = 0; r < n_freqs; ++r) order[r] = int(r);
+            std::stable_sort(order.begin(), order.end(), [&](int x1, int x2) { return len[x1] > len[x2]; });
+            std::vector<std::vector<int>> lists(n_warps);
+            std::vector<int64_t> load(n_warps, 0);
+            for (int r : order) {
+                int best = 0;
+                for (int wv = 1; wv < n_warps; ++wv)
+                    if (load[wv] < load[best]) best = wv;
+                lists[best].push_back(r);
+                load[best] += (len[r] + 31) / 32 + 1;  // iterations + the reduction
+            }
+            size_t longest = 1;
+            for (auto& l : lists) longest = l.size() > longest ? l.size() : longest;
+            std::vector<int> sched(n_warps * longest, 0), cnt(n_warps, 0);
+            for (int wv = 0; wv < n_warps; ++wv) {
+                cnt[wv] = int(lists[wv].size());
+                for (size_t i = 0; i < lists[wv].size(); ++i) sched[wv * longest + i] = lists[wv][i];
+            }
+            *stride = int(longest);
+            int r2 = upload_vec(d_sched, sched);
+            if (r2 == ZAFB_OK) r2 = upload_vec(d_cnt, cnt);
+            return r2;
+        };
+        if (rc == ZAFB_OK) rc = deal(kRegThreads / 32, &p->d_sched, &p->d_sched_cnt, &p->sched_stride);
+        if (rc == ZAFB_OK && real && p->d_kern_hi != nullptr) {
+            // even/odd kernel: every row cut into segments of `seg` columns, at most kEoThreads segments in all; seg is the
+            // smallest odd length that fits (odd: consecutive segments of a row start in different shared-memory banks)
+            int seg = 0;
+            for (int cand = 1; cand <= kEoPad - 8; cand += 2) {
+                int64_t count = 0;
+                for (int64_t r = 0; r < n_freqs; ++r) count += len[r] > 0 ? (len[r] + cand - 1) / cand : 0;
+                if (count <= kEoThreads) {
+                    seg = cand;
+                    break;
+                }
+            }
+            if (seg > 0) {
+                const int seg8 = (seg + 7) & ~7;
+                std::vector<int> xoff(kEoThreads, 0);
+                std::vector<float> wt(size_t(seg8) * kEoThreads, 0.f);
+                std::vector<int2> rs(n_freqs, make_int2(0, 0));
+                int next = 0;
+                for (int64_t r = 0; r < n_freqs; ++r) {
+                    const int count = len[r] > 0 ? (len[r] + seg - 1) / seg : 0;
+                    rs[r] = make_int2(next, count);
+                    for (int sg = 0; sg < count; ++sg, ++next) {
+                        xoff[next] = lo[r] - p->col_lo + sg * seg;
+                        for (int e = 0; e < seg && sg * seg + e < len[r]; ++e)
+                            wt[size_t(e) * kEoThreads + next] = w[off[r] + sg * seg + e].x;
+                    }
+                }
+                p->eo_seg = seg;
+                rc = upload_vec(&p->d_eo_seg_xoff, xoff);
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_eo_seg_w, wt);
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_eo_row_seg, rs);
+            }
         }
-        size_t longest = 1;
-        for (auto& l : lists) longest = l.size() > longest ? l.size() : longest;
-        std::vector<int> sched(kW * longest, 0), cnt(kW, 0);
-        for (int wv = 0; wv < kW; ++wv) {
-            cnt[wv] = int(lists[wv].size());
-            for (size_t i = 0; i < lists[wv].size(); ++i) sched[wv * longest + i] = lists[wv][i];
+        if (rc == ZAFB_OK) {  // twiddles of the even/odd kernel's 8192-point transforms
+            std::vector<double> e1(2 * 1024), e2(2 * 256), e3(2 * 256);
+            for (int k1 = 0; k1 < 32; ++k1) {
+                for (int tl = 0; tl < 32; ++tl) {
+                    const double ang = -2.0 * pi * double(tl * k1) / 8192.0;
+                    e1[2 * (k1 * 32 + tl)] = std::cos(ang);
+                    e1[2 * (k1 * 32 + tl) + 1] = std::sin(ang);
+                }
+                for (int th = 0; th < 8; ++th) {
+                    const double ang = -2.0 * pi * double((th * k1) % 256) / 256.0;
+                    e2[2 * (k1 * 8 + th)] = std::cos(ang);
+                    e2[2 * (k1 * 8 + th) + 1] = std::sin(ang);
+                }
+            }
+            for (int k2 = 0; k2 < 16; ++k2)
+                for (int t0 = 0; t0 < 16; ++t0) {
+                    const double ang = -2.0 * pi * double(t0 * k2) / 256.0;
+                    e3[2 * (k2 * 16 + t0)] = std::cos(ang);
+                    e3[2 * (k2 * 16 + t0) + 1] = std::sin(ang);
+                }
+            rc = upload_c32(&p->d_eo_t1, e1.data(), 1024);
+            if (rc == ZAFB_OK) rc = upload_c32(&p->d_eo_t2, e2.data(), 256);
+            if (rc == ZAFB_OK) rc = upload_c32(&p->d_eo_t3, e3.data(), 256);
         }
-        p->sched_stride = int(longest);
-        if (rc == ZAFB_OK) rc = upload_vec(&p->d_sched, sched);
-        if (rc == ZAFB_OK) rc = upload_vec(&p->d_sched_cnt, cnt);
     }
     if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, fft_length, m + 1);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
@@ -604,6 +940,12 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
     cudaFree(p->d_sched_cnt);
     cudaFree(p->d_kern_hi);
     cudaFree(p->d_kern_lo);
+    cudaFree(p->d_eo_t1);
+    cudaFree(p->d_eo_t2);
+    cudaFree(p->d_eo_t3);
+    cudaFree(p->d_eo_seg_xoff);
+    cudaFree(p->d_eo_seg_w);
+    cudaFree(p->d_eo_row_seg);
     delete p;
     return ZAFB_OK;
 }
@@ -617,9 +959,9 @@ int zafb_cqt_plan_set_route(zafb_cqt_plan* p, int route) {
     return ZAFB_OK;
 }
 
-// test hook: 0 = auto, 1 = generic kernel only, 2 = require the register-FFT kernel
+// test hook: 0 = auto, 1 = generic kernel only, 2 = require the register-FFT kernel, 3 = require the even/odd kernel
 int zafb_cqt_plan_force_kernel(zafb_cqt_plan* p, int which) {
-    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 2, "bad plan / kernel id");
+    ZAFB_REQUIRE(p != nullptr && which >= 0 && which <= 3, "bad plan / kernel id");
     p->force_kernel = which;
     return ZAFB_OK;
 }
@@ -654,6 +996,26 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
             smem_reg += size_t(p->packed) * sizeof(float);
         }
         if (p->force_kernel == 2 && !ok) return fail(ZAFB_E_UNSUPPORTED, "cqt register-FFT kernel needs fft_length 32768");
+        // even/odd kernel: real weights, every band inside [0, L/2), the unpacked bins fit next to the 64 KB transform buffer
+        const int64_t nb = int64_t(p->col_hi) - p->col_lo + 1;
+        const size_t smem_eo = size_t(kEoBuf + 1536 + (nb > 0 ? nb : 0) + kEoPad + kEoThreads) * sizeof(float2) +
+                               size_t((p->n_freqs + 1) & ~int64_t(1)) * sizeof(float) + 16;
+        const bool eo_ok = ok && p->real_weights && p->d_eo_t1 != nullptr && p->eo_seg > 0 && p->d_kern_hi != nullptr &&
+                           p->col_hi < p->fft_length / 2 && p->col_lo >= 0 && smem_eo <= size_t(kMaxDynSmem);
+        if (p->force_kernel == 3 && !eo_ok)
+            return fail(ZAFB_E_UNSUPPORTED, "cqt even/odd kernel needs fft_length 32768 and a real kernel with bands below fft_length/2");
+        const bool use_eo = eo_ok && (p->force_kernel == 3 || (p->force_kernel == 0 && env_flag("ZAFB_CQT_EO", 1)));
+        auto launch_eo = [&](auto kern, const float* xs, int64_t frames, float* o, float* ah, float* al, cudaStream_t st) {
+            // two CTAs per SM when the shared memory allows it (it does for every kernel zaf.cqtkernel builds up to ~4700 bins)
+            const int64_t per_sm = 2 * (smem_eo + 1024) <= size_t(232448) ? 2 : 1;
+            const int64_t cap = int64_t(sm_count()) * per_sm;
+            const int64_t grid = frames < cap ? frames : cap;
+            kern<<<unsigned(grid), kEoThreads, smem_eo, st>>>(
+                xs, ns, clip_stride, nt, p->step, front, p->d_eo_t1, p->d_eo_t2, p->d_eo_t3, p->d_tw_full, p->d_band_lo,
+                p->d_band_len, p->d_band_off, p->d_weights_re, p->d_eo_seg_xoff, p->d_eo_seg_w, p->d_eo_row_seg, (p->eo_seg + 7) & ~7,
+                int(p->n_freqs), int(octave_resolution), p->col_lo, p->col_hi, o, layout, frames, ah, al, p->kp);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        };
         if (p->route == ZAFB_CQT_ROUTE_TENSOR) {
             // The kernel application as a dense contraction on the tensor cores (BASELINE cfg 5: "sparse CQT kernel as packed
             // tensor-core GEMM"): per chunk of clips (1) cqt32768_kernel<true>: FFT + real-input split, Re / Im of the bins
@@ -685,13 +1047,17 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
                                   (smem_split ? split_bytes : 0);
             for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += clips_per) {
                 const int64_t nc = std::min(clips_per, n_clips - c0), frames = nc * nt;
-                const int64_t grid = frames < int64_t(sm_count()) ? frames : int64_t(sm_count());
-                cqt32768_kernel<true><<<unsigned(grid), kRegThreads, smem_x, st>>>(
-                    x + c0 * clip_stride, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo,
-                    p->d_band_len, p->d_band_off, p->d_weights, p->d_weights_re, int(p->packed), 0, smem_split, p->d_sched,
-                    p->d_sched_cnt, p->sched_stride, int(nf), 0, p->pair_lo, p->pair_hi, nullptr, layout, frames, a_hi, a_lo,
-                    p->col_lo, p->col_hi, kp);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
+                if (use_eo) {
+                    launch_eo(cqt_eo_kernel<true>, x + c0 * clip_stride, frames, nullptr, a_hi, a_lo, st);
+                } else {
+                    const int64_t grid = frames < int64_t(sm_count()) ? frames : int64_t(sm_count());
+                    cqt32768_kernel<true><<<unsigned(grid), kRegThreads, smem_x, st>>>(
+                        x + c0 * clip_stride, ns, clip_stride, nt, p->step, front, p->d_t1, p->d_t2, p->d_tw_full, p->d_band_lo,
+                        p->d_band_len, p->d_band_off, p->d_weights, p->d_weights_re, int(p->packed), 0, smem_split, p->d_sched,
+                        p->d_sched_cnt, p->sched_stride, int(nf), 0, p->pair_lo, p->pair_hi, nullptr, layout, frames, a_hi, a_lo,
+                        p->col_lo, p->col_hi, kp);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
                 rc = gemm3xtf32(a_hi, a_lo, kp, p->d_kern_hi, p->d_kern_lo, kp, cbuf, nf, 2 * frames, nf, kp, st);
                 if (rc == ZAFB_OK) {
                     const int rows = octave_resolution > 0 ? int(octave_resolution) : int(nf);
@@ -705,6 +1071,11 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
             cudaFreeAsync(ws, st);
             if (rc == ZAFB_OK) ZAFB_CUDA(cudaGetLastError());
             return rc;
+        }
+        if (use_eo) {
+            launch_eo(cqt_eo_kernel<false>, x, total, out, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+            ZAFB_CUDA(cudaGetLastError());
+            return ZAFB_OK;
         }
         if (ok && p->force_kernel != 1) {
             const int64_t grid = total < int64_t(sm_count()) ? total : int64_t(sm_count());

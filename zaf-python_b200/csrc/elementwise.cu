@@ -111,6 +111,22 @@ __global__ void binary_kernel(const float* __restrict__ a, const float* __restri
     for (int64_t i = done + tid; i < n; i += nth) out[i] = apply<OP>(a[i], OP == kOpQuantize ? 0.f : b[i], step);
 }
 
+// two-sided frames from one-sided ones: dst[f][k] = src[f][k] (k <= n/2, skipped when src == dst) and
+// dst[f][n - k] = conj(src[f][k]) (1 <= k <= (n - 1) / 2); reads ascend, mirrored writes descend, both coalesced
+__global__ void mirror_kernel(const float2* __restrict__ src, int64_t src_pitch, int64_t frames, int n, float2* __restrict__ dst,
+                              int copy_low) {
+    const int half = n / 2 + 1;
+    const int last_mirrored = (n - 1) / 2;
+    const int64_t total = frames * half;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t f = i / half;
+        const int k = int(i - f * half);
+        const float2 v = src[f * src_pitch + k];
+        if (copy_low) dst[f * n + k] = v;
+        if (k >= 1 && k <= last_mirrored) dst[f * n + (n - k)] = make_float2(v.x, -v.y);
+    }
+}
+
 __global__ void mismatch_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n,
                                 unsigned long long* __restrict__ count) {
     unsigned long long local = 0;
@@ -189,6 +205,18 @@ int zafb_mul_f32(const float* a, const float* b, int64_t n, float* out, void* st
 int zafb_quantize_f32(const float* x, int64_t n, float step, float* out, void* stream) {
     ZAFB_REQUIRE(step > 0.f, "quantiser step must be > 0");
     return launch_binary<kOpQuantize>(x, nullptr, n, step, out, stream);
+}
+
+int zafb_spec_mirror_f32(const float* src, int64_t src_pitch, int64_t frames, int64_t n, float* dst, void* stream) {
+    ZAFB_REQUIRE(frames >= 0 && n >= 1 && n < (int64_t(1) << 30), "bad frame geometry");
+    ZAFB_REQUIRE(src_pitch >= n / 2 + 1, "src_pitch %lld < %lld one-sided bins", (long long)src_pitch, (long long)(n / 2 + 1));
+    if (frames == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(src != nullptr && dst != nullptr, "src/dst is NULL");
+    ZAFB_REQUIRE(src != dst || src_pitch == n, "in place needs src_pitch == window_length");
+    mirror_kernel<<<unsigned(grid_for(frames * (n / 2 + 1))), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(src), src_pitch, frames, int(n), reinterpret_cast<float2*>(dst), src != dst ? 1 : 0);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
 }
 
 int zafb_count_mismatch_u32(const void* a, const void* b, int64_t n_words, int64_t* count, void* stream) {

@@ -193,6 +193,38 @@ __device__ __forceinline__ void warp_fft512(float2 (&v)[16], const float2* __res
     fft_reg<16>(v);
 }
 
+// The same four-step FFT in double precision (the float64 route of mfcc).  buf: 16 x kFft1024Pitch double2,
+// tw[k1 * 32 + n2] = W_512^{k1 n2} in double.  In / out conventions as warp_fft512.
+__device__ __forceinline__ void warp_fft512_f64(double2 (&v)[16], const double2* __restrict__ tw, double2* buf, int lane) {
+    fft_reg<16>(v);
+    static_for<0, 16>([&](auto k1c) {
+        constexpr int k1 = decltype(k1c)::value;
+        double2 y = v[bitrev(k1, 4)];
+        if constexpr (k1 > 0) y = cmul(y, tw[k1 * 32 + lane]);
+        buf[k1 * kFft1024Pitch + lane] = y;
+    });
+    __syncwarp();
+    const double2* row = buf + (lane & 15) * kFft1024Pitch;
+    const bool odd = lane >= 16;
+    const double sgn = odd ? -1.0 : 1.0;
+    static_for<0, 16>([&](auto nc) {
+        constexpr int n2 = decltype(nc)::value;
+        const double2 a = row[n2];
+        const double2 b = row[n2 + 16];
+        const double2 d = make_double2(fma(sgn, b.x, a.x), fma(sgn, b.y, a.y));
+        if constexpr (n2 == 0) {
+            v[n2] = d;
+        } else {
+            constexpr double cr = ct::cos2pi(n2, 32), ci = -ct::sin2pi(n2, 32);
+            const double wr = odd ? cr : 1.0;
+            const double wi = odd ? ci : 0.0;
+            v[n2] = make_double2(d.x * wr - d.y * wi, d.x * wi + d.y * wr);
+        }
+    });
+    __syncwarp();
+    fft_reg<16>(v);
+}
+
 // ---------------------------------------------------------------- one warp, 256 complex points
 // Four-step FFT 256 = 8 x 32 by ONE warp.  In: v[r] = x[lane + 32 r], r < 8.  Out: X[lane + 32 k] is v[bitrev(k, 3)].
 // tw[k1 * 32 + n2] = W_256^{k1 n2} (shared memory, 8 x 32); buf: 8 x kFft1024Pitch float2.

@@ -44,11 +44,13 @@ struct zafb_mel_plan {
     int qm4 = 0;                    // float4 per quarter of the folded mel axis: ceil(half_mels / 16)
     int half_mels = 0;              // ceil(n_mels / 2)
     int force_kernel = 0;           // 0 auto, 1 generic, 2 warp (tests)
-    // float64 route (ZAFB_MEL_PRECISION_F64): window and twiddles in double, any power-of-two window length
-    int precision = 32;
+    // float64 route: window and twiddles in double, any power-of-two window length.  precision 0 = automatic (mfcc: fp32,
+    // then the frames whose quietest mel band lies below the fp32 floor of the FFT are recomputed in float64), 32, 64.
+    int precision = 0;
     double* d_window64 = nullptr;
     double2* d_tw_half64 = nullptr;  // W_{N/2}^t
     double2* d_tw_full64 = nullptr;  // W_N^t, t < N/2
+    double2* d_tw_4step64 = nullptr; // N = 1024: W_512^{k1 n2}, [k1][n2]
     // tensor-core route (ZAFB_MEL_ROUTE_TENSOR): the filterbank and the MFCC DCT rows as dense TF32 hi/lo operands
     int route = 0;
     float* d_fb_hi = nullptr;       // n_mels x (n/2)
@@ -68,16 +70,22 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
                                  const float2* __restrict__ tw_full, const int* __restrict__ band_lo,
                                  const int* __restrict__ band_len, const int* __restrict__ band_off,
                                  const float* __restrict__ weights, const float* __restrict__ dct, int n_mels, int n_coef,
-                                 int mode, float* __restrict__ out, int layout, int64_t total_frames) {
+                                 int mode, float* __restrict__ out, int layout, int64_t total_frames,
+                                 int* __restrict__ risk_count, int* __restrict__ risk_list, float risk_ratio) {
     extern __shared__ float2 smem2[];
     const int n = 1 << log2n, m = n >> 1;
     float2* a = smem2;
     float2* b = smem2 + m;
     float* spec = reinterpret_cast<float*>(smem2 + 2 * m);  // m floats: column c <-> FFT bin c + 1
     float* mel = spec + m;                                  // n_mels floats
+    __shared__ unsigned s_pmax, s_emin;                     // fp32 bit patterns of non-negative values order like integers
     const int tid = threadIdx.x, nth = blockDim.x;
     const int rows = mode == 0 ? n_mels : n_coef;
     for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        if (tid == 0) {
+            s_pmax = 0u;
+            s_emin = 0x7f800000u;
+        }
         const int64_t clip = f / nt, j = f - clip * nt;
         const int64_t start = j * hop - m;
         const float* xc = x + clip * clip_stride;
@@ -105,6 +113,7 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
             }
             const float p = re * re + im * im;
             spec[k - 1] = mode == 0 ? sqrtf(p) : p;
+            if (risk_count != nullptr) atomicMax(&s_pmax, __float_as_uint(p));
         }
         __syncthreads();
         for (int r = tid; r < n_mels; r += nth) {
@@ -117,10 +126,15 @@ __global__ void mel_frame_kernel(const float* __restrict__ x, int64_t ns, int64_
                 else out[(clip * n_mels + r) * nt + j] = acc;
             } else {
                 mel[r] = acc + 2.220446049250313e-16f;  // np.finfo(float).eps, zaf.py:445
+                if (risk_count != nullptr && acc > 0.f) atomicMin(&s_emin, __float_as_uint(acc));  // exact zeros are ln(eps) in either precision
             }
         }
         if (mode == 1) {
             __syncthreads();
+            // a mel band below risk_ratio x the strongest bin sits at the fp32 floor of this FFT: the frame is queued for the
+            // float64 kernel that runs next on the stream and overwrites this frame's coefficients
+            if (risk_count != nullptr && tid == 0 && __uint_as_float(s_emin) < risk_ratio * __uint_as_float(s_pmax))
+                risk_list[atomicAdd(risk_count, 1)] = int(f);
             // ln(mel_r) - ln(mel_0) instead of ln(mel_r): rows k >= 1 of the DCT-II matrix sum to zero, so the
             // constant drops out exactly, and the log of a ratio keeps ~1e-7 absolute accuracy where the log
             // itself (values ~10) only has ~1e-6 in fp32.
@@ -158,7 +172,8 @@ __global__ void mel_frame_kernel_f64(const float* __restrict__ x, int64_t ns, in
                                      const double2* __restrict__ tw_full, const int* __restrict__ band_lo,
                                      const int* __restrict__ band_len, const int* __restrict__ band_off,
                                      const float* __restrict__ weights, const float* __restrict__ dct, int n_mels, int n_coef,
-                                     int mode, float* __restrict__ out, int layout, int64_t total_frames) {
+                                     int mode, float* __restrict__ out, int layout, int64_t total_frames,
+                                     const int* __restrict__ list, const int* __restrict__ list_count) {
     extern __shared__ double2 smem_d[];
     const int n = 1 << log2n, m = n >> 1;
     double2* a = smem_d;
@@ -167,7 +182,9 @@ __global__ void mel_frame_kernel_f64(const float* __restrict__ x, int64_t ns, in
     double* mel = spec + m;                                    // n_mels doubles
     const int tid = threadIdx.x, nth = blockDim.x;
     const int rows = mode == 0 ? n_mels : n_coef;
-    for (int64_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+    const int64_t n_items = list != nullptr ? int64_t(*list_count) : total_frames;  // all frames, or the queued ones
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int64_t f = list != nullptr ? int64_t(list[it]) : it;
         const int64_t clip = f / nt, j = f - clip * nt;
         const int64_t start = j * hop - m;
         const float* xc = x + clip * clip_stride;
@@ -258,7 +275,7 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
                 const float2* __restrict__ tw_full, const float* __restrict__ wt, const int* __restrict__ lo_tab,
                 int4 grp_len, int4 grp_off, int wt_total, const float4* __restrict__ dh, int n_mels, int half_mels,
                 int n_coef, int dct_shape, float* __restrict__ out, int64_t total_frames,
-                float* __restrict__ out_lo) {
+                float* __restrict__ out_lo, int* __restrict__ risk_count, int* __restrict__ risk_list, float risk_ratio) {
     const int tgroups = dct_shape >> 8, qm4 = dct_shape & 255;  // MFCC DCT: coefficient groups of 8, float4 per mel quarter
     constexpr int M = N / 2, REGS = M / 32, LOGR = clog2(REGS);
     static_assert(N == 512 || N == 1024 || N == 2048, "warp kernels exist for window lengths 512, 1024 and 2048");
@@ -335,6 +352,7 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
         // X[k] = E + W_N^k O,  E = Z[k] + conj(Z[M-k]),  O = -i (Z[k] - conj(Z[M-k])),  k = lane + 32 kap;
         // column c = k - 1 (zaf.py:370 drops DC, keeps Nyquist); lane 0 / kap 0 produces the Nyquist bin instead of DC.
         const int src = (32 - lane) & 31;
+        float pmax = 0.f;  // strongest bin of the frame (MODE 1: the reference level of the fp32-floor test below)
         static_for<0, REGS>([&](auto kc) {
             constexpr int kap = decltype(kc)::value;
             const float2 z = v[bitrev(kap, LOGR)];
@@ -349,6 +367,7 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
             float2 xk = cadd(e, t);
             if (kap == 0 && lane == 0) xk = csub(e, t);  // X[M] = E[0] - O[0]
             const float p2 = xk.x * xk.x + xk.y * xk.y;
+            if constexpr (MODE == 1 && !SPLIT) pmax = fmaxf(pmax, p2);
             // (the spectrum overwrites the transpose tile: every lane finished reading it inside the FFT)
             const int col = (kap == 0 && lane == 0) ? M - 1 : lane + 32 * kap - 1;
             s_spec[col] = MODE == 0 ? sqrtf(p2) : p2;
@@ -385,6 +404,21 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
             for (int g = 0; g < 4; ++g)
                 if (lane + 32 * g < n_mels) o[lane + 32 * g] = mel[g];
         } else {
+            if (risk_count != nullptr) {
+                // A mel band below risk_ratio x the strongest bin sits at the fp32 floor of this FFT (a bin is resolved to
+                // ~1e-8 of the peak amplitude) and the logarithm would turn that into an absolute error: the frame is queued
+                // for the float64 kernel that runs next on the stream and overwrites this frame's coefficients.
+                float emin = 3.4e38f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    if (lane + 32 * g < n_mels && mel[g] > 0.f) emin = fminf(emin, mel[g]);  // an exact zero (silence, an empty row) is ln(eps) in either precision
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+                    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+                }
+                if (lane == 0 && emin < risk_ratio * pmax) risk_list[atomicAdd(risk_count, 1)] = int(f);
+            }
             // ln(mel_r + eps) - ln(mel_0 + eps): rows k >= 1 of the DCT-II matrix sum to zero, so the constant drops
             // out exactly, and the log of a ratio keeps fp32 absolute accuracy where the log itself does not.
             const float ref0 = __shfl_sync(0xffffffffu, mel[0], 0) + 2.220446049250313e-16f;
@@ -444,6 +478,108 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// N = 1024 in double precision, one warp per frame: the mfcc frames the fp32 kernel queued (list != nullptr), or every
+// frame (precision = 64).  The pipeline of mel_warp_kernel with window, FFT (warp_fft512_f64), unpack, |X|^2 (or |X|),
+// filterbank sums, logarithm and DCT-II sums in FP64 (B200: half the FP32 rate); inputs, weights and outputs stay fp32.
+// ------------------------------------------------------------------------------------------
+constexpr int kWarps64 = 8;
+constexpr int kMelTile64 = 16 * kFft1024Pitch;  // double2 per warp
+
+__global__ void __launch_bounds__(kWarps64 * 32, 1)
+mel_warp_kernel_f64(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
+                    const double* __restrict__ window, const double2* __restrict__ tw4, const double2* __restrict__ tw_full,
+                    const int* __restrict__ band_lo, const int* __restrict__ band_len, const int* __restrict__ band_off,
+                    const float* __restrict__ weights, const float* __restrict__ dct, int n_mels, int n_coef, int mode,
+                    float* __restrict__ out, int64_t total_frames, const int* __restrict__ list,
+                    const int* __restrict__ list_count) {
+    constexpr int N = 1024, M = 512, REGS = 16, LOGR = 4;
+    extern __shared__ double2 smem_d[];
+    double2* s_tw = smem_d;                                   // 512: W_512^{k1 n2}
+    double2* s_win = smem_d + M;                              // 512: 0.5 * window pairs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double2* s_buf = smem_d + 2 * M + warp * kMelTile64;
+    double* s_spec = reinterpret_cast<double*>(s_buf);        // 512 doubles once the FFT is done, then 128 log-mel values
+    for (int i = tid; i < M; i += kWarps64 * 32) {
+        s_tw[i] = tw4[i];
+        s_win[i] = make_double2(0.5 * window[2 * i], 0.5 * window[2 * i + 1]);
+    }
+    const double2 c_lane = tw_full[lane];  // W_N^lane
+    __syncthreads();
+    const int rows = mode == 0 ? n_mels : n_coef;
+    const int64_t n_items = list != nullptr ? int64_t(*list_count) : total_frames;
+    for (int64_t it = int64_t(blockIdx.x) * kWarps64 + warp; it < n_items; it += int64_t(gridDim.x) * kWarps64) {
+        const int64_t f = list != nullptr ? int64_t(list[it]) : it;
+        const int64_t clip = f / nt, j = f - clip * nt;
+        const int64_t start = j * hop - M;
+        const float* xc = x + clip * clip_stride;
+        double2 v[REGS];
+#pragma unroll
+        for (int r = 0; r < REGS; ++r) {
+            const int64_t s0 = start + 2 * (lane + 32 * r);
+            const double x0 = (s0 >= 0 && s0 < ns) ? double(__ldg(xc + s0)) : 0.0;
+            const double x1 = (s0 + 1 >= 0 && s0 + 1 < ns) ? double(__ldg(xc + s0 + 1)) : 0.0;
+            const double2 w = s_win[lane + 32 * r];
+            v[r] = make_double2(x0 * w.x, x1 * w.y);
+        }
+        warp_fft512_f64(v, s_tw, s_buf, lane);  // Z[lane + 32 k] = v[bitrev(k, 4)]
+        const int src = (32 - lane) & 31;
+        static_for<0, REGS>([&](auto kc) {
+            constexpr int kap = decltype(kc)::value;
+            const double2 z = v[bitrev(kap, LOGR)];
+            const double2 mine = v[bitrev(REGS - 1 - kap, LOGR)];
+            double2 pz;
+            pz.x = __shfl_sync(0xffffffffu, mine.x, src);
+            pz.y = __shfl_sync(0xffffffffu, mine.y, src);
+            if (lane == 0) pz = v[bitrev((REGS - kap) & (REGS - 1), LOGR)];
+            const double2 e = make_double2(z.x + pz.x, z.y - pz.y);
+            const double2 od = make_double2(z.y + pz.y, pz.x - z.x);
+            const double2 t = cmul(mul_tw<kap, N / 32>(c_lane), od);
+            double2 xk = cadd(e, t);
+            if (kap == 0 && lane == 0) xk = csub(e, t);  // X[M] = E[0] - O[0]
+            const double p2 = xk.x * xk.x + xk.y * xk.y;
+            const int col = (kap == 0 && lane == 0) ? M - 1 : lane + 32 * kap - 1;
+            s_spec[col] = mode == 0 ? sqrt(p2) : p2;
+        });
+        __syncwarp();
+        double mel[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int r = lane + 32 * g;
+            double acc = 0.0;
+            if (r < n_mels) {
+                const int lo = band_lo[r], len = band_len[r];
+                const float* w = weights + band_off[r];
+                for (int c = 0; c < len; ++c) acc = fma(double(__ldg(w + c)), s_spec[lo + c], acc);
+            }
+            mel[g] = acc;
+        }
+        __syncwarp();  // every lane is done reading the spectrum
+        if (mode == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (lane + 32 * g < n_mels) out[f * n_mels + lane + 32 * g] = float(mel[g]);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (lane + 32 * g < n_mels) s_spec[lane + 32 * g] = log(mel[g] + 2.220446049250313e-16);  // zaf.py:445
+            __syncwarp();
+            for (int i = lane; i < n_coef; i += 32) {
+                const float* d = dct + int64_t(i) * n_mels;
+                double a0 = 0.0, a1 = 0.0;
+                int r = 0;
+                for (; r + 1 < n_mels; r += 2) {
+                    a0 = fma(double(__ldg(d + r)), s_spec[r], a0);
+                    a1 = fma(double(__ldg(d + r + 1)), s_spec[r + 1], a1);
+                }
+                if (r < n_mels) a0 = fma(double(__ldg(d + r)), s_spec[r], a0);
+                out[f * rows + i] = float(a0 + a1);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // tensor route, MFCC: ln((mel_r + eps) / (mel_0 + eps)) of a [frames][n_mels] matrix as TF32 hi/lo halves (pitch ld);
 // the common term ln(mel_0 + eps) drops out of DCT rows >= 1 exactly (their weights sum to zero).
 __global__ void mel_log_split_kernel(const float* __restrict__ mel, int64_t frames, int n_mels, int64_t ld,
@@ -467,6 +603,7 @@ int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(mel_frame_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA(cudaFuncSetAttribute(mel_warp_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(mel_warp_kernel<1024, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
@@ -530,7 +667,7 @@ int launch_tensor(const zafb_mel_plan* p, int mode, const float* x, int64_t n_cl
         kern<<<unsigned(ctas), kWarps * 32, smem, st>>>(x + c0 * clip_stride, ns, clip_stride, nt, int(p->hop),
                                                          reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                                                          p->d_wt, p->d_lo, zero4, zero4, 0, nullptr, int(n_mels), 0, 0, 0, spec_hi, frames,
-                                                         spec_lo);
+                                                         spec_lo, nullptr, nullptr, 0.f);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         float* mel_out = mode == 0 ? out + c0 * nt * n_mels : mel_buf;
         rc = gemm3xtf32(spec_hi, spec_lo, 512, p->d_fb_hi, p->d_fb_lo, 512, mel_out, n_mels, frames, n_mels, 512, st);
@@ -561,7 +698,28 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
     const int64_t rows = mode == 0 ? p->n_mels : p->n_coef;
     if (total == 0 || rows == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
-    if (p->precision == 64) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
+        if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->warp_ok && aligned && p->force_kernel != 1) {
+            // the reference's C-order memory: the frame-major kernels into scratch, then a tiled transpose
+            return bin_major_from_frame_major(out, n_clips, nt, rows, st, [&](int64_t c0, int64_t n, float* scratch) {
+                return launch(p, mode, x + c0 * clip_stride, n, ns, clip_stride, scratch, ZAFB_LAYOUT_FRAME_MAJOR, stream);
+            });
+        }
+    }
+    // float64 kernels: every frame (list == nullptr) or the frames queued in `list` (count read on the device)
+    auto launch_f64 = [&](float* o, int lay, const int* list, const int* list_count) -> int {
+        if (p->n == 1024 && p->n_mels <= 128 && lay == ZAFB_LAYOUT_FRAME_MAJOR && p->d_tw_4step64 != nullptr) {
+            const size_t smem64 = size_t(1024 + kWarps64 * kMelTile64) * sizeof(double2);
+            int64_t ctas = list != nullptr ? int64_t(sm_count()) : ceil_div(total, kWarps64);
+            if (ctas > int64_t(sm_count())) ctas = int64_t(sm_count());
+            mel_warp_kernel_f64<<<unsigned(ctas), kWarps64 * 32, smem64, st>>>(
+                x, ns, clip_stride, nt, int(p->hop), p->d_window64, p->d_tw_4step64, p->d_tw_full64, p->d_band_lo, p->d_band_len,
+                p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, o, total, list, list_count);
+            ZAFB_LAUNCH_CHECK();
+            return ZAFB_OK;
+        }
         const int mh = int(p->n / 2);
         const size_t smem64 = size_t(p->n) * sizeof(double2) + size_t(mh + p->n_mels) * sizeof(double) + 16;
         if (smem64 > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mel float64 route: window_length %lld too large", (long long)p->n);
@@ -569,25 +727,50 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
         if (th < 64) th = 64;
         if (th > 256) th = 256;
         const int64_t grid = total < int64_t(sm_count()) * 16 ? total : int64_t(sm_count()) * 16;
-        mel_frame_kernel_f64<<<unsigned(grid), th, smem64, static_cast<cudaStream_t>(stream)>>>(
+        mel_frame_kernel_f64<<<unsigned(grid), th, smem64, st>>>(
             x, ns, clip_stride, nt, p->hop, p->log2n, p->d_window64, p->d_tw_half64, p->d_tw_full64, p->d_band_lo, p->d_band_len,
-            p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, out, layout, total);
+            p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, o, lay, total, list, list_count);
         ZAFB_LAUNCH_CHECK();
         return ZAFB_OK;
+    };
+    if (p->precision == 64) return launch_f64(out, layout, nullptr, nullptr);
+    // precision 0 (automatic), mfcc only: the fp32 kernels queue the frames whose quietest mel band lies below the fp32
+    // floor of their FFT (risk_ratio x the strongest bin's power); the float64 kernel then recomputes exactly those
+    // frames, stream-ordered, no host round trip.  Scratch: a counter and one int per frame from the stream's pool.
+    const bool auto_f64 = mode == 1 && p->precision == 0 && p->route != ZAFB_MEL_ROUTE_TENSOR && total < (int64_t(1) << 31) &&
+                          p->d_window64 != nullptr;
+    int* risk = nullptr;
+    const float risk_ratio = 1e-8f;  // -80 dB: a band that far below the strongest bin has ~1e-4 relative error in fp32 (the bin floor is ~1e-8 of the peak amplitude)
+    if (auto_f64) {
+        static bool pool_ready = false;
+        if (!pool_ready) {  // keep the stream-ordered scratch in the pool between calls
+            int dev = 0;
+            cudaMemPool_t pool;
+            uint64_t keep = UINT64_MAX;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pool_ready = true;
+        }
+        ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&risk), size_t(total + 32) * sizeof(int), st));
+        ZAFB_CUDA(cudaMemsetAsync(risk, 0, sizeof(int), st));
     }
+    int* const risk_count = risk;
+    int* const risk_list = risk ? risk + 32 : nullptr;
+    auto finish = [&](int rc_fp32, float* o, int lay) -> int {  // the float64 pass over the queued frames, then the scratch goes back
+        int rc2 = rc_fp32;
+        if (risk != nullptr) {
+            if (rc2 == ZAFB_OK) rc2 = launch_f64(o, lay, risk_list, risk_count);
+            cudaFreeAsync(risk, st);
+        }
+        return rc2;
+    };
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
-        if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->warp_ok && aligned && p->force_kernel != 1) {
-            // the reference's C-order memory: the frame-major kernels into scratch, then a tiled transpose
-            return bin_major_from_frame_major(out, n_clips, nt, rows, static_cast<cudaStream_t>(stream),
-                                              [&](int64_t c0, int64_t n, float* scratch) {
-                                                  return launch(p, mode, x + c0 * clip_stride, n, ns, clip_stride, scratch,
-                                                                ZAFB_LAYOUT_FRAME_MAJOR, stream);
-                                              });
-        }
         const bool ok = p->warp_ok && layout == ZAFB_LAYOUT_FRAME_MAJOR && aligned;
-        if (p->force_kernel == 2 && !ok)
+        if (p->force_kernel == 2 && !ok) {
+            if (risk) cudaFreeAsync(risk, st);
             return fail(ZAFB_E_UNSUPPORTED, "mel warp kernel needs N = 512, 1024 or 2048, <=128 mels, <=64 coefficients, frame-major layout, even hop/stride");
+        }
         if (p->route == ZAFB_MEL_ROUTE_TENSOR) {
             if (!ok || p->d_fb_hi == nullptr)
                 return fail(ZAFB_E_UNSUPPORTED, "mel tensor-core route needs N=1024, <=128 mels, frame-major layout, even hop/stride");
@@ -615,24 +798,28 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
                 kern<<<unsigned(ctas), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
                     x, ns, clip_stride, nt, int(p->hop), reinterpret_cast<const float2*>(p->d_window), p->d_tw_4step, p->d_tw_n,
                     p->d_wt, p->d_lo, gl, go, wt_total, reinterpret_cast<const float4*>(p->d_dh), int(p->n_mels), p->half_mels,
-                    int(p->n_coef), (p->coef_pad << 8) | p->qm4, out, total, nullptr);
-                ZAFB_LAUNCH_CHECK();
-                return ZAFB_OK;
+                    int(p->n_coef), (p->coef_pad << 8) | p->qm4, out, total, nullptr, risk_count, risk_list, risk_ratio);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                return finish(cudaGetLastError() == cudaSuccess ? ZAFB_OK : fail(ZAFB_E_CUDA, "mel_warp_kernel launch failed"), out, layout);
             }
         }
     }
     const int m = int(p->n / 2);
     const size_t smem = size_t(p->n) * sizeof(float2) + size_t(m + p->n_mels) * sizeof(float) + 16;
-    if (smem > size_t(kMaxDynSmem)) return fail(ZAFB_E_UNSUPPORTED, "mel: window_length %lld too large", (long long)p->n);
+    if (smem > size_t(kMaxDynSmem)) {
+        if (risk) cudaFreeAsync(risk, st);
+        return fail(ZAFB_E_UNSUPPORTED, "mel: window_length %lld too large", (long long)p->n);
+    }
     int th = m / 4;
     if (th < 64) th = 64;
     if (th > 256) th = 256;
     const int64_t grid = total < int64_t(sm_count()) * 32 ? total : int64_t(sm_count()) * 32;
-    mel_frame_kernel<<<unsigned(grid), th, smem, static_cast<cudaStream_t>(stream)>>>(
+    mel_frame_kernel<<<unsigned(grid), th, smem, st>>>(
         x, ns, clip_stride, nt, p->hop, p->log2n, p->d_window, p->d_tw_half, p->d_tw_full, p->d_band_lo, p->d_band_len,
-        p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, out, layout, total);
-    ZAFB_LAUNCH_CHECK();
-    return ZAFB_OK;
+        p->d_band_off, p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, out, layout, total, risk_count, risk_list,
+        risk_ratio);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return finish(cudaGetLastError() == cudaSuccess ? ZAFB_OK : fail(ZAFB_E_CUDA, "mel_frame_kernel launch failed"), out, layout);
 }
 
 }  // namespace
@@ -686,6 +873,27 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct, d);
+    if (rc == ZAFB_OK) {  // the float64 tables (mfcc recomputes at-risk frames in double; precision = 64 runs everything there)
+        const int64_t h = n / 2;
+        std::vector<double2> th(h), tf(h);
+        for (int64_t t = 0; t < h; ++t) {
+            th[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(h)), std::sin(-2.0 * pi * double(t) / double(h)));
+            tf[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(n)), std::sin(-2.0 * pi * double(t) / double(n)));
+        }
+        std::vector<double> w64(window, window + n);
+        rc = upload_vec(&p->d_window64, w64);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_half64, th);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_full64, tf);
+        if (rc == ZAFB_OK && n == 1024) {
+            std::vector<double2> t4(h);
+            for (int64_t k1 = 0; k1 < h / 32; ++k1)
+                for (int64_t n2 = 0; n2 < 32; ++n2) {
+                    const double a = -2.0 * pi * double((k1 * n2) % h) / double(h);
+                    t4[k1 * 32 + n2] = make_double2(std::cos(a), std::sin(a));
+                }
+            rc = upload_vec(&p->d_tw_4step64, t4);
+        }
+    }
     if (rc == ZAFB_OK && (n == 512 || n == 1024 || n == 2048) && n_mels <= 128 && p->n_coef <= 64) {
         // row groups of 32 rows, zero-padded to the longest band of the group; the band start is clamped so that
         // lo + grp_len never leaves the 512-column spectrum (the padding weights are zero)
@@ -774,22 +982,8 @@ int zafb_mel_plan_force_kernel(zafb_mel_plan* p, int which) {
 
 int zafb_mel_plan_set_precision(zafb_mel_plan* p, int bits, const double* window) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
-    ZAFB_REQUIRE(bits == 32 || bits == 64, "precision must be 32 or 64 (got %d)", bits);
-    if (bits == 64 && p->d_window64 == nullptr) {
-        ZAFB_REQUIRE(window != nullptr, "the float64 route needs the window again (float64)");
-        const double pi = 3.14159265358979323846264338327950288;
-        const int64_t n = p->n, h = n / 2;
-        std::vector<double2> th(h), tf(h);
-        for (int64_t t = 0; t < h; ++t) {
-            th[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(h)), std::sin(-2.0 * pi * double(t) / double(h)));
-            tf[t] = make_double2(std::cos(-2.0 * pi * double(t) / double(n)), std::sin(-2.0 * pi * double(t) / double(n)));
-        }
-        std::vector<double> w(window, window + n);
-        int rc = upload_vec(&p->d_window64, w);
-        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_half64, th);
-        if (rc == ZAFB_OK) rc = upload_vec(&p->d_tw_full64, tf);
-        if (rc != ZAFB_OK) return rc;
-    }
+    ZAFB_REQUIRE(bits == 0 || bits == 32 || bits == 64, "precision must be 0 (automatic), 32 or 64 (got %d)", bits);
+    (void)window;  // the float64 tables are built from the window handed to zafb_mel_plan_create
     p->precision = bits;
     return ZAFB_OK;
 }
@@ -808,6 +1002,7 @@ int zafb_mel_plan_destroy(zafb_mel_plan* p) {
     cudaFree(p->d_window64);
     cudaFree(p->d_tw_half64);
     cudaFree(p->d_tw_full64);
+    cudaFree(p->d_tw_4step64);
     cudaFree(p->d_fb_hi);
     cudaFree(p->d_fb_lo);
     cudaFree(p->d_dct_hi);

@@ -127,7 +127,10 @@ template <int N, bool BULK, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, WarpGeom<N>::CTAS_PER_SM)
 stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                  const float2* __restrict__ win_half, const float2* __restrict__ tw4,
-                 const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int sequential) {
+                 const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int sequential,
+                 int64_t out_pitch, int onesided) {
+    // out_pitch: complex elements between consecutive frames of `out` (N for the reference's two-sided spectrum).
+    // onesided (non-reference extension, needs `sequential`): only bins 0 .. N/2 are stored.
     using G = WarpGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
     static_assert(!BULK || N == 2048, "the bulk-store variant is written for N = 2048");
@@ -204,7 +207,7 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
             // [1536,2048) = conj(X[k]) mirrored.  Two 4 KB halves of the warp's transpose tile ping-pong.
             float2* q0 = s_buf;
             float2* q1 = s_buf + 512;
-            float2* g = out + f * 2048;
+            float2* g = out + f * out_pitch;
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) q0[lane + 32 * k2] = v[bitrev(k2, 5)];
             fence_async_smem();
@@ -243,8 +246,9 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
             __syncwarp();
             continue;
         }
-        float2* o = out + f * N + lane;
-        float2* om = out + f * N + M - lane;
+        float2* const of = out + f * out_pitch;
+        float2* o = of + lane;
+        float2* om = of + M - lane;
         if (sequential) {
             // the same unpack, but the results first replace the registers they were computed from (descending k2,
             // see the bulk variant), then the frame is written in ascending address order, quarter by quarter
@@ -267,16 +271,20 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
                 constexpr int k2 = decltype(kc)::value;
                 st_stream(o + 32 * k2, v[bitrev(k2, LOGR)]);
             });
-            if (lane == 0) st_stream(out + f * N + M / 2, make_float2(2.f * zmid.x, -2.f * zmid.y));
+            if (lane == 0) st_stream(of + M / 2, make_float2(2.f * zmid.x, -2.f * zmid.y));
             static_for<0, REGS / 2>([&](auto ic) {            // (M/2, M): conj(X[k + M]) mirrored, ascending addresses
                 constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
                 if (k2 > 0 || lane != 0) st_stream(om - 32 * k2, cconj(v[bitrev(REGS - 1 - k2, LOGR)]));
             });
+            if (onesided) {                                   // bins 0 .. M only: the Nyquist bin X[M] closes the frame
+                if (lane == 0) st_stream(of + M, v[bitrev(REGS - 1, LOGR)]);
+                continue;
+            }
             static_for<0, REGS / 2>([&](auto kc) {            // [M, 3M/2): X[k + M]
                 constexpr int k2 = decltype(kc)::value;
                 st_stream(o + M + 32 * k2, v[bitrev(REGS - 1 - k2, LOGR)]);
             });
-            if (lane == 0) st_stream(out + f * N + M + M / 2, make_float2(2.f * zmid.x, 2.f * zmid.y));
+            if (lane == 0) st_stream(of + M + M / 2, make_float2(2.f * zmid.x, 2.f * zmid.y));
             static_for<0, REGS / 2>([&](auto ic) {            // (3M/2, N): conj(X[k]) mirrored
                 constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
                 if (k2 > 0 || lane != 0) st_stream(om + M - 32 * k2, cconj(v[bitrev(k2, LOGR)]));
@@ -305,8 +313,8 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
         });
         if (lane == 0) {  // k = M/2: Z[M/2] pairs with itself, w = -i
             const float2 z = v[bitrev(REGS / 2, LOGR)];
-            st_stream(out + f * N + M / 2, make_float2(2.f * z.x, -2.f * z.y));
-            st_stream(out + f * N + M + M / 2, make_float2(2.f * z.x, 2.f * z.y));
+            st_stream(of + M / 2, make_float2(2.f * z.x, -2.f * z.y));
+            st_stream(of + M + M / 2, make_float2(2.f * z.x, 2.f * z.y));
         }
     }
 }
@@ -530,7 +538,9 @@ template <int N, int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, istft_ctas_per_sm(N))
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
-                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch) {
+                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch, int64_t spec_pitch, int onesided) {
+    // spec_pitch: complex elements between consecutive frames (N for the two-sided spectrum).  onesided (non-reference
+    // extension): only bins 0 .. N/2 are given, the rest is their Hermitian mirror -- half the reads.
     using G = WarpGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
     constexpr int HOP = N / R;
@@ -568,10 +578,11 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
         int slot0 = int((h_begin - (R - 1)) % SLOTS);  // ring slot of block j
 
         for (int64_t j = h_begin - (R - 1); j < h_end; ++j) {
-            const float2* X = spec + (clip * nt + j) * N;
+            const float2* X = spec + (clip * nt + j) * spec_pitch;
             if (prefetch && j + 1 < h_end) {  // the next frame of this run towards L2: N * 8 / 128 lines, N / 512 per lane
 #pragma unroll
-                for (int i = 0; i < N / 512; ++i) prefetch_l2(X + N + (lane + 32 * i) * 16);  // (N = 512: one line per lane)
+                for (int i = 0; i < N / 512; ++i)  // (N = 512: one line per lane; one-sided frames are half as long)
+                    if (!onesided || (lane + 32 * i) * 16 <= M) prefetch_l2(X + spec_pitch + (lane + 32 * i) * 16);
             }
             float2 v[REGS];
             // r and REGS - 1 - r back to back: the mirrored loads (c, d) of one hit the lines the direct
@@ -581,11 +592,17 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
                 constexpr int r = (t % 2 == 0) ? t / 2 : REGS - 1 - t / 2;
                 const int k = lane + 32 * r;
                 const float2 a = __ldg(X + k);
-                const float2 b = __ldg(X + M + k);
                 const float2 c = __ldg(X + M - k);
-                const float2 d = __ldg(X + ((N - k) & (N - 1)));
-                const float2 h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
-                const float2 h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + M]
+                float2 h0, h1;
+                if (onesided) {  // X[N - k] = conj(X[k]), X[M + k] = conj(X[M - k]); k = 0 pairs X[0] and X[M] with themselves
+                    h0 = make_float2(2.f * a.x, k == 0 ? 0.f : 2.f * a.y);
+                    h1 = make_float2(2.f * c.x, k == 0 ? 0.f : -2.f * c.y);
+                } else {
+                    const float2 b = __ldg(X + M + k);
+                    const float2 d = __ldg(X + ((N - k) & (N - 1)));
+                    h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
+                    h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + M]
+                }
                 const float2 e = cadd(h0, h1);
                 const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, N / 32>(c_lane));
                 // conj(Z) = conj(e + i o)
@@ -841,7 +858,7 @@ int launch_stft_binmajor(const zafb_stft_plan* p, const float* x, int64_t n_clip
 
 template <int N, int R, int WARPS>
 int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                        int64_t y_stride, cudaStream_t st) {
+                        int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided) {
     static bool attr = false;
     if (!attr) {
         ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
@@ -871,19 +888,20 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
     istft_warp_kernel<N, R, WARPS><<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
-        env_flag("ZAFB_ISTFT_PREFETCH", 1));
+        env_flag("ZAFB_ISTFT_PREFETCH", 1), spec_pitch, onesided);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
 
 template <int N, int R>
 int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                      int64_t y_stride, cudaStream_t st) {
+                      int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided) {
     // N = 4096: 6 warps (a 17 KB transpose tile plus up to 14 KB of overlap-add ring per warp)
-    if constexpr (N == 4096) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
+    if constexpr (N == 4096) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
     else {
-        if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st);
-        return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st);
+        if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6)
+            return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
+        return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
     }
 }
 
@@ -959,8 +977,9 @@ int zafb_stft_plan_force_kernel(zafb_stft_plan* p, int which) {
     return ZAFB_OK;
 }
 
-int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
-                  float* out, int layout, void* stream) {
+// out_pitch / onesided: see stft_warp_kernel (warp kernels, FRAME_MAJOR only).  The public two-sided entry point passes (N, 0).
+static int stft_impl(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                     float* out, int layout, void* stream, int64_t out_pitch, int onesided) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
     ZAFB_REQUIRE(n_clips >= 0 && ns >= 0, "n_clips and ns must be >= 0");
     ZAFB_REQUIRE(clip_stride >= ns, "clip_stride %lld < ns %lld", (long long)clip_stride, (long long)ns);
@@ -983,9 +1002,10 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     if (warp_ok && p->force_kernel != 1) {
         // measured on cfg 2 (B200), profiles/r01_stft_experiments.txt: direct streaming stores 3.04-3.11 ms, TMA bulk stores
         // 3.13-3.20 ms; 6 warps per CTA 3.04, 8 -> 3.11, 10 -> 3.36, 4 -> 3.40.  The defaults are the fastest combination.
-        const int bulk = p->n == 2048 ? env_flag("ZAFB_STFT_BULK", 0) : 0;
+        const int bulk = (p->n == 2048 && !onesided && out_pitch == p->n) ? env_flag("ZAFB_STFT_BULK", 0) : 0;
         const int n = int(p->n);
-        auto run = [&](const float* xs, int64_t clips, float2* dst) -> int {
+        auto run = [&](const float* xs, int64_t clips, float2* dst, int64_t pitch = -1) -> int {
+            if (pitch < 0) pitch = n;
             const int64_t frames = clips * nt;
             const int warps = n == 4096 ? ZAFB_STFT4096_WARPS : (n == 2048 && !bulk && env_flag("ZAFB_STFT_WARPS", 6) == 6) ? 6 : 8;
             const size_t smem = (size_t(n) + size_t(warps) * (n / 64) * kFft1024Pitch) * sizeof(float2);
@@ -1001,11 +1021,12 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
                                                                              : stft_warp_kernel<2048, false, 8>);
             kern<<<static_cast<unsigned>(ctas), warps * 32, smem, st>>>(
                 xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
-                env_flag("ZAFB_STFT_SEQ", 1));
+                onesided ? 1 : env_flag("ZAFB_STFT_SEQ", 1), pitch, onesided);
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         };
-        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
+        if (onesided) return run(x, n_clips, o, out_pitch);
+        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o, out_pitch);
         // the reference's C-order memory, written directly by stft_warp_binmajor_kernel (ZAFB_STFT_BM_DIRECT=0: the
         // older route, frame-major into scratch + tiled transpose)
         if (n <= 2048 && env_flag("ZAFB_STFT_BM_DIRECT", 1) && nt < (int64_t(1) << 27) && reinterpret_cast<uintptr_t>(out) % 8 == 0)
@@ -1014,6 +1035,8 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
             return run(x + c0 * clip_stride, nc, scratch);
         });
     }
+    if (onesided || out_pitch != p->n)
+        return fail(ZAFB_E_UNSUPPORTED, "one-sided stft: internal error (the caller compacts the spectrum for this geometry)");
     // generic kernels: one CTA per frame.  They can store either layout, but a BIN_MAJOR store is one 8-byte element per
     // row (measured 0.035 of the HBM peak at N = 256), so that layout goes through frame-major scratch and the tiled
     // transpose as well (ZAFB_GENERIC_BM_DIRECT=1 keeps the strided stores).
@@ -1045,8 +1068,14 @@ int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int6
     });
 }
 
-int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
-                   int64_t y_stride, void* stream) {
+int zafb_stft_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride,
+                  float* out, int layout, void* stream) {
+    return stft_impl(p, x, n_clips, ns, clip_stride, out, layout, stream, p ? p->n : 0, 0);
+}
+
+// spec_pitch / onesided: see istft_warp_kernel.  The public two-sided entry point passes (N, 0).
+static int istft_impl(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                      int64_t y_stride, void* stream, int64_t spec_pitch, int onesided) {
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
     ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "n_clips and nt must be >= 0");
     ZAFB_REQUIRE(layout == ZAFB_LAYOUT_FRAME_MAJOR || layout == ZAFB_LAYOUT_BIN_MAJOR, "bad layout %d", layout);
@@ -1068,37 +1097,38 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
             return fail(ZAFB_E_UNSUPPORTED, "istft warp kernel needs N = 256 ... 4096, hop = N/2, N/4 or N/8 (N/8: N >= 512), even y_stride");
         if (warp_ok && p->force_kernel != 1) {
             cudaStream_t st = static_cast<cudaStream_t>(stream);
-            auto run = [&](const float2* s2, int64_t clips, float* yy) -> int {
+            auto run = [&](const float2* s2, int64_t clips, float* yy, int64_t pitch) -> int {
                 if (n == 4096) {
-                    if (ratio == 2) return launch_istft_warp<4096, 2>(p, s2, clips, nt, yy, y_stride, st);
-                    if (ratio == 4) return launch_istft_warp<4096, 4>(p, s2, clips, nt, yy, y_stride, st);
-                    return launch_istft_warp<4096, 8>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 2) return launch_istft_warp<4096, 2>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    if (ratio == 4) return launch_istft_warp<4096, 4>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    return launch_istft_warp<4096, 8>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
                 }
                 if (n == 2048) {
-                    if (ratio == 2) return launch_istft_warp<2048, 2>(p, s2, clips, nt, yy, y_stride, st);
-                    if (ratio == 4) return launch_istft_warp<2048, 4>(p, s2, clips, nt, yy, y_stride, st);
-                    return launch_istft_warp<2048, 8>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 2) return launch_istft_warp<2048, 2>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    if (ratio == 4) return launch_istft_warp<2048, 4>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    return launch_istft_warp<2048, 8>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
                 }
                 if (n == 1024) {
-                    if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st);
-                    if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st);
-                    return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 2) return launch_istft_warp<1024, 2>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    if (ratio == 4) return launch_istft_warp<1024, 4>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    return launch_istft_warp<1024, 8>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
                 }
                 if (n == 256) {
-                    if (ratio == 2) return launch_istft_warp<256, 2>(p, s2, clips, nt, yy, y_stride, st);
-                    return launch_istft_warp<256, 4>(p, s2, clips, nt, yy, y_stride, st);
+                    if (ratio == 2) return launch_istft_warp<256, 2>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                    return launch_istft_warp<256, 4>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
                 }
-                if (ratio == 2) return launch_istft_warp<512, 2>(p, s2, clips, nt, yy, y_stride, st);
-                if (ratio == 4) return launch_istft_warp<512, 4>(p, s2, clips, nt, yy, y_stride, st);
-                return launch_istft_warp<512, 8>(p, s2, clips, nt, yy, y_stride, st);
+                if (ratio == 2) return launch_istft_warp<512, 2>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                if (ratio == 4) return launch_istft_warp<512, 4>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
+                return launch_istft_warp<512, 8>(p, s2, clips, nt, yy, y_stride, st, pitch, onesided);
             };
             const float2* s2 = reinterpret_cast<const float2*>(spec);
-            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y);
+            if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y, spec_pitch);
             return frame_major_from_bin_major(s2, n_clips, nt, int64_t(n), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
-                return run(scratch, nc, y + c0 * y_stride);
+                return run(scratch, nc, y + c0 * y_stride, int64_t(n));
             });
         }
     }
+    if (onesided) return fail(ZAFB_E_UNSUPPORTED, "one-sided istft: internal error (the caller expands the spectrum for this geometry)");
     // tile: about 4 windows of output, bounded by shared memory (2 n float2 + tile floats)
     const size_t fft_bytes = size_t(2) * n * sizeof(float2);
     if (fft_bytes + 4096 > size_t(kMaxDynSmem))
@@ -1127,6 +1157,89 @@ int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, 
     return frame_major_from_bin_major(s2, n_clips, nt, int64_t(n), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
         return run_generic(scratch, nc, y + c0 * y_stride, ZAFB_LAYOUT_FRAME_MAJOR);
     });
+}
+
+int zafb_istft_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int layout, float* y,
+                   int64_t y_stride, void* stream) {
+    return istft_impl(p, spec, n_clips, nt, layout, y, y_stride, stream, p ? p->n : 0, 0);
+}
+
+// ------------------------------------------------------------------ one-sided spectra (non-reference extension)
+// Bins 0 .. floor(N/2) of every frame, FRAME_MAJOR, `pitch` complex elements between frames: the rest of zaf.stft's
+// two-sided spectrum is the Hermitian mirror (zafb_spec_mirror_f32 rebuilds it).  Warp kernels store / load the half
+// directly (half the HBM traffic of the spectrum); other geometries go through two-sided scratch.
+static bool onesided_warp_ok(const zafb_stft_plan* p, const void* sig, int64_t n_clips, int64_t stride, const void* spec) {
+    return (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512 || p->n == 256) && p->hop % 2 == 0 &&
+           reinterpret_cast<uintptr_t>(sig) % 8 == 0 && (n_clips <= 1 || stride % 2 == 0) && reinterpret_cast<uintptr_t>(spec) % 8 == 0 &&
+           p->force_kernel != 1;
+}
+
+int zafb_stft_onesided_f32(const zafb_stft_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, float* out,
+                           int64_t out_pitch, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && ns >= 0 && clip_stride >= ns, "bad batch geometry");
+    const int64_t n = p->n, bins = n / 2 + 1;
+    ZAFB_REQUIRE(out_pitch >= bins, "out_pitch %lld < %lld one-sided bins", (long long)out_pitch, (long long)bins);
+    int64_t nt = 0;
+    zafb_stft_geometry(ns, n, p->hop, nullptr, &nt, nullptr);
+    if (n_clips * nt == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
+    if (onesided_warp_ok(p, x, n_clips, clip_stride, out))
+        return stft_impl(p, x, n_clips, ns, clip_stride, out, ZAFB_LAYOUT_FRAME_MAJOR, stream, out_pitch, 1);
+    // two-sided into scratch (at most ~1 GB at a time), then a strided device copy of the lower half
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t clip_bytes = size_t(nt) * n * sizeof(float2);
+    int64_t per = int64_t((size_t(1) << 30) / (clip_bytes ? clip_bytes : 1));
+    if (per < 1) per = 1;
+    if (per > n_clips) per = n_clips;
+    float* scratch = nullptr;
+    ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(per) * clip_bytes, st));
+    int rc = ZAFB_OK;
+    for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += per) {
+        const int64_t nc = std::min(per, n_clips - c0);
+        rc = stft_impl(p, x + c0 * clip_stride, nc, ns, clip_stride, scratch, ZAFB_LAYOUT_FRAME_MAJOR, stream, n, 0);
+        if (rc == ZAFB_OK) {
+            const cudaError_t e = cudaMemcpy2DAsync(out + size_t(c0) * nt * out_pitch * 2, size_t(out_pitch) * sizeof(float2), scratch,
+                                                    size_t(n) * sizeof(float2), size_t(bins) * sizeof(float2), size_t(nc * nt),
+                                                    cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "one-sided stft: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+int zafb_istft_onesided_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int64_t spec_pitch, float* y,
+                            int64_t y_stride, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "n_clips and nt must be >= 0");
+    const int64_t n = p->n, bins = n / 2 + 1;
+    ZAFB_REQUIRE(spec_pitch >= bins, "spec_pitch %lld < %lld one-sided bins", (long long)spec_pitch, (long long)bins);
+    int64_t len = 0;
+    zafb_istft_geometry(n, nt, p->hop, nullptr, nullptr, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride %lld < output length %lld", (long long)y_stride, (long long)len);
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
+    const int64_t ratio = (p->hop > 0 && n % p->hop == 0) ? n / p->hop : 0;
+    if (onesided_warp_ok(p, y, n_clips, y_stride, spec) && (ratio == 2 || ratio == 4 || (ratio == 8 && n != 256)))
+        return istft_impl(p, spec, n_clips, nt, ZAFB_LAYOUT_FRAME_MAJOR, y, y_stride, stream, spec_pitch, 1);
+    // other geometries: rebuild the two-sided spectrum in scratch (at most ~1 GB at a time) and run the two-sided transform
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t clip_bytes = size_t(nt) * n * sizeof(float2);
+    int64_t per = int64_t((size_t(1) << 30) / (clip_bytes ? clip_bytes : 1));
+    if (per < 1) per = 1;
+    if (per > n_clips) per = n_clips;
+    float* scratch = nullptr;
+    ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(per) * clip_bytes, st));
+    int rc = ZAFB_OK;
+    for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += per) {
+        const int64_t nc = std::min(per, n_clips - c0);
+        rc = zafb_spec_mirror_f32(spec + size_t(c0) * nt * spec_pitch * 2, spec_pitch, nc * nt, n, scratch, stream);
+        if (rc == ZAFB_OK)
+            rc = istft_impl(p, scratch, nc, nt, ZAFB_LAYOUT_FRAME_MAJOR, y + c0 * y_stride, y_stride, stream, n, 0);
+    }
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
