@@ -530,18 +530,29 @@ class Item:
         return max(o.parity_metrics(got, ref))
 
 
-def time_item(zaf, item, in_ptr, out_ptr, stream, steps, warmup=3):
-    for _ in range(warmup):
-        item.launch(in_ptr, item.clips, out_ptr, stream)
-    stream.synchronize()
+def time_item(zaf, item, in_ptr, out_ptr, stream, steps, warmup=3, gpu_index=0):
+    """(ms per launch, launches per step, clocks during the timed region).  The SMs may have idled through a host-bound
+    leg just before: warm-up launches run until ~30 ms of work have passed so that the clocks are back up."""
+    sampler = ClockSampler(gpu_index)
+    sampler.start()
     e0, e1 = zaf.Event(), zaf.Event()
+    spent, runs = 0.0, 0
+    while runs < warmup or (spent < 30.0 and runs < 50):
+        e0.record(stream)
+        item.launch(in_ptr, item.clips, out_ptr, stream)
+        e1.record(stream)
+        e1.synchronize()
+        spent += e0.elapsed_ms(e1)
+        runs += 1
     l0 = zaf.launch_count()
+    tb = time.time()
     e0.record(stream)
     for _ in range(steps):
         item.launch(in_ptr, item.clips, out_ptr, stream)
     e1.record(stream)
     e1.synchronize()
-    return e0.elapsed_ms(e1) / steps, (zaf.launch_count() - l0) // steps
+    te = time.time()
+    return e0.elapsed_ms(e1) / steps, (zaf.launch_count() - l0) // steps, sampler.stop(tb, te)
 
 
 def config_line(item, ms, launches, world, peak, sm_max_mhz, parity, cpu):
@@ -593,13 +604,15 @@ def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
                 if route:
                     item.set_route(route)
                 outd = zaf.empty((item.clips, item.out_row), np.float32)
-                ms, nl = time_item(zaf, item, ind.ptr, outd.ptr, stream, args.config_steps)
+                ms, nl, clk = time_item(zaf, item, ind.ptr, outd.ptr, stream, args.config_steps, gpu_index=dist.local_rank)
                 ms = dist.max(ms)
                 parity = None
                 if dist.rank == 0:
                     parity = max(item.parity(ind.ptr, outd.ptr, c) for c in (0, item.clips - 1))
                     assert parity <= TOL, f"{full}: parity broken: {parity}"
-                out.append(config_line(item, ms, nl, dist.world, peak, sm_max_mhz, parity, cpu_lines.get(name)))
+                line = config_line(item, ms, nl, dist.world, peak, sm_max_mhz, parity, cpu_lines.get(name))
+                line["clocks"] = clk
+                out.append(line)
             except AssertionError:
                 raise
             except Exception as exc:  # noqa: BLE001
@@ -752,46 +765,121 @@ def split_merge_legs(zaf, dist, args, stream):
 
 
 def stft_merge_variants(zaf, dist, comm, args, stream, reps=2):
-    """cfg-2 STFT merge without a full-spectrum gather.  (1) direct_store: every rank's STFT kernel stores straight into
-    rank 0's buffer through a CUDA-IPC mapping (the stores cross NVLink while the kernel computes).  Both are checked
-    bitwise against the unsharded result."""
+    """cfg-2 STFT merges that move less than the two-sided spectrum, each checked BITWISE against the unsharded result:
+      direct_store       every rank's STFT kernel stores straight into rank 0's buffer through a CUDA-IPC mapping (the
+                         stores cross NVLink while the kernel computes; no gather);
+      half_gather        every rank computes the ONE-SIDED spectrum (bins 0 .. N/2), NCCL gathers half the bytes, a device
+                         mirror kernel on rank 0 rebuilds the two-sided spectrum;
+      direct_store_half  the peers' one-sided kernels store the lower half of their frames into rank 0's buffer over NVLink,
+                         rank 0 transforms its own shard two-sided and then mirrors the peers' frames in place."""
     clips = args.config_clips or CLIPS
     item = Item(zaf, "stft", clips=clips)
     nt = item.nt
+    lib, C = zaf._lib.lib(), zaf._lib.C
     lo, hi = comm.shard_range(clips)
     xd = device_batch(zaf, clips, NS, 20261017 + 2)[0] if dist.rank == 0 else None
     shard = zaf.empty((hi - lo, NS), np.float32)
     full = zaf.empty((clips, nt, N_WIN), np.complex64) if dist.rank == 0 else None
-    e0, e1, e3 = zaf.Event(), zaf.Event(), zaf.Event()
-    out = {}
-    view = comm.map_from_root(full, (clips, nt, N_WIN), np.complex64)
-    mine = comm.rows(view, lo, hi)
-    direct = None
-    for _ in range(reps + 1):
-        dist.barrier()
-        e0.record(stream)
-        comm.scatter(xd, clips, (NS,), np.float32, stream=stream, out=shard)
-        e1.record(stream)
-        item.launch(shard.ptr, hi - lo, mine.ptr, stream)
-        comm.barrier(stream)
-        e3.record(stream)
-        e3.synchronize()
-        t = [dist.max(e0.elapsed_ms(e1)), dist.max(e1.elapsed_ms(e3)), dist.max(e0.elapsed_ms(e3))]
-        if direct is None or t[2] < direct[2]:
-            direct = t
-    mismatch = None
+    ref = None
     if dist.rank == 0:
         ref = zaf.empty((clips, nt, N_WIN), np.complex64)
         item.launch(xd.ptr, clips, ref.ptr, stream)
+        stream.synchronize()
+    ev = [zaf.Event() for _ in range(4)]
+    out = {}
+
+    def check(tag):
+        if dist.rank != 0:
+            return None
         mismatch = zaf.count_mismatch(full, ref, stream=stream)
-        ref.free()
-        assert mismatch == 0, f"direct-store merge differs from the unsharded result in {mismatch} words"
+        assert mismatch == 0, f"{tag}: differs from the unsharded result in {mismatch} words"
+        zaf._lib.check(lib.zafb_memset(C.c_void_p(full.ptr), 0xff, full.nbytes, stream.ptr))  # the next variant starts from garbage
+        stream.synchronize()
+        return True
+
+    def scatter():
+        comm.scatter(xd, clips, (NS,), np.float32, stream=stream, out=shard)
+
+    view = comm.map_from_root(full, (clips, nt, N_WIN), np.complex64)
+    mine = comm.rows(view, lo, hi)
+
+    # ---- direct_store (two-sided)
+    best = None
+    for _ in range(reps + 1):
+        dist.barrier()
+        ev[0].record(stream)
+        scatter()
+        ev[1].record(stream)
+        item.launch(shard.ptr, hi - lo, mine.ptr, stream)
+        comm.barrier(stream)
+        ev[3].record(stream)
+        ev[3].synchronize()
+        t = [dist.max(ev[0].elapsed_ms(ev[1])), dist.max(ev[1].elapsed_ms(ev[3])), dist.max(ev[0].elapsed_ms(ev[3]))]
+        if best is None or t[2] < best[2]:
+            best = t
+    out["direct_store_merge"] = {"scatter_ms": best[0], "stft_into_root_ms": best[1], "total_ms": best[2],
+                                 "frames_per_sec": clips * nt / (best[2] * 1e-3), "bitwise_equal": check("direct_store"),
+                                 "nvlink_bytes_into_root": int((clips - (hi - lo if dist.rank == 0 else 0)) * nt * N_WIN * 8) if dist.rank == 0 else None,
+                                 "note": "no gather: each rank's STFT kernel writes into rank 0's HBM through a CUDA-IPC mapping"}
+
+    # ---- direct_store_half: peers store bins 0 .. N/2 with the two-sided frame pitch, rank 0 mirrors them in place
+    plan = item.plan
+    root_hi = comm.shard_range(clips)[1] if dist.rank == 0 else None
+    best = None
+    for _ in range(reps + 1):
+        dist.barrier()
+        ev[0].record(stream)
+        scatter()
+        ev[1].record(stream)
+        if dist.rank == 0:
+            item.launch(shard.ptr, hi - lo, mine.ptr, stream)
+        else:
+            zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(shard.ptr), hi - lo, NS, NS, C.c_void_p(mine.ptr), N_WIN, stream.ptr))
+        comm.barrier(stream)
+        ev[2].record(stream)
+        if dist.rank == 0 and root_hi < clips:
+            tail = full.ptr + root_hi * nt * N_WIN * 8
+            zaf._lib.check(lib.zafb_spec_mirror_f32(C.c_void_p(tail), N_WIN, (clips - root_hi) * nt, N_WIN, C.c_void_p(tail), stream.ptr))
+        ev[3].record(stream)
+        ev[3].synchronize()
+        t = [dist.max(ev[0].elapsed_ms(ev[1])), dist.max(ev[1].elapsed_ms(ev[2])), dist.max(ev[2].elapsed_ms(ev[3])),
+             dist.max(ev[0].elapsed_ms(ev[3]))]
+        if best is None or t[3] < best[3]:
+            best = t
+    out["direct_store_half_merge"] = {"scatter_ms": best[0], "stft_into_root_ms": best[1], "mirror_fill_ms": best[2], "total_ms": best[3],
+                                      "frames_per_sec": clips * nt / (best[3] * 1e-3), "bitwise_equal": check("direct_store_half"),
+                                      "note": "peers store bins 0..N/2 into rank 0's two-sided buffer over NVLink (half the bytes); "
+                                              "rank 0 fills the Hermitian half of those frames with zafb_spec_mirror_f32 in place"}
     dist.barrier()
     comm.unmap(view)
-    out["direct_store_merge"] = {"scatter_ms": direct[0], "stft_into_root_ms": direct[1], "total_ms": direct[2],
-                                 "frames_per_sec": clips * nt / (direct[2] * 1e-3), "bitwise_equal": (mismatch == 0) if mismatch is not None else None,
-                                 "note": "no gather: each rank's STFT kernel writes into rank 0's HBM through a CUDA-IPC mapping"}
-    for d in (shard, full, xd):
+
+    # ---- half_gather: one-sided shards (frame pitch padded to 4 bins = 32 bytes), NCCL gather, mirror kernel on rank 0
+    bins = N_WIN // 2 + 1
+    pitch = (bins + 3) & ~3
+    half = zaf.empty((hi - lo, nt, pitch), np.complex64)
+    staging = zaf.empty((clips, nt, pitch), np.complex64) if dist.rank == 0 else None
+    best = None
+    for _ in range(reps + 1):
+        dist.barrier()
+        ev[0].record(stream)
+        scatter()
+        ev[1].record(stream)
+        zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(shard.ptr), hi - lo, NS, NS, C.c_void_p(half.ptr), pitch, stream.ptr))
+        ev[2].record(stream)
+        comm.gather(half, clips, stream=stream, out=staging)
+        if dist.rank == 0:
+            zaf._lib.check(lib.zafb_spec_mirror_f32(C.c_void_p(staging.ptr), pitch, clips * nt, N_WIN, C.c_void_p(full.ptr), stream.ptr))
+        ev[3].record(stream)
+        ev[3].synchronize()
+        t = [dist.max(ev[0].elapsed_ms(ev[1])), dist.max(ev[1].elapsed_ms(ev[2])), dist.max(ev[2].elapsed_ms(ev[3])),
+             dist.max(ev[0].elapsed_ms(ev[3]))]
+        if best is None or t[3] < best[3]:
+            best = t
+    out["half_gather_merge"] = {"scatter_ms": best[0], "stft_onesided_ms": best[1], "gather_and_mirror_ms": best[2], "total_ms": best[3],
+                                "frames_per_sec": clips * nt / (best[3] * 1e-3), "bitwise_equal": check("half_gather"),
+                                "gather_bytes": int(clips * nt * pitch * 8 * (dist.world - 1) / dist.world),
+                                "note": "NCCL gather of bins 0..N/2 only (frame pitch 1028), then zafb_spec_mirror_f32 on rank 0"}
+    for d in (shard, full, xd, ref, half, staging):
         if d is not None:
             d.free()
     return out

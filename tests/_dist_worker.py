@@ -35,6 +35,25 @@ def main():
     zaf.stft(shard, w, hop, out=comm.rows(view, lo, hi))
     zaf.synchronize()
     comm.barrier()
+    # one-sided merges: (a) NCCL gather of bins 0 .. N/2 + device mirror kernel on the root, (b) every peer's one-sided
+    # kernel stores the lower half of its frames straight into the root's two-sided buffer, the root mirrors in place
+    half = zaf.stft(shard, w, hop, onesided=True)
+    merged_half = comm.gather_onesided(half, clips, n)
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    plan, _ = zaf._stft_plan(w, hop)
+    direct2 = zaf.empty((clips, nt, n), np.complex64) if rank == 0 else None
+    view2 = comm.map_from_root(direct2, (clips, nt, n), np.complex64)
+    mine2 = comm.rows(view2, lo, hi)
+    if rank == 0:
+        zaf.stft(shard, w, hop, out=mine2)
+    else:
+        zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(shard.ptr), hi - lo, ns, shard.pitch, C.c_void_p(mine2.ptr), n, None))
+    zaf.synchronize()
+    comm.barrier()
+    if rank == 0 and hi < clips:
+        tail = comm.rows(direct2, hi, clips)
+        zaf._lib.check(lib.zafb_spec_mirror_f32(C.c_void_p(tail.ptr), n, (clips - hi) * nt, n, C.c_void_p(tail.ptr), None))
+        zaf.synchronize()
     table = zaf.to_device(np.arange(1000, dtype=np.float32) * (1.0 if rank == 0 else 0.0))
     comm.broadcast(table)
     slowest = comm.max(float(rank + 1))
@@ -46,11 +65,14 @@ def main():
         res["gather_bitwise"] = bool(np.array_equal(full.to_host(), whole))
         res["shape"] = list(full.shape)
         res["direct_bitwise"] = bool(np.array_equal(np.swapaxes(direct.to_host(), 1, 2), whole))
+        res["half_gather_bitwise"] = bool(np.array_equal(merged_half.to_host(), whole))
+        res["half_direct_bitwise"] = bool(np.array_equal(np.swapaxes(direct2.to_host(), 1, 2), whole))
         res["nccl"] = zaf.dist.nccl_version()
     with open(f"{out_path}.{rank}", "w") as f:
         json.dump(res, f)
     comm.barrier()
     comm.unmap(view)
+    comm.unmap(view2)
     comm.close()
 
 

@@ -69,6 +69,10 @@ def test_single_rank_collectives(zaf_gpu):
     assert np.array_equal(comm.allgather(shard, 5).to_host(), x)
     assert np.array_equal(comm.broadcast(xd).to_host(), x)
     assert comm.max(2.5) == 2.5
+    # one-sided merge on a single rank: gather = copy, then the device mirror kernel rebuilds the two-sided spectrum
+    w = 0.54 - 0.46 * np.cos(2.0 * np.pi * np.arange(1024) / 1024)
+    half = zaf.stft(xd, w, 256, onesided=True)
+    assert np.array_equal(comm.gather_onesided(half, 5, 1024).to_host(), zaf.stft(x, w, 256))
     comm.close()
 
 
@@ -89,3 +93,4 @@ def test_two_rank_split_merge_bitwise(zaf_gpu, tmp_path):
     res = [json.load(open(f"{out}.{r}")) for r in range(2)]
     assert all(r["max"] == 2.0 and r["table_ok"] and r["allgather_bitwise"] for r in res), res
     assert res[0]["gather_bitwise"] and res[0]["direct_bitwise"] and res[0]["shape"] == [11, 2048, 48], res
+    assert res[0]["half_gather_bitwise"] and res[0]["half_direct_bitwise"], res

@@ -29,19 +29,16 @@
 #include <type_traits>
 #include <vector>
 
-#if defined(__x86_64__) || defined(__i386__)
-#include <emmintrin.h>
-#define ZAFB_HOST_SSE 1
-#else
-#define ZAFB_HOST_SSE 0  // aarch64 (Grace) and other hosts: the plain loops below, vectorised by the host compiler
-#endif
 #include <sched.h>
 
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
 #include "transpose.cuh"
 
-namespace zafb {}
+namespace zafb {
+void host_mirror_fill_frames(void* out, int64_t frames, int64_t n);                                  // host_mirror.cpp
+void host_mirror_fill_rows(void* out, int64_t nt, int64_t n, int64_t r_lo, int64_t r_hi);
+}  // namespace zafb
 using namespace zafb;
 
 struct zafb_stft_plan {
@@ -1247,62 +1244,9 @@ int zafb_istft_onesided_f32(const zafb_stft_plan* p, const float* spec, int64_t 
 
 namespace {
 
-// out[N - k] = conj(out[k]), k = 1 .. N/2 - 1, for `frames` consecutive frame-major frames (N a multiple of 4).
-// Streaming 16-byte stores when the frames are 16-byte aligned: the mirrored half is written once and not read again here.
-void mirror_fill(float2* out, int64_t frames, int64_t n) {
-#if ZAFB_HOST_SSE
-    const bool aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
-    const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));  // negate the imaginary parts
-    for (int64_t f = 0; f < frames; ++f) {
-        float2* o = out + f * n;
-        const int64_t h = n / 2;
-        o[h + 1] = make_float2(o[h - 1].x, -o[h - 1].y);
-        // destinations (n - k, n - k + 1) <- sources (k, k - 1), k = h - 2, h - 4, ..., 2 (k even: destination 16-byte aligned)
-        for (int64_t k = h - 2; k >= 2; k -= 2) {
-            const __m128 v = _mm_loadu_ps(reinterpret_cast<const float*>(o + k - 1));  // (o[k-1], o[k])
-            const __m128 r = _mm_xor_ps(_mm_shuffle_ps(v, v, _MM_SHUFFLE(1, 0, 3, 2)), sign);  // (conj o[k], conj o[k-1])
-            if (aligned) _mm_stream_ps(reinterpret_cast<float*>(o + n - k), r);
-            else _mm_storeu_ps(reinterpret_cast<float*>(o + n - k), r);
-        }
-    }
-    _mm_sfence();
-#else
-    for (int64_t f = 0; f < frames; ++f) {
-        float2* o = out + f * n;
-        for (int64_t k = 1; k < n / 2; ++k) o[n - k] = make_float2(o[k].x, -o[k].y);
-    }
-#endif
-}
-
-// BIN_MAJOR twin: rows [r_lo, r_hi) of the flattened (clip, k) index, k = 1 .. N/2 - 1: row N - k of the clip = conj(row k).
-void mirror_fill_rows(float2* out, int64_t nt, int64_t n, int64_t r_lo, int64_t r_hi) {
-#if ZAFB_HOST_SSE
-    const __m128 sign = _mm_castsi128_ps(_mm_set_epi32(int(0x80000000u), 0, int(0x80000000u), 0));
-#endif
-    const int64_t per_clip = n / 2 - 1;
-    for (int64_t r = r_lo; r < r_hi; ++r) {
-        const int64_t clip = r / per_clip, k = 1 + (r - clip * per_clip);
-        const float2* src = out + (clip * n + k) * nt;
-        float2* dst = out + (clip * n + (n - k)) * nt;
-        int64_t j = 0;
-#if ZAFB_HOST_SSE
-        if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 && nt > 0) {  // peel one element: the rest of the row is 16-byte aligned
-            dst[0] = make_float2(src[0].x, -src[0].y);
-            j = 1;
-        }
-        const bool aligned = reinterpret_cast<uintptr_t>(dst + j) % 16 == 0;
-        for (; j + 2 <= nt; j += 2) {
-            const __m128 v = _mm_xor_ps(_mm_loadu_ps(reinterpret_cast<const float*>(src + j)), sign);
-            if (aligned) _mm_stream_ps(reinterpret_cast<float*>(dst + j), v);
-            else _mm_storeu_ps(reinterpret_cast<float*>(dst + j), v);
-        }
-#endif
-        for (; j < nt; ++j) dst[j] = make_float2(src[j].x, -src[j].y);
-    }
-#if ZAFB_HOST_SSE
-    _mm_sfence();
-#endif
-}
+// The fills themselves live in host_mirror.cpp (plain C++ for the host compiler: AVX2 / SSE2 / portable loops).
+void mirror_fill(float2* out, int64_t frames, int64_t n) { host_mirror_fill_frames(out, frames, n); }
+void mirror_fill_rows(float2* out, int64_t nt, int64_t n, int64_t r_lo, int64_t r_hi) { host_mirror_fill_rows(out, nt, n, r_lo, r_hi); }
 
 // Fill threads: ZAFB_HOST_MIRROR_THREADS, else min(16, host cores / processes sharing the host), where the process count
 // is LOCAL_WORLD_SIZE (set by torchrun: one rank per GPU) or 1.  Measured on a 16-core B200 host (cfg 2, 15.75 GB
