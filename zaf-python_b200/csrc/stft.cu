@@ -120,14 +120,16 @@ __device__ __forceinline__ void warp_fft_half(float2 (&v)[N / 64], const float2*
 // N = 2048 or 1024, one warp per frame.
 // BULK = true (N = 2048 only): the spectrum leaves through shared memory and four 4 KB cp.async.bulk stores per frame
 // (issued by one lane, executed by the TMA engine) instead of 64 st.global per lane.
-template <int N, bool BULK, int WARPS>
+template <int N, bool BULK, int WARPS, bool ONESIDED = false>
 __global__ void __launch_bounds__(WARPS * 32, WarpGeom<N>::CTAS_PER_SM)
 stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, int64_t nt, int hop,
                  const float2* __restrict__ win_half, const float2* __restrict__ tw4,
                  const float2* __restrict__ tw_full, float2* __restrict__ out, int64_t total_frames, int sequential,
-                 int64_t out_pitch, int onesided) {
-    // out_pitch: complex elements between consecutive frames of `out` (N for the reference's two-sided spectrum).
-    // onesided (non-reference extension, needs `sequential`): only bins 0 .. N/2 are stored.
+                 int64_t out_pitch_arg) {
+    // ONESIDED (non-reference extension, runs the `sequential` store order): only bins 0 .. N/2 are stored, out_pitch_arg
+    // complex elements apart; the reference's two-sided spectrum has a compile-time frame pitch of N.
+    const int64_t out_pitch = ONESIDED ? out_pitch_arg : int64_t(N);
+    constexpr bool onesided = ONESIDED;
     using G = WarpGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
     static_assert(!BULK || N == 2048, "the bulk-store variant is written for N = 2048");
@@ -246,7 +248,7 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
         float2* const of = out + f * out_pitch;
         float2* o = of + lane;
         float2* om = of + M - lane;
-        if (sequential) {
+        if (ONESIDED || sequential) {
             // the same unpack, but the results first replace the registers they were computed from (descending k2,
             // see the bulk variant), then the frame is written in ascending address order, quarter by quarter
             const float2 zmid = v[bitrev(REGS / 2, LOGR)];
@@ -273,7 +275,7 @@ stft_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, i
                 constexpr int k2 = REGS / 2 - 1 - decltype(ic)::value;
                 if (k2 > 0 || lane != 0) st_stream(om - 32 * k2, cconj(v[bitrev(REGS - 1 - k2, LOGR)]));
             });
-            if (onesided) {                                   // bins 0 .. M only: the Nyquist bin X[M] closes the frame
+            if constexpr (onesided) {                         // bins 0 .. M only: the Nyquist bin X[M] closes the frame
                 if (lane == 0) st_stream(of + M, v[bitrev(REGS - 1, LOGR)]);
                 continue;
             }
@@ -531,13 +533,15 @@ __host__ __device__ constexpr int istft_ctas_per_sm(int n) { return n == 4096 ? 
 // floats of transpose tile per warp
 __host__ __device__ constexpr int istft_tile_floats(int n) { return n == 2048 ? 32 * kFft1024Pitch : 2 * (n / 64) * kFft1024Pitch; }
 
-template <int N, int R, int WARPS>
+template <int N, int R, int WARPS, bool ONESIDED = false>
 __global__ void __launch_bounds__(WARPS * 32, istft_ctas_per_sm(N))
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
-                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch, int64_t spec_pitch, int onesided) {
-    // spec_pitch: complex elements between consecutive frames (N for the two-sided spectrum).  onesided (non-reference
-    // extension): only bins 0 .. N/2 are given, the rest is their Hermitian mirror -- half the reads.
+                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch, int64_t spec_pitch_arg) {
+    // ONESIDED (non-reference extension): only bins 0 .. N/2 are given, spec_pitch_arg complex elements apart, the rest is
+    // their Hermitian mirror -- half the reads.  The two-sided spectrum has a compile-time frame pitch of N.
+    const int64_t spec_pitch = ONESIDED ? spec_pitch_arg : int64_t(N);
+    constexpr bool onesided = ONESIDED;
     using G = WarpGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
     constexpr int HOP = N / R;
@@ -588,14 +592,16 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
                 constexpr int t = decltype(tc)::value;
                 constexpr int r = (t % 2 == 0) ? t / 2 : REGS - 1 - t / 2;
                 const int k = lane + 32 * r;
-                const float2 a = __ldg(X + k);
-                const float2 c = __ldg(X + M - k);
                 float2 h0, h1;
-                if (onesided) {  // X[N - k] = conj(X[k]), X[M + k] = conj(X[M - k]); k = 0 pairs X[0] and X[M] with themselves
+                if constexpr (onesided) {  // X[N - k] = conj(X[k]), X[M + k] = conj(X[M - k]); k = 0 pairs X[0] and X[M] with themselves
+                    const float2 a = __ldg(X + k);
+                    const float2 c = __ldg(X + M - k);
                     h0 = make_float2(2.f * a.x, k == 0 ? 0.f : 2.f * a.y);
                     h1 = make_float2(2.f * c.x, k == 0 ? 0.f : -2.f * c.y);
                 } else {
+                    const float2 a = __ldg(X + k);
                     const float2 b = __ldg(X + M + k);
+                    const float2 c = __ldg(X + M - k);
                     const float2 d = __ldg(X + ((N - k) & (N - 1)));
                     h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
                     h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + M]
@@ -801,6 +807,12 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<256, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<2048, false, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<1024, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<512, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(stft_warp_kernel<256, false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(stft_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(istft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -858,7 +870,8 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
                         int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided) {
     static bool attr = false;
     if (!attr) {
-        ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
         attr = true;
     }
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
@@ -883,9 +896,10 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
                                                                                istft_tile_floats(N) * sizeof(float));
     static_assert(smem <= size_t(kMaxDynSmem), "istft warp kernel: shared memory");
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
-    istft_warp_kernel<N, R, WARPS><<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
+    auto kern = onesided ? istft_warp_kernel<N, R, WARPS, true> : istft_warp_kernel<N, R, WARPS, false>;
+    kern<<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
-        env_flag("ZAFB_ISTFT_PREFETCH", 1), spec_pitch, onesided);
+        env_flag("ZAFB_ISTFT_PREFETCH", 1), spec_pitch);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
@@ -1009,7 +1023,13 @@ static int stft_impl(const zafb_stft_plan* p, const float* x, int64_t n_clips, i
             int64_t ctas = ceil_div(frames, warps);
             const int64_t resident = int64_t(sms) * (n == 4096 ? 1 : n == 2048 ? 2 : n == 256 ? ZAFB_STFT256_CTAS : 3);
             if (ctas > resident) ctas = resident;
-            auto kern = n == 4096 ? stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS>
+            auto kern = onesided ? (n == 4096 ? stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS, true>
+                                    : n == 256 ? stft_warp_kernel<256, false, 8, true>
+                                    : n == 512 ? stft_warp_kernel<512, false, 8, true>
+                                    : n == 1024 ? stft_warp_kernel<1024, false, 8, true>
+                                    : warps == 6 ? stft_warp_kernel<2048, false, 6, true>
+                                                 : stft_warp_kernel<2048, false, 8, true>)
+                        : n == 4096 ? stft_warp_kernel<4096, false, ZAFB_STFT4096_WARPS>
                         : n == 256 ? stft_warp_kernel<256, false, 8>
                         : n == 512 ? stft_warp_kernel<512, false, 8>
                         : n == 1024 ? stft_warp_kernel<1024, false, 8>
@@ -1018,12 +1038,12 @@ static int stft_impl(const zafb_stft_plan* p, const float* x, int64_t n_clips, i
                                                                              : stft_warp_kernel<2048, false, 8>);
             kern<<<static_cast<unsigned>(ctas), warps * 32, smem, st>>>(
                 xs, ns, clip_stride, nt, static_cast<int>(p->hop), p->d_window_half, p->d_tw_4step, p->d_tw_full, dst, frames,
-                onesided ? 1 : env_flag("ZAFB_STFT_SEQ", 1), pitch, onesided);
+                env_flag("ZAFB_STFT_SEQ", 1), pitch);
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
         };
         if (onesided) return run(x, n_clips, o, out_pitch);
-        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o, out_pitch);
+        if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(x, n_clips, o);
         // the reference's C-order memory, written directly by stft_warp_binmajor_kernel (ZAFB_STFT_BM_DIRECT=0: the
         // older route, frame-major into scratch + tiled transpose)
         if (n <= 2048 && env_flag("ZAFB_STFT_BM_DIRECT", 1) && nt < (int64_t(1) << 27) && reinterpret_cast<uintptr_t>(out) % 8 == 0)
