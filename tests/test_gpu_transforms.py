@@ -516,3 +516,24 @@ def test_mel_mfcc_float64_route(zaf_gpu, n, hop, n_mels, ncoef, fs):
     assert np.array_equal(zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64", layout="bin_major"), cep)
     with pytest.raises(ValueError):
         zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float16")
+
+
+@pytest.mark.parametrize("n,hop,fs,n_mels,ncoef", [(1000, 250, 16000, 64, 20), (1764, 441, 44100, 128, 40), (300, 75, 8000, 30, 12)])
+def test_mel_mfcc_window_lengths_that_are_not_powers_of_two(zaf_gpu, n, hop, fs, n_mels, ncoef):
+    """The reference accepts any window length (zaf.py:369 -> stft with pocketfft); here the any-length STFT kernels feed
+    mel_from_spectrum_kernel.  Both layouts, batches, host and device inputs."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (3, 9001)).astype(np.float32)
+    w = np.hanning(n + 2)[1:-1]
+    fb = zaf_gpu.melfilterbank(fs, n, n_mels)
+    dense = fb.toarray()
+    assert dense.shape == (n_mels, n // 2)
+    mel = zaf_gpu.melspectrogram(x, w, hop, fb)
+    cep = zaf_gpu.mfcc(x, w, hop, fb, ncoef)
+    for c in range(3):
+        assert_parity(mel[c], oracle.melspectrogram(x[c], w, hop, dense))
+        assert_parity(cep[c], oracle.mfcc(x[c], w, hop, dense, ncoef))
+    assert np.array_equal(zaf_gpu.melspectrogram(x, w, hop, fb, layout="bin_major"), mel)
+    assert np.array_equal(zaf_gpu.mfcc(zaf_gpu.to_device(x), w, hop, fb, ncoef).to_host(), cep)
+    with pytest.raises(NotImplementedError):
+        zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64")

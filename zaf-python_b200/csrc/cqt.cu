@@ -56,6 +56,15 @@ struct zafb_cqt_plan {
     int64_t kp = 0;                // col_hi - col_lo + 1 rounded up to 4
     float* d_kern_hi = nullptr;
     float* d_kern_lo = nullptr;
+    // the same operand PACKED: groups of 16 consecutive rows, each stored dense over the union of its rows' bands only
+    // (62 080 elements instead of 269 976 at cfg 5); group g multiplies spectrum columns
+    // [pk_col0[g], pk_col0[g] + pk_k[g]) and produces operator rows [16 g, 16 g + 16)
+    std::vector<int> pk_col0, pk_k;
+    int pk_ld = 0;                 // common row pitch of the packed groups (the longest union span, rounded up to 4)
+    float* d_pk_hi = nullptr;      // [groups * 16][pk_ld]
+    float* d_pk_lo = nullptr;
+    GemmTile* d_pk_tiles = nullptr;
+    int64_t pk_elems = 0;          // elements inside the union spans (the packed operand proper)
 };
 
 namespace {
@@ -824,6 +833,37 @@ int zafb_cqt_plan_create(zafb_cqt_plan** out, int64_t n_freqs, int64_t fft_lengt
                 split_tf32_host(dense.data(), dense.size(), hi.data(), lo_.data());
                 rc = upload_vec(&p->d_kern_hi, hi);
                 if (rc == ZAFB_OK) rc = upload_vec(&p->d_kern_lo, lo_);
+                // packed form: 16-row groups over the union of their bands, all groups stored with one row pitch
+                std::vector<int> glo_v, ghi_v;
+                for (int64_t r0 = 0; r0 < n_freqs; r0 += 16) {
+                    const int64_t r1 = std::min<int64_t>(n_freqs, r0 + 16);
+                    int glo = int(fft_length), ghi = -1;
+                    for (int64_t r = r0; r < r1; ++r) {
+                        if (len[r] == 0) continue;
+                        glo = std::min(glo, lo[r]);
+                        ghi = std::max(ghi, lo[r] + len[r] - 1);
+                    }
+                    if (ghi < glo) glo = ghi = clo;  // an all-zero group still needs a (1-column, zero) operand
+                    const int c0 = ((glo - clo) / 4) * 4;  // TMA box origins must be 16-byte aligned: 4 columns
+                    const int kg = ghi - clo - c0 + 1;
+                    p->pk_col0.push_back(c0);
+                    p->pk_k.push_back(kg);
+                    p->pk_elems += int64_t(16) * kg;
+                    p->pk_ld = std::max(p->pk_ld, (kg + 3) & ~3);
+                }
+                const size_t groups = p->pk_k.size();
+                std::vector<double> packed(groups * 16 * size_t(p->pk_ld), 0.0);
+                for (int64_t r = 0; r < n_freqs; ++r)
+                    for (int c = 0; c < len[r]; ++c)
+                        packed[size_t(r) * p->pk_ld + (lo[r] - clo - p->pk_col0[r / 16] + c)] = double(w[off[r] + c].x);
+                std::vector<float> phi(packed.size()), plo(packed.size());
+                split_tf32_host(packed.data(), packed.size(), phi.data(), plo.data());
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_pk_hi, phi);
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_pk_lo, plo);
+                std::vector<GemmTile> tiles(groups);
+                for (size_t g = 0; g < groups; ++g)
+                    tiles[g] = GemmTile{p->pk_col0[g], p->pk_k[g], int(16 * g), 1, int(std::min<int64_t>(16, n_freqs - int64_t(16 * g)))};
+                if (rc == ZAFB_OK) rc = upload_vec(&p->d_pk_tiles, tiles);
             }
         }
         // longest-processing-time-first deal of the rows to the warps of a CTA (16 for the register-FFT kernel, 8 for the
@@ -940,6 +980,9 @@ int zafb_cqt_plan_destroy(zafb_cqt_plan* p) {
     cudaFree(p->d_sched_cnt);
     cudaFree(p->d_kern_hi);
     cudaFree(p->d_kern_lo);
+    cudaFree(p->d_pk_hi);
+    cudaFree(p->d_pk_lo);
+    cudaFree(p->d_pk_tiles);
     cudaFree(p->d_eo_t1);
     cudaFree(p->d_eo_t2);
     cudaFree(p->d_eo_t3);
@@ -1058,7 +1101,13 @@ int zafb_cqt_f32(const zafb_cqt_plan* p, const float* x, int64_t n_clips, int64_
                         p->col_lo, p->col_hi, kp);
                     g_launches.fetch_add(1, std::memory_order_relaxed);
                 }
-                rc = gemm3xtf32(a_hi, a_lo, kp, p->d_kern_hi, p->d_kern_lo, kp, cbuf, nf, 2 * frames, nf, kp, st);
+                if (p->d_pk_hi != nullptr && !env_flag("ZAFB_CQT_TENSOR_DENSE", 0)) {
+                    // the PACKED banded contraction: every 16-row group multiplies only the union of its rows' bands
+                    rc = gemm3xtf32_tiled(16, a_hi, a_lo, kp, kp, p->d_pk_hi, p->d_pk_lo, p->pk_ld, int(p->pk_k.size()), p->d_pk_tiles, cbuf,
+                                          nf, 2 * frames, st);
+                } else {  // the dense (n_freqs x kp) block
+                    rc = gemm3xtf32(a_hi, a_lo, kp, p->d_kern_hi, p->d_kern_lo, kp, cbuf, nf, 2 * frames, nf, kp, st);
+                }
                 if (rc == ZAFB_OK) {
                     const int rows = octave_resolution > 0 ? int(octave_resolution) : int(nf);
                     int64_t blocks = ceil_div(frames * rows, 256);

@@ -47,6 +47,14 @@ struct zafb_dct_plan {
     float* d_mat_hi = nullptr;
     float* d_mat_lo = nullptr;
     int64_t ldk = 0;              // row pitch of the matrix and of the split input (n rounded up to 4)
+    // even / odd form of the matrix path (types I and II): Mat[k][n-1-m] = (-1)^k Mat[k][m], so the even outputs are a
+    // product with s[m] = x[m] + x[n-1-m] and the odd ones with d[m] = x[m] - x[n-1-m] -- two half-size products, run as
+    // ONE tiled launch over the stacked operand [Mat_even ; Mat_odd] and the folded input [s | d]
+    float* d_eo_hi = nullptr;
+    float* d_eo_lo = nullptr;
+    GemmTile* d_eo_tiles = nullptr;
+    int eo_tiles = 0;
+    int64_t eo_ldb = 0, eo_lda = 0, eo_dcol = 0;  // operand pitches, first column of d in the folded input
 };
 
 namespace {
@@ -350,6 +358,28 @@ dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, 
     }
 }
 
+// Input of the even / odd matrix path: s[m] = x[m] + x[n-1-m] (the middle sample of an odd n once) in columns [0, ceil(n/2)),
+// d[m] = x[m] - x[n-1-m] in columns [dcol, dcol + n/2), zeros elsewhere, split into TF32 hi / lo halves (row pitch ld).
+__global__ void fold_split_tf32_kernel(const float* __restrict__ x, int64_t rows, int n, int64_t ldx, float* __restrict__ hi,
+                                       float* __restrict__ lo, int64_t ld, int64_t dcol) {
+    const int nh = (n + 1) / 2, nd = n / 2;
+    const int64_t total = rows * ld;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / ld;
+        const int c = int(i - r * ld);
+        const float* xr = x + r * ldx;
+        float v = 0.f;
+        if (c < nh) v = (c == n - 1 - c) ? xr[c] : xr[c] + xr[n - 1 - c];
+        else if (c >= dcol && c < dcol + nd) v = xr[c - dcol] - xr[n - 1 - (c - dcol)];
+        uint32_t h, l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hv = __uint_as_float(h);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hv));
+        hi[i] = hv;
+        lo[i] = __uint_as_float(l);
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
@@ -483,6 +513,44 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
         if (e == cudaSuccess) e = cudaMemcpy(p->d_mat_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(p->d_mat_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "dct: uploading the transform matrix failed: %s", cudaGetErrorString(e));
+        // even / odd form: only where the symmetry holds to float64 rounding (it does for types I and II of both kinds)
+        bool sym = type <= 2;
+        double worst = 0.0;
+        for (int64_t k = 0; k < n && sym; ++k)
+            for (int64_t m = 0; m < n / 2; ++m) {
+                const double a = mat[k * p->ldk + m], b = mat[k * p->ldk + (n - 1 - m)];
+                worst = std::max(worst, std::fabs(b - ((k & 1) ? -a : a)));
+            }
+        if (worst > 1e-12) sym = false;
+        if (rc == ZAFB_OK && sym) {
+            const int64_t nh = (n + 1) / 2, nd = n / 2;        // columns of s (with the middle sample of an odd n) and of d
+            const int64_t ne = (n + 1) / 2, no = n / 2;        // even and odd outputs
+            const int64_t te = (ne + 127) / 128, to = (no + 127) / 128;
+            p->eo_ldb = (nh + 3) & ~int64_t(3);
+            p->eo_dcol = p->eo_ldb;
+            p->eo_lda = p->eo_ldb + ((nd + 3) & ~int64_t(3));
+            p->eo_tiles = int(te + to);
+            std::vector<double> st(size_t(te + to) * 128 * p->eo_ldb, 0.0);
+            for (int64_t k = 0; k < n; ++k) {
+                const int64_t row = (k & 1) ? te * 128 + k / 2 : k / 2;
+                const int64_t cols = (k & 1) ? nd : nh;
+                for (int64_t m = 0; m < cols; ++m) st[row * p->eo_ldb + m] = mat[k * p->ldk + m];
+            }
+            std::vector<GemmTile> tiles;
+            for (int64_t t = 0; t < te; ++t)
+                tiles.push_back(GemmTile{0, int(nh), int(2 * t * 128), 2, int(std::min<int64_t>(128, ne - t * 128))});
+            for (int64_t t = 0; t < to; ++t)
+                tiles.push_back(GemmTile{int(p->eo_dcol), int(nd), int(2 * t * 128 + 1), 2, int(std::min<int64_t>(128, no - t * 128))});
+            std::vector<float> ehi(st.size()), elo(st.size());
+            split_tf32_host(st.data(), st.size(), ehi.data(), elo.data());
+            e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_hi), ehi.size() * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_lo), elo.size() * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_tiles), tiles.size() * sizeof(GemmTile));
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_hi, ehi.data(), ehi.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_lo, elo.data(), elo.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "dct: uploading the even/odd transform matrix failed: %s", cudaGetErrorString(e));
+        }
     }
     if (rc != ZAFB_OK) {
         zafb_dct_plan_destroy(p);
@@ -502,6 +570,9 @@ int zafb_dct_plan_destroy(zafb_dct_plan* p) {
     cudaFree(p->d_tw_b);
     cudaFree(p->d_mat_hi);
     cudaFree(p->d_mat_lo);
+    cudaFree(p->d_eo_hi);
+    cudaFree(p->d_eo_lo);
+    cudaFree(p->d_eo_tiles);
     cudaFree(p->d_tw_4step);
     delete p;
     return ZAFB_OK;
@@ -540,6 +611,19 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
             pool_ready = true;
         }
         float* ws = nullptr;
+        if (p->d_eo_tiles != nullptr && !env_flag("ZAFB_DCT_DENSE", 0)) {
+            // even / odd form: fold the input into [s | d] while splitting it, then one tiled product with half the work
+            const size_t half = size_t(batch) * size_t(p->eo_lda);
+            ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * half * sizeof(float), st));
+            int64_t blocks = ceil_div(int64_t(half), 256);
+            if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+            fold_split_tf32_kernel<<<unsigned(blocks), 256, 0, st>>>(x, batch, n, stride, ws, ws + half, p->eo_lda, p->eo_dcol);
+            ZAFB_LAUNCH_CHECK();
+            rc = gemm3xtf32_tiled(128, ws, ws + half, p->eo_lda, p->eo_lda, p->d_eo_hi, p->d_eo_lo, p->eo_ldb, p->eo_tiles,
+                                  p->d_eo_tiles, out, out_stride, batch, st);
+            cudaFreeAsync(ws, st);
+            return rc;
+        }
         const size_t half = size_t(batch) * size_t(p->ldk);
         ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * half * sizeof(float), st));
         rc = split_tf32(x, batch, n, stride, ws, ws + half, p->ldk, st);

@@ -105,6 +105,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major operand tile, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart
 // (cute::UMMA::SmemDescriptor: start >> 4 | LBO 1 << 16 | SBO 64 << 32 | version 1 << 46 | SWIZZLE_128B 2 << 61)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
@@ -126,7 +139,10 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                   const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
-                  float* __restrict__ C, int64_t M, int64_t N, int64_t K, int64_t ldc) {
+                  float* __restrict__ C, int64_t M, int64_t N, int64_t K, int64_t ldc, const GemmTile* __restrict__ tiles) {
+    // tiles (structured operators; nullptr = dense): output-column block n_blk multiplies A columns [a_col0, a_col0 + k_len)
+    // with columns [0, k_len) of B rows [n_blk BN, n_blk BN + BN) and writes its n_valid columns to C columns
+    // c_col0 + i * c_stride.
     using S = Smem<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -136,9 +152,17 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + S::kTmemPtr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_blk = blockIdx.x, m_blk = blockIdx.y;
-    const int num_kb = int((K + kBK - 1) / kBK);
+    GemmTile tile;
+    tile.a_col0 = 0;
+    tile.k_len = int(K);
+    tile.c_col0 = n_blk * BN;
+    tile.c_stride = 1;
+    tile.n_valid = int(N - int64_t(n_blk) * BN < BN ? N - int64_t(n_blk) * BN : BN);
+    if (tiles != nullptr) tile = tiles[n_blk];
+    const int a_col0 = tile.a_col0;
+    const int num_kb = (tile.k_len + kBK - 1) / kBK;
     const int num_chunks = (num_kb + kChunkKb - 1) / kChunkKb;
-    constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator buffers (a power of two >= 32)
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers (a power of two >= 32)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -164,8 +188,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
                 mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
                 const uint32_t st = base + s * S::kStage;
                 mbar_expect_tx(bar_full + 8 * s, S::kStage);
-                tma_load_2d(st, &tm_ahi, bar_full + 8 * s, kb * kBK, m_blk * kBM);
-                tma_load_2d(st + S::kATile, &tm_alo, bar_full + 8 * s, kb * kBK, m_blk * kBM);
+                tma_load_2d(st, &tm_ahi, bar_full + 8 * s, a_col0 + kb * kBK, m_blk * kBM);
+                tma_load_2d(st + S::kATile, &tm_alo, bar_full + 8 * s, a_col0 + kb * kBK, m_blk * kBM);
                 tma_load_2d(st + 2 * S::kATile, &tm_bhi, bar_full + 8 * s, kb * kBK, n_blk * BN);
                 tma_load_2d(st + 2 * S::kATile + S::kBTile, &tm_blo, bar_full + 8 * s, kb * kBK, n_blk * BN);
             }
@@ -206,12 +230,19 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
             const int buf = chunk & 1;
             mbar_wait(bar_tfull + 8 * buf, (chunk >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if constexpr (BN == 16) {  // the packed banded contraction: 16 operator rows per tile
+                float v[16];
+                tmem_ld16(tmem_acc + (uint32_t(32 * warp) << 16) + uint32_t(buf * BN), v);
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_acc + (uint32_t(32 * warp) << 16) + uint32_t(buf * BN + c0), v);
+                for (int i = 0; i < 16; ++i) sum[i] += v[i];
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) sum[c0 + i] += v[i];
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_acc + (uint32_t(32 * warp) << 16) + uint32_t(buf * BN + c0), v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum[c0 + i] += v[i];
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -219,16 +250,16 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
         }
         const int64_t row = int64_t(m_blk) * kBM + 32 * warp + lane;
         if (row < M) {
-            float* crow = C + row * ldc + int64_t(n_blk) * BN;
-            const int64_t ncol = N - int64_t(n_blk) * BN;
-            if ((ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ncol >= BN) {
+            float* crow = C + row * ldc + tile.c_col0;
+            const int ncol = tile.n_valid;
+            if (tile.c_stride == 1 && (ldc % 4 == 0) && (tile.c_col0 % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0) && ncol >= BN) {
 #pragma unroll
                 for (int i = 0; i < BN; i += 4)
                     *reinterpret_cast<float4*>(crow + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
             } else {
 #pragma unroll
                 for (int i = 0; i < BN; ++i)
-                    if (i < ncol) crow[i] = sum[i];
+                    if (i < ncol) crow[i * tile.c_stride] = sum[i];
             }
         }
     }
@@ -303,12 +334,45 @@ int launch(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi,
     if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, N, K, ldb, BN);
     if (rc != ZAFB_OK) return rc;
     const dim3 grid(unsigned((N + BN - 1) / BN), unsigned((M + kBM - 1) / kBM));
-    gemm3xtf32_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(ma, mal, mb, mbl, c, M, N, K, ldc);
+    gemm3xtf32_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(ma, mal, mb, mbl, c, M, N, K, ldc, nullptr);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
 
 }  // namespace
+
+// Structured operators in ONE launch: output-column block t (BN columns of B rows [t BN, t BN + BN)) has its own A column
+// range, K length and output columns (GemmTile, a DEVICE array of n_tiles entries).  Used for
+//   * the PACKED banded contraction (BN = 16: 16-row groups of a banded operator, each over the union of its bands only);
+//   * the even / odd split of a transform matrix with input symmetry (BN = 128: DCT / DST types I and II, half the work).
+template <int BN>
+static int launch_tiled(const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
+                        int64_t ldb, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal));
+        attr = true;
+    }
+    CUtensorMap ma, mal, mb, mbl;
+    int rc = make_map(&ma, a_hi, M, a_cols, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mal, a_lo, M, a_cols, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mb, b_hi, int64_t(n_tiles) * BN, ldb, ldb, BN);
+    if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, int64_t(n_tiles) * BN, ldb, ldb, BN);
+    if (rc != ZAFB_OK) return rc;
+    const dim3 grid(unsigned(n_tiles), unsigned((M + kBM - 1) / kBM));
+    gemm3xtf32_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, st>>>(ma, mal, mb, mbl, c, M, int64_t(n_tiles) * BN, a_cols, ldc, d_tiles);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
+                     int64_t ldb, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st) {
+    ZAFB_REQUIRE(M >= 0 && n_tiles >= 1 && (bn == 16 || bn == 128), "tiled gemm: bad shape");
+    if (M == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "tiled gemm: operand row pitches must be multiples of 4 elements");
+    if (bn == 16) return launch_tiled<16>(a_hi, a_lo, lda, a_cols, b_hi, b_lo, ldb, n_tiles, d_tiles, c, ldc, M, st);
+    return launch_tiled<128>(a_hi, a_lo, lda, a_cols, b_hi, b_lo, ldb, n_tiles, d_tiles, c, ldc, M, st);
+}
 
 int split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo, int64_t ld_out, cudaStream_t st) {
     if (rows * ld_out == 0) return ZAFB_OK;
@@ -346,7 +410,8 @@ int gemm3xtf32(const float* a_hi, const float* a_lo, int64_t lda, const float* b
                  "gemm: operands must be 16-byte aligned");
     ZAFB_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31), "gemm: dimension too large");
     if (N > 64) return launch<128>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);
-    return launch<64>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);
+    if (N > 16) return launch<64>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);
+    return launch<16>(a_hi, a_lo, lda, b_hi, b_lo, ldb, c, ldc, M, N, K, st);  // one 16-row group of a packed banded operator
 }
 
 }  // namespace zafb

@@ -18,4 +18,19 @@ void split_tf32_host(const double* x, size_t n, float* hi, float* lo);
 int gemm3xtf32(const float* a_hi, const float* a_lo, int64_t lda, const float* b_hi, const float* b_lo, int64_t ldb, float* c,
                int64_t ldc, int64_t M, int64_t N, int64_t K, cudaStream_t st);
 
+// One output-column block of a structured product (see gemm3xtf32_tiled)
+struct GemmTile {
+    int a_col0;    // first A column this block multiplies
+    int k_len;     // number of A / B columns
+    int c_col0;    // first output column
+    int c_stride;  // distance between its output columns
+    int n_valid;   // output columns actually written (<= the block width)
+};
+
+// Structured operators in one launch: block t = B rows [t bn, t bn + bn) (bn = 16 or 128, all blocks share the row pitch
+// ldb and store their k_len columns from column 0), multiplied with A columns [a_col0, a_col0 + k_len) and written to
+// C columns c_col0 + i c_stride.  d_tiles is a DEVICE array of n_tiles entries.
+int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
+                     int64_t ldb, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st);
+
 }  // namespace zafb

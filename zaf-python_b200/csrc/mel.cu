@@ -58,6 +58,9 @@ struct zafb_mel_plan {
     float* d_dct_hi = nullptr;      // n_coef x ld_mel
     float* d_dct_lo = nullptr;
     int64_t ld_mel = 0;             // n_mels rounded up to 4
+    // window lengths that are not powers of two (the reference accepts any, zaf.py:369 -> stft): the any-length STFT kernels
+    // write the spectrum to scratch and mel_from_spectrum_kernel applies |.|, the filterbank and the logarithm / DCT
+    zafb_stft_plan* stft_any = nullptr;
 };
 
 namespace {
@@ -479,6 +482,66 @@ mel_warp_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_stride, in
 }
 
 // ------------------------------------------------------------------------------------------
+// Any window length (not a power of two): the two-sided spectrum comes from the any-length STFT kernels (frame-major
+// scratch); one CTA per frame applies |X| or |X|^2 of bins 1 .. floor(N/2), the banded filterbank and, for mfcc, the
+// logarithm and the DCT-II rows -- the tail of mel_frame_kernel on a spectrum read from memory.
+// ------------------------------------------------------------------------------------------
+__global__ void mel_from_spectrum_kernel(const float2* __restrict__ spec, int n, int64_t nt, int64_t frame0,
+                                         const int* __restrict__ band_lo, const int* __restrict__ band_len,
+                                         const int* __restrict__ band_off, const float* __restrict__ weights,
+                                         const float* __restrict__ dct, int n_mels, int n_coef, int mode, float* __restrict__ out,
+                                         int layout, int64_t frames) {
+    extern __shared__ float smem_f[];
+    const int m = n / 2;
+    float* sp = smem_f;      // m floats: column c <-> bin c + 1
+    float* mel = sp + m;     // n_mels floats
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int rows = mode == 0 ? n_mels : n_coef;
+    for (int64_t fl = blockIdx.x; fl < frames; fl += gridDim.x) {
+        const float2* X = spec + fl * n;
+        const int64_t f = frame0 + fl, clip = f / nt, j = f - clip * nt;
+        for (int c = tid; c < m; c += nth) {
+            const float2 v = X[c + 1];
+            const float p = v.x * v.x + v.y * v.y;
+            sp[c] = mode == 0 ? sqrtf(p) : p;
+        }
+        __syncthreads();
+        for (int r = tid; r < n_mels; r += nth) {
+            const int lo = band_lo[r], len = band_len[r];
+            const float* w = weights + band_off[r];
+            float acc = 0.f;
+            for (int c = 0; c < len; ++c) acc = fmaf(w[c], sp[lo + c], acc);
+            if (mode == 0) {
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * n_mels + r] = acc;
+                else out[(clip * n_mels + r) * nt + j] = acc;
+            } else {
+                mel[r] = acc + 2.220446049250313e-16f;  // np.finfo(float).eps, zaf.py:445
+            }
+        }
+        if (mode == 1) {
+            __syncthreads();
+            const float ref0 = mel[0];  // log of a ratio: see mel_frame_kernel
+            __syncthreads();
+            for (int r = tid; r < n_mels; r += nth) mel[r] = logf(mel[r] / ref0);
+            __syncthreads();
+            for (int i = tid; i < n_coef; i += nth) {
+                const float* d = dct + int64_t(i) * n_mels;
+                float acc0 = 0.f, acc1 = 0.f;
+                int r = 0;
+                for (; r + 1 < n_mels; r += 2) {
+                    acc0 = fmaf(d[r], mel[r], acc0);
+                    acc1 = fmaf(d[r + 1], mel[r + 1], acc1);
+                }
+                if (r < n_mels) acc0 = fmaf(d[r], mel[r], acc0);
+                if (layout == ZAFB_LAYOUT_FRAME_MAJOR) out[f * rows + i] = acc0 + acc1;
+                else out[(clip * rows + i) * nt + j] = acc0 + acc1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // N = 1024 in double precision, one warp per frame: the mfcc frames the fp32 kernel queued (list != nullptr), or every
 // frame (precision = 64).  The pipeline of mel_warp_kernel with window, FFT (warp_fft512_f64), unpack, |X|^2 (or |X|),
 // filterbank sums, logarithm and DCT-II sums in FP64 (B200: half the FP32 rate); inputs, weights and outputs stay fp32.
@@ -699,6 +762,29 @@ int launch(const zafb_mel_plan* p, int mode, const float* x, int64_t n_clips, in
     if (total == 0 || rows == 0) return ZAFB_OK;
     ZAFB_REQUIRE(out != nullptr && (x != nullptr || ns == 0), "x/out is NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p->stft_any != nullptr) {  // window length not a power of two: spectrum through scratch, at most ~512 MB at a time
+        const size_t clip_bytes = size_t(nt) * p->n * sizeof(float2);
+        int64_t per = int64_t((size_t(512) << 20) / (clip_bytes ? clip_bytes : 1));
+        if (per < 1) per = 1;
+        if (per > n_clips) per = n_clips;
+        float* scratch = nullptr;
+        ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), size_t(per) * clip_bytes, st));
+        const size_t smem = size_t(p->n / 2 + p->n_mels) * sizeof(float) + 16;
+        rc = ZAFB_OK;
+        for (int64_t c0 = 0; c0 < n_clips && rc == ZAFB_OK; c0 += per) {
+            const int64_t nc = std::min(per, n_clips - c0), frames = nc * nt;
+            rc = zafb_stft_f32(p->stft_any, x + c0 * clip_stride, nc, ns, clip_stride, scratch, ZAFB_LAYOUT_FRAME_MAJOR, stream);
+            if (rc != ZAFB_OK) break;
+            const int64_t grid = frames < int64_t(sm_count()) * 16 ? frames : int64_t(sm_count()) * 16;
+            mel_from_spectrum_kernel<<<unsigned(grid), 128, smem, st>>>(
+                reinterpret_cast<const float2*>(scratch), int(p->n), nt, c0 * nt, p->d_band_lo, p->d_band_len, p->d_band_off,
+                p->d_weights, p->d_dct, int(p->n_mels), int(p->n_coef), mode, out, layout, frames);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ZAFB_E_CUDA, "mel_from_spectrum_kernel launch failed");
+        }
+        cudaFreeAsync(scratch, st);
+        return rc;
+    }
     {
         const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) && p->hop % 2 == 0;
         if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->warp_ok && aligned && p->force_kernel != 1) {
@@ -830,9 +916,10 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
                          int64_t n_mels, int64_t n_coef) {
     ZAFB_REQUIRE(out != nullptr && window != nullptr && fb != nullptr, "plan/window/filterbank is NULL");
     ZAFB_REQUIRE(n >= 2 && hop >= 1 && n_mels >= 1 && n_coef >= 0, "bad mel plan parameters");
-    if (!is_pow2(n) || n < 4)
-        return fail(ZAFB_E_UNSUPPORTED, "melspectrogram/mfcc: window_length %lld is not a power of two >= 4", (long long)n);
     if (n_mels > 4096) return fail(ZAFB_E_UNSUPPORTED, "too many mel filters (%lld)", (long long)n_mels);
+    const bool any_length = !is_pow2(n) || n < 4;  // not a power of two: the any-length STFT + mel_from_spectrum_kernel
+    if (any_length && size_t(n / 2 + n_mels) * sizeof(float) + 16 > size_t(kMaxDynSmem))
+        return fail(ZAFB_E_UNSUPPORTED, "melspectrogram/mfcc: window_length %lld too large", (long long)n);
     zafb_mel_plan* p = new zafb_mel_plan();
     p->n = n;
     p->hop = hop;
@@ -866,6 +953,21 @@ int zafb_mel_plan_create(zafb_mel_plan** out, const double* window, int64_t n, i
             d[i * n_mels + mm] =
                 static_cast<float>(std::sqrt(2.0 / double(n_mels)) * std::cos(pi * double(2 * mm + 1) * double(i + 1) / double(2 * n_mels)));
     int rc = upload_f32(&p->d_window, window, n);
+    if (any_length) {
+        if (rc == ZAFB_OK) rc = zafb_stft_plan_create(&p->stft_any, window, n, hop);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_len, len);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_off, off);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_weights, w);
+        if (rc == ZAFB_OK) rc = upload_vec(&p->d_dct, d);
+        if (rc != ZAFB_OK) {
+            zafb_mel_plan_destroy(p);
+            return rc;
+        }
+        p->precision = 32;  // this route is fp32 throughout
+        *out = p;
+        return ZAFB_OK;
+    }
     if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_half, n / 2, n / 2);
     if (rc == ZAFB_OK) rc = upload_twiddles(&p->d_tw_full, n, n / 2);
     if (rc == ZAFB_OK) rc = upload_vec(&p->d_band_lo, lo);
@@ -984,6 +1086,10 @@ int zafb_mel_plan_set_precision(zafb_mel_plan* p, int bits, const double* window
     ZAFB_REQUIRE(p != nullptr, "plan is NULL");
     ZAFB_REQUIRE(bits == 0 || bits == 32 || bits == 64, "precision must be 0 (automatic), 32 or 64 (got %d)", bits);
     (void)window;  // the float64 tables are built from the window handed to zafb_mel_plan_create
+    if (p->stft_any != nullptr) {  // window length not a power of two: fp32 only
+        if (bits == 64) return fail(ZAFB_E_UNSUPPORTED, "the float64 route needs a power-of-two window length");
+        return ZAFB_OK;
+    }
     p->precision = bits;
     return ZAFB_OK;
 }
@@ -999,6 +1105,7 @@ int zafb_mel_plan_set_route(zafb_mel_plan* p, int route) {
 
 int zafb_mel_plan_destroy(zafb_mel_plan* p) {
     if (!p) return ZAFB_OK;
+    zafb_stft_plan_destroy(p->stft_any);
     cudaFree(p->d_window64);
     cudaFree(p->d_tw_half64);
     cudaFree(p->d_tw_full64);
