@@ -388,3 +388,40 @@ def test_stft_host_half_spectrum_path(zaf_gpu, monkeypatch):
         for k in ("ZAFB_HOST_MIRROR", "ZAFB_HOST_MIRROR_MIN_MB", "ZAFB_PIPE_CHUNK_MB", "ZAFB_HOST_MIRROR_THREADS"):
             monkeypatch.delenv(k)
         assert_parity(ref[-1], oracle.stft(x[-1], w, hop))
+
+
+@pytest.mark.parametrize("n", [2048, 1024])
+@pytest.mark.parametrize("ratio", [2, 4])
+def test_istft_bin_major_direct_kernel(zaf_gpu, monkeypatch, n, ratio):
+    """istft of a spectrum in the reference's C-order memory is read directly by istft_binmajor_kernel (16-frame tiles,
+    the spectrum combined to X[k] + conj(X[N-k]) while loading), on NON-Hermitian spectra, frame counts around the tile
+    size, several clips per CTA, clips split into runs."""
+    hop = n // ratio
+    rng = np.random.default_rng(n + ratio)
+    w = oracle.hamming_periodic(n)
+    for clips, nt in ((3, 97), (1, 16), (2, 17), (2, ratio), (1, ratio - 1), (160, 35), (400, 40)):
+        spec = (rng.standard_normal((clips, n, nt)) + 1j * rng.standard_normal((clips, n, nt))).astype(np.complex64)  # C order
+        direct = zaf_gpu.istft(spec, w, hop)
+        monkeypatch.setenv("ZAFB_ISTFT_BM_RUNS_PER_CLIP", "3")   # the same clips cut into three runs with warm-up frames
+        assert np.array_equal(zaf_gpu.istft(spec, w, hop), direct)
+        monkeypatch.delenv("ZAFB_ISTFT_BM_RUNS_PER_CLIP")
+        frame_major = zaf_gpu.istft(np.swapaxes(np.ascontiguousarray(np.swapaxes(spec, 1, 2)), 1, 2), w, hop)
+        assert direct.shape == (clips, max(0, nt * hop - (n - hop)))
+        # same arithmetic, same summation order; the two kernels differ by the compiler's choice of fused multiply-adds
+        # (last-bit differences), so the comparison is at a few fp32 ulps of the signal's peak rather than bitwise
+        if direct.size:
+            peak = float(np.max(np.abs(frame_major)))
+            assert np.max(np.abs(direct - frame_major)) <= 4e-7 * peak, (clips, nt)
+        monkeypatch.setenv("ZAFB_ISTFT_BM_DIRECT", "0")
+        assert np.array_equal(zaf_gpu.istft(spec, w, hop), frame_major)  # the route through transposed scratch IS bitwise
+        monkeypatch.delenv("ZAFB_ISTFT_BM_DIRECT")
+        # a clip's result does not depend on the batch around it
+        if clips > 1 and direct.size:
+            assert np.array_equal(zaf_gpu.istft(spec[clips - 1], w, hop), direct[clips - 1])
+        if direct.size:
+            assert_parity(direct[clips - 1], oracle.istft(spec[clips - 1].astype(np.complex128), w, hop))
+    # device-resident C-order spectrum straight from the direct STFT kernel
+    x = rng.uniform(-1, 1, (4, 30000)).astype(np.float32)
+    sd = zaf_gpu.stft(zaf_gpu.to_device(x), w, hop, layout="bin_major")
+    back = zaf_gpu.istft(sd, w, hop).to_host()
+    assert np.max(np.abs(back - zaf_gpu.istft(zaf_gpu.stft(x, w, hop), w, hop))) <= 4e-7

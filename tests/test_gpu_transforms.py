@@ -431,7 +431,9 @@ def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
     a = zaf_gpu.stft(x, w, 512)
     b = zaf_gpu.stft(x, w, 512, layout="bin_major")
     assert b.flags.c_contiguous and not a.flags.c_contiguous and np.array_equal(a, b)
-    assert np.array_equal(zaf_gpu.istft(b, w, 512), zaf_gpu.istft(a, w, 512))
+    # C-order input goes through istft_binmajor_kernel: the same arithmetic in the same order, but a different kernel
+    # (the compiler fuses multiply-adds differently): equal to a few fp32 ulps of the peak, not bit for bit
+    assert np.max(np.abs(zaf_gpu.istft(b, w, 512) - zaf_gpu.istft(a, w, 512))) <= 4e-7
     assert_parity(b[3], oracle.stft(x[3], w, 512))
     wk = oracle.kbd_window(2048)
     ma = zaf_gpu.mdct(x, wk)
@@ -451,7 +453,7 @@ def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
     a2 = zaf_gpu.stft(x2, w, 512)
     sd = zaf_gpu.stft(zaf_gpu.to_device(x2), w, 512, layout="bin_major")
     assert not sd.transposed and np.array_equal(sd.to_host(), a2)
-    assert np.array_equal(zaf_gpu.istft(sd, w, 512).to_host(), zaf_gpu.istft(a2, w, 512))
+    assert np.max(np.abs(zaf_gpu.istft(sd, w, 512).to_host() - zaf_gpu.istft(a2, w, 512))) <= 4e-7
 
 
 def test_sum_of_sinusoids_parity_and_the_fp32_floor_of_mfcc(zaf_gpu):

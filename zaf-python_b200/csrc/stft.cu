@@ -916,6 +916,155 @@ int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_cli
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// ISTFT reading BIN_MAJOR memory [clip][bin][frame] -- the reference's C order (zaf.py:214: the (N, nt) array zaf.stft
+// returns) -- directly, instead of a tiled transpose into frame-major scratch (three passes over the spectrum).
+//
+// A CTA of 16 warps walks along one clip in tiles of F = 16 consecutive frames.  Load phase: thread (u, w) reads frame
+// w of bin rows k = u, u + 32, ... and of their mirror rows N - k -- 16 frames of a row are one 128-byte run -- and parks
+// Hs[k] = X[k] + conj(X[N-k]), k = 0 .. N/2, in the frame's slot of a ring of F + R - 1 shared-memory regions (the only
+// combination of the two-sided spectrum that Re(ifft) depends on, zaf.py:223).  Transform phase: warp w runs the packed
+// c2r transform of istft_warp_kernel on its frame (the slot doubles as the FFT's transpose tile, then receives the N
+// time samples).  Overlap-add phase: every finished hop-block is the sum of R frame parts, added in increasing frame
+// order like the reference (zaf.py:227-233) and like istft_warp_kernel -- the results are bit-identical to the
+// frame-major path -- and leaves as contiguous 16-byte stores.  The R - 1 last frames of a tile stay in the ring.
+// ------------------------------------------------------------------------------------------
+template <int N>
+struct IstftBinMajorGeom {
+    static constexpr int F = 16;
+    static constexpr int M = N / 2;
+    static constexpr int TILE = N == 2048 ? (32 * kFft1024Pitch + 1) / 2 : (N / 64) * kFft1024Pitch;  // float2 units
+    static constexpr int NEED = (M + 1) > TILE ? (M + 1) : TILE;
+    static constexpr int PITCH = NEED | 1;  // odd: the 16 frames of one bin land in distinct bank pairs
+};
+
+template <int N, int R>
+__global__ void __launch_bounds__(512, 1)
+istft_binmajor_kernel(const float2* __restrict__ spec, int nt, const float2* __restrict__ tw4,
+                      const float2* __restrict__ tw_full, float scale, float* __restrict__ y, int64_t y_stride,
+                      int runs_per_clip, int tiles_per_run, int64_t total_runs) {
+    using G = WarpGeom<N>;
+    using B = IstftBinMajorGeom<N>;
+    constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
+    constexpr int F = B::F, SLOTS = F + R - 1, PITCH = B::PITCH, HOP = N / R;
+    extern __shared__ __align__(16) float2 smem[];
+    float2* s_tw = smem;          // M: W_M^{k1 n2}
+    float2* s_reg = smem + M;     // SLOTS regions of PITCH float2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < M; i += 512) s_tw[i] = tw4[i];
+    const float2 c_lane = tw_full[lane];  // W_N^lane
+    LaneTw<N> lt;
+    lt.init(lane);
+    const int lw = tid & (F - 1), lu = tid / F;  // load phase: frame within the tile, bin index mod 32
+    const int tiles_per_clip = (nt + F - 1) / F;
+    __syncthreads();
+
+    for (int64_t run = blockIdx.x; run < total_runs; run += gridDim.x) {
+        const int64_t clip = run / runs_per_clip;
+        const int t0 = int(run - clip * runs_per_clip) * tiles_per_run;
+        const int t1 = min(t0 + tiles_per_run, tiles_per_clip);
+        const float2* sc = spec + clip * int64_t(N) * nt;
+        float* yc = y + clip * y_stride;
+        // a run that starts inside a clip first transforms the R - 1 frames before it (no output: they belong to the
+        // previous run's blocks, but their later parts overlap into this run's first blocks)
+        for (int t = t0 > 0 ? t0 - 1 : t0; t < t1; ++t) {
+            const bool warmup = t < t0;
+            const int j0 = warmup ? t0 * F - (R - 1) : t * F;
+            const int cnt = warmup ? R - 1 : F;
+            // ---- load: Hs[k] = X[k] + conj(X[N - k]) for the tile's frames
+            {
+                const int j = j0 + lw;
+                if (lw < cnt && j < nt) {
+                    float2* slot = s_reg + (j % SLOTS) * PITCH;
+                    const float2* col = sc + j;
+#pragma unroll 4
+                    for (int k = lu; k <= M; k += 32) {
+                        const float2 a = __ldg(col + int64_t(k) * nt);
+                        const float2 d = __ldg(col + int64_t((N - k) & (N - 1)) * nt);
+                        slot[k] = make_float2(a.x + d.x, a.y - d.y);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- transform: warp w, frame j0 + w
+            {
+                const int j = j0 + warp;
+                if (warp < cnt && j < nt) {  // warp-uniform
+                    float2* slot = s_reg + (j % SLOTS) * PITCH;
+                    float2 v[REGS];
+                    static_for<0, REGS>([&](auto tc) {
+                        constexpr int r = decltype(tc)::value;
+                        const int k = lane + 32 * r;
+                        const float2 h0 = slot[k];                    // 2 H[k]
+                        const float2 hm = slot[M - k];
+                        const float2 h1 = make_float2(hm.x, -hm.y);   // 2 H[k + M] = conj(Hs[M - k])
+                        const float2 e = cadd(h0, h1);
+                        const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, N / 32>(c_lane));
+                        v[r] = make_float2(e.x - o.y, -(e.y + o.x));  // conj(Z), Z = E + i O
+                    });
+                    __syncwarp();  // every lane has read the spectrum: the slot becomes the transpose tile
+                    if constexpr (N == 2048) warp_fft1024<true>(v, s_tw, reinterpret_cast<float*>(slot), lane);
+                    else if constexpr (N == 1024) warp_fft512(v, s_tw, slot, lane);
+                    else if constexpr (N == 512) warp_fft256(v, s_tw, slot, lane, lt.tq);
+                    else warp_fft128(v, s_tw, slot, lane, lt.tq);
+                    __syncwarp();
+                    static_for<0, REGS>([&](auto k2c) {   // y[2n] + i y[2n+1] = conj(v[bitrev(k2)]), n = lane + 32 k2
+                        constexpr int k2 = decltype(k2c)::value;
+                        slot[lane + 32 * k2] = make_float2(v[bitrev(k2, LOGR)].x, -v[bitrev(k2, LOGR)].y);
+                    });
+                }
+            }
+            __syncthreads();
+            // ---- overlap-add: hop-blocks h in [j0, j0 + F) that exist (h >= R - 1, h < nt), two samples per thread
+            if (!warmup) {
+                const int h_lo = j0 > R - 1 ? j0 : R - 1;
+                const int h_hi = (j0 + F < nt ? j0 + F : nt);
+                const int pairs = (h_hi - h_lo) * (HOP / 2);
+                for (int pr = tid; pr < pairs; pr += 512) {
+                    const int h = h_lo + pr / (HOP / 2);
+                    const int i2 = pr % (HOP / 2);
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = R - 1; q >= 0; --q) {  // frames h - R + 1 ... h, in the reference's order
+                        const float2 part = s_reg[((h - q) % SLOTS) * PITCH + q * (HOP / 2) + i2];
+                        if (q == R - 1) acc = part;
+                        else acc = make_float2(acc.x + part.x, acc.y + part.y);
+                    }
+                    reinterpret_cast<float2*>(yc + int64_t(h - (R - 1)) * HOP)[i2] = make_float2(acc.x * scale, acc.y * scale);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+template <int N, int R>
+int launch_istft_binmajor(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y, int64_t y_stride,
+                          cudaStream_t st) {
+    using B = IstftBinMajorGeom<N>;
+    constexpr size_t smem = (size_t(N / 2) + size_t(B::F + R - 1) * B::PITCH) * sizeof(float2);
+    static_assert(smem <= size_t(kMaxDynSmem), "istft bin-major kernel: shared memory");
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA((cudaFuncSetAttribute(istft_binmajor_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        attr = true;
+    }
+    // runs of consecutive tiles of one clip: whole clips when there are enough of them, else about two runs per SM
+    const int64_t sms = sm_count();
+    const int64_t tiles_per_clip = ceil_div(nt, B::F);
+    int64_t runs_per_clip = n_clips >= 2 * sms ? 1 : std::min<int64_t>(tiles_per_clip, ceil_div(2 * sms, n_clips));
+    if (const int forced = env_flag("ZAFB_ISTFT_BM_RUNS_PER_CLIP", 0); forced > 0) runs_per_clip = std::min<int64_t>(tiles_per_clip, forced);  // tests
+    const int64_t tiles_per_run = ceil_div(tiles_per_clip, runs_per_clip);
+    runs_per_clip = ceil_div(tiles_per_clip, tiles_per_run);
+    const int64_t runs = n_clips * runs_per_clip;
+    const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
+    const int64_t ctas = std::min<int64_t>(runs, sms);
+    istft_binmajor_kernel<N, R><<<unsigned(ctas), 512, smem, st>>>(spec, int(nt), p->d_tw_4step, p->d_tw_full, scale, y, y_stride,
+                                                                    int(runs_per_clip), int(tiles_per_run), runs);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
 int fft_threads(int points) {  // threads for a block FFT of `points` complex points
     int t = points / 4;
     if (t < 32) t = 32;
@@ -1140,6 +1289,15 @@ static int istft_impl(const zafb_stft_plan* p, const float* spec, int64_t n_clip
             };
             const float2* s2 = reinterpret_cast<const float2*>(spec);
             if (layout == ZAFB_LAYOUT_FRAME_MAJOR) return run(s2, n_clips, y, spec_pitch);
+            // the reference's C order read directly, for every batch size (a clip's result must not depend on the batch
+            // around it); ZAFB_ISTFT_BM_DIRECT=0: the older route through frame-major scratch
+            if ((n == 2048 || n == 1024) && (ratio == 2 || ratio == 4) && nt < (int64_t(1) << 26) && env_flag("ZAFB_ISTFT_BM_DIRECT", 1)) {
+                if (n == 2048)
+                    return ratio == 2 ? launch_istft_binmajor<2048, 2>(p, s2, n_clips, nt, y, y_stride, st)
+                                      : launch_istft_binmajor<2048, 4>(p, s2, n_clips, nt, y, y_stride, st);
+                return ratio == 2 ? launch_istft_binmajor<1024, 2>(p, s2, n_clips, nt, y, y_stride, st)
+                                  : launch_istft_binmajor<1024, 4>(p, s2, n_clips, nt, y, y_stride, st);
+            }
             return frame_major_from_bin_major(s2, n_clips, nt, int64_t(n), st, [&](int64_t c0, int64_t nc, const float2* scratch) {
                 return run(scratch, nc, y + c0 * y_stride, int64_t(n));
             });
