@@ -1488,6 +1488,7 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
     }
     std::atomic<int64_t> recorded{0};
     std::atomic<int> stop{0};
+    const bool nofill = env_flag("ZAFB_HOST_MIRROR_NOFILL", 0) != 0;
     float2* o2 = reinterpret_cast<float2*>(out);
     std::vector<std::thread> pool;
     pool.reserve(threads);
@@ -1502,6 +1503,7 @@ int stft_host_mirrored(const zafb_stft_plan* p, const float* x, int64_t n_clips,
                 if (cudaEventSynchronize(events[c]) != cudaSuccess) return;
                 const int64_t c0 = c * per;
                 const int64_t nc = (c0 + per <= n_clips) ? per : n_clips - c0;
+                if (nofill) continue;  // measurement only (ZAFB_HOST_MIRROR_NOFILL=1): the copy pipeline without the fill
                 if (frame_major) {
                     const int64_t frames = nc * nt;
                     const int64_t f_lo = frames * w / threads, f_hi = frames * (w + 1) / threads;
