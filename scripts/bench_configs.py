@@ -338,6 +338,21 @@ def main():
                 emit(line(f"{name}-{t}", f"{batch} vectors x {n}", batch, "vectors", ms, batch * n * 8, nl))
         xd.free()
 
+    # ---- dct / dst at the other warp-kernel lengths (types II-IV)
+    if "dctsizes" in only:
+        lib, C = zaf._lib.lib(), zaf._lib.C
+        for n in (512, 2048):
+            batch = max(1, int((1 << 30) // (4 * n) * args.scale))
+            xd, _ = device_batch(batch, n, 20261017 + n, distinct=1024)
+            od = zaf.empty((batch, n), np.float32)
+            for kind, name in ((0, "dct"), (1, "dst")):
+                for t in (2, 3, 4):
+                    plan = zaf._dct_plans.get((kind, t, n), kind, t, n)
+                    ms, o, nl = timeit(lambda s: zaf._lib.check(lib.zafb_dct_f32(
+                        plan, C.c_void_p(xd.ptr), batch, n, C.c_void_p(od.ptr), n, s.ptr)), max(3, args.steps // 3))
+                    emit(line(f"{name}-{t}-n{n}", f"{batch} vectors x {n}", batch, "vectors", ms, batch * n * 8, nl))
+            xd.free(), od.free()
+
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         with open(args.out, "w") as f:

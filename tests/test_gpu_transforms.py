@@ -539,3 +539,25 @@ def test_mel_mfcc_window_lengths_that_are_not_powers_of_two(zaf_gpu, n, hop, fs,
     assert np.array_equal(zaf_gpu.mfcc(zaf_gpu.to_device(x), w, hop, fb, ncoef).to_host(), cep)
     with pytest.raises(NotImplementedError):
         zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64")
+
+
+@pytest.mark.parametrize("n", [512, 2048])
+def test_dct_dst_warp_kernels_512_2048(zaf_gpu, n):
+    """The one-warp-per-vector kernel (types II-IV and their DST twins) at N = 512 and 2048 (r02; N = 1024 has its own
+    test): forced through the plan hook, against the oracle, plus the orthonormal inverse pairs."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (37, n)).astype(np.float32)
+    lib = zaf_gpu._lib.lib()
+    for kind, fn, ofn in ((0, zaf_gpu.dct, oracle.dct), (1, zaf_gpu.dst, oracle.dst)):
+        for t in (2, 3, 4):
+            plan = zaf_gpu._dct_plans.get((kind, t, n), kind, t, n)
+            zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, 4))  # 4 = require the warp kernel
+            try:
+                got = fn(x, t)
+            finally:
+                lib.zafb_dct_plan_force_direct(plan, 0)
+            for c in (0, 17, 36):
+                assert_parity(got[c], ofn(x[c], t))
+            assert np.array_equal(got, fn(x, t))  # the default route is the same kernel
+        assert np.max(np.abs(fn(fn(x, 2), 3) - x)) <= 1e-5
+        assert np.max(np.abs(fn(fn(x, 4), 4) - x)) <= 1e-5

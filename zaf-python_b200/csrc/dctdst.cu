@@ -218,17 +218,27 @@ __global__ void dct_fft_kernel(const float* __restrict__ x, int64_t batch, int64
 // ---------------------------------------------------------------------------------------------
 constexpr int kDctWarps = 8;
 
-template <int MODE, bool DST>
-__global__ void __launch_bounds__(kDctWarps * 32, MODE == 3 ? 2 : 3)   // type III holds the 1024 inputs AND 512 products
-dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, const float2* __restrict__ tw4,
+// N = 512, 1024, 2048 (r02: the same code, REGS = N / 64 points per lane; warp_fft256 / warp_fft512 / warp_fft1024)
+template <int N, int MODE, bool DST>
+__global__ void __launch_bounds__(kDctWarps * 32, N == 2048 ? 1 : (MODE == 3 ? 2 : 3))   // type III holds the N inputs AND N/2 products
+dct_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, const float2* __restrict__ tw4,
                     const float2* __restrict__ tw_a, const float2* __restrict__ tw_b, float* __restrict__ out,
                     int64_t out_stride) {
+    constexpr int H = N / 2, REGS = H / 32, LOGR = clog2(REGS);
+    static_assert(N == 512 || N == 1024 || N == 2048, "dct warp kernel: N = 512, 1024 or 2048");
     extern __shared__ float2 smem2[];
-    float2* s_tw = smem2;  // 512: W_512^{k1 n2}
+    float2* s_tw = smem2;  // H: W_H^{k1 n2}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* s_buf = smem2 + 512 + warp * (16 * kFft1024Pitch);
-    for (int i = tid; i < 512; i += kDctWarps * 32) s_tw[i] = tw4[i];
-    constexpr float kNorm = 0.04419417382415922f;   // sqrt(2 / 1024)
+    float2* s_buf = smem2 + H + warp * (REGS * kFft1024Pitch);
+    for (int i = tid; i < H; i += kDctWarps * 32) s_tw[i] = tw4[i];
+    constexpr float kNorm = N == 512 ? 0.0625f : N == 1024 ? 0.04419417382415922f : 0.03125f;   // sqrt(2 / N)
+    float2 tq[N == 512 ? 8 : 1];
+    if constexpr (N == 512) warp_fft256_lane_twiddles(tq, lane);
+    auto warp_fft = [&](float2 (&a)[REGS]) {
+        if constexpr (N == 512) warp_fft256(a, s_tw, s_buf, lane, tq);
+        else if constexpr (N == 1024) warp_fft512(a, s_tw, s_buf, lane);
+        else warp_fft1024<false>(a, s_tw, s_buf, lane);
+    };
     constexpr float kR2 = 0.70710678118654752f;
     const float2 ta = tw_a[lane];
     float2 tb = tw_b[lane];
@@ -241,33 +251,33 @@ dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, 
     for (int64_t vec = int64_t(blockIdx.x) * kDctWarps + warp; vec < batch; vec += int64_t(gridDim.x) * kDctWarps) {
         const float* xv = x + vec * stride;
         float* ov = out + vec * out_stride;
-        float2 v[16];
+        float2 v[REGS];
 
         if constexpr (MODE == 4) {
-            float2 xp[16];
+            float2 xp[REGS];
             const float2* P = reinterpret_cast<const float2*>(xv) + lane;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) xp[r] = __ldg(P + 32 * r);
-            static_for<0, 16>([&](auto rc) {
+            for (int r = 0; r < REGS; ++r) xp[r] = __ldg(P + 32 * r);
+            static_for<0, REGS>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
-                const float other = __shfl_xor_sync(0xffffffffu, xp[15 - r].y, 31);  // x[N-1-2m]
+                const float other = __shfl_xor_sync(0xffffffffu, xp[REGS - 1 - r].y, 31);  // x[N-1-2m]
                 const float2 t = DST ? make_float2(other, xp[r].x) : make_float2(xp[r].x, other);
-                v[r] = cmul(t, mul_tw<r, 64>(ta));
+                v[r] = cmul(t, mul_tw<r, N / 16>(ta));
             });
-            warp_fft512(v, s_tw, s_buf, lane);
-            static_for<0, 16>([&](auto kc) {
+            warp_fft(v);
+            static_for<0, REGS>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                v[bitrev(k, 4)] = cmul(v[bitrev(k, 4)], mul_tw<k, 64>(tb));
+                v[bitrev(k, LOGR)] = cmul(v[bitrev(k, LOGR)], mul_tw<k, N / 16>(tb));
             });
             float2* o = reinterpret_cast<float2*>(ov) + lane;
-            static_for<0, 16>([&](auto kc) {
+            static_for<0, REGS>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;
-                const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(15 - k, 4)].y, 31);
-                __stcs(o + 32 * k, make_float2(v[bitrev(k, 4)].x, DST ? im : -im));
+                const float im = __shfl_xor_sync(0xffffffffu, v[bitrev(REGS - 1 - k, LOGR)].y, 31);
+                __stcs(o + 32 * k, make_float2(v[bitrev(k, LOGR)].x, DST ? im : -im));
             });
         } else if constexpr (MODE == 2) {
             const float4* Q = reinterpret_cast<const float4*>(xv) + lane;
-            static_for<0, 8>([&](auto rc) {
+            static_for<0, REGS / 2>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
                 float4 q = __ldg(Q + 32 * r);
                 if constexpr (DST) {  // (-1)^n x[n]
@@ -275,77 +285,77 @@ dct1024_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, 
                     q.w = -q.w;
                 }
                 v[r] = make_float2(q.x, q.z);                                   // z[q]
-                v[15 - r].x = __shfl_xor_sync(0xffffffffu, q.w, 31);           // z[511 - q'] of lane 31 - lane
-                v[15 - r].y = __shfl_xor_sync(0xffffffffu, q.y, 31);
+                v[REGS - 1 - r].x = __shfl_xor_sync(0xffffffffu, q.w, 31);     // z[H - 1 - q'] of lane 31 - lane
+                v[REGS - 1 - r].y = __shfl_xor_sync(0xffffffffu, q.y, 31);
             });
-            warp_fft512(v, s_tw, s_buf, lane);  // Z[lane + 32 k2] = v[bitrev(k2, 4)]
-            static_for<0, 16>([&](auto kc) {
+            warp_fft(v);  // Z[lane + 32 k2] = v[bitrev(k2, LOGR)]
+            static_for<0, REGS>([&](auto kc) {
                 constexpr int k2 = decltype(kc)::value;
-                const float2 z = v[bitrev(k2, 4)];
-                const float2 mine = v[bitrev(15 - k2, 4)];
+                const float2 z = v[bitrev(k2, LOGR)];
+                const float2 mine = v[bitrev(REGS - 1 - k2, LOGR)];
                 float2 p;
                 p.x = __shfl_sync(0xffffffffu, mine.x, mirror);
                 p.y = __shfl_sync(0xffffffffu, mine.y, mirror);
-                if (lane == 0) p = v[bitrev((16 - k2) & 15, 4)];
+                if (lane == 0) p = v[bitrev((REGS - k2) & (REGS - 1), LOGR)];
                 const float2 e = make_float2(z.x + p.x, z.y - p.y);
                 const float2 od = make_float2(z.y + p.y, p.x - z.x);
-                const float2 V = cadd(e, cmul(mul_tw<k2, 32>(ta), od));
-                const float2 U = cmul(V, mul_tw<k2, 128>(tb));
+                const float2 V = cadd(e, cmul(mul_tw<k2, N / 32>(ta), od));
+                const float2 U = cmul(V, mul_tw<k2, N / 8>(tb));
                 float lo = U.x, hi = -U.y;
                 const int k = lane + 32 * k2;
-                int ihi = 1024 - k;
+                int ihi = N - k;
                 if (k2 == 0 && lane == 0) {  // k = 0: X_0 carries c_0 = 1/sqrt2; the mirror slot holds X_{N/2}
                     lo = tb.x * (e.x + od.x) * kR2;
                     hi = tb.x * (e.x - od.x) * kR2;
-                    ihi = 512;
+                    ihi = H;
                 }
                 if constexpr (DST) {  // reversed output
-                    ov[1023 - k] = lo;
-                    ov[1023 - ihi] = hi;
+                    ov[N - 1 - k] = lo;
+                    ov[N - 1 - ihi] = hi;
                 } else {
                     ov[k] = lo;
                     ov[ihi] = hi;
                 }
             });
         } else {  // MODE 3
-            float xr[32];
+            float xr[2 * REGS];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xr[i] = DST ? __ldg(xv + 1023 - lane - 32 * i) : __ldg(xv + lane + 32 * i);
+            for (int i = 0; i < 2 * REGS; ++i) xr[i] = DST ? __ldg(xv + N - 1 - lane - 32 * i) : __ldg(xv + lane + 32 * i);
             // V_k = (C_k - i C_{N-k}) u_k (scaled by s/2), k = lane + 32 r
-            static_for<0, 16>([&](auto rc) {
+            static_for<0, REGS>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
                 float ck = xr[r];
-                float cn = __shfl_sync(0xffffffffu, xr[31 - r], mirror);
+                float cn = __shfl_sync(0xffffffffu, xr[2 * REGS - 1 - r], mirror);
                 if (lane == 0) {
-                    cn = r == 0 ? 0.f : xr[(32 - r) & 31];
+                    cn = r == 0 ? 0.f : xr[(2 * REGS - r) & (2 * REGS - 1)];
                     if (r == 0) ck *= 1.41421356237309505f;  // C_0 = x_0 / c_0
                 }
-                v[r] = cmul(make_float2(ck, -cn), mul_tw<128 - r, 128>(tb));
+                v[r] = cmul(make_float2(ck, -cn), mul_tw<N / 8 - r, N / 8>(tb));
             });
-            float2 zin[16];
-            static_for<0, 16>([&](auto rc) {
+            float2 zin[REGS];
+            static_for<0, REGS>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
                 float2 pv;
-                pv.x = __shfl_sync(0xffffffffu, v[15 - r].x, mirror);
-                pv.y = __shfl_sync(0xffffffffu, v[15 - r].y, mirror);
+                pv.x = __shfl_sync(0xffffffffu, v[REGS - 1 - r].x, mirror);
+                pv.y = __shfl_sync(0xffffffffu, v[REGS - 1 - r].y, mirror);
                 if (lane == 0) {
-                    if constexpr (r == 0) pv = make_float2(1.41421356237309505f * xr[16] * tb.x, 0.f);  // V_{N/2} is real
-                    else pv = v[16 - r];
+                    if constexpr (r == 0) pv = make_float2(1.41421356237309505f * xr[REGS] * tb.x, 0.f);  // V_{N/2} is real
+                    else pv = v[REGS - r];
                 }
                 const float2 e = make_float2(v[r].x + pv.x, v[r].y - pv.y);   // V_k + conj(V_{N/2-k})
                 const float2 d = make_float2(v[r].x - pv.x, v[r].y + pv.y);
-                const float2 o = cmul_conj(d, mul_tw<r, 32>(ta));
+                const float2 o = cmul_conj(d, mul_tw<r, N / 32>(ta));
                 // Z = E + i O; the inverse FFT runs as conj(FFT(conj Z))
                 zin[r] = make_float2(e.x - o.y, -(e.y + o.x));
             });
-            warp_fft512(zin, s_tw, s_buf, lane);  // conj(z[lane + 32 k2]) = zin[bitrev(k2, 4)]
+            warp_fft(zin);  // conj(z[lane + 32 k2]) = zin[bitrev(k2, LOGR)]
             float4* o4 = reinterpret_cast<float4*>(ov) + lane;
-            static_for<0, 8>([&](auto rc) {
+            static_for<0, REGS / 2>([&](auto rc) {
                 constexpr int r = decltype(rc)::value;
-                const float2 own = zin[bitrev(r, 4)];
+                const float2 own = zin[bitrev(r, LOGR)];
                 float2 oth;
-                oth.x = __shfl_xor_sync(0xffffffffu, zin[bitrev(15 - r, 4)].x, 31);
-                oth.y = __shfl_xor_sync(0xffffffffu, zin[bitrev(15 - r, 4)].y, 31);
+                oth.x = __shfl_xor_sync(0xffffffffu, zin[bitrev(REGS - 1 - r, LOGR)].x, 31);
+                oth.y = __shfl_xor_sync(0xffffffffu, zin[bitrev(REGS - 1 - r, LOGR)].y, 31);
                 // x[4q] = Re z[q], x[4q+1] = Im z[511-q], x[4q+2] = Im z[q], x[4q+3] = Re z[511-q]
                 float4 q = make_float4(own.x, -oth.y, -own.y, oth.x);
                 if constexpr (DST) {
@@ -385,12 +395,24 @@ int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
     ZAFB_CUDA(cudaFuncSetAttribute(dct_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     ZAFB_CUDA(cudaFuncSetAttribute(dct_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    ZAFB_CUDA(cudaFuncSetAttribute(dct1024_warp_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -485,15 +507,16 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_a, ta.data(), ta.size() / 2);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_b, tb.data(), tb.size() / 2);
     }
-    if (rc == ZAFB_OK && p->log2n == 10) {  // W_512^{k1*n2} laid out [k1][n2] for the N = 1024 warp kernel
-        std::vector<double> t(2 * 512);
-        for (int k1 = 0; k1 < 16; ++k1)
-            for (int n2 = 0; n2 < 32; ++n2) {
-                const double a = -2.0 * pi * double((k1 * n2) % 512) / 512.0;
+    if (rc == ZAFB_OK && p->log2n >= 9 && p->log2n <= 11) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels (N = 512, 1024, 2048)
+        const int64_t hh = n / 2;
+        std::vector<double> t(2 * hh);
+        for (int64_t k1 = 0; k1 < hh / 32; ++k1)
+            for (int64_t n2 = 0; n2 < 32; ++n2) {
+                const double a = -2.0 * pi * double((k1 * n2) % hh) / double(hh);
                 t[2 * (k1 * 32 + n2)] = std::cos(a);
                 t[2 * (k1 * 32 + n2) + 1] = std::sin(a);
             }
-        rc = upload_c32(&p->d_tw_4step, t.data(), 512);
+        rc = upload_c32(&p->d_tw_4step, t.data(), hh);
     }
     // matrix path for everything the FFT path does not cover: Mat[k][m] = s_out[k] s_in[m] T[(a(m) b(k)) mod P]
     if (rc == ZAFB_OK && p->log2n < 2 && n >= 16 && n <= 8192) {
@@ -637,18 +660,25 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
                              stride % 4 == 0 && out_stride % 4 == 0;
         const bool warp_ok = p->d_tw_4step != nullptr && p->type >= 2 && aligned;
         if (p->force_direct == 4 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "dct warp kernel needs N = 1024, type 2..4, 16-byte aligned rows");
+            return fail(ZAFB_E_UNSUPPORTED, "dct warp kernel needs N = 512, 1024 or 2048, type 2..4, 16-byte aligned rows");
         if (warp_ok && (p->force_direct == 0 || p->force_direct == 4)) {
-            const size_t smem = (512 + kDctWarps * 16 * kFft1024Pitch) * sizeof(float2);
+            const size_t smem = size_t(n / 2 + kDctWarps * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(batch, kDctWarps);
-            const int occ = p->type == 3 ? 2 : 3;
+            const int occ = n == 2048 ? 1 : (p->type == 3 ? 2 : 3);
             if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
             const unsigned g = unsigned(ctas), b = kDctWarps * 32;
+#define ZAFB_DCT_WARP_N(NN, MODE, DST)                                                                            \
+    dct_warp_kernel<NN, MODE, DST><<<g, b, smem, st>>>(x, batch, stride, p->d_tw_4step, p->d_tw_a, p->d_tw_b, out, out_stride)
 #define ZAFB_DCT_WARP(MODE, DST)                                                                                  \
-    dct1024_warp_kernel<MODE, DST><<<g, b, smem, st>>>(x, batch, stride, p->d_tw_4step, p->d_tw_a, p->d_tw_b, out, out_stride)
+    do {                                                                                                          \
+        if (n == 512) ZAFB_DCT_WARP_N(512, MODE, DST);                                                            \
+        else if (n == 1024) ZAFB_DCT_WARP_N(1024, MODE, DST);                                                     \
+        else ZAFB_DCT_WARP_N(2048, MODE, DST);                                                                    \
+    } while (0)
             if (p->type == 2) { if (p->kind) ZAFB_DCT_WARP(2, true); else ZAFB_DCT_WARP(2, false); }
             else if (p->type == 3) { if (p->kind) ZAFB_DCT_WARP(3, true); else ZAFB_DCT_WARP(3, false); }
             else { if (p->kind) ZAFB_DCT_WARP(4, true); else ZAFB_DCT_WARP(4, false); }
+#undef ZAFB_DCT_WARP_N
 #undef ZAFB_DCT_WARP
             ZAFB_LAUNCH_CHECK();
             return ZAFB_OK;
