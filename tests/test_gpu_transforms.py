@@ -157,6 +157,37 @@ def test_dct_dst_tensor_core_matrix_path(zaf_gpu, n):
                 assert np.array_equal(got, fn(x, t))  # the default route for batch >= 8 is the same path
 
 
+@pytest.mark.parametrize("n", [257, 1000, 1024])
+def test_dct_dst_cta_pair_matrix_path(zaf_gpu, n, monkeypatch):
+    """Batches of 256 vectors and more take the CTA-pair form of the matrix path (tcgen05 cta_group::2, 256 x 256 tiles,
+    persistent over M blocks): a batch that is not a multiple of the 256-row tile, a batch with more M blocks than
+    resident pairs (the persistent loop), every type that has a matrix (even/odd form for types I / II, dense for the
+    rest); against the oracle and against the single-CTA kernel."""
+    rng = np.random.default_rng(2000 + n)
+    lib = zaf_gpu._lib.lib()
+    for batch in (700, 74 * 256 * 2 + 300):
+        x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        for kind, fn, ofn in ((0, zaf_gpu.dct, oracle.dct), (1, zaf_gpu.dst, oracle.dst)):
+            for t in (1, 2, 3, 4):
+                if t >= 2 and n & (n - 1) == 0:
+                    continue  # FFT path, no matrix
+                if batch > 700 and t >= 3:
+                    continue  # the large batch once per operand form is enough
+                plan = zaf_gpu._dct_plans.get((kind, t, n), kind, t, n)
+                zaf_gpu._lib.check(lib.zafb_dct_plan_force_direct(plan, 2))
+                try:
+                    got = fn(x, t)
+                    monkeypatch.setenv("ZAFB_GEMM_PAIR", "0")
+                    single = fn(x, t)
+                    monkeypatch.delenv("ZAFB_GEMM_PAIR")
+                finally:
+                    lib.zafb_dct_plan_force_direct(plan, 0)
+                for c in (0, 127, 128, 255, 256, batch // 2, batch - 1):
+                    assert_parity(got[c], ofn(x[c], t), what=f"kind {kind} type {t} batch {batch} vec {c}")
+                # same chains, same chunk sums: the two kernels agree to the last bits over the whole batch
+                assert np.max(np.abs(got - single)) <= 2e-6 * np.max(np.abs(single)), (kind, t, batch)
+
+
 def test_dct_dst_1024_warp_kernel(zaf_gpu):
     """N = 1024, types II-IV: the one-warp-per-vector kernel (forced), the block FFT kernel (forced) and the default
     route against the oracle; a batch that does not fill the last CTA; bit-identical results between calls."""

@@ -55,6 +55,13 @@ struct zafb_dct_plan {
     GemmTile* d_eo_tiles = nullptr;
     int eo_tiles = 0;
     int64_t eo_ldb = 0, eo_lda = 0, eo_dcol = 0;  // operand pitches, first column of d in the folded input
+    // the same operands cut into 256-row blocks for the CTA-pair kernel (gemm3xtf32_pair_tiled); dense form likewise
+    float* d_eo2_hi = nullptr;
+    float* d_eo2_lo = nullptr;
+    GemmTile* d_eo2_tiles = nullptr;
+    int eo2_tiles = 0;
+    GemmTile* d_mat2_tiles = nullptr;
+    int mat2_tiles = 0;
 };
 
 namespace {
@@ -390,6 +397,45 @@ __global__ void fold_split_tf32_kernel(const float* __restrict__ x, int64_t rows
     }
 }
 
+// The same for n a multiple of 8 (no padding columns: ld = n, s in columns [0, n/2), d in [n/2, n)): one thread per
+// group of four columns of s AND d -- two 16-byte loads (forward and mirrored), four 16-byte stores, no index division.
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+    auto one = [](float x, float& hv, float& lv) {
+        uint32_t a, b;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x));
+        hv = __uint_as_float(a);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x - hv));
+        lv = __uint_as_float(b);
+    };
+    one(v.x, h.x, l.x);
+    one(v.y, h.y, l.y);
+    one(v.z, h.z, l.z);
+    one(v.w, h.w, l.w);
+}
+__global__ void fold_split_tf32_vec_kernel(const float* __restrict__ x, int64_t rows, int n, int64_t ldx, float* __restrict__ hi,
+                                           float* __restrict__ lo) {
+    const int groups = n / 8;  // float4 groups per half row
+    const int rows_per_block = blockDim.x / groups > 0 ? blockDim.x / groups : 1;
+    const int g0 = threadIdx.x % groups, rr = threadIdx.x / groups;
+    if (rr >= rows_per_block && blockDim.x >= groups) return;
+    for (int64_t r = int64_t(blockIdx.x) * rows_per_block + rr; r < rows; r += int64_t(gridDim.x) * rows_per_block) {
+        const float* xr = x + r * ldx;
+        for (int g = g0; g < groups; g += blockDim.x) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(xr + 4 * g));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(xr + n - 4 - 4 * g));
+            const float4 s = make_float4(a.x + b.w, a.y + b.z, a.z + b.y, a.w + b.x);
+            const float4 d = make_float4(a.x - b.w, a.y - b.z, a.z - b.y, a.w - b.x);
+            float4 h, l;
+            split4(s, h, l);
+            *reinterpret_cast<float4*>(hi + r * n + 4 * g) = h;
+            *reinterpret_cast<float4*>(lo + r * n + 4 * g) = l;
+            split4(d, h, l);
+            *reinterpret_cast<float4*>(hi + r * n + n / 2 + 4 * g) = h;
+            *reinterpret_cast<float4*>(lo + r * n + n / 2 + 4 * g) = l;
+        }
+    }
+}
+
 bool g_attr_done = false;
 int set_kernel_attrs() {
     if (g_attr_done) return ZAFB_OK;
@@ -545,33 +591,47 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
                 worst = std::max(worst, std::fabs(b - ((k & 1) ? -a : a)));
             }
         if (worst > 1e-12) sym = false;
+        if (rc == ZAFB_OK) {  // dense form on the CTA-pair kernel: 256-row blocks of Mat
+            std::vector<GemmTile> tiles;
+            for (int64_t t = 0; t * 256 < n; ++t) tiles.push_back(GemmTile{0, int(n), int(t * 256), 1, int(std::min<int64_t>(256, n - t * 256))});
+            p->mat2_tiles = int(tiles.size());
+            e = cudaMalloc(reinterpret_cast<void**>(&p->d_mat2_tiles), tiles.size() * sizeof(GemmTile));
+            if (e == cudaSuccess) e = cudaMemcpy(p->d_mat2_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "dct: uploading the tile table failed: %s", cudaGetErrorString(e));
+        }
         if (rc == ZAFB_OK && sym) {
             const int64_t nh = (n + 1) / 2, nd = n / 2;        // columns of s (with the middle sample of an odd n) and of d
             const int64_t ne = (n + 1) / 2, no = n / 2;        // even and odd outputs
-            const int64_t te = (ne + 127) / 128, to = (no + 127) / 128;
             p->eo_ldb = (nh + 3) & ~int64_t(3);
             p->eo_dcol = p->eo_ldb;
             p->eo_lda = p->eo_ldb + ((nd + 3) & ~int64_t(3));
-            p->eo_tiles = int(te + to);
-            std::vector<double> st(size_t(te + to) * 128 * p->eo_ldb, 0.0);
-            for (int64_t k = 0; k < n; ++k) {
-                const int64_t row = (k & 1) ? te * 128 + k / 2 : k / 2;
-                const int64_t cols = (k & 1) ? nd : nh;
-                for (int64_t m = 0; m < cols; ++m) st[row * p->eo_ldb + m] = mat[k * p->ldk + m];
-            }
-            std::vector<GemmTile> tiles;
-            for (int64_t t = 0; t < te; ++t)
-                tiles.push_back(GemmTile{0, int(nh), int(2 * t * 128), 2, int(std::min<int64_t>(128, ne - t * 128))});
-            for (int64_t t = 0; t < to; ++t)
-                tiles.push_back(GemmTile{int(p->eo_dcol), int(nd), int(2 * t * 128 + 1), 2, int(std::min<int64_t>(128, no - t * 128))});
-            std::vector<float> ehi(st.size()), elo(st.size());
-            split_tf32_host(st.data(), st.size(), ehi.data(), elo.data());
-            e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_hi), ehi.size() * sizeof(float));
-            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_lo), elo.size() * sizeof(float));
-            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_eo_tiles), tiles.size() * sizeof(GemmTile));
-            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_hi, ehi.data(), ehi.size() * sizeof(float), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_lo, elo.data(), elo.size() * sizeof(float), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(p->d_eo_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice);
+            // stacked operand [Mat_even ; Mat_odd] in blocks of `blk` rows + one tile descriptor per block
+            auto build = [&](int64_t blk, float** d_hi, float** d_lo, GemmTile** d_tiles, int* n_tiles) -> cudaError_t {
+                const int64_t te = (ne + blk - 1) / blk, to = (no + blk - 1) / blk;
+                *n_tiles = int(te + to);
+                std::vector<double> st(size_t(te + to) * blk * p->eo_ldb, 0.0);
+                for (int64_t k = 0; k < n; ++k) {
+                    const int64_t row = (k & 1) ? te * blk + k / 2 : k / 2;
+                    const int64_t cols = (k & 1) ? nd : nh;
+                    for (int64_t m = 0; m < cols; ++m) st[row * p->eo_ldb + m] = mat[k * p->ldk + m];
+                }
+                std::vector<GemmTile> tiles;
+                for (int64_t t = 0; t < te; ++t)
+                    tiles.push_back(GemmTile{0, int(nh), int(2 * t * blk), 2, int(std::min<int64_t>(blk, ne - t * blk))});
+                for (int64_t t = 0; t < to; ++t)
+                    tiles.push_back(GemmTile{int(p->eo_dcol), int(nd), int(2 * t * blk + 1), 2, int(std::min<int64_t>(blk, no - t * blk))});
+                std::vector<float> ehi(st.size()), elo(st.size());
+                split_tf32_host(st.data(), st.size(), ehi.data(), elo.data());
+                cudaError_t e2 = cudaMalloc(reinterpret_cast<void**>(d_hi), ehi.size() * sizeof(float));
+                if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(d_lo), elo.size() * sizeof(float));
+                if (e2 == cudaSuccess) e2 = cudaMalloc(reinterpret_cast<void**>(d_tiles), tiles.size() * sizeof(GemmTile));
+                if (e2 == cudaSuccess) e2 = cudaMemcpy(*d_hi, ehi.data(), ehi.size() * sizeof(float), cudaMemcpyHostToDevice);
+                if (e2 == cudaSuccess) e2 = cudaMemcpy(*d_lo, elo.data(), elo.size() * sizeof(float), cudaMemcpyHostToDevice);
+                if (e2 == cudaSuccess) e2 = cudaMemcpy(*d_tiles, tiles.data(), tiles.size() * sizeof(GemmTile), cudaMemcpyHostToDevice);
+                return e2;
+            };
+            e = build(128, &p->d_eo_hi, &p->d_eo_lo, &p->d_eo_tiles, &p->eo_tiles);
+            if (e == cudaSuccess) e = build(256, &p->d_eo2_hi, &p->d_eo2_lo, &p->d_eo2_tiles, &p->eo2_tiles);
             if (e != cudaSuccess) rc = fail(ZAFB_E_CUDA, "dct: uploading the even/odd transform matrix failed: %s", cudaGetErrorString(e));
         }
     }
@@ -596,6 +656,10 @@ int zafb_dct_plan_destroy(zafb_dct_plan* p) {
     cudaFree(p->d_eo_hi);
     cudaFree(p->d_eo_lo);
     cudaFree(p->d_eo_tiles);
+    cudaFree(p->d_eo2_hi);
+    cudaFree(p->d_eo2_lo);
+    cudaFree(p->d_eo2_tiles);
+    cudaFree(p->d_mat2_tiles);
     cudaFree(p->d_tw_4step);
     delete p;
     return ZAFB_OK;
@@ -634,23 +698,38 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
             pool_ready = true;
         }
         float* ws = nullptr;
+        const bool pair = env_flag("ZAFB_GEMM_PAIR", 1) != 0 && batch >= 256;  // CTA-pair kernel (256 x 256 tiles)
         if (p->d_eo_tiles != nullptr && !env_flag("ZAFB_DCT_DENSE", 0)) {
             // even / odd form: fold the input into [s | d] while splitting it, then one tiled product with half the work
             const size_t half = size_t(batch) * size_t(p->eo_lda);
             ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * half * sizeof(float), st));
             int64_t blocks = ceil_div(int64_t(half), 256);
             if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
-            fold_split_tf32_kernel<<<unsigned(blocks), 256, 0, st>>>(x, batch, n, stride, ws, ws + half, p->eo_lda, p->eo_dcol);
+            if (n % 8 == 0 && stride % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && p->eo_lda == n && p->eo_dcol == n / 2) {
+                const int groups = n / 8, threads = groups >= 256 ? 256 : (256 / groups) * groups;
+                int64_t vb = ceil_div(batch, int64_t(threads / groups > 0 ? threads / groups : 1));
+                if (vb > int64_t(sm_count()) * 16) vb = int64_t(sm_count()) * 16;
+                fold_split_tf32_vec_kernel<<<unsigned(vb), threads, 0, st>>>(x, batch, n, stride, ws, ws + half);
+            } else {
+                fold_split_tf32_kernel<<<unsigned(blocks), 256, 0, st>>>(x, batch, n, stride, ws, ws + half, p->eo_lda, p->eo_dcol);
+            }
             ZAFB_LAUNCH_CHECK();
-            rc = gemm3xtf32_tiled(128, ws, ws + half, p->eo_lda, p->eo_lda, p->d_eo_hi, p->d_eo_lo, p->eo_ldb, p->eo_tiles,
-                                  p->d_eo_tiles, out, out_stride, batch, st);
+            if (pair)
+                rc = gemm3xtf32_pair_tiled(ws, ws + half, p->eo_lda, p->eo_lda, p->d_eo2_hi, p->d_eo2_lo, p->eo_ldb,
+                                           int64_t(p->eo2_tiles) * 256, p->eo2_tiles, p->d_eo2_tiles, out, out_stride, batch, st);
+            else
+                rc = gemm3xtf32_tiled(128, ws, ws + half, p->eo_lda, p->eo_lda, p->d_eo_hi, p->d_eo_lo, p->eo_ldb, p->eo_tiles,
+                                      p->d_eo_tiles, out, out_stride, batch, st);
             cudaFreeAsync(ws, st);
             return rc;
         }
         const size_t half = size_t(batch) * size_t(p->ldk);
         ZAFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * half * sizeof(float), st));
         rc = split_tf32(x, batch, n, stride, ws, ws + half, p->ldk, st);
-        if (rc == ZAFB_OK)
+        if (rc == ZAFB_OK && pair)
+            rc = gemm3xtf32_pair_tiled(ws, ws + half, p->ldk, n, p->d_mat_hi, p->d_mat_lo, p->ldk, n, p->mat2_tiles, p->d_mat2_tiles,
+                                       out, out_stride, batch, st);
+        else if (rc == ZAFB_OK)
             rc = gemm3xtf32(ws, ws + half, p->ldk, p->d_mat_hi, p->d_mat_lo, p->ldk, out, out_stride, batch, n, n, st);
         cudaFreeAsync(ws, st);
         return rc;

@@ -270,19 +270,244 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair form (tcgen05 cta_group::2): two CTAs of one cluster (two SMs of one TPC) compute a 256 x 256 output tile.
+// CTA r of the pair stages rows [128 r, 128 r + 128) of the A tile AND rows [128 r, 128 r + 128) of the B tile; the
+// tensor cores of both SMs read both halves of B, so each SM loads 64 KB per 32-column K block for 128 x 256 outputs --
+// half the operand bytes per output of the single-CTA 128 x 128 kernel, whose time is the L2 -> SM operand stream
+// (profiles/r02_dct1_ncu_summary.txt: tensor pipe 32 % active, 148 SMs x 1 MB per tile through L2).  The kernel is
+// persistent: a pair walks over the work items (M block, column tile) pair, pair + G, ..., so the TMA producer runs
+// ahead across tiles and the epilogue of one tile (registers -> shared-memory transpose -> coalesced
+// stores) overlaps the first accumulation chains of the next.
+//   warps 0-7  epilogue (warp w: TMEM lanes 32 (w & 3) .. + 32, columns 128 (w >> 2) .. + 128 of each chain buffer)
+//   warp 8     TMA producer (both CTAs; complete_tx on the LEADER's full barrier)
+//   warp 9     TMEM allocation (both CTAs), MMA issue (leader CTA only), commits multicast to both CTAs
+constexpr int kPairBN = 256;
+constexpr int kPairThreads = 320;
+constexpr int kPairTile = kBM * kBK * 4;               // 16 KB: A_hi, A_lo, B_hi, B_lo tiles of one CTA
+constexpr int kPairStage = 4 * kPairTile;              // 64 KB
+constexpr int kPairBars = kStages * kPairStage;        // full[3], empty[3], tfull[2], tempty[2]
+constexpr int kPairTmemPtr = kPairBars + 8 * (2 * kStages + 4);
+constexpr int kPairXpose = kPairTmemPtr + 16;          // 8 warps x 32 x 33 floats
+constexpr int kPairSmem = kPairXpose + 8 * 32 * 33 * 4 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(uint16_t(3)) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                       const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                       float* __restrict__ C, int64_t M, int64_t ldc, int m_pairs, int n_tiles,
+                       const GemmTile* __restrict__ tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_full = base + kPairBars, bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kPairTmemPtr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    // work item w = (M block, column tile), column tile fastest: pairs that run side by side share an M block, so its A
+    // columns are fetched from HBM once and the interleaved even / odd output columns of a row meet in L2
+    const int64_t work = int64_t(m_pairs) * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);   // the leader's expect_tx arrival; bytes of both CTAs complete on it
+            mbar_init(bar_empty + 8 * s, 1);  // one multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 16);  // 8 epilogue warps of each CTA arrive on the leader's barrier
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(const_cast<uint32_t*>(tmem_slot))), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 8) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs)
+            const uint32_t full_leader = mapa_rank(bar_full, 0);
+            uint32_t g = 0;
+            for (int64_t w = pair; w < work; w += num_pairs) {
+                const int mp = int(w / n_tiles), t = int(w - int64_t(mp) * n_tiles);
+                const int a_row = (2 * mp + int(rank)) * kBM;
+                {
+                    const GemmTile tile = tiles[t];
+                    const int num_kb = (tile.k_len + kBK - 1) / kBK;
+                    const int b_row = t * kPairBN + int(rank) * kBM;
+                    for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                        const uint32_t s = g % kStages, it = g / kStages;
+                        mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
+                        const uint32_t st = base + s * kPairStage;
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * kPairStage);
+                        const uint32_t fb = full_leader + 8 * s;
+                        tma_load_2d_pair(st, &tm_ahi, fb, tile.a_col0 + kb * kBK, a_row);
+                        tma_load_2d_pair(st + kPairTile, &tm_alo, fb, tile.a_col0 + kb * kBK, a_row);
+                        tma_load_2d_pair(st + 2 * kPairTile, &tm_bhi, fb, kb * kBK, b_row);
+                        tma_load_2d_pair(st + 3 * kPairTile, &tm_blo, fb, kb * kBK, b_row);
+                    }
+                }
+            }
+            // tail: every multicast commit aimed at this CTA's empty barriers has landed before the CTA may exit
+            for (int i = 0; i < kStages; ++i, ++g) mbar_wait(bar_empty + 8 * (g % kStages), ((g / kStages) & 1) ^ 1);
+        }
+    } else if (warp == 9) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA)
+            // D = F32, A = B = TF32, K-major both, N = 256, M = 256 (128 rows in each CTA's TMEM)
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kPairBN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+            uint32_t g = 0, gc = 0;
+            for (int64_t w = pair; w < work; w += num_pairs) {
+                {
+                    const int num_kb = (tiles[w % n_tiles].k_len + kBK - 1) / kBK;
+                    for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                        const uint32_t s = g % kStages, it = g / kStages;
+                        const uint32_t buf = gc & 1;
+                        if (kb % kChunkKb == 0) {
+                            mbar_wait(bar_tempty + 8 * buf, ((gc >> 1) & 1) ^ 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        mbar_wait(bar_full + 8 * s, it & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t st = base + s * kPairStage;
+                        const uint32_t acc = tmem_acc + buf * kPairBN;
+                        const uint64_t a_hi = umma_desc_k_sw128(st), a_lo = umma_desc_k_sw128(st + kPairTile);
+                        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * kPairTile), b_lo = umma_desc_k_sw128(st + 3 * kPairTile);
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint64_t adv = uint64_t((k * kUmmaK * 4) >> 4);
+                            umma_tf32_pair(acc, a_lo + adv, b_hi + adv, idesc, ((kb % kChunkKb) | k) != 0);
+                            umma_tf32_pair(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32_pair(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                        }
+                        umma_commit_pair(bar_empty + 8 * s);
+                        if (kb % kChunkKb == kChunkKb - 1 || kb == num_kb - 1) {
+                            umma_commit_pair(bar_tfull + 8 * buf);
+                            ++gc;
+                        }
+                    }
+                }
+            }
+            // tail: the last arrivals of both CTAs' epilogue warps have landed on this CTA's barriers
+            for (int i = 0; i < 2; ++i, ++gc) mbar_wait(bar_tempty + 8 * (gc & 1), ((gc >> 1) & 1) ^ 1);
+        }
+    } else {  // ===== epilogue (both CTAs): TMEM lanes = the CTA's own 128 rows
+        const int q = warp & 3, ch = warp >> 2;
+        const uint32_t tempty_leader = mapa_rank(bar_tempty, 0);
+        float* xp = reinterpret_cast<float*>(base_ptr + kPairXpose) + warp * (32 * 33);
+        uint32_t gc = 0;
+        for (int64_t w = pair; w < work; w += num_pairs) {
+            const int mp = int(w / n_tiles), t = int(w - int64_t(mp) * n_tiles);
+            const int64_t row0 = int64_t(2 * mp + int(rank)) * kBM + 32 * q;
+            {
+                const GemmTile tile = tiles[t];
+                const int num_kb = (tile.k_len + kBK - 1) / kBK;
+                const int num_chunks = (num_kb + kChunkKb - 1) / kChunkKb;
+                float sum[128];
+#pragma unroll
+                for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+                for (int chunk = 0; chunk < num_chunks; ++chunk, ++gc) {
+                    const uint32_t buf = gc & 1;
+                    mbar_wait(bar_tfull + 8 * buf, (gc >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(tmem_acc + (uint32_t(32 * q) << 16) + buf * kPairBN + uint32_t(128 * ch + c0), v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[c0 + i] += v[i];
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(tempty_leader + 8 * buf);
+                }
+                // registers (lane = row) -> 32 x 33 tile -> lane = column: every store instruction writes one row segment
+                const int col_base = 128 * ch;
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = sum[c0 + i];
+                    __syncwarp();
+                    const int col = col_base + c0 + lane;
+                    if (col < tile.n_valid) {
+                        float* cp = C + row0 * ldc + tile.c_col0 + int64_t(col) * tile.c_stride;
+#pragma unroll 8
+                        for (int j = 0; j < 32; ++j)
+                            if (row0 + j < M) cp[int64_t(j) * ldc] = xp[j * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // both CTAs are done with the pair's TMEM and with each other's barriers
+    if (warp == 9) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512u) : "memory");
+    }
+}
+
 // hi = tf32(x) (round to nearest), lo = tf32(x - hi)
 __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ldx, float* __restrict__ hi,
                                   float* __restrict__ lo, int64_t ld_out) {
-    const int64_t total = rows * ld_out;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t r = i / ld_out, c = i - r * ld_out;
-        const float v = c < cols ? x[r * ldx + c] : 0.f;
-        uint32_t h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float hv = __uint_as_float(h);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hv));
-        hi[i] = hv;
-        lo[i] = __uint_as_float(l);
+    // 32 x 8 threads: eight rows per block step, a warp walks along one row (no index division, coalesced)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int64_t r = int64_t(blockIdx.x) * 8 + ty; r < rows; r += int64_t(gridDim.x) * 8) {
+        const float* xr = x + r * ldx;
+        for (int64_t c = tx; c < ld_out; c += 32) {
+            const float v = c < cols ? xr[c] : 0.f;
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+            const float hv = __uint_as_float(h);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hv));
+            hi[r * ld_out + c] = hv;
+            lo[r * ld_out + c] = __uint_as_float(l);
+        }
     }
 }
 
@@ -374,9 +599,36 @@ int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, 
     return launch_tiled<128>(a_hi, a_lo, lda, a_cols, b_hi, b_lo, ldb, n_tiles, d_tiles, c, ldc, M, st);
 }
 
+// CTA-pair kernel over 256-row blocks of B (block t = B rows [256 t, 256 t + 256), its own A column range / output columns)
+int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
+                          int64_t ldb, int64_t b_rows, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M,
+                          cudaStream_t st) {
+    ZAFB_REQUIRE(M >= 0 && n_tiles >= 1 && d_tiles != nullptr && b_rows >= 1, "pair gemm: bad shape");
+    if (M == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "pair gemm: operand row pitches must be multiples of 4 elements");
+    ZAFB_REQUIRE(M < (int64_t(1) << 31), "pair gemm: dimension too large");
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+        attr = true;
+    }
+    CUtensorMap ma, mal, mb, mbl;
+    int rc = make_map(&ma, a_hi, M, a_cols, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mal, a_lo, M, a_cols, lda, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mb, b_hi, b_rows, ldb, ldb, kBM);  // rows past b_rows read as zeros
+    if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, b_rows, ldb, ldb, kBM);
+    if (rc != ZAFB_OK) return rc;
+    const int64_t m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
+    int64_t pairs = sm_count() / 2;
+    if (pairs > m_pairs * n_tiles) pairs = m_pairs * n_tiles;
+    gemm3xtf32_pair_kernel<<<unsigned(2 * pairs), kPairThreads, kPairSmem, st>>>(ma, mal, mb, mbl, c, M, ldc, int(m_pairs), n_tiles, d_tiles);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
 int split_tf32(const float* x, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo, int64_t ld_out, cudaStream_t st) {
     if (rows * ld_out == 0) return ZAFB_OK;
-    int64_t blocks = (rows * ld_out + 255) / 256;
+    int64_t blocks = (rows + 7) / 8;
     const int64_t cap = int64_t(sm_count()) * 16;
     if (blocks > cap) blocks = cap;
     split_tf32_kernel<<<unsigned(blocks), 256, 0, st>>>(x, rows, cols, ldx, hi, lo, ld_out);

@@ -33,4 +33,11 @@ struct GemmTile {
 int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
                      int64_t ldb, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st);
 
+// The same structured product on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, persistent): block t = B rows
+// [256 t, 256 t + 256) of the b_rows x ldb operand (rows past b_rows read as zeros).  Half the operand bytes per output
+// of the single-CTA kernel.
+int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
+                          int64_t ldb, int64_t b_rows, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M,
+                          cudaStream_t st);
+
 }  // namespace zafb
