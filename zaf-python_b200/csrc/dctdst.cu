@@ -617,9 +617,9 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
                 }
                 std::vector<GemmTile> tiles;
                 for (int64_t t = 0; t < te; ++t)
-                    tiles.push_back(GemmTile{0, int(nh), int(2 * t * blk), 2, int(std::min<int64_t>(blk, ne - t * blk))});
+                    tiles.push_back(GemmTile{0, int(nh), int(2 * t * blk), 2, int(std::min<int64_t>(blk, ne - t * blk)), 1});
                 for (int64_t t = 0; t < to; ++t)
-                    tiles.push_back(GemmTile{int(p->eo_dcol), int(nd), int(2 * t * blk + 1), 2, int(std::min<int64_t>(blk, no - t * blk))});
+                    tiles.push_back(GemmTile{int(p->eo_dcol), int(nd), int(2 * t * blk + 1), 2, int(std::min<int64_t>(blk, no - t * blk)), 2});
                 std::vector<float> ehi(st.size()), elo(st.size());
                 split_tf32_host(st.data(), st.size(), ehi.data(), elo.data());
                 cudaError_t e2 = cudaMalloc(reinterpret_cast<void**>(d_hi), ehi.size() * sizeof(float));
@@ -699,6 +699,12 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
         }
         float* ws = nullptr;
         const bool pair = env_flag("ZAFB_GEMM_PAIR", 1) != 0 && batch >= 256;  // CTA-pair kernel (256 x 256 tiles)
+        if (p->d_eo_tiles != nullptr && !env_flag("ZAFB_DCT_DENSE", 0) && pair && n % 8 == 0 && stride % 4 == 0 &&
+            reinterpret_cast<uintptr_t>(x) % 16 == 0 && env_flag("ZAFB_GEMM_FUSED_FOLD", 1)) {
+            // even / odd form with the fold and the TF32 split inside the GEMM kernel: the input is read as it is
+            return gemm3xtf32_pair_fold(x, stride, n, p->d_eo2_hi, p->d_eo2_lo, p->eo_ldb, int64_t(p->eo2_tiles) * 256, p->eo2_tiles,
+                                        p->d_eo2_tiles, out, out_stride, batch, st);
+        }
         if (p->d_eo_tiles != nullptr && !env_flag("ZAFB_DCT_DENSE", 0)) {
             // even / odd form: fold the input into [s | d] while splitting it, then one tiled product with half the work
             const size_t half = size_t(batch) * size_t(p->eo_lda);

@@ -284,10 +284,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_const
 //   warp 9     TMEM allocation (both CTAs), MMA issue (leader CTA only), commits multicast to both CTAs
 constexpr int kPairBN = 256;
 constexpr int kPairThreads = 320;
+constexpr int kPairThreadsFold = 384;
 constexpr int kPairTile = kBM * kBK * 4;               // 16 KB: A_hi, A_lo, B_hi, B_lo tiles of one CTA
 constexpr int kPairStage = 4 * kPairTile;              // 64 KB
-constexpr int kPairBars = kStages * kPairStage;        // full[3], empty[3], tfull[2], tempty[2]
-constexpr int kPairTmemPtr = kPairBars + 8 * (2 * kStages + 4);
+constexpr int kPairBars = kStages * kPairStage;        // full[3], empty[3], tfull[2], tempty[2], raw[3]
+constexpr int kPairTmemPtr = kPairBars + 8 * (3 * kStages + 4);
 constexpr int kPairXpose = kPairTmemPtr + 16;          // 8 warps x 32 x 33 floats
 constexpr int kPairSmem = kPairXpose + 8 * 32 * 33 * 4 + 1024;
 
@@ -306,7 +307,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope), as in CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release
+    // compiles to MEMBAR.ALL.GPU + ERRBAR on every arrival (measured: the hottest instructions of the converter warps)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
@@ -328,16 +331,21 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on 
                  ::"r"(bar), "h"(uint16_t(3)) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+// FOLD = true: the A operand is never staged in HBM.  TMA loads the raw fp32 blocks x[row][32 kb ..) and the mirrored
+// x[row][n - 32 (kb + 1) ..) into the stage's two A slots; two converter warps per CTA (warps 10, 11) form
+// s = x[m] + x[n-1-m] or d = x[m] - x[n-1-m] (GemmTile::fold = 1 | 2), split it into TF32 hi / lo halves and overwrite
+// the slots in place (generic-proxy stores + fence.proxy.async + an arrival on the leader's full barrier).
+template <bool FOLD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FOLD ? kPairThreadsFold : kPairThreads, 1)
 gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                        const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                        float* __restrict__ C, int64_t M, int64_t ldc, int m_pairs, int n_tiles,
-                       const GemmTile* __restrict__ tiles) {
+                       const GemmTile* __restrict__ tiles, const float* __restrict__ x, int64_t ldx, int n_fold) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bar_full = base + kPairBars, bar_empty = bar_full + 8 * kStages;
-    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16, bar_raw = bar_tempty + 16;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + kPairTmemPtr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -348,7 +356,9 @@ gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_full + 8 * s, 1);   // the leader's expect_tx arrival; bytes of both CTAs complete on it
+            mbar_init(bar_full + 8 * s, FOLD ? 5 : 1);  // the leader's expect_tx arrival (bytes of both CTAs complete on it)
+                                                        // + FOLD: two converter warps of each CTA
+            mbar_init(bar_raw + 8 * s, 1);              // FOLD: this CTA's raw x tiles have landed
             mbar_init(bar_empty + 8 * s, 1);  // one multicast commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -383,10 +393,16 @@ gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
                         const uint32_t s = g % kStages, it = g / kStages;
                         mbar_wait(bar_empty + 8 * s, (it & 1) ^ 1);
                         const uint32_t st = base + s * kPairStage;
-                        if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * kPairStage);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * s, FOLD ? 4 * kPairTile : 2 * kPairStage);
                         const uint32_t fb = full_leader + 8 * s;
-                        tma_load_2d_pair(st, &tm_ahi, fb, tile.a_col0 + kb * kBK, a_row);
-                        tma_load_2d_pair(st + kPairTile, &tm_alo, fb, tile.a_col0 + kb * kBK, a_row);
+                        if constexpr (!FOLD) {
+                            tma_load_2d_pair(st, &tm_ahi, fb, tile.a_col0 + kb * kBK, a_row);
+                            tma_load_2d_pair(st + kPairTile, &tm_alo, fb, tile.a_col0 + kb * kBK, a_row);
+                        } else {  // raw rows (tm_ahi = the map of x): forward block, mirrored block
+                            mbar_expect_tx(bar_raw + 8 * s, 2 * kPairTile);
+                            tma_load_2d(st, &tm_ahi, bar_raw + 8 * s, kb * kBK, a_row);
+                            tma_load_2d(st + kPairTile, &tm_ahi, bar_raw + 8 * s, n_fold - kBK * (kb + 1), a_row);
+                        }
                         tma_load_2d_pair(st + 2 * kPairTile, &tm_bhi, fb, kb * kBK, b_row);
                         tma_load_2d_pair(st + 3 * kPairTile, &tm_blo, fb, kb * kBK, b_row);
                     }
@@ -433,6 +449,57 @@ gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
             }
             // tail: the last arrivals of both CTAs' epilogue warps have landed on this CTA's barriers
             for (int i = 0; i < 2; ++i, ++gc) mbar_wait(bar_tempty + 8 * (gc & 1), ((gc >> 1) & 1) ^ 1);
+        }
+    } else if (FOLD && warp >= 10) {  // ===== converter warps (both CTAs): raw tiles -> folded, split A tiles, in place
+        // The producer's TMA put x[row][32 kb .. + 32) into the A_hi slot and the mirrored block x[row][n - 32 (kb + 1) .. + 32)
+        // into the A_lo slot.  Fold index m = 32 kb + i pairs with element 31 - i of the mirrored block, i.e. 16-byte chunk j
+        // with chunk 7 - j reversed; one thread owns chunks j and 7 - j of a row in both slots, reads all four, then
+        // overwrites them with hi / lo of s = x[m] + x[n-1-m] (fold 1) or d = x[m] - x[n-1-m] (fold 2).
+        const int cw = warp - 10, rl = lane & 7, jp = lane >> 3;
+        const uint32_t full_leader = mapa_rank(bar_full, 0);
+        auto tf32_split = [](float v, float& hv, float& lv) {
+            uint32_t p, q2;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(p) : "f"(v));
+            hv = __uint_as_float(p);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q2) : "f"(v - hv));
+            lv = __uint_as_float(q2);
+        };
+        auto fold4 = [&](const float4 f, const float4 mrev, float sg, float4& hv, float4& lv) {
+            tf32_split(fmaf(sg, mrev.w, f.x), hv.x, lv.x);
+            tf32_split(fmaf(sg, mrev.z, f.y), hv.y, lv.y);
+            tf32_split(fmaf(sg, mrev.y, f.z), hv.z, lv.z);
+            tf32_split(fmaf(sg, mrev.x, f.w), hv.w, lv.w);
+        };
+        uint32_t g = 0;
+        for (int64_t w = pair; w < work; w += num_pairs) {
+            const GemmTile tile = tiles[w % n_tiles];
+            const int num_kb = (tile.k_len + kBK - 1) / kBK;
+            const float sg = tile.fold == 2 ? -1.f : 1.f;
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const uint32_t s = g % kStages;
+                mbar_wait(bar_raw + 8 * s, (g / kStages) & 1);
+                uint8_t* hi_slot = base_ptr + s * kPairStage;
+                uint8_t* lo_slot = hi_slot + kPairTile;
+#pragma unroll 4
+                for (int it = 0; it < 8; ++it) {
+                    const int row = 64 * cw + 8 * it + rl;
+                    const int oa = row * 128 + ((jp ^ (row & 7)) << 4), ob = row * 128 + (((7 - jp) ^ (row & 7)) << 4);
+                    const float4 f0 = *reinterpret_cast<const float4*>(hi_slot + oa);
+                    const float4 f1 = *reinterpret_cast<const float4*>(hi_slot + ob);
+                    const float4 m0 = *reinterpret_cast<const float4*>(lo_slot + oa);
+                    const float4 m1 = *reinterpret_cast<const float4*>(lo_slot + ob);
+                    float4 h0, l0, h1, l1;
+                    fold4(f0, m1, sg, h0, l0);
+                    fold4(f1, m0, sg, h1, l1);
+                    *reinterpret_cast<float4*>(hi_slot + oa) = h0;
+                    *reinterpret_cast<float4*>(hi_slot + ob) = h1;
+                    *reinterpret_cast<float4*>(lo_slot + oa) = l0;
+                    *reinterpret_cast<float4*>(lo_slot + ob) = l1;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(full_leader + 8 * s);
+            }
         }
     } else {  // ===== epilogue (both CTAs): TMEM lanes = the CTA's own 128 rows
         const int q = warp & 3, ch = warp >> 2;
@@ -609,7 +676,7 @@ int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int
     ZAFB_REQUIRE(M < (int64_t(1) << 31), "pair gemm: dimension too large");
     static bool attr = false;
     if (!attr) {
-        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
         attr = true;
     }
     CUtensorMap ma, mal, mb, mbl;
@@ -621,7 +688,34 @@ int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int
     const int64_t m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
     int64_t pairs = sm_count() / 2;
     if (pairs > m_pairs * n_tiles) pairs = m_pairs * n_tiles;
-    gemm3xtf32_pair_kernel<<<unsigned(2 * pairs), kPairThreads, kPairSmem, st>>>(ma, mal, mb, mbl, c, M, ldc, int(m_pairs), n_tiles, d_tiles);
+    gemm3xtf32_pair_kernel<false><<<unsigned(2 * pairs), kPairThreads, kPairSmem, st>>>(ma, mal, mb, mbl, c, M, ldc, int(m_pairs),
+                                                                                        n_tiles, d_tiles, nullptr, 0, 0);
+    ZAFB_LAUNCH_CHECK();
+    return ZAFB_OK;
+}
+
+int gemm3xtf32_pair_fold(const float* x, int64_t ldx, int n, const float* b_hi, const float* b_lo, int64_t ldb, int64_t b_rows,
+                         int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st) {
+    ZAFB_REQUIRE(M >= 0 && n_tiles >= 1 && d_tiles != nullptr && b_rows >= 1, "pair gemm: bad shape");
+    if (M == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(n % 8 == 0 && ldx % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && ldb % 4 == 0,
+                 "fused fold: n must be a multiple of 8 and the rows 16-byte aligned");
+    ZAFB_REQUIRE(M < (int64_t(1) << 31), "pair gemm: dimension too large");
+    static bool attr = false;
+    if (!attr) {
+        ZAFB_CUDA(cudaFuncSetAttribute(gemm3xtf32_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
+        attr = true;
+    }
+    CUtensorMap mx, mb, mbl;
+    int rc = make_map(&mx, x, M, n, ldx, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mb, b_hi, b_rows, ldb, ldb, kBM);
+    if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, b_rows, ldb, ldb, kBM);
+    if (rc != ZAFB_OK) return rc;
+    const int64_t m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
+    int64_t pairs = sm_count() / 2;
+    if (pairs > m_pairs * n_tiles) pairs = m_pairs * n_tiles;
+    gemm3xtf32_pair_kernel<true><<<unsigned(2 * pairs), kPairThreadsFold, kPairSmem, st>>>(mx, mx, mb, mbl, c, M, ldc, int(m_pairs),
+                                                                                           n_tiles, d_tiles, x, ldx, n);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }

@@ -25,6 +25,7 @@ struct GemmTile {
     int c_col0;    // first output column
     int c_stride;  // distance between its output columns
     int n_valid;   // output columns actually written (<= the block width)
+    int fold;      // gemm3xtf32_pair_fold only: 1 = the block multiplies s[m] = x[m] + x[n-1-m], 2 = d[m] = x[m] - x[n-1-m]
 };
 
 // Structured operators in one launch: block t = B rows [t bn, t bn + bn) (bn = 16 or 128, all blocks share the row pitch
@@ -39,5 +40,11 @@ int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, 
 int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
                           int64_t ldb, int64_t b_rows, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M,
                           cudaStream_t st);
+
+// The CTA-pair kernel with the even / odd fold of a transform with input symmetry fused into the operand path: A is never
+// staged -- converter warps read the raw rows x (M x n, pitch ldx, n a multiple of 8, 16-byte aligned rows), form
+// s / d per GemmTile::fold for m < n/2 and write the TF32 hi / lo operand tiles into shared memory themselves.
+int gemm3xtf32_pair_fold(const float* x, int64_t ldx, int n, const float* b_hi, const float* b_lo, int64_t ldb, int64_t b_rows,
+                         int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M, cudaStream_t st);
 
 }  // namespace zafb
