@@ -462,14 +462,14 @@ class Item:
             self.algo_bytes_per_clip = self.ns * 4 + self.nt * self.nf * 4
             L = self.kern.shape[1]
             self.flops_per_unit = 2.5 * L * np.log2(L) + 8 * int(self.kern.nnz)
-            self.bound, self.kernel = "fp32", "cqt32768_kernel"
+            self.bound, self.kernel = "fp32", "cqt_eo_kernel"
         self.units_per_clip = self.nt
 
     def set_route(self, route):
         """cqtspectrogram only: 'fused' | 'tensor' (a second plan)."""
         self.route = route
         self.plan, _, _ = self.zaf._cqt_plan(self.kern, self.step, route)
-        self.kernel = "cqt32768_kernel" + ("<export> + gemm3xtf32_kernel + cqt_magnitude_kernel" if route == "tensor" else "")
+        self.kernel = "cqt_eo_kernel" + ("<export> + gemm3xtf32_kernel<16> (packed bands) + cqt_magnitude_kernel" if route == "tensor" else "")
 
     def launch(self, in_ptr, clips, out_ptr, stream):
         lib, C, c, p = self.lib, self.C, self.c, self.plan
@@ -885,6 +885,61 @@ def stft_merge_variants(zaf, dist, comm, args, stream, reps=2):
     return out
 
 
+def dct_leg(zaf, dist, stream, peak, steps=5):
+    """dct / dst (zaf.py:703-981) on 2^20 vectors of 1024 samples, the reference's example length: type I runs on the
+    tensor cores (the CTA-pair 3xTF32 GEMM with the even/odd fold fused into its operand path), types II-IV on the warp
+    FFT kernel.  Device-timed, two vectors checked against the oracle afterwards."""
+    import oracle
+
+    lib, C = zaf._lib.lib(), zaf._lib.C
+    batch, n = 1 << 20, 1024
+    rng = np.random.default_rng(SEED + 77)
+    host = rng.uniform(-1, 1, (4096, n)).astype(np.float32)
+    xd = zaf.empty((batch, n), np.float32)
+    od = zaf.empty((batch, n), np.float32)
+    for r0 in range(0, batch, 4096):
+        zaf._lib.check(lib.zafb_memcpy_h2d(C.c_void_p(xd.ptr + r0 * n * 4), host.ctypes.data, host.nbytes, None))
+    zaf.synchronize()
+    out = []
+    e0, e1 = zaf.Event(), zaf.Event()
+    for kind, name, ofn in ((0, "dct", oracle.dct), (1, "dst", oracle.dst)):
+        for t in (1, 2, 4):
+            plan = zaf._dct_plans.get((kind, t, n), kind, t, n)
+
+            def launch():
+                zaf._lib.check(lib.zafb_dct_f32(plan, C.c_void_p(xd.ptr), batch, n, C.c_void_p(od.ptr), n, stream.ptr))
+
+            for _ in range(3):
+                launch()
+            e0.record(stream)
+            for _ in range(steps):
+                launch()
+            e1.record(stream)
+            e1.synchronize()
+            ms = dist.max(e0.elapsed_ms(e1) / steps)
+            parity = None
+            if dist.rank == 0:
+                got = np.empty(n, np.float32)
+                worst = 0.0
+                for v in (0, batch - 1):
+                    zaf._lib.check(lib.zafb_memcpy_d2h(got.ctypes.data, C.c_void_p(od.ptr + v * n * 4), got.nbytes, None))
+                    zaf.synchronize()
+                    worst = max(worst, *oracle.parity_metrics(got, ofn(host[v % 4096], t)))
+                parity = worst
+                assert worst <= TOL, f"{name}-{t}: parity broken: {worst}"
+            gbs = batch * n * 8 / (ms * 1e-3) / 1e9
+            out.append({"transform": f"{name}-{t}", "config": f"{batch} vectors x {n} per GPU", "ms_per_step": ms,
+                        "vectors_per_sec": batch * dist.world / (ms * 1e-3),
+                        "roofline": {"bound": "tensor" if t == 1 else "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                     "frac": gbs / peak, "algorithmic_bytes_per_launch": batch * n * 8,
+                                     "kernel": "gemm3xtf32_pair_kernel<fold>" if t == 1 else "dct_warp_kernel<1024>",
+                                     **({"tensor_tflops_3xtf32": 3 * 2 * batch * n * (n / 2) / (ms * 1e-3) / 1e12} if t == 1 else {})},
+                        "parity_max_rel_err": parity, "parity_tolerance": TOL})
+    xd.free()
+    od.free()
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     dist = Dist(args.gpus)
@@ -1074,6 +1129,13 @@ def run_ours(args):
     # every other BASELINE config on its own shape, with parity and its own CPU baseline
     if not args.no_configs:
         extra["configs"] = run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines)
+        if not args.only_configs or "dct" in args.only_configs:
+            try:
+                extra["dct"] = dct_leg(zaf, dist, stream, peak)
+            except AssertionError:
+                raise
+            except Exception as exc:  # noqa: BLE001
+                extra["dct"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # N > 1: the batch split / merge legs (strong scaling): rank 0 holds one whole batch in HBM, scatters the clips over
     # NCCL, every rank transforms its shard, the results are gathered back on rank 0 and compared bitwise with the
