@@ -341,7 +341,7 @@ def main():
     # ---- dct / dst at the other warp-kernel lengths (types II-IV)
     if "dctsizes" in only:
         lib, C = zaf._lib.lib(), zaf._lib.C
-        for n in (512, 2048):
+        for n in (512, 2048, 4096):
             batch = max(1, int((1 << 30) // (4 * n) * args.scale))
             xd, _ = device_batch(batch, n, 20261017 + n, distinct=1024)
             od = zaf.empty((batch, n), np.float32)

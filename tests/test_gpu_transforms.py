@@ -572,9 +572,9 @@ def test_mel_mfcc_window_lengths_that_are_not_powers_of_two(zaf_gpu, n, hop, fs,
         zaf_gpu.mfcc(x, w, hop, fb, ncoef, precision="float64")
 
 
-@pytest.mark.parametrize("n", [512, 2048])
+@pytest.mark.parametrize("n", [512, 2048, 4096])
 def test_dct_dst_warp_kernels_512_2048(zaf_gpu, n):
-    """The one-warp-per-vector kernel (types II-IV and their DST twins) at N = 512 and 2048 (r02; N = 1024 has its own
+    """The one-warp-per-vector kernel (types II-IV and their DST twins) at N = 512, 2048 and 4096 (r02; N = 1024 has its own
     test): forced through the plan hook, against the oracle, plus the orthonormal inverse pairs."""
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, (37, n)).astype(np.float32)

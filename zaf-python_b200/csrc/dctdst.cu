@@ -225,26 +225,28 @@ __global__ void dct_fft_kernel(const float* __restrict__ x, int64_t batch, int64
 // ---------------------------------------------------------------------------------------------
 constexpr int kDctWarps = 8;
 
-// N = 512, 1024, 2048 (r02: the same code, REGS = N / 64 points per lane; warp_fft256 / warp_fft512 / warp_fft1024)
+// N = 512, 1024, 2048, 4096 (r02: the same code, REGS = N / 64 points per lane; warp_fft256 / warp_fft512 / warp_fft1024 /
+// warp_fft2048)
 template <int N, int MODE, bool DST>
-__global__ void __launch_bounds__(kDctWarps * 32, N == 2048 ? 1 : (MODE == 3 ? 2 : 3))   // type III holds the N inputs AND N/2 products
+__global__ void __launch_bounds__(kDctWarps * 32, N >= 2048 ? 1 : (MODE == 3 ? 2 : 3))   // type III holds the N inputs AND N/2 products
 dct_warp_kernel(const float* __restrict__ x, int64_t batch, int64_t stride, const float2* __restrict__ tw4,
                     const float2* __restrict__ tw_a, const float2* __restrict__ tw_b, float* __restrict__ out,
                     int64_t out_stride) {
     constexpr int H = N / 2, REGS = H / 32, LOGR = clog2(REGS);
-    static_assert(N == 512 || N == 1024 || N == 2048, "dct warp kernel: N = 512, 1024 or 2048");
+    static_assert(N == 512 || N == 1024 || N == 2048 || N == 4096, "dct warp kernel: N = 512, 1024, 2048 or 4096");
     extern __shared__ float2 smem2[];
     float2* s_tw = smem2;  // H: W_H^{k1 n2}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* s_buf = smem2 + H + warp * (REGS * kFft1024Pitch);
     for (int i = tid; i < H; i += kDctWarps * 32) s_tw[i] = tw4[i];
-    constexpr float kNorm = N == 512 ? 0.0625f : N == 1024 ? 0.04419417382415922f : 0.03125f;   // sqrt(2 / N)
+    constexpr float kNorm = N == 512 ? 0.0625f : N == 1024 ? 0.04419417382415922f : N == 2048 ? 0.03125f : 0.022097086912079608f;   // sqrt(2 / N)
     float2 tq[N == 512 ? 8 : 1];
     if constexpr (N == 512) warp_fft256_lane_twiddles(tq, lane);
     auto warp_fft = [&](float2 (&a)[REGS]) {
         if constexpr (N == 512) warp_fft256(a, s_tw, s_buf, lane, tq);
         else if constexpr (N == 1024) warp_fft512(a, s_tw, s_buf, lane);
-        else warp_fft1024<false>(a, s_tw, s_buf, lane);
+        else if constexpr (N == 2048) warp_fft1024<false>(a, s_tw, s_buf, lane);
+        else warp_fft2048(a, s_tw, s_buf, lane);
     };
     constexpr float kR2 = 0.70710678118654752f;
     const float2 ta = tw_a[lane];
@@ -444,21 +446,27 @@ int set_kernel_attrs() {
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<512, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<2048, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+    ZAFB_CUDA((cudaFuncSetAttribute(dct_warp_kernel<4096, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
     g_attr_done = true;
     return ZAFB_OK;
 }
@@ -553,7 +561,7 @@ int zafb_dct_plan_create(zafb_dct_plan** out, int kind, int type, int64_t n) {
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_a, ta.data(), ta.size() / 2);
         if (rc == ZAFB_OK) rc = upload_c32(&p->d_tw_b, tb.data(), tb.size() / 2);
     }
-    if (rc == ZAFB_OK && p->log2n >= 9 && p->log2n <= 11) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels (N = 512, 1024, 2048)
+    if (rc == ZAFB_OK && p->log2n >= 9 && p->log2n <= 12) {  // W_H^{k1*n2} laid out [k1][n2] for the warp kernels (N = 512 ... 4096)
         const int64_t hh = n / 2;
         std::vector<double> t(2 * hh);
         for (int64_t k1 = 0; k1 < hh / 32; ++k1)
@@ -745,11 +753,11 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
                              stride % 4 == 0 && out_stride % 4 == 0;
         const bool warp_ok = p->d_tw_4step != nullptr && p->type >= 2 && aligned;
         if (p->force_direct == 4 && !warp_ok)
-            return fail(ZAFB_E_UNSUPPORTED, "dct warp kernel needs N = 512, 1024 or 2048, type 2..4, 16-byte aligned rows");
+            return fail(ZAFB_E_UNSUPPORTED, "dct warp kernel needs N = 512, 1024, 2048 or 4096, type 2..4, 16-byte aligned rows");
         if (warp_ok && (p->force_direct == 0 || p->force_direct == 4)) {
             const size_t smem = size_t(n / 2 + kDctWarps * (n / 64) * kFft1024Pitch) * sizeof(float2);
             int64_t ctas = ceil_div(batch, kDctWarps);
-            const int occ = n == 2048 ? 1 : (p->type == 3 ? 2 : 3);
+            const int occ = n >= 2048 ? 1 : (p->type == 3 ? 2 : 3);
             if (ctas > int64_t(sm_count()) * occ) ctas = int64_t(sm_count()) * occ;
             const unsigned g = unsigned(ctas), b = kDctWarps * 32;
 #define ZAFB_DCT_WARP_N(NN, MODE, DST)                                                                            \
@@ -758,7 +766,8 @@ int zafb_dct_f32(const zafb_dct_plan* p, const float* x, int64_t batch, int64_t 
     do {                                                                                                          \
         if (n == 512) ZAFB_DCT_WARP_N(512, MODE, DST);                                                            \
         else if (n == 1024) ZAFB_DCT_WARP_N(1024, MODE, DST);                                                     \
-        else ZAFB_DCT_WARP_N(2048, MODE, DST);                                                                    \
+        else if (n == 2048) ZAFB_DCT_WARP_N(2048, MODE, DST);                                                     \
+        else ZAFB_DCT_WARP_N(4096, MODE, DST);                                                                    \
     } while (0)
             if (p->type == 2) { if (p->kind) ZAFB_DCT_WARP(2, true); else ZAFB_DCT_WARP(2, false); }
             else if (p->type == 3) { if (p->kind) ZAFB_DCT_WARP(3, true); else ZAFB_DCT_WARP(3, false); }

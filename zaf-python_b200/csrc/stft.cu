@@ -942,7 +942,7 @@ template <int N, int R>
 __global__ void __launch_bounds__(512, 1)
 istft_binmajor_kernel(const float2* __restrict__ spec, int nt, const float2* __restrict__ tw4,
                       const float2* __restrict__ tw_full, float scale, float* __restrict__ y, int64_t y_stride,
-                      int runs_per_clip, int tiles_per_run, int64_t total_runs) {
+                      int runs_per_clip, int tiles_per_run, int64_t total_runs, int prefetch) {
     using G = WarpGeom<N>;
     using B = IstftBinMajorGeom<N>;
     constexpr int M = G::M, REGS = G::REGS, LOGR = G::LOGR;
@@ -986,6 +986,18 @@ istft_binmajor_kernel(const float2* __restrict__ spec, int nt, const float2* __r
                 }
             }
             __syncthreads();
+            // the next tile's 128-byte runs (one per bin row and mirror row, up to two L2 lines each) start their way
+            // to L2 now, so that its load phase finds them there instead of waiting on HBM after the transform
+            if (prefetch && t + 1 < t1) {
+                const int jn = (t + 1) * F;
+                const int jl = jn + F - 1 < nt ? jn + F - 1 : nt - 1;
+                for (int idx = tid; idx < 2 * (M + 1); idx += 512) {
+                    const int k = idx >> 1;
+                    const int64_t row = (idx & 1) ? int64_t((N - k) & (N - 1)) : int64_t(k);
+                    prefetch_l2(sc + row * nt + jn);
+                    prefetch_l2(sc + row * nt + jl);
+                }
+            }
             // ---- transform: warp w, frame j0 + w
             {
                 const int j = j0 + warp;
@@ -1060,7 +1072,8 @@ int launch_istft_binmajor(const zafb_stft_plan* p, const float2* spec, int64_t n
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
     const int64_t ctas = std::min<int64_t>(runs, sms);
     istft_binmajor_kernel<N, R><<<unsigned(ctas), 512, smem, st>>>(spec, int(nt), p->d_tw_4step, p->d_tw_full, scale, y, y_stride,
-                                                                    int(runs_per_clip), int(tiles_per_run), runs);
+                                                                    int(runs_per_clip), int(tiles_per_run), runs,
+                                                                    env_flag("ZAFB_ISTFT_BM_PREFETCH", 0));
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
