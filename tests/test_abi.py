@@ -99,6 +99,32 @@ def test_operator_constructors_match_reference(zaf, golden):
         assert np.allclose(k.data, gc.get(tag, "kernel_data"), rtol=0, atol=1e-18)
 
 
+def test_operator_memo_reuses_the_prepared_operator_per_object(zaf):
+    """melspectrogram / cqtspectrogram calls in a loop pass the same operator object: its densified / sorted form and
+    its plan-cache key are prepared once per object, again after an in-place edit, never for a different object."""
+    memo, calls = zaf._OperatorMemo(), []
+
+    def prep(o):
+        calls.append(1)
+        return zaf._prepare_filterbank(o)
+
+    fb = zaf.melfilterbank(16000, 1024, 128)
+    first = memo.get(fb, prep)
+    assert memo.get(fb, prep) is first and len(calls) == 1
+    assert np.array_equal(first[0], fb.toarray()) and first[1] == first[0].tobytes()
+    fb.data[0] += 1.0  # edited in place: the fingerprint changes
+    assert memo.get(fb, prep) is not first and len(calls) == 2
+    other = zaf.melfilterbank(16000, 1024, 128)
+    assert np.array_equal(memo.get(other, prep)[0], other.toarray()) and len(calls) == 3
+    memo.get([[1.0, 2.0]], prep)  # objects without weak references are prepared every time
+    memo.get([[1.0, 2.0]], prep)
+    assert len(calls) == 5
+    kern = zaf.cqtkernel(44100, 12, 32.70, 4186.01)
+    shape, data, indptr, indices, key = zaf._cqt_ops.get(kern, zaf._prepare_cqt_kernel)
+    assert zaf._cqt_ops.get(kern, zaf._prepare_cqt_kernel)[1] is data
+    assert shape == kern.shape and len(data) == kern.nnz and indptr[-1] == kern.nnz and len(key) == 3
+
+
 def test_no_cpu_fallback(zaf):
     """Without a CUDA device every compute entry point raises; nothing is computed on the host."""
     if zaf.device_count() > 0:

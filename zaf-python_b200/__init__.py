@@ -20,6 +20,7 @@ CUDA device the functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -577,17 +578,60 @@ _MEL_ROUTES = {"fused": 0, "tensor": 1}
 _MEL_PRECISIONS = {"auto": 0, "float32": 32, "float64": 64}
 
 
-def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused", precision="auto"):
-    w = _window64(window_function)
+class _OperatorMemo:
+    """Prepared form of an operator argument (densified float64 filterbank, sorted CSR arrays of a CQT kernel) + the
+    bytes that key the plan cache, remembered per OBJECT: a caller that passes the same filterbank / kernel object again
+    (the usual loop over clips) does not pay toarray() + tobytes() + hashing of the whole operator on every call.
+    An entry is used only while the object is alive (weak reference) and its cheap fingerprint (shape, dtype, sum of the
+    stored values) is unchanged, so an operator edited in place is prepared afresh."""
+
+    def __init__(self, capacity=8):
+        self._d = OrderedDict()
+        self._cap = capacity
+
+    @staticmethod
+    def _fingerprint(obj):
+        vals = obj.data if hasattr(obj, "indptr") else obj
+        vals = np.asarray(vals)
+        return (getattr(obj, "shape", None), str(vals.dtype), getattr(obj, "nnz", vals.size), complex(vals.sum()))
+
+    def get(self, obj, prepare):
+        try:
+            ref = weakref.ref(obj)
+        except TypeError:  # lists etc.: no memo
+            return prepare(obj)
+        hit = self._d.get(id(obj))
+        fp = self._fingerprint(obj)
+        if hit is not None and hit[0]() is obj and hit[1] == fp:
+            self._d.move_to_end(id(obj))
+            return hit[2]
+        prepared = prepare(obj)
+        self._d[id(obj)] = (ref, fp, prepared)
+        while len(self._d) > self._cap:
+            self._d.popitem(last=False)
+        return prepared
+
+
+_mel_ops = _OperatorMemo()
+_cqt_ops = _OperatorMemo()
+
+
+def _prepare_filterbank(mel_filterbank):
     fb = mel_filterbank.toarray() if hasattr(mel_filterbank, "toarray") else np.asarray(mel_filterbank)  # zaf.py:373
     fb = np.ascontiguousarray(fb, dtype=np.float64)
+    return fb, fb.tobytes() if fb.ndim == 2 else b""
+
+
+def _mel_plan(window_function, step_length, mel_filterbank, number_coefficients, route="fused", precision="auto"):
+    w = _window64(window_function)
+    fb, fb_key = _mel_ops.get(mel_filterbank, _prepare_filterbank)
     if fb.ndim != 2 or fb.shape[1] != len(w) // 2:
         raise ValueError(f"mel_filterbank must have shape (number_mels, window_length/2 = {len(w) // 2})")
     if route not in _MEL_ROUTES:
         raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
     if precision not in _MEL_PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(_MEL_PRECISIONS)}")
-    key = ("mel", len(w), int(step_length), int(number_coefficients), route, precision, w.tobytes(), fb.tobytes())
+    key = ("mel", len(w), int(step_length), int(number_coefficients), route, precision, w.tobytes(), fb_key)
     fresh = key not in _mel_plans._d
     plan = _mel_plans.get(key, w.ctypes.data, len(w), int(step_length), fb.ctypes.data, fb.shape[0],
                           int(number_coefficients))
@@ -645,7 +689,7 @@ def mfcc(audio_signal, window_function, step_length, mel_filterbank, number_coef
 
 
 # ------------------------------------------------------------------ CQT
-def _cqt_plan(cqt_kernel, step, route="fused"):
+def _prepare_cqt_kernel(cqt_kernel):
     import scipy.sparse
 
     k = scipy.sparse.csr_matrix(cqt_kernel)
@@ -653,10 +697,14 @@ def _cqt_plan(cqt_kernel, step, route="fused"):
     data = np.ascontiguousarray(k.data, dtype=np.complex128)
     indptr = np.ascontiguousarray(k.indptr, dtype=np.int32)
     indices = np.ascontiguousarray(k.indices, dtype=np.int32)
-    nf, fft_length = k.shape
+    return k.shape, data, indptr, indices, (data.tobytes(), indices.tobytes(), indptr.tobytes())
+
+
+def _cqt_plan(cqt_kernel, step, route="fused"):
+    (nf, fft_length), data, indptr, indices, op_key = _cqt_ops.get(cqt_kernel, _prepare_cqt_kernel)
     if route not in _MEL_ROUTES:
         raise ValueError(f"route must be one of {sorted(_MEL_ROUTES)}")
-    key = ("cqt", nf, fft_length, int(step), route, data.tobytes(), indices.tobytes(), indptr.tobytes())
+    key = ("cqt", nf, fft_length, int(step), route) + op_key
     fresh = key not in _cqt_plans._d
     plan = _cqt_plans.get(key, nf, fft_length, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, int(step))
     if fresh and route != "fused":
