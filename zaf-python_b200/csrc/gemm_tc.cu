@@ -457,12 +457,11 @@ gemm3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_
         // overwrites them with hi / lo of s = x[m] + x[n-1-m] (fold 1) or d = x[m] - x[n-1-m] (fold 2).
         const int cw = warp - 10, rl = lane & 7, jp = lane >> 3;
         const uint32_t full_leader = mapa_rank(bar_full, 0);
+        // round to nearest, ties away, on the 13 dropped mantissa bits: what cvt.rna.tf32.f32 returns for finite values
+        // (and split_tf32_host computes), in two integer instructions instead of the five the cvt expands to
         auto tf32_split = [](float v, float& hv, float& lv) {
-            uint32_t p, q2;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(p) : "f"(v));
-            hv = __uint_as_float(p);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q2) : "f"(v - hv));
-            lv = __uint_as_float(q2);
+            hv = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+            lv = __uint_as_float((__float_as_uint(v - hv) + 0x1000u) & 0xFFFFE000u);
         };
         auto fold4 = [&](const float4 f, const float4 mrev, float sg, float4& hv, float4& lv) {
             tf32_split(fmaf(sg, mrev.w, f.x), hv.x, lv.x);
