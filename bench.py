@@ -850,7 +850,65 @@ def stft_merge_variants(zaf, dist, comm, args, stream, reps=2):
                                       "frames_per_sec": clips * nt / (best[3] * 1e-3), "bitwise_equal": check("direct_store_half"),
                                       "note": "peers store bins 0..N/2 into rank 0's two-sided buffer over NVLink (half the bytes); "
                                               "rank 0 fills the Hermitian half of those frames with zafb_spec_mirror_f32 in place"}
+    # ---- pulled + pipelined (r02): no scatter step and no serial mirror step.  Rank 0 exports its INPUT batch as well; the
+    # peers take their clips from it in chunks -- either their STFT kernels read rank 0's HBM directly ("remote_read") or a
+    # copy stream pulls chunk c + 1 while chunk c is transformed ("pull_copy") -- and store bins 0 .. N/2 into rank 0's result
+    # as above.  After every chunk a stream-ordered barrier tells rank 0 that the chunk has landed: it mirrors those frames
+    # while the next chunk crosses NVLink.
+    xview = comm.map_from_root(xd, (clips, NS), np.float32)
+    copy_stream = zaf.Stream()
+    fb = nt * N_WIN * 8  # bytes of one clip's spectrum
+    for mode, n_ch in (("remote_read", 4), ("pull_copy", 4), ("pull_copy", 8)):
+        def chunk_edges(b, e):
+            return [b + (e - b) * c // n_ch for c in range(n_ch + 1)]
+
+        my_edges = chunk_edges(lo, hi)
+        peer_edges = [chunk_edges(*zaf.shard_range(clips, r, dist.world)) for r in range(dist.world)]
+        cev = [zaf.Event() for _ in range(n_ch)]
+        best = None
+        for _ in range(reps + 1):
+            dist.barrier()
+            ev[0].record(stream)
+            if mode == "pull_copy" and dist.rank != 0:
+                copy_stream.wait_event(ev[0])
+                for c in range(n_ch):
+                    a, b = my_edges[c], my_edges[c + 1]
+                    if b > a:
+                        zaf._lib.check(lib.zafb_memcpy_d2d(C.c_void_p(shard.ptr + (a - lo) * NS * 4), C.c_void_p(xview.ptr + a * NS * 4),
+                                                           (b - a) * NS * 4, copy_stream.ptr))
+                    cev[c].record(copy_stream)
+            for c in range(n_ch):
+                a, b = my_edges[c], my_edges[c + 1]
+                if dist.rank == 0:
+                    if b > a:
+                        item.launch(xd.ptr + a * NS * 4, b - a, full.ptr + a * fb, stream)
+                else:
+                    src = xview.ptr + a * NS * 4
+                    if mode == "pull_copy":
+                        stream.wait_event(cev[c])
+                        src = shard.ptr + (a - lo) * NS * 4
+                    if b > a:
+                        zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(src), b - a, NS, NS, C.c_void_p(view.ptr + a * fb),
+                                                                  N_WIN, stream.ptr))
+                comm.barrier(stream)
+                if dist.rank == 0:
+                    for r in range(1, dist.world):
+                        a2, b2 = peer_edges[r][c], peer_edges[r][c + 1]
+                        if b2 > a2:
+                            part = full.ptr + a2 * fb
+                            zaf._lib.check(lib.zafb_spec_mirror_f32(C.c_void_p(part), N_WIN, (b2 - a2) * nt, N_WIN, C.c_void_p(part), stream.ptr))
+            ev[3].record(stream)
+            ev[3].synchronize()
+            t = dist.max(ev[0].elapsed_ms(ev[3]))
+            if best is None or t < best:
+                best = t
+        out[f"pipelined_{mode}{'' if n_ch == 4 else '_' + str(n_ch)}_merge"] = {
+            "total_ms": best, "chunks": n_ch, "frames_per_sec": clips * nt / (best * 1e-3), "bitwise_equal": check(f"pipelined_{mode}_{n_ch}"),
+            "note": "no scatter: the peers take their clips from rank 0's exported input ("
+                    + ("their STFT kernels load it over NVLink" if mode == "remote_read" else "a copy stream pulls chunk c + 1 during chunk c")
+                    + "), store bins 0..N/2 into rank 0's result; rank 0 mirrors chunk c while chunk c + 1 arrives"}
     dist.barrier()
+    comm.unmap(xview)
     comm.unmap(view)
 
     # ---- half_gather: one-sided shards (frame pitch padded to 4 bins = 32 bytes), NCCL gather, mirror kernel on rank 0

@@ -78,6 +78,8 @@ int zafb_event_create(void** event);
 int zafb_event_destroy(void* event);
 int zafb_event_record(void* event, void* stream);
 int zafb_event_sync(void* event);
+/* the work queued on `stream` after this call starts only when `event` (recorded on another stream) has completed */
+int zafb_stream_wait_event(void* stream, void* event);
 int zafb_event_elapsed_ms(void* start, void* stop, float* ms);
 /* zaf.wavread's normalisation (zaf.py:1199-1202) on the device: interleaved (frame, channel) int16 PCM ->
  * planar fp32 [channel][frame] (row pitch out_stride), x / 2^15 exactly; mono != 0 writes the channel mean instead. */

@@ -188,6 +188,10 @@ class Stream:
     def synchronize(self):
         _lib.check(_lib.lib().zafb_stream_sync(self.ptr))
 
+    def wait_event(self, event):
+        """Work queued on this stream from now on starts only after ``event`` (recorded on another stream) completed."""
+        _lib.check(_lib.lib().zafb_stream_wait_event(self.ptr, event.ptr))
+
     def __del__(self):
         try:
             _lib.lib().zafb_stream_destroy(self.ptr)

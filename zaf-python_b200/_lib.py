@@ -42,6 +42,7 @@ PROTOTYPES = {
     "zafb_event_create": (_int, [_pvp]),
     "zafb_event_destroy": (_int, [_vp]),
     "zafb_event_record": (_int, [_vp, _vp]),
+    "zafb_stream_wait_event": (_int, [_vp, _vp]),
     "zafb_event_sync": (_int, [_vp]),
     "zafb_event_elapsed_ms": (_int, [_vp, _vp, C.POINTER(C.c_float)]),
     "zafb_pcm16_to_f32": (_int, [_vp, _i64, _int, _int, _vp, _i64, _vp]),

@@ -27,6 +27,7 @@ using namespace zafb;
 struct zafb_comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    double* d_scalar = nullptr;  // device word of zafb_dist_max_f64 (allocated once: cudaMalloc / cudaFree synchronise the device)
 };
 
 namespace {
@@ -180,6 +181,7 @@ int zafb_dist_destroy(zafb_comm* c) {
     if (!c) return ZAFB_OK;
     NcclApi& nc = api();
     if (nc.handle && c->comm) nc.CommDestroy(c->comm);
+    cudaFree(c->d_scalar);
     delete c;
     return ZAFB_OK;
 }
@@ -282,14 +284,13 @@ int zafb_dist_max_f64(zafb_comm* c, double* value, void* stream) {
     ZAFB_REQUIRE(c != nullptr && value != nullptr, "comm/value is NULL");
     ZAFB_NCCL_READY();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double* d = nullptr;
-    ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(double)));
+    if (c->d_scalar == nullptr) ZAFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalar), sizeof(double)));
+    double* d = c->d_scalar;
     cudaError_t e = cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, st);
     ncclResult_t r = ncclSuccess;
     if (e == cudaSuccess) r = nc.AllReduce(d, d, 1, ncclDouble, ncclMax, c->comm, st);
     if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && r == ncclSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d);
     if (r != ncclSuccess) return fail(ZAFB_E_NCCL, "ncclAllReduce failed: %s", nc.GetErrorString(r));
     if (e != cudaSuccess) return fail(ZAFB_E_CUDA, "max over ranks failed: %s", cudaGetErrorString(e));
     return ZAFB_OK;

@@ -306,6 +306,11 @@ int zafb_event_sync(void* e) {
     ZAFB_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(e)));
     return ZAFB_OK;
 }
+int zafb_stream_wait_event(void* s, void* e) {
+    ZAFB_REQUIRE(e != nullptr, "event is NULL");
+    ZAFB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(s), static_cast<cudaEvent_t>(e), 0));
+    return ZAFB_OK;
+}
 int zafb_event_elapsed_ms(void* a, void* b, float* ms) {
     ZAFB_REQUIRE(ms != nullptr, "ms is NULL");
     ZAFB_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
