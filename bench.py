@@ -571,6 +571,44 @@ def config_line(item, ms, launches, world, peak, sm_max_mhz, parity, cpu):
             "parity_max_rel_err": parity, "parity_tolerance": TOL, "parity_clips_checked": 2, "cpu_baseline": cpu}
 
 
+def config_e2e(zaf, item, steps=2):
+    """The same transform end to end through the drop-in call with HOST buffers: a pinned (clips, ns) float32 batch in, the
+    result in (pooled, pinned) host memory out, host<->device copies inside the timed region; first and last clip of what
+    the timed calls returned are checked against the oracle."""
+    import oracle
+
+    c = item.c
+    pin = zaf.PinnedArray((item.clips, item.ns), np.float32)
+    base = np.random.default_rng(SEED + c["cfg"]).uniform(-1, 1, (min(32, item.clips), item.ns)).astype(np.float32)
+    for c0 in range(0, item.clips, len(base)):
+        pin.array[c0:c0 + len(base)] = base[: min(len(base), item.clips - c0)]
+    x = pin.array
+    if item.name == "melspectrogram":
+        call, ref_fn = (lambda: zaf.melspectrogram(x, item.w, c["hop"], item.fb)), (lambda v: oracle.melspectrogram(v, item.w, c["hop"], item.fb))
+    elif item.name == "mfcc":
+        call, ref_fn = (lambda: zaf.mfcc(x, item.w, c["hop"], item.fb, item.ncoef)), (lambda v: oracle.mfcc(v, item.w, c["hop"], item.fb, item.ncoef))
+    elif item.name == "mdct":
+        call, ref_fn = (lambda: zaf.mdct(x, item.w)), (lambda v: oracle.mdct(v, item.w))
+    else:
+        call, ref_fn = (lambda: zaf.cqtspectrogram(x, c["fs"], c["tr"], item.kern)), (lambda v: oracle.cqtspectrogram(v, c["fs"], c["tr"], item.kern))
+    res = call()  # warm-up: the result block comes from the pinned pool from the second call on
+    b0 = zaf.host_copy_bytes()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = None  # hand the previous result back to the pool first
+        res = call()
+    sec = (time.perf_counter() - t0) / steps
+    b1 = zaf.host_copy_bytes()
+    worst = max(max(oracle.parity_metrics(res[k], ref_fn(x[k]))) for k in (0, item.clips - 1))
+    assert worst <= TOL, f"{item.name}: e2e parity broken: {worst}"
+    out = {"value": item.clips * item.units_per_clip / sec, "unit": "frames/s", "ms_per_step": 1e3 * sec,
+           "h2d_bytes_per_step": (b1[0] - b0[0]) // steps, "d2h_bytes_per_step": (b1[1] - b0[1]) // steps,
+           "parity_max_rel_err": worst, "api": f"zaf.{item.name}(x_host_batch, ...) -> zafb_*_host_f32"}
+    res = None
+    pin.free()
+    return out
+
+
 def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
     """Every other BASELINE config on its own shape, one group at a time (a group shares its input; buffers are freed
     in between)."""
@@ -613,6 +651,18 @@ def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
                 line = config_line(item, ms, nl, dist.world, peak, sm_max_mhz, parity, cpu_lines.get(name))
                 line["clocks"] = clk
                 out.append(line)
+                if dist.world == 1 and not route and args.e2e_steps > 0 and name in ("melspectrogram", "mfcc", "mdct", "cqtspectrogram"):
+                    outd.free()  # room for the host pipeline's staging buffers
+                    outd = None
+                    try:
+                        line["e2e"] = config_e2e(zaf, item)
+                        cpu = line.get("cpu_baseline") or {}
+                        if cpu.get("value"):
+                            line["e2e"]["vs_cpu_baseline"] = line["e2e"]["value"] / cpu["value"]
+                    except AssertionError:
+                        raise
+                    except Exception as exc:  # noqa: BLE001
+                        line["e2e"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             except AssertionError:
                 raise
             except Exception as exc:  # noqa: BLE001
