@@ -651,18 +651,7 @@ def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
                 line = config_line(item, ms, nl, dist.world, peak, sm_max_mhz, parity, cpu_lines.get(name))
                 line["clocks"] = clk
                 out.append(line)
-                if dist.world == 1 and not route and args.e2e_steps > 0 and name in ("melspectrogram", "mfcc", "mdct", "cqtspectrogram"):
-                    outd.free()  # room for the host pipeline's staging buffers
-                    outd = None
-                    try:
-                        line["e2e"] = config_e2e(zaf, item)
-                        cpu = line.get("cpu_baseline") or {}
-                        if cpu.get("value"):
-                            line["e2e"]["vs_cpu_baseline"] = line["e2e"]["value"] / cpu["value"]
-                    except AssertionError:
-                        raise
-                    except Exception as exc:  # noqa: BLE001
-                        line["e2e"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
             except AssertionError:
                 raise
             except Exception as exc:  # noqa: BLE001
@@ -671,6 +660,26 @@ def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
                 outd.free()
         ind.free()
     return out
+
+
+def run_config_e2e(zaf, dist, args, lines):
+    """N = 1: the end-to-end leg of every forward transform with a host-sized result, AFTER all device-timed legs (a
+    host-bound leg lets the SM and memory clocks drop, which would colour the next device timing)."""
+    if dist.world != 1 or args.e2e_steps <= 0:
+        return
+    for line in lines:
+        name = line.get("transform")
+        if name not in ("melspectrogram", "mfcc", "mdct", "cqtspectrogram") or "error" in line:
+            continue
+        try:
+            line["e2e"] = config_e2e(zaf, Item(zaf, name, clips=args.config_clips or None))
+            cpu = line.get("cpu_baseline") or {}
+            if cpu.get("value"):
+                line["e2e"]["vs_cpu_baseline"] = line["e2e"]["value"] / cpu["value"]
+        except AssertionError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            line["e2e"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def chain_leg(zaf, stream, xd, clips, nt, w, spec):
@@ -1244,6 +1253,7 @@ def run_ours(args):
                 raise
             except Exception as exc:  # noqa: BLE001
                 extra["dct"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        run_config_e2e(zaf, dist, args, extra["configs"])
 
     # N > 1: the batch split / merge legs (strong scaling): rank 0 holds one whole batch in HBM, scatters the clips over
     # NCCL, every rank transforms its shard, the results are gathered back on rank 0 and compared bitwise with the
