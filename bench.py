@@ -1263,6 +1263,15 @@ def run_ours(args):
             legs, variants = split_merge_legs(zaf, dist, args, stream)
             extra["split_merge"] = {"legs": legs, "stft_variants": variants,
                                     "note": "rank 0 holds the batch; grouped ncclSend/ncclRecv over NVLink; best of 2 after a warm-up"}
+            # one number for the cfg-2 STFT split -> transform -> merge: the fastest bitwise-checked route, next to the
+            # plain NCCL scatter / two-sided gather route r01 reported under this key
+            cands = {k: v["total_ms"] for k, v in variants.items() if isinstance(v, dict) and v.get("total_ms") and v.get("bitwise_equal")}
+            nccl = next((l.get("total_ms") for l in legs if l.get("transform") == "stft"), None)
+            if nccl:
+                cands["nccl_scatter_gather_two_sided"] = nccl
+            if cands and dist.rank == 0:
+                best = min(cands, key=cands.get)
+                extra["split_merge"].update({"total_ms": cands[best], "route": best, "nccl_two_sided_total_ms": nccl})
         except AssertionError:
             raise
         except Exception as exc:  # noqa: BLE001 -- the headline number does not depend on this leg
