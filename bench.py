@@ -684,54 +684,86 @@ def run_config_e2e(zaf, dist, args, lines):
 
 def chain_leg(zaf, stream, xd, clips, nt, w, spec):
     """stft -> |X| -> mask -> X*mask -> istft with every stage on the device: the reference's
-    centre-extraction demo (zaf.py:166-191) on the cfg-2 batch, clip pairs (2i, 2i+1) as left/right."""
+    centre-extraction demo (zaf.py:166-191) on the cfg-2 batch, clips (i, i + clips/2) as left / right channel."""
+    import oracle
+
     lib, C = zaf._lib.lib(), zaf._lib.C
     n, k = N_WIN, N_WIN // 2 + 1
     plan, _ = zaf._stft_plan(w, HOP)
-    mag = zaf.empty((clips, nt, k), np.float32)
-    swp = zaf.empty((clips, nt, k), np.float32)
     ylen = zaf.istft_geometry(n, nt, HOP)[2]
     yd = zaf.empty((clips, ylen), np.float32)
-    pair = nt * k * 4
-
-    def run():
-        zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(spec.ptr), 0, stream.ptr))
-        zaf._lib.check(lib.zafb_spec_abs_f32(C.c_void_p(spec.ptr), clips, n, nt, 0, k, C.c_void_p(mag.ptr), stream.ptr))
-        # the other channel's magnitudes: swap the rows of each (left, right) pair
-        zaf._lib.check(lib.zafb_memcpy2d(C.c_void_p(swp.ptr), 2 * pair, C.c_void_p(mag.ptr + pair), 2 * pair, pair, clips // 2, 2, stream.ptr))
-        zaf._lib.check(lib.zafb_memcpy2d(C.c_void_p(swp.ptr + pair), 2 * pair, C.c_void_p(mag.ptr), 2 * pair, pair, clips // 2, 2, stream.ptr))
-        zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr), C.c_void_p(swp.ptr), clips * nt * k, C.c_void_p(mag.ptr), stream.ptr))
-        zaf._lib.check(lib.zafb_spec_mask_f32(C.c_void_p(spec.ptr), clips, n, nt, 0, C.c_void_p(mag.ptr), k, C.c_void_p(spec.ptr), stream.ptr))
-        zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, stream.ptr))
-
-    for _ in range(2):
-        run()
-    stream.synchronize()
+    hc = clips // 2
     e0, e1 = zaf.Event(), zaf.Event()
-    e0.record(stream)
-    for _ in range(3):
-        run()
-    e1.record(stream)
-    e1.synchronize()
-    ms = e0.elapsed_ms(e1) / 3
-    import oracle
-
     got = np.empty((2, ylen), np.float32)
     x2 = np.empty((2, NS), np.float32)
-    zaf._lib.check(lib.zafb_memcpy_d2h(got.ctypes.data, C.c_void_p(yd.ptr), got.nbytes, None))
-    zaf._lib.check(lib.zafb_memcpy_d2h(x2.ctypes.data, C.c_void_p(xd.ptr), x2.nbytes, None))
+    for i, c in enumerate((0, hc)):
+        zaf._lib.check(lib.zafb_memcpy_d2h(x2[i].ctypes.data, C.c_void_p(xd.ptr + c * NS * 4), x2[i].nbytes, None))
     zaf.synchronize()
     s1, s2 = oracle.stft(x2[0], w, HOP), oracle.stft(x2[1], w, HOP)
     a1, a2 = np.abs(s1[:k]), np.abs(s2[:k])
-    worst = 0.0
-    for s, a, g in ((s1, a1, got[0]), (s2, a2, got[1])):
-        m = np.minimum(a1, a2) / a
-        worst = max(worst, *oracle.parity_metrics(g, oracle.istft(np.concatenate((m, m[-2:0:-1])) * s, w, HOP)))
-    assert worst <= TOL, f"device chain parity broken: {worst}"
-    for d in (mag, swp, yd):
-        d.free()
+
+    def timed(run):
+        for _ in range(2):
+            run()
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(3):
+            run()
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_ms(e1) / 3
+        for i, c in enumerate((0, hc)):
+            zaf._lib.check(lib.zafb_memcpy_d2h(got[i].ctypes.data, C.c_void_p(yd.ptr + c * ylen * 4), got[i].nbytes, None))
+        zaf.synchronize()
+        worst = 0.0
+        for s, a, g in ((s1, a1, got[0]), (s2, a2, got[1])):
+            m = np.minimum(a1, a2) / a
+            worst = max(worst, *oracle.parity_metrics(g, oracle.istft(np.concatenate((m, m[-2:0:-1])) * s, w, HOP)))
+        assert worst <= TOL, f"device chain parity broken: {worst}"
+        return ms, worst
+
+    def chain(spec_ptr, bins, cols, stft_call, istft_call):
+        """cols = magnitude / mask columns per frame; the left and right halves of the batch are each other's partner."""
+        mag = zaf.empty((clips, nt, cols), np.float32)
+        msk = zaf.empty((clips, nt, cols), np.float32)
+        half_n = hc * nt * cols
+
+        def run():
+            stft_call()
+            zaf._lib.check(lib.zafb_spec_abs_f32(C.c_void_p(spec_ptr), clips, bins, nt, 0, cols, C.c_void_p(mag.ptr), stream.ptr))
+            zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr), C.c_void_p(mag.ptr + half_n * 4), half_n, C.c_void_p(msk.ptr), stream.ptr))
+            zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr + half_n * 4), C.c_void_p(mag.ptr), half_n,
+                                                  C.c_void_p(msk.ptr + half_n * 4), stream.ptr))
+            zaf._lib.check(lib.zafb_spec_mask_f32(C.c_void_p(spec_ptr), clips, bins, nt, 0, C.c_void_p(msk.ptr), cols, C.c_void_p(spec_ptr), stream.ptr))
+            istft_call()
+
+        try:
+            return timed(run)
+        finally:
+            mag.free()
+            msk.free()
+
+    # two-sided spectra, exactly the arrays of the reference's demo
+    ms, worst = chain(
+        spec.ptr, n, k,
+        lambda: zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(spec.ptr), 0, stream.ptr)),
+        lambda: zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, stream.ptr)))
+    # the same chain on ONE-SIDED spectra (the non-reference option of stft / istft): a real mask that is mirrored onto
+    # the upper bins keeps the spectrum Hermitian, so bins 0 .. N/2 carry the whole chain -- half the bytes in every stage
+    pitch = (k + 3) & ~3
+    half = zaf.empty((clips, nt, pitch), np.complex64)
+    zaf._lib.check(lib.zafb_memset(C.c_void_p(half.ptr), 0, half.nbytes, stream.ptr))  # the padding bins: finite values
+    ms1, worst1 = chain(
+        half.ptr, pitch, pitch,
+        lambda: zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(half.ptr), pitch, stream.ptr)),
+        lambda: zaf._lib.check(lib.zafb_istft_onesided_f32(plan, C.c_void_p(half.ptr), clips, nt, pitch, C.c_void_p(yd.ptr), ylen, stream.ptr)))
+    half.free()
+    yd.free()
     return {"chain": "stft -> abs -> min-ratio mask -> mask multiply (mirrored) -> istft, device-resident (zaf.py:166-191)",
             "ms_per_batch": ms, "frames_per_sec": clips * nt / (ms * 1e-3), "parity_max_rel_err": worst,
+            "onesided": {"ms_per_batch": ms1, "frames_per_sec": clips * nt / (ms1 * 1e-3), "parity_max_rel_err": worst1,
+                         "note": "the same chain on bins 0..N/2 only (zafb_stft_onesided_f32 ... zafb_istft_onesided_f32): a mirrored "
+                                 "real mask keeps the spectrum Hermitian, so the half spectrum carries the whole chain"},
             "pcie_bytes": 0}
 
 

@@ -28,56 +28,134 @@ int64_t grid_for(int64_t items) {
     return blocks < 1 ? 1 : blocks;
 }
 
+// x: blocks over the `items` of one clip, y: clips -- about sm_count() * 8 blocks in all
+dim3 grid_2d(int64_t items, int64_t clips) {
+    const int64_t cap = int64_t(sm_count()) * 8;
+    int64_t gy = clips < cap ? clips : cap;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    int64_t gx = ceil_div(items, kThreads);
+    const int64_t per = ceil_div(cap, gy);
+    if (gx > per) gx = per;
+    if (gx < 1) gx = 1;
+    return dim3(unsigned(gx), unsigned(gy));
+}
+
+// The four spectrum kernels walk rows (frames, or bin rows of a clip) with one warp per row and no index division: a
+// 64-bit division per element made them instruction-bound (the same finding as for the GEMM pre-pass in dctdst.cu).
+//
 // FRAME_MAJOR: spec[row][bins] (row = clip * frames + frame) -> out[row][keep]
-__global__ void abs_frame_major_kernel(const float2* __restrict__ spec, int64_t rows, int bins, int keep, float* __restrict__ out) {
-    const int64_t total = rows * keep;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t r = i / keep;
-        const int k = int(i - r * keep);
-        const float2 v = __ldg(spec + r * bins + k);
-        out[i] = sqrtf(v.x * v.x + v.y * v.y);
+__global__ void abs_frame_major_kernel(const float2* __restrict__ spec, int64_t rows, int bins, int keep, float* __restrict__ out,
+                                       int vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = int64_t(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nwarps) {
+        const float2* in = spec + r * bins;
+        float* o = out + r * keep;
+        int k0 = 0;
+        if (vec) {  // two bins per access (16-byte loads, 8-byte stores when the rows allow), four accesses in flight per lane
+            const float4* in4 = reinterpret_cast<const float4*>(in);
+            float2* o2 = reinterpret_cast<float2*>(o);
+            const int pairs = keep >> 1;
+            for (int p = lane; p < pairs; p += 128) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (p + 32 * u < pairs) v[u] = __ldg(in4 + p + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (p + 32 * u < pairs) {
+                        const float m0 = sqrtf(v[u].x * v[u].x + v[u].y * v[u].y), m1 = sqrtf(v[u].z * v[u].z + v[u].w * v[u].w);
+                        if (vec == 2) {  // odd `keep`: the output rows are only 4-byte aligned
+                            o[2 * (p + 32 * u)] = m0;
+                            o[2 * (p + 32 * u) + 1] = m1;
+                        } else {
+                            o2[p + 32 * u] = make_float2(m0, m1);
+                        }
+                    }
+            }
+            k0 = pairs * 2;
+        }
+        for (int k = k0 + lane; k < keep; k += 32) {
+            const float2 v = __ldg(in + k);
+            o[k] = sqrtf(v.x * v.x + v.y * v.y);
+        }
     }
 }
 
 // BIN_MAJOR: spec[clip][bins][frames] -> out[clip][keep][frames]; the kept rows of a clip are one contiguous run
 __global__ void abs_bin_major_kernel(const float2* __restrict__ spec, int64_t clips, int64_t bins_frames, int64_t keep_frames,
                                      float* __restrict__ out) {
-    const int64_t total = clips * keep_frames;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t c = i / keep_frames;
-        const float2 v = __ldg(spec + c * bins_frames + (i - c * keep_frames));
-        out[i] = sqrtf(v.x * v.x + v.y * v.y);
+    const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t c = blockIdx.y; c < clips; c += gridDim.y) {
+        const float2* in = spec + c * bins_frames;
+        float* o = out + c * keep_frames;
+        for (int64_t i = tid; i < keep_frames; i += nth) {
+            const float2 v = __ldg(in + i);
+            o[i] = sqrtf(v.x * v.x + v.y * v.y);
+        }
     }
 }
 
 // FRAME_MAJOR: out[row][k] = spec[row][k] * mask[row][k <= bins/2 or full ? k : bins - k]
-__global__ void mask_frame_major_kernel(const float2* __restrict__ spec, int64_t rows, int bins, const float* __restrict__ mask,
-                                        int mask_bins, float2* __restrict__ out) {
-    const int64_t total = rows * bins;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t r = i / bins;
-        const int k = int(i - r * bins);
-        const int km = k < mask_bins ? k : bins - k;
-        const float m = __ldg(mask + r * mask_bins + km);
-        const float2 v = spec[i];
-        out[i] = make_float2(v.x * m, v.y * m);
+__global__ void mask_frame_major_kernel(const float2* spec, int64_t rows, int bins, const float* __restrict__ mask, int mask_bins,
+                                        float2* out, int vec) {
+    // spec and out may be the same buffer (in place): every lane reads its own elements before it writes them
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = int64_t(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nwarps) {
+        const float2* in = spec + r * bins;
+        float2* o = out + r * bins;
+        const float* mr = mask + r * mask_bins;
+        int k0 = 0;
+        if (vec) {  // two bins per access, four accesses in flight per lane
+            const float4* in4 = reinterpret_cast<const float4*>(in);
+            float4* o4 = reinterpret_cast<float4*>(o);
+            const int pairs = bins >> 1;
+            for (int p = lane; p < pairs; p += 128) {
+                float4 v[4];
+                float m0[4], m1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = p + 32 * u;
+                    if (q < pairs) {
+                        v[u] = in4[q];
+                        const int ka = 2 * q, kb = 2 * q + 1;
+                        m0[u] = __ldg(mr + (ka < mask_bins ? ka : bins - ka));
+                        m1[u] = __ldg(mr + (kb < mask_bins ? kb : bins - kb));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (p + 32 * u < pairs) o4[p + 32 * u] = make_float4(v[u].x * m0[u], v[u].y * m0[u], v[u].z * m1[u], v[u].w * m1[u]);
+            }
+            k0 = pairs * 2;
+        }
+        for (int k = k0 + lane; k < bins; k += 32) {
+            const float m = __ldg(mr + (k < mask_bins ? k : bins - k));
+            const float2 v = in[k];
+            o[k] = make_float2(v.x * m, v.y * m);
+        }
     }
 }
 
-// BIN_MAJOR: out[clip][k][j] = spec[clip][k][j] * mask[clip][k < mask_bins ? k : bins - k][j]
+// BIN_MAJOR: out[clip][k][j] = spec[clip][k][j] * mask[clip][k < mask_bins ? k : bins - k][j]; one warp per bin row
 __global__ void mask_bin_major_kernel(const float2* __restrict__ spec, int64_t clips, int bins, int64_t frames,
                                       const float* __restrict__ mask, int mask_bins, float2* __restrict__ out) {
-    const int64_t per_clip = int64_t(bins) * frames;
-    const int64_t total = clips * per_clip;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t c = i / per_clip;
-        const int64_t rem = i - c * per_clip;
-        const int k = int(rem / frames);
-        const int64_t j = rem - int64_t(k) * frames;
-        const int km = k < mask_bins ? k : bins - k;
-        const float m = __ldg(mask + (c * mask_bins + km) * frames + j);
-        const float2 v = spec[i];
-        out[i] = make_float2(v.x * m, v.y * m);
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = int64_t(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t c = blockIdx.y; c < clips; c += gridDim.y) {
+        for (int64_t k = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); k < bins; k += nwarps) {
+            const int km = k < mask_bins ? int(k) : bins - int(k);
+            const float2* in = spec + (c * bins + k) * frames;
+            float2* o = out + (c * bins + k) * frames;
+            const float* mr = mask + (c * mask_bins + km) * frames;
+            for (int64_t j = lane; j < frames; j += 32) {
+                const float m = __ldg(mr + j);
+                const float2 v = in[j];
+                o[j] = make_float2(v.x * m, v.y * m);
+            }
+        }
     }
 }
 
@@ -165,9 +243,12 @@ int zafb_spec_abs_f32(const float* spec, int64_t n_clips, int64_t bins, int64_t 
     const float2* s2 = reinterpret_cast<const float2*>(spec);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (layout == ZAFB_LAYOUT_FRAME_MAJOR)
-        abs_frame_major_kernel<<<unsigned(grid_for(total)), kThreads, 0, st>>>(s2, n_clips * frames, int(bins), int(keep_bins), out);
+        abs_frame_major_kernel<<<unsigned(grid_for(n_clips * frames * 32)), kThreads, 0, st>>>(
+            s2, n_clips * frames, int(bins), int(keep_bins), out,
+            (bins % 2 == 0 && reinterpret_cast<uintptr_t>(spec) % 16 == 0)
+                ? ((keep_bins % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0) ? 1 : 2) : 0);
     else
-        abs_bin_major_kernel<<<unsigned(grid_for(total)), kThreads, 0, st>>>(s2, n_clips, bins * frames, keep_bins * frames, out);
+        abs_bin_major_kernel<<<grid_2d(keep_bins * frames, n_clips), kThreads, 0, st>>>(s2, n_clips, bins * frames, keep_bins * frames, out);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
@@ -187,9 +268,11 @@ int zafb_spec_mask_f32(const float* spec, int64_t n_clips, int64_t bins, int64_t
     float2* o2 = reinterpret_cast<float2*>(out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (layout == ZAFB_LAYOUT_FRAME_MAJOR)
-        mask_frame_major_kernel<<<unsigned(grid_for(total)), kThreads, 0, st>>>(s2, n_clips * frames, int(bins), mask, int(mask_bins), o2);
+        mask_frame_major_kernel<<<unsigned(grid_for(n_clips * frames * 32)), kThreads, 0, st>>>(
+            s2, n_clips * frames, int(bins), mask, int(mask_bins), o2,
+            int(bins % 2 == 0 && reinterpret_cast<uintptr_t>(spec) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0));
     else
-        mask_bin_major_kernel<<<unsigned(grid_for(total)), kThreads, 0, st>>>(s2, n_clips, int(bins), frames, mask, int(mask_bins), o2);
+        mask_bin_major_kernel<<<grid_2d(bins * kThreads / 8, n_clips), kThreads, 0, st>>>(s2, n_clips, int(bins), frames, mask, int(mask_bins), o2);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
