@@ -31,8 +31,8 @@ for k, h in hist.items():
         print("    " + ", ".join(f"{kk} x{v}" for kk, v in found.items() if v))
 PY
 echo
-for k in gemm3xtf32_kernelILi128 gemm3xtf32_kernelILi64 stft_warp_kernelILi2048ELb0ELi6ELb0 stft_warp_kernelILi2048ELb1ELi8 stft_warp_binmajor_kernelILi2048ELb0 \
-         istft_warp_kernelILi2048ELi4ELi8ELb0 mdct_warp_kernelILi2048 imdct_warp_kernelILi2048 mel_warp_kernelILi1024ELi1ELb0 mel_warp_kernel_f64 cqt_eo_kernelILb0 cqt32768_kernelILb0 dct1024_warp_kernelILi2ELb0; do
+for k in gemm3xtf32_pair_kernelILb1 gemm3xtf32_pair_kernelILb0 gemm3xtf32_kernelILi128 gemm3xtf32_kernelILi64 stft_warp_kernelILi2048ELb0ELi6ELb0 stft_warp_kernelILi2048ELb1ELi8 stft_warp_binmajor_kernelILi2048ELb0 \
+         istft_warp_kernelILi2048ELi4ELi8ELb0 mdct_warp_kernelILi2048 imdct_warp_kernelILi2048 mel_warp_kernelILi1024ELi1ELb0 mel_warp_kernel_f64 cqt_eo_kernelILb0 cqt32768_kernelILb0 dct_warp_kernelILi1024ELi2ELb0; do
   echo "## $k"
   python3 scripts/sass_hist.py $k < $TMP 2>/dev/null | head -16
   echo
