@@ -23,7 +23,7 @@ for line in open(sys.argv[1]):
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and cur:
         hist[cur][m.group(1)] += 1
-keys = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOM", "SYNCS")
+keys = ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOM", "SYNCS")
 for k, h in hist.items():
     found = {kk: sum(v for op, v in h.items() if op.startswith(kk)) for kk in keys}
     if any(found.values()):
