@@ -157,7 +157,7 @@ def test_dct_dst_tensor_core_matrix_path(zaf_gpu, n):
                 assert np.array_equal(got, fn(x, t))  # the default route for batch >= 8 is the same path
 
 
-@pytest.mark.parametrize("n", [257, 1000, 1024])
+@pytest.mark.parametrize("n", [16, 40, 257, 1000, 1024])
 def test_dct_dst_cta_pair_matrix_path(zaf_gpu, n, monkeypatch):
     """Batches of 256 vectors and more take the CTA-pair form of the matrix path (tcgen05 cta_group::2, 256 x 256 tiles,
     persistent over M blocks): a batch that is not a multiple of the 256-row tile, a batch with more M blocks than
