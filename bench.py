@@ -734,8 +734,7 @@ def chain_leg(zaf, stream, xd, clips, nt, w, spec):
             zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr), C.c_void_p(mag.ptr + half_n * 4), half_n, C.c_void_p(msk.ptr), stream.ptr))
             zaf._lib.check(lib.zafb_ratio_min_f32(C.c_void_p(mag.ptr + half_n * 4), C.c_void_p(mag.ptr), half_n,
                                                   C.c_void_p(msk.ptr + half_n * 4), stream.ptr))
-            zaf._lib.check(lib.zafb_spec_mask_f32(C.c_void_p(spec_ptr), clips, bins, nt, 0, C.c_void_p(msk.ptr), cols, C.c_void_p(spec_ptr), stream.ptr))
-            istft_call()
+            istft_call(msk.ptr, cols)  # the mirrored mask multiply is fused into the ISTFT's loads (zafb_istft_masked_f32)
 
         try:
             return timed(run)
@@ -747,7 +746,8 @@ def chain_leg(zaf, stream, xd, clips, nt, w, spec):
     ms, worst = chain(
         spec.ptr, n, k,
         lambda: zaf._lib.check(lib.zafb_stft_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(spec.ptr), 0, stream.ptr)),
-        lambda: zaf._lib.check(lib.zafb_istft_f32(plan, C.c_void_p(spec.ptr), clips, nt, 0, C.c_void_p(yd.ptr), ylen, stream.ptr)))
+        lambda m, mp: zaf._lib.check(lib.zafb_istft_masked_f32(plan, C.c_void_p(spec.ptr), clips, nt, n, 0, C.c_void_p(m), mp,
+                                                               C.c_void_p(yd.ptr), ylen, stream.ptr)))
     # the same chain on ONE-SIDED spectra (the non-reference option of stft / istft): a real mask that is mirrored onto
     # the upper bins keeps the spectrum Hermitian, so bins 0 .. N/2 carry the whole chain -- half the bytes in every stage
     pitch = (k + 3) & ~3
@@ -756,10 +756,12 @@ def chain_leg(zaf, stream, xd, clips, nt, w, spec):
     ms1, worst1 = chain(
         half.ptr, pitch, pitch,
         lambda: zaf._lib.check(lib.zafb_stft_onesided_f32(plan, C.c_void_p(xd.ptr), clips, NS, NS, C.c_void_p(half.ptr), pitch, stream.ptr)),
-        lambda: zaf._lib.check(lib.zafb_istft_onesided_f32(plan, C.c_void_p(half.ptr), clips, nt, pitch, C.c_void_p(yd.ptr), ylen, stream.ptr)))
+        lambda m, mp: zaf._lib.check(lib.zafb_istft_masked_f32(plan, C.c_void_p(half.ptr), clips, nt, pitch, 1, C.c_void_p(m), mp,
+                                                               C.c_void_p(yd.ptr), ylen, stream.ptr)))
     half.free()
     yd.free()
-    return {"chain": "stft -> abs -> min-ratio mask -> mask multiply (mirrored) -> istft, device-resident (zaf.py:166-191)",
+    return {"chain": "stft -> abs -> min-ratio mask -> istft of the (mirrored) masked spectrum, device-resident (zaf.py:166-191); "
+                     "the mask multiply is fused into the ISTFT's loads",
             "ms_per_batch": ms, "frames_per_sec": clips * nt / (ms * 1e-3), "parity_max_rel_err": worst,
             "onesided": {"ms_per_batch": ms1, "frames_per_sec": clips * nt / (ms1 * 1e-3), "parity_max_rel_err": worst1,
                          "note": "the same chain on bins 0..N/2 only (zafb_stft_onesided_f32 ... zafb_istft_onesided_f32): a mirrored "

@@ -146,6 +146,13 @@ int zafb_istft_onesided_f32(const zafb_stft_plan* plan, const float* spec, int64
                             int64_t spec_pitch, float* y, int64_t y_stride, void* stream);
 int zafb_spec_mirror_f32(const float* src, int64_t src_pitch, int64_t frames, int64_t window_length,
                          float* dst, void* stream);
+/* zaf.istft of np.concatenate((mask, mask[-2:0:-1])) * X (zaf.py:185-190) with the multiply fused into the ISTFT's loads:
+ * `mask` holds a real value for bins 0 .. N/2 of every frame (mask_pitch floats per frame); spec is FRAME_MAJOR, two-sided
+ * (onesided = 0, spec_pitch = N) or one-sided (bins 0 .. N/2, spec_pitch complex elements per frame).  The fused kernel
+ * exists for window_length 2048, hop 512; other geometries return ZAFB_E_UNSUPPORTED (multiply with zafb_spec_mask_f32
+ * first). */
+int zafb_istft_masked_f32(const zafb_stft_plan* plan, const float* spec, int64_t n_clips, int64_t nt, int64_t spec_pitch,
+                          int onesided, const float* mask, int64_t mask_pitch, float* y, int64_t y_stride, void* stream);
 
 /* The host-side half of that path, usable on its own: given `frames` frame-major frames of `window_length` complex64
  * bins (window_length a multiple of 4) whose bins 0 .. N/2 are valid, writes bins N/2+1 .. N-1 as conj of bins

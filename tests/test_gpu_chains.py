@@ -186,3 +186,37 @@ def test_onesided_stft_istft(zaf_gpu, n, hop):
     assert_parity(zaf.istft(spec, w, hop, onesided=True), oracle.istft(two.astype(np.complex128), w, hop))
     with pytest.raises(ValueError):
         zaf.istft(spec[:-1], w, hop, onesided=True)
+
+
+@pytest.mark.parametrize("n,hop", [(2048, 512), (1024, 256), (2048, 1024)])
+@pytest.mark.parametrize("onesided", [False, True])
+def test_istft_with_mask_fused_into_the_loads(zaf_gpu, n, hop, onesided):
+    """zaf.istft(X, w, hop, mask=M) == istft(np.concatenate((M, M[-2:0:-1])) * X) (zaf.py:185-190): the fused kernel
+    (N = 2048, hop = 512) and the multiply-then-transform fallback of every other geometry, two-sided and one-sided
+    spectra, a batch and a single clip; also against the unfused device chain."""
+    zaf = zaf_gpu
+    w = oracle.hamming_periodic(n)
+    rng = np.random.default_rng(n + hop)
+    x = rng.uniform(-1, 1, (3, 20000)).astype(np.float32)
+    xd = zaf.to_device(x)
+    spec = zaf.stft(xd, w, hop, onesided=onesided)
+    nt = spec.shape[-1]
+    m_host = rng.uniform(0, 1, (3, n // 2 + 1, nt)).astype(np.float32)
+    mask = zaf.to_device(np.ascontiguousarray(np.swapaxes(m_host, 1, 2)))       # frame-major memory (3, nt, N/2+1)
+    mask = zaf.DeviceArray(mask.mem_shape, np.float32, ptr=mask.ptr, owner=mask, transposed=True)
+    got = zaf.istft(spec, w, hop, onesided=onesided, mask=mask).to_host()
+    unfused = zaf.istft(zaf.spec_mask(spec, mask), w, hop, onesided=onesided).to_host()
+    for c in range(3):
+        m = m_host[c].astype(np.float64)
+        ref = oracle.istft(np.concatenate((m, m[-2:0:-1])) * oracle.stft(x[c], w, hop), w, hop)
+        assert_parity(got[c], ref)
+        assert_parity(unfused[c], ref)
+    one = zaf.stft(zaf.to_device(x[1]), w, hop, onesided=onesided)
+    m1_host = np.ascontiguousarray(m_host[1].T)  # (nt, N/2+1): to_device would pad the odd row length like a signal batch
+    m1 = zaf.DeviceArray(m1_host.shape, np.float32, transposed=True)
+    zaf._lib.check(zaf._lib.lib().zafb_memcpy_h2d(zaf._lib.C.c_void_p(m1.ptr), m1_host.ctypes.data, m1_host.nbytes, None))
+    zaf.synchronize()
+    y1 = zaf.istft(one, w, hop, onesided=onesided, mask=m1).to_host()
+    assert np.max(np.abs(y1 - got[1])) <= 1e-6 * np.max(np.abs(got[1]))
+    with pytest.raises(ValueError):
+        zaf.istft(spec.to_host(), w, hop, onesided=onesided, mask=mask)

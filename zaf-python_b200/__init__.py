@@ -295,10 +295,12 @@ def _spec_memory(audio_stft, dtype):
     return np.ascontiguousarray(a), LAYOUT_BIN_MAJOR, one, a.shape
 
 
-def _istft_onesided(plan, w, audio_stft, step_length, stream):
+def _istft_onesided(plan, w, audio_stft, step_length, stream, mask=None):
     n = len(w)
     bins = n // 2 + 1
     on_device = isinstance(audio_stft, DeviceArray)
+    if mask is not None and not on_device:
+        raise ValueError("mask= needs DeviceArray spectrum and mask (device-resident chains)")
     if on_device:
         s = audio_stft
         one, batch = _device_matrix(s, np.complex64, "(N/2+1, nt) or (B, N/2+1, nt)")
@@ -321,6 +323,14 @@ def _istft_onesided(plan, w, audio_stft, step_length, stream):
     length = istft_geometry(n, nt, step_length)[2]
     pitch = _even(length)
     out = DeviceArray((pitch,) if one else (batch, pitch), np.float32, cols=length)
+    if mask is not None:
+        mp = _mask_pitch(mask, s, n)
+        try:
+            _lib.check(_lib.lib().zafb_istft_masked_f32(plan, C.c_void_p(s.ptr), batch, nt, bins, 1, C.c_void_p(mask.ptr), mp,
+                                                        C.c_void_p(out.ptr), pitch, _stream_ptr(stream)))
+            return out
+        except NotImplementedError:  # no fused kernel for this geometry: multiply the half spectrum, then transform
+            s = spec_mask(s, mask, stream=stream)
     _lib.check(_lib.lib().zafb_istft_onesided_f32(plan, C.c_void_p(s.ptr), batch, nt, bins, C.c_void_p(out.ptr), pitch,
                                                   _stream_ptr(stream)))
     if on_device:
@@ -346,17 +356,31 @@ def spec_mirror(audio_stft_onesided, window_length, *, stream=None):
     return out
 
 
-def istft(audio_stft, window_function, step_length, *, stream=None, onesided=False):
+def _mask_pitch(mask, spec, n):
+    """Validate a (N/2+1, nt) / (B, N/2+1, nt) float32 frame-major DeviceArray mask for ``spec``; returns its row pitch."""
+    if not isinstance(mask, DeviceArray) or not isinstance(spec, DeviceArray):
+        raise ValueError("mask= needs DeviceArray spectrum and mask (device-resident chains)")
+    if mask.dtype != np.float32 or not mask.transposed or not spec.transposed:
+        raise ValueError("mask= needs a float32 frame-major mask and a frame-major spectrum (as zaf.stft / zaf.spec_abs return them)")
+    if mask.shape[-2] != n // 2 + 1 or mask.shape[-1] != spec.shape[-1] or mask.shape[:-2] != spec.shape[:-2]:
+        raise ValueError(f"mask must have {n // 2 + 1} rows and the spectrum's frames and batch, not {mask.shape}")
+    return mask.mem_shape[-1]
+
+
+def istft(audio_stft, window_function, step_length, *, stream=None, onesided=False, mask=None):
     """Inverse STFT by constant overlap-add -- drop-in for ``zaf.istft`` (zaf.py:144-243).
 
     Output length nt*hop - (N - hop); only the real part of the inverse transform is kept, no
     synthesis window, division by sum(w[0:N:hop]) -- all as in the reference (including its
     N-hop trim, which makes the round trip an identity only for hop = N/2).  ``onesided=True``
     (non-reference mode) takes rows 0 .. N/2 only and treats the rest as their conjugate mirror.
+    ``mask=`` (non-reference, DeviceArrays only): the transform of ``np.concatenate((mask, mask[-2:0:-1])) * X``
+    (zaf.py:185-190) for a real mask with rows 0 .. N/2 -- fused into the ISTFT's loads for N = 2048, hop = 512, a
+    ``spec_mask`` pass followed by the plain transform otherwise.
     """
     plan, w = _stft_plan(window_function, step_length)
     if onesided:
-        return _istft_onesided(plan, w, audio_stft, step_length, stream)
+        return _istft_onesided(plan, w, audio_stft, step_length, stream, mask)
     n = len(w)
     if isinstance(audio_stft, DeviceArray):
         s = audio_stft
@@ -367,10 +391,20 @@ def istft(audio_stft, window_function, step_length, *, stream=None, onesided=Fal
         nt = shape[-1]
         length = istft_geometry(n, nt, step_length)[2]
         out = DeviceArray((length,) if one else (batch, length), np.float32)
+        if mask is not None:
+            mp = _mask_pitch(mask, s, n)
+            try:
+                _lib.check(_lib.lib().zafb_istft_masked_f32(plan, C.c_void_p(s.ptr), batch, nt, n, 0, C.c_void_p(mask.ptr), mp,
+                                                            C.c_void_p(out.ptr), length, _stream_ptr(stream)))
+                return out
+            except NotImplementedError:  # no fused kernel for this geometry: multiply, then transform
+                s = spec_mask(s, mask, stream=stream)
         lay = LAYOUT_FRAME_MAJOR if s.transposed else LAYOUT_BIN_MAJOR
         _lib.check(_lib.lib().zafb_istft_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), length,
                                              _stream_ptr(stream)))
         return out
+    if mask is not None:
+        raise ValueError("mask= needs DeviceArray spectrum and mask (device-resident chains)")
     mem, lay, one, shape = _spec_memory(audio_stft, np.complex64)
     batch, bins, nt = shape
     if bins != n:

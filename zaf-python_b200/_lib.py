@@ -60,6 +60,7 @@ PROTOTYPES = {
     "zafb_stft_host_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int]),
     "zafb_stft_onesided_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "zafb_istft_onesided_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
+    "zafb_istft_masked_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _i64, _vp]),
     "zafb_spec_mirror_f32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "zafb_host_mirror_fill": (_int, [_vp, _i64, _i64]),
     "zafb_istft_host_f32": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64]),

@@ -665,6 +665,29 @@ int gemm3xtf32_tiled(int bn, const float* a_hi, const float* a_lo, int64_t lda, 
     return launch_tiled<128>(a_hi, a_lo, lda, a_cols, b_hi, b_lo, ldb, n_tiles, d_tiles, c, ldc, M, st);
 }
 
+// Number of CTA pairs that are resident at once (the kernels are persistent: a pair that had to wait for another one to
+// finish would double the run time).  cudaOccupancyMaxActiveClusters knows the GPC layout; half the SM count is the fallback.
+template <class K>
+int resident_pairs(K kernel, int threads, size_t smem) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(sm_count()) & ~1u);
+    cfg.blockDim = dim3(unsigned(threads));
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess || clusters < 1) {
+        cudaGetLastError();
+        clusters = sm_count() / 2;
+    }
+    return clusters;
+}
+
 // CTA-pair kernel over 256-row blocks of B (block t = B rows [256 t, 256 t + 256), its own A column range / output columns)
 int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int64_t a_cols, const float* b_hi, const float* b_lo,
                           int64_t ldb, int64_t b_rows, int n_tiles, const GemmTile* d_tiles, float* c, int64_t ldc, int64_t M,
@@ -685,7 +708,8 @@ int gemm3xtf32_pair_tiled(const float* a_hi, const float* a_lo, int64_t lda, int
     if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, b_rows, ldb, ldb, kBM);
     if (rc != ZAFB_OK) return rc;
     const int64_t m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
-    int64_t pairs = sm_count() / 2;
+    static const int resident = resident_pairs(gemm3xtf32_pair_kernel<false>, kPairThreads, kPairSmem);
+    int64_t pairs = resident;
     if (pairs > m_pairs * n_tiles) pairs = m_pairs * n_tiles;
     gemm3xtf32_pair_kernel<false><<<unsigned(2 * pairs), kPairThreads, kPairSmem, st>>>(ma, mal, mb, mbl, c, M, ldc, int(m_pairs),
                                                                                         n_tiles, d_tiles, nullptr, 0, 0);
@@ -711,7 +735,8 @@ int gemm3xtf32_pair_fold(const float* x, int64_t ldx, int n, const float* b_hi, 
     if (rc == ZAFB_OK) rc = make_map(&mbl, b_lo, b_rows, ldb, ldb, kBM);
     if (rc != ZAFB_OK) return rc;
     const int64_t m_pairs = (M + 2 * kBM - 1) / (2 * kBM);
-    int64_t pairs = sm_count() / 2;
+    static const int resident = resident_pairs(gemm3xtf32_pair_kernel<true>, kPairThreadsFold, kPairSmem);
+    int64_t pairs = resident;
     if (pairs > m_pairs * n_tiles) pairs = m_pairs * n_tiles;
     gemm3xtf32_pair_kernel<true><<<unsigned(2 * pairs), kPairThreadsFold, kPairSmem, st>>>(mx, mx, mb, mbl, c, M, ldc, int(m_pairs),
                                                                                            n_tiles, d_tiles, x, ldx, n);

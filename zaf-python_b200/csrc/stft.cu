@@ -533,11 +533,16 @@ __host__ __device__ constexpr int istft_ctas_per_sm(int n) { return n == 4096 ? 
 // floats of transpose tile per warp
 __host__ __device__ constexpr int istft_tile_floats(int n) { return n == 2048 ? 32 * kFft1024Pitch : 2 * (n / 64) * kFft1024Pitch; }
 
-template <int N, int R, int WARPS, bool ONESIDED = false>
+// MASKED (non-reference extension, instantiated for N = 2048, hop = N/4 only): a real time-frequency mask given for bins
+// 0 .. N/2 of every frame (mask_pitch floats apart) and mirrored onto the upper bins like np.concatenate((m, m[-2:0:-1]))
+// (zaf.py:185-186) is applied while loading -- m[k] X[k] + conj(m[k] X[N-k]) = m[k] (X[k] + conj X[N-k]) -- so the
+// stft -> mask -> istft chain needs no pass that rewrites the spectrum.
+template <int N, int R, int WARPS, bool ONESIDED = false, bool MASKED = false>
 __global__ void __launch_bounds__(WARPS * 32, istft_ctas_per_sm(N))
 istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __restrict__ tw4,
                   const float2* __restrict__ tw_full, float scale, int64_t runs_per_clip, int run_len,
-                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch, int64_t spec_pitch_arg) {
+                  int64_t total_runs, float* __restrict__ y, int64_t y_stride, int prefetch, int64_t spec_pitch_arg,
+                  const float* __restrict__ mask, int64_t mask_pitch) {
     // ONESIDED (non-reference extension): only bins 0 .. N/2 are given, spec_pitch_arg complex elements apart, the rest is
     // their Hermitian mirror -- half the reads.  The two-sided spectrum has a compile-time frame pitch of N.
     const int64_t spec_pitch = ONESIDED ? spec_pitch_arg : int64_t(N);
@@ -580,6 +585,7 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
 
         for (int64_t j = h_begin - (R - 1); j < h_end; ++j) {
             const float2* X = spec + (clip * nt + j) * spec_pitch;
+            const float* mrow = MASKED ? mask + (clip * nt + j) * mask_pitch : nullptr;
             if (prefetch && j + 1 < h_end) {  // the next frame of this run towards L2: N * 8 / 128 lines, N / 512 per lane
 #pragma unroll
                 for (int i = 0; i < N / 512; ++i)  // (N = 512: one line per lane; one-sided frames are half as long)
@@ -605,6 +611,11 @@ istft_warp_kernel(const float2* __restrict__ spec, int64_t nt, const float2* __r
                     const float2 d = __ldg(X + ((N - k) & (N - 1)));
                     h0 = make_float2(a.x + d.x, a.y - d.y);  // 2 H[k]
                     h1 = make_float2(b.x + c.x, b.y - c.y);  // 2 H[k + M]
+                }
+                if constexpr (MASKED) {  // bins k and N - k carry m[k]; bins M + k and M - k carry m[M - k]
+                    const float m0 = __ldg(mrow + k), m1 = __ldg(mrow + M - k);
+                    h0 = make_float2(h0.x * m0, h0.y * m0);
+                    h1 = make_float2(h1.x * m1, h1.y * m1);
                 }
                 const float2 e = cadd(h0, h1);
                 const float2 o = cmul_conj(csub(h0, h1), mul_tw<r, N / 32>(c_lane));
@@ -867,11 +878,19 @@ int launch_stft_binmajor(const zafb_stft_plan* p, const float* x, int64_t n_clip
 
 template <int N, int R, int WARPS>
 int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                        int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided) {
+                        int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided, const float* mask = nullptr,
+                        int64_t mask_pitch = 0) {
+    constexpr bool kHasMasked = N == 2048 && R == 4 && WARPS == 8;  // the masked kernels exist for the BASELINE geometry
+    if (mask != nullptr && !kHasMasked)
+        return fail(ZAFB_E_UNSUPPORTED, "masked istft: fused kernel exists for window_length 2048, hop 512 only");
     static bool attr = false;
     if (!attr) {
         ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
         ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        if constexpr (kHasMasked) {
+            ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+            ZAFB_CUDA((cudaFuncSetAttribute(istft_warp_kernel<N, R, WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem)));
+        }
         attr = true;
     }
     const int64_t nblocks = nt - (R - 1);  // finished hop-blocks per clip == output length / hop
@@ -897,22 +916,26 @@ int launch_istft_warp_w(const zafb_stft_plan* p, const float2* spec, int64_t n_c
     static_assert(smem <= size_t(kMaxDynSmem), "istft warp kernel: shared memory");
     const float scale = static_cast<float>(1.0 / (2.0 * double(N) * p->gain));
     auto kern = onesided ? istft_warp_kernel<N, R, WARPS, true> : istft_warp_kernel<N, R, WARPS, false>;
+    if constexpr (kHasMasked) {
+        if (mask != nullptr) kern = onesided ? istft_warp_kernel<N, R, WARPS, true, true> : istft_warp_kernel<N, R, WARPS, false, true>;
+    }
     kern<<<static_cast<unsigned>(ctas), WARPS * 32, smem, st>>>(
         spec, nt, p->d_tw_4step, p->d_tw_full, scale, runs_per_clip, int(best_len), total, y, y_stride,
-        env_flag("ZAFB_ISTFT_PREFETCH", 1), spec_pitch);
+        env_flag("ZAFB_ISTFT_PREFETCH", 1), spec_pitch, mask, mask_pitch);
     ZAFB_LAUNCH_CHECK();
     return ZAFB_OK;
 }
 
 template <int N, int R>
 int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_clips, int64_t nt, float* y,
-                      int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided) {
+                      int64_t y_stride, cudaStream_t st, int64_t spec_pitch, int onesided, const float* mask = nullptr,
+                      int64_t mask_pitch = 0) {
     // N = 4096: 6 warps (a 17 KB transpose tile plus up to 14 KB of overlap-add ring per warp)
-    if constexpr (N == 4096) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
+    if constexpr (N == 4096) return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided, mask, mask_pitch);
     else {
-        if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6)
+        if (env_flag("ZAFB_ISTFT_WARPS", 8) == 6 && mask == nullptr)
             return launch_istft_warp_w<N, R, 6>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
-        return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided);
+        return launch_istft_warp_w<N, R, 8>(p, spec, n_clips, nt, y, y_stride, st, spec_pitch, onesided, mask, mask_pitch);
     }
 }
 
@@ -1428,6 +1451,32 @@ int zafb_istft_onesided_f32(const zafb_stft_plan* p, const float* spec, int64_t 
     }
     cudaFreeAsync(scratch, st);
     return rc;
+}
+
+// ISTFT of mask * X with the mask multiply fused into the loads (see istft_warp_kernel, MASKED).  FRAME_MAJOR spectra of
+// the BASELINE geometry (window_length 2048, hop 512), two-sided (onesided = 0, frame pitch N) or one-sided (bins 0 .. N/2,
+// spec_pitch complex elements per frame); every other geometry returns ZAFB_E_UNSUPPORTED and the caller multiplies
+// first (zafb_spec_mask_f32).
+int zafb_istft_masked_f32(const zafb_stft_plan* p, const float* spec, int64_t n_clips, int64_t nt, int64_t spec_pitch, int onesided,
+                          const float* mask, int64_t mask_pitch, float* y, int64_t y_stride, void* stream) {
+    ZAFB_REQUIRE(p != nullptr, "plan is NULL");
+    ZAFB_REQUIRE(n_clips >= 0 && nt >= 0, "n_clips and nt must be >= 0");
+    const int64_t n = p->n, bins = n / 2 + 1;
+    ZAFB_REQUIRE(mask_pitch >= bins, "mask_pitch %lld < %lld mask bins", (long long)mask_pitch, (long long)bins);
+    ZAFB_REQUIRE(onesided ? spec_pitch >= bins : spec_pitch == n, "bad spectrum pitch %lld", (long long)spec_pitch);
+    int64_t len = 0;
+    zafb_istft_geometry(n, nt, p->hop, nullptr, nullptr, &len);
+    ZAFB_REQUIRE(y_stride >= len, "y_stride %lld < output length %lld", (long long)y_stride, (long long)len);
+    if (n_clips == 0 || len == 0) return ZAFB_OK;
+    ZAFB_REQUIRE(spec != nullptr && y != nullptr && mask != nullptr, "spec/mask/y is NULL");
+    const bool aligned = reinterpret_cast<uintptr_t>(spec) % 8 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 &&
+                         (n_clips <= 1 || y_stride % 2 == 0);
+    if (n != 2048 || p->hop != 512 || !aligned)
+        return fail(ZAFB_E_UNSUPPORTED, "masked istft: fused kernel exists for window_length 2048, hop 512, 8-byte aligned buffers only");
+    int rc = set_kernel_attrs();
+    if (rc != ZAFB_OK) return rc;
+    return launch_istft_warp<2048, 4>(p, reinterpret_cast<const float2*>(spec), n_clips, nt, y, y_stride, static_cast<cudaStream_t>(stream),
+                                      spec_pitch, onesided ? 1 : 0, mask, mask_pitch);
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
