@@ -10,10 +10,14 @@ drop-in call with pinned HOST buffers (H2D and D2H inside the timed region).
 The same JSON line carries, under `extra.configs`, EVERY other BASELINE config on its own shape
 (cfg 2 istft, cfg 3 melspectrogram + mfcc, cfg 4 mdct + imdct, cfg 5 cqtspectrogram on both routes):
 device-timed ms, units/s, roofline (HBM fraction and, for the compute-bound ones, FP32 fraction), a
-CPU baseline of that function and a post-timing parity check of two clips against the oracle (1e-5).
+CPU baseline of that function, a post-timing parity check of two clips against the oracle (1e-5) and, at
+N = 1, the transform's own end-to-end leg through host buffers (`extra.configs[].e2e`).  `extra.dct` times
+dct / dst on 2^20 x 1024 (type I: the CTA-pair tensor-core GEMM), `extra.device_chain` the reference's
+stft -> mask -> istft demo with every stage on the device.
 At N > 1 `extra.split_merge` holds one strong-scaling leg per transform -- scatter (NCCL) ->
 transform -> gather (NCCL) of ONE batch held by rank 0 -- each with a BITWISE comparison of the merged
-result against rank 0's unsharded result.
+result against rank 0's unsharded result, the cfg-2 STFT merge variants that move half the bytes or
+pipeline the transfer (`stft_variants`), and `total_ms` = the fastest bitwise-checked of them.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                         # the reference's own CPU implementation
