@@ -220,3 +220,11 @@ def test_istft_with_mask_fused_into_the_loads(zaf_gpu, n, hop, onesided):
     assert np.max(np.abs(y1 - got[1])) <= 1e-6 * np.max(np.abs(got[1]))
     with pytest.raises(ValueError):
         zaf.istft(spec.to_host(), w, hop, onesided=onesided, mask=mask)
+    if not onesided:  # the reference's C-order memory: mask in the same layout, multiply-then-transform
+        spec_c = zaf.stft(xd, w, hop, layout="bin_major")
+        mask_c = zaf.to_device(m_host.reshape(-1)).to_host().reshape(m_host.shape)  # round trip: plain (3, N/2+1, nt) memory
+        md = zaf.DeviceArray(m_host.shape, np.float32)
+        zaf._lib.check(zaf._lib.lib().zafb_memcpy_h2d(zaf._lib.C.c_void_p(md.ptr), mask_c.ctypes.data, mask_c.nbytes, None))
+        zaf.synchronize()
+        yc = zaf.istft(spec_c, w, hop, mask=md).to_host()
+        assert np.max(np.abs(yc - got)) <= 1e-5 * np.max(np.abs(got))

@@ -357,14 +357,15 @@ def spec_mirror(audio_stft_onesided, window_length, *, stream=None):
 
 
 def _mask_pitch(mask, spec, n):
-    """Validate a (N/2+1, nt) / (B, N/2+1, nt) float32 frame-major DeviceArray mask for ``spec``; returns its row pitch."""
+    """Validate a (N/2+1, nt) / (B, N/2+1, nt) float32 DeviceArray mask for ``spec``.  Returns its row pitch when both are
+    frame-major (the layout the fused kernel reads), else None: the caller multiplies first (``spec_mask``)."""
     if not isinstance(mask, DeviceArray) or not isinstance(spec, DeviceArray):
         raise ValueError("mask= needs DeviceArray spectrum and mask (device-resident chains)")
-    if mask.dtype != np.float32 or not mask.transposed or not spec.transposed:
-        raise ValueError("mask= needs a float32 frame-major mask and a frame-major spectrum (as zaf.stft / zaf.spec_abs return them)")
+    if mask.dtype != np.float32 or mask.transposed != spec.transposed:
+        raise ValueError("mask= needs a float32 mask in the layout of the spectrum (as zaf.spec_abs / zaf.ratio_min return it)")
     if mask.shape[-2] != n // 2 + 1 or mask.shape[-1] != spec.shape[-1] or mask.shape[:-2] != spec.shape[:-2]:
         raise ValueError(f"mask must have {n // 2 + 1} rows and the spectrum's frames and batch, not {mask.shape}")
-    return mask.mem_shape[-1]
+    return mask.mem_shape[-1] if mask.transposed else None
 
 
 def istft(audio_stft, window_function, step_length, *, stream=None, onesided=False, mask=None):
@@ -394,10 +395,12 @@ def istft(audio_stft, window_function, step_length, *, stream=None, onesided=Fal
         if mask is not None:
             mp = _mask_pitch(mask, s, n)
             try:
+                if mp is None:
+                    raise NotImplementedError
                 _lib.check(_lib.lib().zafb_istft_masked_f32(plan, C.c_void_p(s.ptr), batch, nt, n, 0, C.c_void_p(mask.ptr), mp,
                                                             C.c_void_p(out.ptr), length, _stream_ptr(stream)))
                 return out
-            except NotImplementedError:  # no fused kernel for this geometry: multiply, then transform
+            except NotImplementedError:  # no fused kernel for this geometry / layout: multiply, then transform
                 s = spec_mask(s, mask, stream=stream)
         lay = LAYOUT_FRAME_MAJOR if s.transposed else LAYOUT_BIN_MAJOR
         _lib.check(_lib.lib().zafb_istft_f32(plan, C.c_void_p(s.ptr), batch, nt, lay, C.c_void_p(out.ptr), length,
