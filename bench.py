@@ -536,12 +536,13 @@ class Item:
 
 def time_item(zaf, item, in_ptr, out_ptr, stream, steps, warmup=3, gpu_index=0):
     """(ms per launch, launches per step, clocks during the timed region).  The SMs may have idled through a host-bound
-    leg just before: warm-up launches run until ~100 ms of work have passed so that the clocks are back up."""
+    leg just before: warm-up launches run until ~30 ms of work have passed so that the clocks are back up (100 ms was tried: the
+    board then reaches its power cap and the HBM-bound legs lose 5-8 %)."""
     sampler = ClockSampler(gpu_index)
     sampler.start()
     e0, e1 = zaf.Event(), zaf.Event()
     spent, runs = 0.0, 0
-    while runs < warmup or (spent < 100.0 and runs < 100):
+    while runs < warmup or (spent < 30.0 and runs < 50):
         e0.record(stream)
         item.launch(in_ptr, item.clips, out_ptr, stream)
         e1.record(stream)
