@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Device-resident timing of the transforms in the reference's C-order memory (layout = BIN_MAJOR) on BASELINE shapes
 (a fraction of the batch): stft, istft (cfg 2), mdct, imdct (cfg 4).  Environment switches select the route
-(ZAFB_STFT_BM_DIRECT, ZAFB_TRANSPOSE_CHUNK_MB, ...).  usage: python scripts/probes/corder_probe.py [scale]"""
+(ZAFB_STFT_BM_DIRECT, ZAFB_MDCT_BM_DIRECT, ZAFB_IMDCT_BM_DIRECT, ZAFB_TRANSPOSE_CHUNK_MB, ...).
+usage: python scripts/probes/corder_probe.py [scale] [mdct]   ("mdct": the cfg-4 half only)"""
 import ctypes as C
 import json
 import os
@@ -26,7 +27,8 @@ def emit(name, ms, nbytes, launches):
                       "launches": launches, "env": tag}), flush=True)
 
 
-clips, ns, n, hop = int(1024 * scale), 480000, 2048, 512
+mdct_only = len(sys.argv) > 2 and sys.argv[2] == "mdct"
+clips, ns, n, hop = (1 if mdct_only else int(1024 * scale)), 480000, 2048, 512
 w = hamming_periodic(n)
 xd, _ = device_batch(clips, ns, 1)
 nt = zaf.stft_geometry(ns, n, hop)[1]

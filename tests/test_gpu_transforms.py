@@ -469,8 +469,13 @@ def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
     wk = oracle.kbd_window(2048)
     ma = zaf_gpu.mdct(x, wk)
     mb = zaf_gpu.mdct(x, wk, layout="bin_major")
-    assert mb.flags.c_contiguous and np.array_equal(ma, mb)
-    assert np.array_equal(zaf_gpu.imdct(mb, wk), zaf_gpu.imdct(ma, wk))
+    # C-order MDCT comes from mdct_binmajor_kernel: the arithmetic of the frame-major kernel in another kernel (the
+    # compiler fuses multiply-adds differently): equal to an fp32 ulp of the peak, not bit for bit
+    assert mb.flags.c_contiguous and np.max(np.abs(ma - mb)) <= 4e-7 * np.max(np.abs(ma))
+    assert np.max(np.abs(zaf_gpu.imdct(mb, wk) - zaf_gpu.imdct(ma, wk))) <= 1e-6
+    monkeypatch.setenv("ZAFB_MDCT_BM_DIRECT", "0")  # the scratch + transpose route is bit-identical to frame-major
+    assert np.array_equal(zaf_gpu.mdct(x, wk, layout="bin_major"), ma)
+    monkeypatch.delenv("ZAFB_MDCT_BM_DIRECT")
     w1 = oracle.hamming_periodic(1024)
     fb = zaf_gpu.melfilterbank(16000, 1024, 128)
     for route in ("fused", "tensor"):
@@ -485,6 +490,64 @@ def test_bin_major_layout_on_the_warp_kernels(zaf_gpu, monkeypatch):
     sd = zaf_gpu.stft(zaf_gpu.to_device(x2), w, 512, layout="bin_major")
     assert not sd.transposed and np.array_equal(sd.to_host(), a2)
     assert np.max(np.abs(zaf_gpu.istft(sd, w, 512).to_host() - zaf_gpu.istft(a2, w, 512))) <= 4e-7
+
+
+@pytest.mark.parametrize("n", [2048, 1024])
+def test_mdct_imdct_bin_major_direct_kernels(zaf_gpu, monkeypatch, n):
+    """layout="bin_major" MDCT at window lengths 2048 / 1024 is written by mdct_binmajor_kernel (tiles of 32 frames in a
+    shared-memory ring, every row stored through its own sector-aligned window) and C-order IMDCT input is read by
+    imdct_binmajor_kernel: same arithmetic as the frame-major warp kernels.  Frame counts of every residue mod 8 and
+    around the 32-frame tile, single-frame and two-frame clips, whole-clip and split runs, result pointers at every
+    4-byte phase of a 32-byte sector; ZAFB_*_BM_DIRECT=0 (scratch + transpose route) must agree.  Another kernel means
+    other multiply-add fusions: agreement to a few fp32 ulps (4e-7 of the peak for one transform, 1e-6 for two in a
+    row), not bit for bit; the oracle check at 1e-5 is separate."""
+    import ctypes as C
+    rng = np.random.default_rng(20261017 + n)
+    w = oracle.kbd_window(n)
+    m = n // 2
+    monkeypatch.setenv("ZAFB_IMDCT_BM_MIN_CLIPS", "1")
+    lens = [m * k + 2 for k in range(1, 10)] + [m * 31, m * 32 + 10, m * 33 + 4, m * 70 + 6, 10, 2]
+    for i, ns in enumerate(lens):
+        clips = 3 if i % 2 else 2
+        x = rng.uniform(-1, 1, (clips, ns)).astype(np.float32)
+        ref = zaf_gpu.mdct(x, w)
+        y_ref = zaf_gpu.imdct(ref, w)
+        peak = max(1.0, float(np.max(np.abs(ref))))
+        for env in ({}, {"ZAFB_MDCT_BM_DIRECT": "0", "ZAFB_IMDCT_BM_DIRECT": "0"}, {"ZAFB_MDCT_BM_RUNS_PER_CLIP": "1"},
+                    {"ZAFB_MDCT_BM_RUNS_PER_CLIP": "2"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = zaf_gpu.mdct(x, w, layout="bin_major")
+            y = zaf_gpu.imdct(got, w)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert got.flags.c_contiguous and got.shape == ref.shape
+            assert np.max(np.abs(got - ref), initial=0.0) <= 4e-7 * peak, (ns, env)
+            assert y.shape == y_ref.shape and np.max(np.abs(y - y_ref), initial=0.0) <= 1e-6, (ns, env)
+        assert_parity(ref[-1], oracle.mdct(x[-1], w))
+        assert_parity(y_ref[-1], oracle.imdct(oracle.mdct(x[-1], w), w))
+    # many short clips (every CTA walks several clips), device-resident, result pointers at every sector phase
+    x = rng.uniform(-1, 1, (300, 5 * m + 2)).astype(np.float32)
+    ref = zaf_gpu.mdct(x, w)
+    xd = zaf_gpu.to_device(x)
+    sd = zaf_gpu.mdct(xd, w, layout="bin_major")
+    assert not sd.transposed
+    peak = float(np.max(np.abs(ref)))
+    assert np.max(np.abs(sd.to_host() - ref)) <= 4e-7 * peak
+    assert np.max(np.abs(zaf_gpu.imdct(sd, w).to_host() - zaf_gpu.imdct(ref, w))) <= 1e-6
+    plan, _ = zaf_gpu._mdct_plan(w)
+    lib = zaf_gpu._lib.lib()
+    count = int(np.prod(ref.shape))
+    nt = ref.shape[-1]
+    length = zaf_gpu.imdct_geometry(m, nt)[1]
+    for off in range(1, 8):
+        buf = zaf_gpu.empty((count + 8,), np.float32)
+        zaf_gpu._lib.check(lib.zafb_mdct_f32(plan, C.c_void_p(xd.ptr), 300, x.shape[1], xd.pitch, C.c_void_p(buf.ptr + 4 * off), 1, None))
+        yb = zaf_gpu.empty((300, length + 1), np.float32)
+        zaf_gpu._lib.check(lib.zafb_imdct_f32(plan, C.c_void_p(buf.ptr + 4 * off), 300, nt, 1, C.c_void_p(yb.ptr), length + 1, None))
+        zaf_gpu.synchronize()
+        assert np.max(np.abs(buf.to_host()[off:off + count].reshape(ref.shape) - ref)) <= 4e-7 * peak, off
+        assert np.max(np.abs(yb.to_host()[:, :length] - zaf_gpu.imdct(ref, w))) <= 1e-6, off
 
 
 def test_sum_of_sinusoids_parity_and_the_fp32_floor_of_mfcc(zaf_gpu):

@@ -19,20 +19,18 @@
 #include "fft_core.cuh"
 #include "host_pipe.cuh"
 #include "transpose.cuh"
+#include "mdct_common.cuh"
 
 using namespace zafb;
 
-struct zafb_mdct_plan {
-    int64_t n = 0, m = 0;
-    int log2m = -1;               // power-of-two M only
-    float* d_window = nullptr;    // n floats
-    float2* d_tw_fft = nullptr;   // W_{M/2}^t, t < M/2
-    float2* d_pre = nullptr;      // e^{-i pi m / M}, m < M/2
-    float2* d_post = nullptr;     // e^{-i pi (m + 1/4) / M}, m < M/2
-    float* d_cos = nullptr;       // direct path: cos(2 pi t / (8M)), t < 8M
-    float2* d_tw_4step = nullptr; // n == 2048 / 1024: W_H^{k1*n2} at [k1*32 + n2], H = n/4 (warp kernels)
-    int force_kernel = 0;         // 0 auto, 1 generic, 2 warp (tests)
-};
+namespace zafb {  // mdct_binmajor.cu: the kernels that write / read the reference's C-order memory directly
+bool mdct_binmajor_supported(const zafb_mdct_plan* p, int64_t nt);
+int mdct_binmajor_launch(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int64_t ns, int64_t clip_stride, int64_t nt,
+                         float* out, cudaStream_t st);
+int imdct_binmajor_launch(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, int64_t nt, int64_t out_len, float* y,
+                          int64_t y_stride, cudaStream_t st);
+}  // namespace zafb
+
 
 namespace {
 
@@ -140,22 +138,6 @@ constexpr int kWarps = 8;
 #define ZAFB_IMDCT_SMALL_OCC 3  // CTAs per SM of imdct_warp_kernel<512> (2 -> 5.39 ms, 3 -> 5.21; N = 1024 spills with 3: 4.54 -> 4.88)
 #endif
 
-// N = 4096 (M = 2048, 1024-point FFT, warp_fft1024), N = 2048 (M = 1024, 512-point FFT, warp_fft512),
-// N = 1024 (M = 512, 256-point FFT, warp_fft256) or N = 512 (M = 256, 128-point FFT, warp_fft128)
-template <int N>
-struct MdctGeom {
-    static_assert(N == 512 || N == 1024 || N == 2048 || N == 4096, "mdct warp kernels exist for window lengths 512 ... 4096");
-    static constexpr int NTQ = N == 1024 ? 8 : N == 512 ? 12 : 1;  // per-lane twiddles of the warp FFT
-    static constexpr int M = N / 2;          // coefficients per frame
-    static constexpr int H = M / 2;          // complex FFT length
-    static constexpr int REGS = H / 32;      // float2 per lane
-    static constexpr int LOGR = clog2(REGS);
-    static constexpr int Q = M / 4;          // quarter of the frame, in sample pairs
-    static constexpr int TWDEN = M / 16;     // pre[lane + 32 r] = pre[lane] W_TWDEN^r (e^{-i pi 32 r / M})
-    static constexpr int TABLES = M + H;     // float2: window pairs, W_H four-step table
-    static constexpr int TILE = REGS * kFft1024Pitch;
-};
-
 template <int N>
 __device__ __forceinline__ void load_tables(float2* smem, const float2* __restrict__ win_pairs,
                                             const float2* __restrict__ tw4, int tid, float win_scale = 1.0f) {
@@ -165,15 +147,6 @@ __device__ __forceinline__ void load_tables(float2* smem, const float2* __restri
         smem[i] = make_float2(w.x * win_scale, w.y * win_scale);
     }
     for (int i = tid; i < G::H; i += kWarps * 32) smem[G::M + i] = tw4[i];
-}
-
-template <int N>
-__device__ __forceinline__ void mdct_warp_fft(float2 (&v)[MdctGeom<N>::REGS], const float2* __restrict__ tw, float2* buf, int lane,
-                                              const float2 (&tq)[MdctGeom<N>::NTQ]) {
-    if constexpr (N == 4096) warp_fft1024<false>(v, tw, buf, lane);
-    else if constexpr (N == 2048) warp_fft512(v, tw, buf, lane);
-    else if constexpr (N == 1024) warp_fft256(v, tw, buf, lane, tq);
-    else warp_fft128(v, tw, buf, lane, tq);
 }
 
 template <int N, int OCC>
@@ -539,8 +512,13 @@ int zafb_mdct_f32(const zafb_mdct_plan* p, const float* x, int64_t n_clips, int6
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int m = int(p->m);
     {
-        const bool aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0) &&
-                             reinterpret_cast<uintptr_t>(out) % 8 == 0;
+        const bool x_aligned = reinterpret_cast<uintptr_t>(x) % 8 == 0 && (n_clips <= 1 || clip_stride % 2 == 0);
+        // the reference's C-order memory, written directly at any 4-byte phase of the result (ZAFB_MDCT_BM_DIRECT=0:
+        // frame-major scratch + tiled transpose)
+        if (layout == ZAFB_LAYOUT_BIN_MAJOR && x_aligned && p->force_kernel != 1 && mdct_binmajor_supported(p, nt) &&
+            env_flag("ZAFB_MDCT_BM_DIRECT", 1))
+            return mdct_binmajor_launch(p, x, n_clips, ns, clip_stride, nt, out, st);
+        const bool aligned = x_aligned && reinterpret_cast<uintptr_t>(out) % 8 == 0;
         const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && aligned;
         if (p->force_kernel == 2 && !warp_ok)
             return fail(ZAFB_E_UNSUPPORTED, "mdct warp kernel needs N = 512, 1024, 2048 or 4096, even clip_stride, 8-byte aligned x/out");
@@ -611,6 +589,11 @@ int zafb_imdct_f32(const zafb_mdct_plan* p, const float* spec, int64_t n_clips, 
     if (n_clips == 0 || len == 0) return ZAFB_OK;
     ZAFB_REQUIRE(spec != nullptr && y != nullptr, "spec/y is NULL");
     const int m = int(p->m);
+    // C-order input read directly (any 4-byte phase): one CTA per clip, so only when the batch fills the SMs
+    // (ZAFB_IMDCT_BM_MIN_CLIPS, default half the SM count); ZAFB_IMDCT_BM_DIRECT=0: tiled transpose into scratch first
+    if (layout == ZAFB_LAYOUT_BIN_MAJOR && p->force_kernel != 1 && mdct_binmajor_supported(p, nt) &&
+        env_flag("ZAFB_IMDCT_BM_DIRECT", 1) && n_clips >= env_flag("ZAFB_IMDCT_BM_MIN_CLIPS", sm_count() / 2))
+        return imdct_binmajor_launch(p, spec, n_clips, nt, len, y, y_stride, static_cast<cudaStream_t>(stream));
     {
         const bool warp_ok = (p->n == 4096 || p->n == 2048 || p->n == 1024 || p->n == 512) && reinterpret_cast<uintptr_t>(spec) % 8 == 0;
         if (p->force_kernel == 2 && !warp_ok)
