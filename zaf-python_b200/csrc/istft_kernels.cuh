@@ -236,6 +236,9 @@ int launch_istft_warp(const zafb_stft_plan* p, const float2* spec, int64_t n_cli
 // order like the reference (zaf.py:227-233) and like istft_warp_kernel -- the results are bit-identical to the
 // frame-major path -- and leaves as contiguous 16-byte stores.  The R - 1 last frames of a tile stay in the ring.
 // ------------------------------------------------------------------------------------------
+#ifndef ZAFB_ISTFT_BM_LOAD_BATCH
+#define ZAFB_ISTFT_BM_LOAD_BATCH 8  // cfg 2: 4 -> 6.2 ms, 8 -> 5.38 ms, 16 -> 5.98 ms (spills)
+#endif
 template <int N>
 struct IstftBinMajorGeom {
     static constexpr int F = 16;
@@ -284,8 +287,22 @@ istft_binmajor_kernel(const float2* __restrict__ spec, int nt, const float2* __r
                 if (lw < cnt && j < nt) {
                     float2* slot = s_reg + (j % SLOTS) * PITCH;
                     const float2* col = sc + j;
-#pragma unroll 4
-                    for (int k = lu; k <= M; k += 32) {
+                    // kLoadBatch bins = 2 kLoadBatch independent 8-byte loads in flight per thread before the first use
+                    // (the phase waits on HBM latency: 4 bins at a time 6.2 ms on cfg 2)
+                    constexpr int KB = ZAFB_ISTFT_BM_LOAD_BATCH;
+                    int k = lu;
+#pragma unroll 1
+                    for (; k + 32 * (KB - 1) <= M; k += 32 * KB) {
+                        float2 a[KB], d[KB];
+#pragma unroll
+                        for (int b = 0; b < KB; ++b) {
+                            a[b] = __ldg(col + int64_t(k + 32 * b) * nt);
+                            d[b] = __ldg(col + int64_t((N - k - 32 * b) & (N - 1)) * nt);
+                        }
+#pragma unroll
+                        for (int b = 0; b < KB; ++b) slot[k + 32 * b] = make_float2(a[b].x + d[b].x, a[b].y - d[b].y);
+                    }
+                    for (; k <= M; k += 32) {
                         const float2 a = __ldg(col + int64_t(k) * nt);
                         const float2 d = __ldg(col + int64_t((N - k) & (N - 1)) * nt);
                         slot[k] = make_float2(a.x + d.x, a.y - d.y);
