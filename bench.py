@@ -13,7 +13,9 @@ device-timed ms, units/s, roofline (HBM fraction and, for the compute-bound ones
 CPU baseline of that function, a post-timing parity check of two clips against the oracle (1e-5) and, at
 N = 1, the transform's own end-to-end leg through host buffers (`extra.configs[].e2e`).  `extra.dct` times
 dct / dst on 2^20 x 1024 (type I: the CTA-pair tensor-core GEMM), `extra.device_chain` the reference's
-stft -> mask -> istft demo with every stage on the device.
+stft -> mask -> istft demo with every stage on the device, `extra.c_order` cfg 2 stft / istft and cfg 4
+mdct / imdct in the memory order the reference itself produces and consumes (C-order (bins, frames) per clip)
+with their own roofline and parity fields.
 At N > 1 `extra.split_merge` holds one strong-scaling leg per transform -- scatter (NCCL) ->
 transform -> gather (NCCL) of ONE batch held by rank 0 -- each with a BITWISE comparison of the merged
 result against rank 0's unsharded result, the cfg-2 STFT merge variants that move half the bytes or
@@ -419,6 +421,7 @@ class Item:
         lib, C = zaf._lib.lib(), zaf._lib.C
         self.lib, self.C = lib, C
         self.route = None
+        self.layout = 0  # 0 = frame-major (a transposed view for the caller), 1 = BIN_MAJOR: the reference's C order
         if name in ("stft", "istft"):
             self.w = hamming_periodic(c["n"])
             self.plan, _ = zaf._stft_plan(self.w, c["hop"])
@@ -480,17 +483,17 @@ class Item:
         sp = stream.ptr if stream is not None else None
         i, o = C.c_void_p(in_ptr), C.c_void_p(out_ptr)
         if self.name == "stft":
-            rc = lib.zafb_stft_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+            rc = lib.zafb_stft_f32(p, i, clips, self.ns, self.ns, o, self.layout, sp)
         elif self.name == "istft":
-            rc = lib.zafb_istft_f32(p, i, clips, self.nt, 0, o, self.ylen, sp)
+            rc = lib.zafb_istft_f32(p, i, clips, self.nt, self.layout, o, self.ylen, sp)
         elif self.name == "melspectrogram":
             rc = lib.zafb_melspectrogram_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
         elif self.name == "mfcc":
             rc = lib.zafb_mfcc_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
         elif self.name == "mdct":
-            rc = lib.zafb_mdct_f32(p, i, clips, self.ns, self.ns, o, 0, sp)
+            rc = lib.zafb_mdct_f32(p, i, clips, self.ns, self.ns, o, self.layout, sp)
         elif self.name == "imdct":
-            rc = lib.zafb_imdct_f32(p, i, clips, self.nt, 0, o, self.ypitch, sp)
+            rc = lib.zafb_imdct_f32(p, i, clips, self.nt, self.layout, o, self.ypitch, sp)
         else:
             rc = lib.zafb_cqt_f32(p, i, clips, self.ns, self.ns, 0, o, 0, sp)
         self.zaf._lib.check(rc)
@@ -511,11 +514,14 @@ class Item:
         o, c = self.oracle, self.c
         xin = self.d2h_row(in_ptr, clip, self.in_row)
         got = self.d2h_row(out_ptr, clip, self.out_row)
+        def mat(flat, bins):  # the (bins, frames) matrix of one clip in either memory order
+            return flat.reshape(bins, self.nt) if self.layout else flat.reshape(self.nt, bins).T
+
         if self.name == "stft":
             ref = o.stft(xin, self.w, c["hop"])
-            got = got.view(np.complex64).reshape(self.nt, c["n"]).T
+            got = mat(got.view(np.complex64), c["n"])
         elif self.name == "istft":
-            ref = o.istft(xin.view(np.complex64).reshape(self.nt, c["n"]).T, self.w, c["hop"])
+            ref = o.istft(mat(xin.view(np.complex64), c["n"]), self.w, c["hop"])
         elif self.name == "melspectrogram":
             ref = o.melspectrogram(xin, self.w, c["hop"], self.fb)
             got = got.reshape(self.nt, self.rows).T
@@ -524,9 +530,9 @@ class Item:
             got = got.reshape(self.nt, self.rows).T
         elif self.name == "mdct":
             ref = o.mdct(xin, self.w)
-            got = got.reshape(self.nt, self.m).T
+            got = mat(got, self.m)
         elif self.name == "imdct":
-            ref = o.imdct(xin.reshape(self.nt, self.m).T, self.w)
+            ref = o.imdct(mat(xin, self.m), self.w)
             got = got[: self.ylen]
         else:
             ref = o.cqtspectrogram(xin, c["fs"], c["tr"], self.kern)
@@ -664,6 +670,54 @@ def run_configs(zaf, dist, args, stream, peak, sm_max_mhz, cpu_lines):
             if outd is not None:
                 outd.free()
         ind.free()
+    return out
+
+
+C_ORDER_KERNELS = {"stft": "stft_warp_binmajor_kernel<2048>", "istft": "istft_binmajor_kernel<2048,4>",
+                   "mdct": "mdct_binmajor_kernel<2048>", "imdct": "imdct_binmajor_kernel<2048>"}
+
+
+def c_order_legs(zaf, dist, args, stream, peak):
+    """The transforms with a (bins, frames) matrix on one side, in the memory order the reference itself produces and
+    consumes (C-order per clip = layout BIN_MAJOR, zaf.py:128, 214, 1073, 1159) instead of the frame-major order behind a
+    transposed view: cfg 2 stft -> istft and cfg 4 mdct -> imdct, device-timed like extra.configs, the inverse fed the
+    forward transform's own C-order output, two clips of each checked against the oracle."""
+    out = []
+    for fwd, inv in (("stft", "istft"), ("mdct", "imdct")):
+        if args.only_configs and not ({fwd, inv} & set(args.only_configs)):
+            continue
+        bufs = []
+        try:
+            f_item, i_item = (Item(zaf, n, clips=args.config_clips or None) for n in (fwd, inv))
+            f_item.layout = i_item.layout = 1
+            xd, _ = device_batch(zaf, f_item.clips, f_item.ns, 20261017 + f_item.c["cfg"])
+            bufs.append(xd)
+            spec = zaf.empty((f_item.clips, f_item.out_row), np.float32)
+            bufs.append(spec)
+            yd = zaf.empty((i_item.clips, i_item.out_row), np.float32)
+            bufs.append(yd)
+            for item, src, dst in ((f_item, xd, spec), (i_item, spec, yd)):
+                ms, nl, clk = time_item(zaf, item, src.ptr, dst.ptr, stream, args.config_steps, gpu_index=dist.local_rank)
+                ms = dist.max(ms)
+                parity = None
+                if dist.rank == 0:
+                    parity = max(item.parity(src.ptr, dst.ptr, c) for c in (0, item.clips - 1))
+                    assert parity <= TOL, f"{item.name} (C order): parity broken: {parity}"
+                algo = item.clips * item.algo_bytes_per_clip
+                gbs = algo / (ms * 1e-3) / 1e9
+                out.append({"transform": item.name, "layout": "bin_major (the reference's C order)", "config": config_text(item.name),
+                            "clips_per_gpu": item.clips, "ms_per_step": ms,
+                            "frames_per_sec": item.clips * item.units_per_clip * dist.world / (ms * 1e-3),
+                            "launches_per_step": int(nl), "kernel": C_ORDER_KERNELS[item.name],
+                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                         "algorithmic_bytes_per_launch": int(algo)},
+                            "parity_max_rel_err": parity, "parity_tolerance": TOL, "clocks": clk})
+        except AssertionError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            out.append({"transform": f"{fwd}/{inv}", "layout": "bin_major", "error": f"{type(exc).__name__}: {exc}"[:300]})
+        for b in bufs:
+            b.free()
     return out
 
 
@@ -1328,6 +1382,12 @@ def run_ours(args):
                 raise
             except Exception as exc:  # noqa: BLE001
                 extra["dct"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            extra["c_order"] = c_order_legs(zaf, dist, args, stream, peak)
+        except AssertionError:
+            raise
+        except Exception as exc:  # noqa: BLE001
+            extra["c_order"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         run_config_e2e(zaf, dist, args, extra["configs"])
 
     # the headline launch held for ~1 s: the board reaches its power cap and the SM clock drops; reported next to the headline.

@@ -9,3 +9,4 @@ for k,v in sm.get("stft_variants",{}).items():
 print([ (c["transform"], round(c.get("ms_per_step",0),2), c.get("error")) for c in d["extra"]["configs"]])
 print([ (c["transform"], round(c["ms_per_step"],2)) for c in d["extra"]["dct"]])
 c=d["extra"]["device_chain"]; print(c["ms_per_batch"], c["onesided"]["ms_per_batch"]) if c else None
+co=d["extra"].get("c_order"); print("c_order", [ (c["transform"], round(c.get("ms_per_step",0),2), round(c.get("roofline",{}).get("frac",0),3), c.get("parity_max_rel_err"), c.get("error")) for c in co] if isinstance(co,list) else co)
