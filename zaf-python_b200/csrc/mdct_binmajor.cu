@@ -235,7 +235,9 @@ imdct_binmajor_kernel(const float* __restrict__ spec, int nt, const float2* __re
             const int j0 = t * F;
             // load phase: lane w reads frame j0 + w of rows warp + 16 i (one 128-byte run per row and warp).  Measured and
             // not kept: requesting the next tile's values into registers before the combine phase (9.1 -> 9.5 ms on cfg 4,
-            // the 64 live registers spill) and an L2 prefetch of the tile after it (10.6 ms).
+            // the 64 live registers spill), an L2 prefetch of the tile after it (10.6 ms), and a variant with 16-frame
+            // tiles whose next tile arrives by cp.async (4-byte LDGSTS) during the transform (8.26 ms against 8.13;
+            // ncu: MIO throttle is the top stall, 1 666 warp instructions per frame, IPC 1.65 -- DESIGN.md 4.1d).
             {
                 const int j = j0 + lane;
                 if (j < nt) {
