@@ -3,4 +3,4 @@
 OUT=gpurun_out/${1:-mdctbm}; mkdir -p $OUT
 timeout 600 python -m pytest tests -q --tb=short -m gpu -k "bin_major or mdct" 2>&1 | grep -v "^E   " | tail -40 | tee $OUT/pytest.log
 timeout 300 python scripts/probes/corder_probe.py ${SCALE:-1.0} mdct 2>&1 | grep mdct | tee $OUT/probe.txt
-ZAFB_IMDCT_BM_ASYNC=0 timeout 300 python scripts/probes/corder_probe.py ${SCALE:-1.0} mdct 2>&1 | grep imdct | tee -a $OUT/probe.txt
+

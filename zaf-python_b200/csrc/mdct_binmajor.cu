@@ -173,6 +173,7 @@ mdct_binmajor_kernel(const float* __restrict__ x, int64_t ns, int64_t clip_strid
                 });
             }
             __syncthreads();
+            // (16-byte stores -- lane (rr, q) four frames of rows 4 u + rr + 64 i -- were measured: 5.86 -> 6.51 ms on cfg 4)
             const int ja = j0 - s_row + lane;
             if (ja >= jlo && ja < jhi) {
                 const float* r = s_ring + (ja % SLOTS) * PITCH + warp;
