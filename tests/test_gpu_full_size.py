@@ -78,6 +78,36 @@ def test_cfg4_mdct_imdct_full_batch_tdac(zaf_gpu):
     xd.free(), md.free(), yd.free()
 
 
+def test_cfg4_mdct_imdct_full_batch_c_order(zaf_gpu):
+    """The same batch in the reference's own memory order (C-order (M, nt) per clip: mdct_binmajor_kernel ->
+    imdct_binmajor_kernel): TDAC perfect reconstruction, every clip of the result equal to the result of its 32-clip tile
+    (a clip never depends on the batch around it), and one clip's coefficients against the oracle."""
+    zaf = zaf_gpu
+    n, ns, clips = 2048, 1323000, 2048
+    w = oracle.kbd_window(n)
+    xd, host = tiled_batch(zaf, clips, ns, 20261017 + 4)
+    md = zaf.mdct(xd, w, layout="bin_major")
+    assert md.shape == (clips, 1024, 1293) and not md.transposed
+    yd = zaf.imdct(md, w)
+    assert yd.shape == (clips, 1024 * 1292 - 1)
+    lib = zaf._lib.lib()
+    row = np.empty(yd.pitch, np.float32)
+    for c in (0, 1, 777, 1500, 2047):
+        zaf._lib.check(lib.zafb_memcpy_d2h(row.ctypes.data, C.c_void_p(yd.ptr + c * yd.pitch * 4), yd.pitch * 4, None))
+        zaf.synchronize()
+        assert np.max(np.abs(row[:ns] - host[c % DISTINCT])) <= 1e-5
+    a = np.empty((1024, 1293), np.float32)
+    b = np.empty((1024, 1293), np.float32)
+    for c, k in ((3, 31), (17, 60)):
+        zaf._lib.check(lib.zafb_memcpy_d2h(a.ctypes.data, C.c_void_p(md.ptr + c * a.nbytes), a.nbytes, None))
+        zaf._lib.check(lib.zafb_memcpy_d2h(b.ctypes.data, C.c_void_p(md.ptr + (c + DISTINCT * k) * a.nbytes), a.nbytes, None))
+        zaf.synchronize()
+        assert np.array_equal(a, b)
+    mx, l2 = oracle.parity_metrics(a, oracle.mdct(host[17], w))
+    assert mx <= 1e-5 and l2 <= 1e-5
+    xd.free(), md.free(), yd.free()
+
+
 def test_cfg3_mel_mfcc_full_batch(zaf_gpu):
     """4096 clips x 5 s @ 16 kHz: 1 286 144 frames; every clip equals the result of its 32-clip tile
     (bitwise) and one tile matches the oracle."""
