@@ -163,10 +163,13 @@ int zafb_host_mirror_fill(float* spectrum_host, int64_t frames, int64_t window_l
 typedef struct zafb_mdct_plan zafb_mdct_plan;
 int zafb_mdct_plan_create(zafb_mdct_plan** plan, const double* window, int64_t window_length);
 int zafb_mdct_plan_destroy(zafb_mdct_plan* plan);
-/* zaf.mdct (zaf.py:1025-1075): out is n_clips * (N/2) * nt float32 in `layout`. */
+/* zaf.mdct (zaf.py:1025-1075): out is n_clips * (N/2) * nt float32 in `layout`.  ZAFB_LAYOUT_BIN_MAJOR is the (N/2, nt)
+ * C-order array the reference returns (zaf.py:1073); for N = 2048 / 1024 one kernel writes it directly, at any 4-byte
+ * phase of `out` (x rows 8-byte aligned); other lengths go through frame-major scratch and a tiled transpose. */
 int zafb_mdct_f32(const zafb_mdct_plan* plan, const float* x, int64_t n_clips, int64_t ns,
                   int64_t clip_stride, float* out, int layout, void* stream);
-/* zaf.imdct (zaf.py:1125-1184): y rows of M*(nt-1)-1 samples. */
+/* zaf.imdct (zaf.py:1125-1184): y rows of M*(nt-1)-1 samples.  BIN_MAJOR input (the array zaf.mdct returns, zaf.py:1159)
+ * is read directly for N = 2048 / 1024 when n_clips is at least half the SM count (one CTA walks one clip). */
 int zafb_imdct_f32(const zafb_mdct_plan* plan, const float* spec, int64_t n_clips, int64_t nt,
                    int layout, float* y, int64_t y_stride, void* stream);
 
